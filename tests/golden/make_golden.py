@@ -1,0 +1,240 @@
+"""Generate golden fixtures by running the UNMODIFIED reference in this container.
+
+Run from the repo root (only where `/root/reference` exists; the GPU box never runs this):
+
+    python tests/golden/make_golden.py
+
+What runs: the reference's own `highway_branch_dyn.PredictiveModel`,
+`quadruped_branch_dyn.PredictiveModel`, `Init_MPC.init*`, `MPC_branch.BranchMPC`,
+`BranchMPCProx` and `robustMPC`, imported from `/root/reference` on top of the shims in
+`tests/golden/shims/` (casadi -> a small expression graph with forward-mode AD; osqp -> exact
+QP solve + HiGHS cross-check).  So every matrix stored here (H, q, F, b, G, E x + L), every tree
+table and every model-function value was produced by the reference's code; only the third-party
+numerical back-ends are substituted.
+
+Fixtures (tests/golden/*.npz, a few tens of KB each) store the QP in sparse triplets.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import refenv  # noqa: E402
+
+with refenv.reference_imports():
+    import highway_branch_dyn as hw  # noqa: E402
+    import quadruped_branch_dyn as qd  # noqa: E402
+    import utils as rutils  # noqa: E402
+    import MPC_branch  # noqa: E402
+    import Init_MPC  # noqa: E402
+    import osqp  # noqa: E402
+
+
+def highway_cons():
+    # main_branch.py:37
+    return rutils.Branch_constants(s1=2, s2=3, c2=0.5, tran_diag=0.3, alpha=1, R=1.2, am=6.0, rm=0.3,
+                                   J_c=20, s_c=1, ylb=0., yub=7.2, L=4, W=2.5, col_alpha=5, Kpsi=0.1)
+
+
+def highway_policies(names, cons, lc_target, v0=20.0):
+    table = {
+        "maintain": lambda x: hw.backup_maintain(x, cons),
+        "brake": lambda x: hw.backup_brake(x, cons),
+        "lc": lambda x: hw.backup_lc(x, lc_target),
+        "trackv": None,   # MX-only symbolic branch in the reference (highway_branch_dyn.py:80-88): not usable with SX models
+    }
+    return [table[n] for n in names]
+
+
+def quad_cons():
+    # main_quadruped.py:31
+    return rutils.Quad_constants(s1=2, s2=3, c2=0.5, alpha=1, R=1.2, vxm=0.2, vym=0.1, rm=0.5,
+                                 L1=0.5, W1=0.3, L2=1, W2=0.6, col_tol=0.2, col_alpha=5)
+
+
+def tree_tables(mpc):
+    """BFS tables of the reference tree: id, depth, ndx, ndu, parent, w, and stacked trajectories."""
+    ids = {b: k for k, b in enumerate(mpc.ndx)}
+    parent = {mpc.BT: -1}
+    for b in mpc.ndx:
+        for c in b.children:
+            parent[c] = ids[b]
+    rows = []
+    for b in mpc.ndx:
+        rows.append((ids[b], b.depth, mpc.ndx[b], mpc.ndu[b], parent[b]))
+    w = np.array([b.w for b in mpc.ndx], dtype=float)
+    p = np.array([b.p if b.p is not None else np.full(mpc.m, np.nan) for b in mpc.ndx], dtype=float)
+    xbar = np.vstack([b.xtraj for b in mpc.ndx])
+    zbar = np.vstack([b.ztraj for b in mpc.ndx])
+    ubar = np.vstack([b.utraj for b in mpc.ndx])
+    return np.array(rows, dtype=np.int64), w, p, xbar, zbar, ubar
+
+
+def coo(mat):
+    m = sp.coo_matrix(mat)
+    return m.row.astype(np.int32), m.col.astype(np.int32), m.data.astype(float), np.array(m.shape, dtype=np.int64)
+
+
+def record_step(store, k, mpc, x, z, xref, tree=True):
+    lp = osqp.last_problem
+    assert lp["ok"], "oracle QP solve did not certify"
+    pre = "s%d_" % k
+    store[pre + "x0"] = np.array(x, dtype=float)
+    store[pre + "z0"] = np.array(z, dtype=float)
+    store[pre + "xref"] = np.array(xref, dtype=float)
+    for name, mat in (("P", sp.triu(lp["P"])), ("A", lp["A"])):
+        r, c, v, shp = coo(mat)
+        store[pre + name + "_r"] = r
+        store[pre + name + "_c"] = c
+        store[pre + name + "_v"] = v
+        store[pre + name + "_shape"] = shp
+    store[pre + "q"] = lp["q"]
+    store[pre + "l"] = lp["l"]
+    store[pre + "u"] = lp["u"]
+    store[pre + "sol"] = lp["x"]
+    store[pre + "objective"] = np.array(lp["cert"]["objective"])
+    store[pre + "kkt"] = np.array([lp["cert"]["primal"], lp["cert"]["dual"]])
+    store[pre + "highs_objective"] = np.array(lp["highs_objective"])
+    store[pre + "highs_xu_maxdiff"] = np.array(
+        np.abs(lp["highs_x"][: mpc_nxu(mpc)] - lp["x"][: mpc_nxu(mpc)]).max())
+    store[pre + "xPred"] = np.array(mpc.xPred)
+    store[pre + "uPred"] = np.array(mpc.uPred)
+    if tree:
+        tab, w, p, xbar, zbar, ubar = tree_tables(mpc)
+        store[pre + "tree"] = tab
+        store[pre + "w"] = w
+        store[pre + "p"] = p
+        store[pre + "xbar"] = xbar
+        store[pre + "zbar"] = zbar
+        store[pre + "ubar"] = ubar
+        store[pre + "totals"] = np.array([mpc.totalx, mpc.totalu])
+    print("   step %d: obj %.6f  u0 %s  kkt %.1e/%.1e  highs(%s) xu-diff %.1e" % (
+        k, lp["cert"]["objective"], np.array2string(mpc.uPred[0], precision=6),
+        lp["cert"]["primal"], lp["cert"]["dual"], lp["highs_status"], store[pre + "highs_xu_maxdiff"]))
+
+
+def mpc_nxu(mpc):
+    if hasattr(mpc, "totalx") and mpc.totalx:
+        return mpc.totalx * mpc.n + mpc.totalu * mpc.d
+    return mpc.Nx * mpc.n + mpc.Nu * mpc.d
+
+
+def euler_highway(x, u, dt):
+    return x + dt * np.array([x[2] * np.cos(x[3]), x[2] * np.sin(x[3]), u[0], u[1]])
+
+
+def run_highway(name, ctrl, policies, NB, x, z, xref, steps, N=8, lc_target=(0.5, 1.8, 15., 0.), n_lane_mpc=4):
+    print("highway fixture", name)
+    cons = highway_cons()
+    lc_target = np.array(lc_target, dtype=float)
+    model = hw.PredictiveModel(4, 2, N, highway_policies(policies, cons, lc_target), 0.1, cons)
+    par = Init_MPC.initBranchMPC(4, 2, N, NB, lc_target, 6.0, 0.3, n_lane_mpc, cons.W)
+    mpc = getattr(MPC_branch, ctrl)(par, model)
+    store = {"meta_policies": np.array(policies), "meta_ctrl": np.array(ctrl), "meta_NB": np.array(NB),
+             "meta_N": np.array(N), "meta_lc_target": lc_target, "meta_steps": np.array(steps),
+             "meta_n_lane_mpc": np.array(n_lane_mpc)}
+    x = np.array(x, dtype=float)
+    z = np.array(z, dtype=float)
+    for k in range(steps):
+        mpc.solve(x, z, np.array(xref, dtype=float))
+        record_step(store, k, mpc, x, z, xref, tree=(ctrl != "robustMPC"))
+        x = euler_highway(x, mpc.uPred[0], 0.1)
+        z = euler_highway(z, np.array([0., -cons.Kpsi * z[3]]), 0.1)     # obstacle keeps 'maintain'
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+
+
+def run_quadruped(name, x, z, xref, steps, N=25, NB=2):
+    print("quadruped fixture", name)
+    cons = quad_cons()
+    v0 = 0.2
+    policies = [lambda s: qd.backup_forward(s, v0), lambda s: qd.backup_stop(s)]
+    model = qd.PredictiveModel(3, 3, N, policies, 0.2, cons)
+    par = Init_MPC.initquadBranchMPC(3, 3, N, NB, np.array(xref, dtype=float), 0.2, 0.1, 0.5)
+    mpc = MPC_branch.BranchMPCProx(par, model)
+    store = {"meta_ctrl": np.array("BranchMPCProx"), "meta_NB": np.array(NB), "meta_N": np.array(N),
+             "meta_steps": np.array(steps), "meta_v0": np.array(v0)}
+    x = np.array(x, dtype=float)
+    z = np.array(z, dtype=float)
+    for k in range(steps):
+        mpc.solve(x, z, np.array(xref, dtype=float))
+        record_step(store, k, mpc, x, z, xref)
+        u = mpc.uPred[0]
+        x = x + 0.2 * np.array([u[0] * np.cos(x[2]) - u[1] * np.sin(x[2]),
+                                u[0] * np.sin(x[2]) + u[1] * np.cos(x[2]), u[2]])
+        z = z + 0.2 * np.array([v0 * np.cos(z[2]), v0 * np.sin(z[2]), 0.])  # obstacle keeps 'forward'
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+
+
+def model_function_vectors():
+    """Point-wise values of the reference's model Functions at seeded random inputs."""
+    print("model-function fixture")
+    rng = np.random.default_rng(20240607)
+    cons = highway_cons()
+    lc_target = np.array([0.5, 5.4, 18., 0.])
+    model = hw.PredictiveModel(4, 2, 8, highway_policies(["maintain", "brake", "lc"], cons, lc_target), 0.1, cons)
+    K = 24
+    X = np.column_stack([rng.uniform(-5, 60, K), rng.uniform(0.5, 14, K), rng.uniform(5, 30, K), rng.normal(0, 0.1, K)])
+    Z = np.column_stack([X[:, 0] + rng.uniform(-15, 25, K), rng.uniform(0.5, 14, K), rng.uniform(5, 30, K),
+                         rng.normal(0, 0.1, K)])
+    U = np.column_stack([rng.uniform(-6, 6, K), rng.uniform(-0.3, 0.3, K)])
+    out = {"hw_X": X, "hw_Z": Z, "hw_U": U, "hw_lc_target": lc_target}
+    A, B, C, XP, ZP, P, DP, H, DH = [], [], [], [], [], [], [], [], []
+    for k in range(K):
+        a, b, c, xp = model.dyn_linearization(X[k], U[k])
+        A.append(a); B.append(b); C.append(c); XP.append(xp)
+        ZP.append(model.zpred_eval(Z[k]))
+        p, dp = model.branch_eval(X[k], Z[k])
+        P.append(p); DP.append(dp)
+        h, dh = model.col_eval(X[k], Z[k])
+        H.append(h); DH.append(dh)
+    out.update(hw_A=np.array(A), hw_B=np.array(B), hw_C=np.array(C), hw_xp=np.array(XP), hw_zpred=np.array(ZP),
+               hw_p=np.array(P), hw_dp=np.array(DP), hw_hlin=np.array(H), hw_dh=np.array(DH))
+
+    qc = quad_cons()
+    v0 = 0.2
+    qmodel = qd.PredictiveModel(3, 3, 25, [lambda s: qd.backup_forward(s, v0), lambda s: qd.backup_stop(s)], 0.2, qc)
+    X = np.column_stack([rng.uniform(-2, 6, K), rng.uniform(-4, 4, K), rng.uniform(-np.pi, np.pi, K)])
+    Z = np.column_stack([X[:, 0] + rng.uniform(-4, 4, K), X[:, 1] + rng.uniform(-4, 4, K), rng.uniform(-np.pi, np.pi, K)])
+    U = np.column_stack([rng.uniform(0, 0.2, K), rng.uniform(-0.1, 0.1, K), rng.uniform(-0.5, 0.5, K)])
+    out.update(qd_X=X, qd_Z=Z, qd_U=U)
+    A, B, C, XP, ZP, P, DP, H, DH = [], [], [], [], [], [], [], [], []
+    for k in range(K):
+        a, b, c, xp = qmodel.dyn_linearization(X[k], U[k])
+        A.append(a); B.append(b); C.append(c); XP.append(xp)
+        ZP.append(qmodel.zpred_eval(Z[k]))
+        p, dp = qmodel.branch_eval(X[k], Z[k])
+        P.append(p); DP.append(dp)
+        h, dh = qmodel.col_eval(X[k], Z[k])
+        H.append(h); DH.append(dh)
+    out.update(qd_A=np.array(A), qd_B=np.array(B), qd_C=np.array(C), qd_xp=np.array(XP), qd_zpred=np.array(ZP),
+               qd_p=np.array(P), qd_dp=np.array(DP), qd_hlin=np.array(H), qd_dh=np.array(DH))
+    np.savez_compressed(os.path.join(HERE, "model_functions.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "quad"]
+    if "models" in which:
+        model_function_vectors()
+    if "hw_default" in which:
+        # main_branch.py:24-48 constants + Highway_env_branch.py:67 initial states; xRef as in the survey probe
+        run_highway("highway_branch_default", "BranchMPC", ["maintain", "brake", "lc"], 2,
+                    [0, 1.8, 20, 0], [5, 5.4, 20, 0], [0, 1.8, 26.5, 0], steps=4)
+    if "hw_close" in which:
+        # obstacle just ahead in the same lane: collision rows and lane rows become active
+        run_highway("highway_branch_close", "BranchMPC", ["maintain", "brake", "lc"], 2,
+                    [0, 1.9, 22, 0.02], [9, 1.8, 17, 0], [0, 1.8, 25, 0], steps=3, lc_target=(0.5, 5.4, 17., 0.))
+    if "hw_sweep" in which:
+        run_highway("highway_branch_m2_nb3", "BranchMPC", ["maintain", "brake"], 3,
+                    [0, 5.4, 18, -0.01], [12, 5.6, 15, 0], [0, 5.4, 20, 0], steps=2)
+        run_highway("highway_branch_m3_nb1", "BranchMPC", ["maintain", "brake", "lc"], 1,
+                    [0, 9.0, 24, 0.0], [-6, 5.4, 25, 0], [0, 9.0, 22, 0], steps=2, lc_target=(0.5, 9.0, 25., 0.))
+    if "robust" in which:
+        run_highway("highway_robust_default", "robustMPC", ["maintain", "brake", "lc"], 2,
+                    [0, 1.8, 20, 0], [5, 5.4, 20, 0], [0, 1.8, 26.5, 0], steps=3)
+    if "quad" in which:
+        run_quadruped("quadruped_prox_default", [0, 0, 0], [2, 0.3, np.pi], [5., 5., 0.], steps=3)
