@@ -1,0 +1,64 @@
+// Shared declarations for libbranchmpc.so (sm_100a).  See include/branchmpc.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "branchmpc.h"
+
+typedef double real;
+
+#define BMPC_WARP 32
+#define BMPC_BIG_PENALTY 1.0e4 /* stiff penalty (times branch weight) on guessed-active rows in the polish */
+
+// Everything a kernel needs, passed by value (fits the 4 KB kernel-parameter space).
+struct KParams {
+  // ---- tree topology (BFS numbering of MPC_branch.py:928-981; all closed form) ----
+  int m, NB, N;
+  int nbranch, totalu, totalx;
+  int nup;                      // padded node count = totalu + nbranch (one pad slot per branch)
+  int off[BMPC_MAX_NB + 2];     // first branch id of each depth; off[NB+1] = nbranch
+  int pw[BMPC_MAX_NB + 1];      // m^depth
+  // ---- model ----
+  real dt, veh_L, veh_W, Kpsi, s1, lane_lo, lane_hi, quad_margin;
+  int pol_kind[BMPC_MAX_POLICIES];
+  real pol_par[BMPC_MAX_POLICIES][4];
+  // ---- cost / constraints ----
+  int ctrl;
+  real Q[BMPC_MAX_N * BMPC_MAX_N], Qf[BMPC_MAX_N * BMPC_MAX_N], R[BMPC_MAX_D * BMPC_MAX_D], dR[BMPC_MAX_D];
+  real dq_scale;                // dQ = dq_scale * Q  (0.5 BranchMPC :1070, 3 BranchMPCProx :271)
+  real lam_lin;                 // Qslack[1]
+  int nrows;                    // two-sided state rows (collision row not counted)
+  real rf[BMPC_MAX_ROWS][BMPC_MAX_N], rlo[BMPC_MAX_ROWS], rhi[BMPC_MAX_ROWS];
+  real ulo[BMPC_MAX_D], uhi[BMPC_MAX_D];
+  // ---- solver ----
+  int max_iter, polish_first, polish_every, polish_passes;
+  real alpha, theta, theta_u, eps_abs;
+  // ---- batch ----
+  int count;
+  const real* x0;
+  const real* z0;
+  const real* xref;
+  const real* polpar;           // [count][m][4] or null
+  real* uLin;                   // persistent [cap][totalu+1][d]
+  int* pbest;                   // persistent [cap][nbranch]
+  real* oldin;                  // persistent [cap][d]
+  int* started;                 // persistent [cap]
+  bmpc_outputs out;
+  int* counter;                 // work queue head
+  real* gws;                    // global workspace (only when the per-problem slab does not fit shared memory)
+  size_t slab_reals;            // reals per problem slab
+};
+
+__host__ __device__ inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }
+__host__ __device__ inline int bmpc_ndx(const KParams& P, int b) {
+  const int ol = P.off[P.NB];
+  return b < ol ? bmpc_ndu(P, b) : 1 + P.N * (ol - 1) + (P.N + 1) * (b - ol);
+}
+__host__ __device__ inline int bmpc_depth(const KParams& P, int b) {
+  int d = 0;
+  while (b >= P.off[d + 1]) ++d;
+  return d;
+}
+__host__ __device__ inline int bmpc_parent(const KParams& P, int b, int d) { return P.off[d - 1] + (b - P.off[d]) / P.m; }
+__host__ __device__ inline int bmpc_first_child(const KParams& P, int b, int d) { return P.off[d + 1] + (b - P.off[d]) * P.m; }

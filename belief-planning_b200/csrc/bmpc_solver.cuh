@@ -1,0 +1,1231 @@
+// Warp-per-problem tree-QP solver: ADMM whose KKT step is a Riccati sweep over the branch tree,
+// finished by an active-set polish.  One warp owns one scenario-tree MPC problem; the per-node
+// data lives in that warp's shared-memory slab (field-major, one pad slot per branch so the lanes
+// of a sweep hit distinct banks); lanes are the parallel branches of a tree level during sweeps and
+// the nodes during the row phase.  Replaces buildCost + buildEqConstr + buildIneqConstr +
+// osqp_solve_qp + unpackSolution of the reference (MPC_branch.py:984-1274) and the per-node CasADi
+// calls of inittree/updatetree (:928-981, :1024-1061).
+#pragma once
+#include "bmpc_models.cuh"
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ real warp_max(real v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ real warp_sum(real v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// prox of lam*dist(., [lo,hi]) with threshold thr = lam/rho
+__device__ __forceinline__ real prox_range(real s, real lo, real hi, real thr) {
+  if (s > hi + thr) return s - thr;
+  if (s > hi) return hi;
+  if (s >= lo) return s;
+  if (s >= lo - thr) return lo;
+  return s + thr;
+}
+
+enum { ROW_INACTIVE = 0, ROW_UP_KINK = 1, ROW_UP_LIN = 2, ROW_LO_KINK = 3, ROW_LO_LIN = 4, ROW_IGNORED = 7 };
+enum { IN_FREE = 0, IN_AT_HI = 1, IN_AT_LO = 2 };
+enum { FACT_ADMM = 0, FACT_FREE = 1, FACT_POLISH = 2 };
+
+template <class M, int NR>
+struct Solver {
+  static constexpr int NX = M::NX, NU = M::NU;
+  static constexpr int NS = NX * (NX + 1) / 2;
+  static constexpr int NSU = NU * (NU + 1) / 2;
+  // field offsets (each field is one real per padded node)
+  static constexpr int F_LIN = 0;
+  static constexpr int F_CC = F_LIN + M::NLIN;
+  static constexpr int F_Q = F_CC + M::NCC;
+  static constexpr int F_FC = F_Q + NX;      // collision row f (x,y components); holds obstacle (x,y) before setup
+  static constexpr int F_HC = F_FC + 2;      // collision row upper bound
+  static constexpr int F_RHO = F_HC + 1;     // rho of the NR soft rows then of the NU inputs
+  static constexpr int F_K = F_RHO + NR + NU;
+  static constexpr int F_SI = F_K + NU * NX; // S^-1, packed upper triangle
+  static constexpr int F_H0 = F_SI + NSU;    // P+ C
+  static constexpr int F_S = F_H0 + NX;      // ADMM state s = v^ + y/rho per soft row
+  static constexpr int F_SU = F_S + NR;      // same for the inputs
+  static constexpr int F_XQ = F_SU + NU;     // x after a forward sweep / q~x before a backward sweep
+  static constexpr int F_UQ = F_XQ + NX;     // u or kff / q~u
+  static constexpr int F_Y = F_UQ + NU;      // polish multipliers (rows then inputs)
+  static constexpr int NF = F_Y + NR + NU;
+  static constexpr int BR = 1 + NS + 3 * NX; // per-branch reals: w, exchange(NS), x last, z last, x after last
+
+  __host__ __device__ static size_t slab_reals(int nup, int nbranch) {
+    return (size_t)NF * nup + (size_t)(nup + 1) / 2 + (size_t)BR * nbranch;
+  }
+
+  const KParams& P;
+  real* ws;
+  int* st;
+  real* Wb;
+  real* EX;
+  real* EXL;
+  real* EXZ;
+  real* EXX;
+  int lane, nup, prob;
+  real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
+  const real* polpar;
+
+  __device__ Solver(const KParams& P_, real* slab, int lane_) : P(P_), ws(slab), lane(lane_), nup(P_.nup) {
+    st = reinterpret_cast<int*>(ws + (size_t)NF * nup);
+    Wb = ws + (size_t)NF * nup + (nup + 1) / 2;
+    EX = Wb + P.nbranch;
+    EXL = EX + (size_t)NS * P.nbranch;
+    EXZ = EXL + (size_t)NX * P.nbranch;
+    EXX = EXZ + (size_t)NX * P.nbranch;
+  }
+
+  __device__ __forceinline__ real& F(int field, int kp) { return ws[(size_t)field * nup + kp]; }
+  __device__ __forceinline__ int kp_of(int b, int t) const { return bmpc_ndu(P, b) + t + b; }
+  __device__ __forceinline__ void node_of(int k, int& b, int& t) const {
+    if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / P.N; t = (k - 1) % P.N; }
+  }
+  __device__ __forceinline__ const real* pol_par(int i) const {
+    return polpar ? polpar + 4 * i : P.pol_par[i];
+  }
+
+  // ========================================================================================
+  // Tree expansion: obstacle rollouts, branch probabilities/weights, ego linearisation rollouts,
+  // per-node linearisation + collision linearisation + cost vectors   (kernels K1-K3)
+  // ========================================================================================
+  __device__ void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn) {
+    const int kp = kp_of(b, t);
+    real lin[M::NLIN], cc[M::NCC];
+    M::linearize(P, xbar, ubar, lin, cc, xn);
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
+#pragma unroll
+    for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
+    const real* xref = P.xref + (size_t)prob * NX;
+    const real* Ql = (leaf_last && P.ctrl == BMPC_CTRL_BRANCH) ? P.Qf : P.Q;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      real a = 0.0, c = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        a += xref[i] * Ql[i * NX + j];
+        c += xbar[i] * P.Q[i * NX + j];
+      }
+      F(F_Q + j, kp) = -2.0 * w * (a + P.dq_scale * c);
+    }
+    real zxy[2] = {F(F_FC, kp), F(F_FC + 1, kp)};
+    real h, dhx, dhy;
+    M::collision(P, xbar, zxy, h, dhx, dhy);
+    const real fx = -dhx, fy = -dhy;
+    const real hi0 = h - (dhx * xbar[0] + dhy * xbar[1]);
+    F(F_FC, kp) = fx;
+    F(F_FC + 1, kp) = fy;
+    F(F_HC, kp) = hi0;
+    // ADMM start: rows at the linearisation point, projected on their bounds
+    F(F_S, kp) = fmin(fx * xbar[0] + fy * xbar[1], hi0);
+#pragma unroll
+    for (int j = 1; j < NR; ++j) {
+      real v = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += P.rf[j - 1][i] * xbar[i];
+      F(F_S + j, kp) = fmin(fmax(v, P.rlo[j - 1]), P.rhi[j - 1]);
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = fmin(fmax(ubar[a], P.ulo[a]), P.uhi[a]);
+    if (P.out.xLin) {
+      real* o = P.out.xLin + ((size_t)prob * P.totalu + (bmpc_ndu(P, b) + t)) * NX;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) o[i] = xbar[i];
+    }
+  }
+
+  __device__ void expand_tree() {
+    const int started = P.started[prob];
+    const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
+    int* pbest = P.pbest + (size_t)prob * P.nbranch;
+    const real* x0 = P.x0 + (size_t)prob * NX;
+    const real* z0 = P.z0 + (size_t)prob * NX;
+    if (lane == 0) {
+      real ub[NU], xb[NX], xn[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xb[i] = x0[i];
+      const int best = started ? pbest[0] : 0;
+      const int kbest = bmpc_ndu(P, bmpc_first_child(P, 0, 0) + best);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[kbest * NU + a] : 0.0;
+      const int kp = kp_of(0, 0);
+      F(F_FC, kp) = z0[0];
+      F(F_FC + 1, kp) = z0[1];
+      Wb[0] = 1.0;
+      if (P.out.zPred) {
+        real* o = P.out.zPred + (size_t)prob * P.totalu * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) o[i] = z0[i];
+      }
+      node_setup(0, 0, xb, ub, 1.0, false, xn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        EXL[i] = xb[i];
+        EXZ[i] = z0[i];
+        EXX[i] = xn[i];
+      }
+    }
+    __syncwarp();
+    const int m = P.m;
+    const int chunk = (BMPC_WARP / m) * m;
+    for (int d = 0; d < P.NB; ++d) {
+      // (a) obstacle rollouts under each policy + branch probabilities  (zpred_eval, branch_eval)
+      const int cnt = P.pw[d] * m;
+      for (int base = 0; base < cnt; base += chunk) {
+        const int idx = base + lane;
+        const bool act = lane < chunk && idx < cnt;
+        const int b = P.off[d] + (act ? idx / m : 0);
+        const int i = act ? idx % m : 0;
+        const int c = bmpc_first_child(P, b, d) + i;
+        real hi = 0.0;
+        if (act) {
+          real zl[NX];
+          const int kc = bmpc_ndu(P, c);
+          const int kpc = kp_of(c, 0);
+          real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NX : nullptr;
+          hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXL + (size_t)NX * b,
+                                EXZ + (size_t)NX * b, zl, [&](int t, const real* z) {
+                                  F(F_FC, kpc + t) = z[0];
+                                  F(F_FC + 1, kpc + t) = z[1];
+                                  if (zout) {
+#pragma unroll
+                                    for (int q = 0; q < NX; ++q) zout[t * NX + q] = z[q];
+                                  }
+                                });
+#pragma unroll
+          for (int q = 0; q < NX; ++q) EXZ[(size_t)NX * c + q] = zl[q];
+        }
+        const int g0 = (lane / m) * m;
+        real himax = -1e300;
+        if (M::kWeightNeedsMax) {
+          for (int j = 0; j < m; ++j) himax = fmax(himax, __shfl_sync(FULL_MASK, hi, (g0 + j) & 31));
+        }
+        const real wgt = M::branch_weight(P, hi, himax);
+        real sum = 0.0;
+        for (int j = 0; j < m; ++j) sum += __shfl_sync(FULL_MASK, wgt, (g0 + j) & 31);
+        const real p = wgt / sum;
+        int best = 0;
+        real pb = -1.0;
+        for (int j = 0; j < m; ++j) {
+          const real pj = __shfl_sync(FULL_MASK, p, (g0 + j) & 31);
+          if (pj > pb) { pb = pj; best = j; }
+        }
+        if (act) {
+          Wb[c] = Wb[b] * p;
+          if (P.out.branch_p) P.out.branch_p[((size_t)prob * P.nbranch + b) * m + i] = p;
+          if (i == 0) pbest[b] = best;   // read (old value) only before this point, see (b) below
+        }
+      }
+      __syncwarp();
+      // (b) ego linearisation trajectory of every child branch: time-shifted previous inputs
+      //     (updatetree :1025-1033), nonlinear rollout + per-node linearisation (:1048-1059)
+      for (int c = P.off[d + 1] + lane; c < P.off[d + 2]; c += BMPC_WARP) {
+        const int b = bmpc_parent(P, c, d + 1);
+        const bool leaf = (d + 1 == P.NB);
+        const real w = Wb[c];
+        const int kc = bmpc_ndu(P, c);
+        int klast;
+        if (leaf) {
+          klast = kc + P.N - 1;
+        } else {
+          klast = bmpc_ndu(P, bmpc_first_child(P, c, d + 1) + (started ? pbest[c] : 0));
+        }
+        real xb[NX], xn[NX], ub[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xb[i] = EXX[(size_t)NX * b + i];
+        for (int t = 0; t < P.N; ++t) {
+          const int ksrc = (t < P.N - 1) ? kc + t + 1 : klast;
+#pragma unroll
+          for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[ksrc * NU + a] : 0.0;
+          if (t == P.N - 1) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) EXL[(size_t)NX * c + i] = xb[i];
+          }
+          node_setup(c, t, xb, ub, w, leaf && t == P.N - 1, xn);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) xb[i] = xn[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) EXX[(size_t)NX * c + i] = xb[i];
+      }
+      __syncwarp();
+    }
+    if (P.out.branch_w) {
+      for (int b = lane; b < P.nbranch; b += BMPC_WARP) P.out.branch_w[(size_t)prob * P.nbranch + b] = Wb[b];
+    }
+    rlin = 0.0;
+    if (started) {
+#pragma unroll
+      for (int a = 0; a < NU; ++a) rlin += -2.0 * P.oldin[(size_t)prob * NU + a] * P.dR[a];
+    }
+  }
+
+  // ========================================================================================
+  // Riccati factorisation over the tree
+  // ========================================================================================
+  __device__ __forceinline__ void unpack_sym(const real* src, real* Pm) {
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        Pm[i * NX + j] = src[q];
+        Pm[j * NX + i] = src[q];
+        ++q;
+      }
+  }
+  __device__ __forceinline__ void pack_sym(const real* Pm, real* dst) {
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) dst[q++] = Pm[i * NX + j];
+  }
+
+  __device__ static void invert_spd(const real* S, real* Si) {
+    if constexpr (NU == 2) {
+      const real det = S[0] * S[3] - S[1] * S[2];
+      const real id = 1.0 / det;
+      Si[0] = S[3] * id;
+      Si[1] = -S[1] * id;
+      Si[2] = -S[2] * id;
+      Si[3] = S[0] * id;
+    } else {
+      // 3x3 symmetric: cofactors
+      const real a = S[0], b = S[1], c = S[2], d = S[4], e = S[5], f = S[8];
+      const real A = d * f - e * e, B = c * e - b * f, C = b * e - c * d;
+      const real det = a * A + b * B + c * C;
+      const real id = 1.0 / det;
+      Si[0] = A * id;
+      Si[1] = B * id;
+      Si[2] = C * id;
+      Si[3] = B * id;
+      Si[4] = (a * f - c * c) * id;
+      Si[5] = (b * c - a * e) * id;
+      Si[6] = C * id;
+      Si[7] = (b * c - a * e) * id;
+      Si[8] = (a * d - b * b) * id;
+    }
+  }
+
+  // Stiff penalty of a guessed-active row in the polish: at least BMPC_BIG_PENALTY*w and at least 100x the
+  // row's reduced stiffness (rho/theta), so every augmented-Lagrangian step contracts by <= ~1e-2.
+  __device__ __forceinline__ real big_row(int kp, int j, real w) {
+    return fmin(fmax(BMPC_BIG_PENALTY * w, 100.0 * F(F_RHO + j, kp) / P.theta), 1.0e8 * w);
+  }
+  __device__ __forceinline__ real big_in(int kp, int a, real w) {
+    return fmin(fmax(BMPC_BIG_PENALTY * w, 100.0 * F(F_RHO + NR + a, kp) / P.theta_u), 1.0e8 * w);
+  }
+
+  // penalties of the node's soft rows and inputs for the requested factorisation
+  __device__ __forceinline__ void penalties(int kp, real w, int mode, real* pr, real* pu) {
+    if (mode == FACT_ADMM) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) pr[j] = F(F_RHO + j, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) pu[a] = F(F_RHO + NR + a, kp);
+    } else if (mode == FACT_FREE) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) pr[j] = 0.0;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) pu[a] = 0.0;
+    } else {
+      const int code = st[kp];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const int cj = (code >> (3 * j)) & 7;
+        pr[j] = (cj == ROW_UP_KINK || cj == ROW_LO_KINK) ? big_row(kp, j, w) : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const int ca = (code >> (3 * NR + 2 * a)) & 3;
+        pu[a] = (ca != IN_FREE) ? big_in(kp, a, w) : 0.0;
+      }
+    }
+  }
+
+  // one backward Riccati step; Pn (full NX x NX, symmetric) is the successor value Hessian on entry
+  // and this node's on exit
+  __device__ void node_factor(int kp, real w, real* Pn, int mode) {
+    real lin[M::NLIN], cc[M::NCC];
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
+#pragma unroll
+    for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
+    real pr[NR], pu[NU];
+    penalties(kp, w, mode, pr, pu);
+    // h0 = P+ C
+    {
+      real C[NX];
+      M::expandC(cc, C);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        real a = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) a += Pn[i * NX + j] * C[j];
+        F(F_H0 + i, kp) = a;
+      }
+    }
+    real T[NX * NX];  // P+ A  (row i = A' applied to row i of P+)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) M::mulAT(P, lin, Pn + i * NX, T + i * NX);
+    real G[NU * NX];  // B' P+ A
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      real col[NX], g2[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) col[i] = T[i * NX + j];
+      M::mulBT(P, lin, col, g2);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) G[a * NX + j] = g2[a];
+    }
+    real S[NU * NU];
+    {
+      real PB[NX * NU];  // P+ B (row i = B' applied to row i of P+)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) M::mulBT(P, lin, Pn + i * NX, PB + i * NU);
+#pragma unroll
+      for (int b2 = 0; b2 < NU; ++b2) {
+        real col[NX], g2[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) col[i] = PB[i * NU + b2];
+        M::mulBT(P, lin, col, g2);
+#pragma unroll
+        for (int a = 0; a < NU; ++a) S[a * NU + b2] = g2[a] + 2.0 * w * 0.5 * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) S[a * NU + a] += pu[a];
+    }
+    real Si[NU * NU];
+    invert_spd(S, Si);
+    {
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < NU; ++a)
+#pragma unroll
+        for (int b2 = a; b2 < NU; ++b2) F(F_SI + (q++), kp) = 0.5 * (Si[a * NU + b2] + Si[b2 * NU + a]);
+    }
+    real K[NU * NX];
+#pragma unroll
+    for (int a = 0; a < NU; ++a)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        real v = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < NU; ++b2) v += Si[a * NU + b2] * G[b2 * NX + j];
+        K[a * NX + j] = v;
+        F(F_K + a * NX + j, kp) = v;
+      }
+    // P = Q~ + A' T - G' K
+    real Pnew[NX * NX];
+    const real qs = 2.0 * w * (1.0 + P.dq_scale);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      real col[NX], o[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) col[i] = T[i * NX + j];
+      M::mulAT(P, lin, col, o);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        real v = o[i] + qs * 0.5 * (P.Q[i * NX + j] + P.Q[j * NX + i]);
+#pragma unroll
+        for (int a = 0; a < NU; ++a) v -= G[a * NX + i] * K[a * NX + j];
+        Pnew[i * NX + j] = v;
+      }
+    }
+    // soft-row penalties: collision row touches (x,y) only
+    {
+      const real fx = F(F_FC, kp), fy = F(F_FC + 1, kp);
+      Pnew[0] += pr[0] * fx * fx;
+      Pnew[1] += pr[0] * fx * fy;
+      Pnew[NX] += pr[0] * fx * fy;
+      Pnew[NX + 1] += pr[0] * fy * fy;
+#pragma unroll
+      for (int j = 1; j < NR; ++j)
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int i2 = 0; i2 < NX; ++i2) Pnew[i * NX + i2] += pr[j] * P.rf[j - 1][i] * P.rf[j - 1][i2];
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Pn[i * NX + j] = 0.5 * (Pnew[i * NX + j] + Pnew[j * NX + i]);
+  }
+
+  __device__ void factorize(int mode) {
+    for (int d = P.NB; d >= 1; --d) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+        const real w = Wb[b];
+        real Pn[NX * NX];
+        if (d == P.NB) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) Pn[i * NX + j] = w * (P.Qf[i * NX + j] + P.Qf[j * NX + i]);
+        } else {
+          const int fc = bmpc_first_child(P, b, d);
+          unpack_sym(EX + (size_t)NS * fc, Pn);
+          for (int c = 1; c < P.m; ++c) {
+            real Pc[NX * NX];
+            unpack_sym(EX + (size_t)NS * (fc + c), Pc);
+#pragma unroll
+            for (int i = 0; i < NX * NX; ++i) Pn[i] += Pc[i];
+          }
+        }
+        for (int t = P.N - 1; t >= 0; --t) node_factor(kp_of(b, t), w, Pn, mode);
+        pack_sym(Pn, EX + (size_t)NS * b);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      real Pn[NX * NX];
+      const int fc = bmpc_first_child(P, 0, 0);
+      unpack_sym(EX + (size_t)NS * fc, Pn);
+      for (int c = 1; c < P.m; ++c) {
+        real Pc[NX * NX];
+        unpack_sym(EX + (size_t)NS * (fc + c), Pc);
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) Pn[i] += Pc[i];
+      }
+      node_factor(kp_of(0, 0), 1.0, Pn, mode);
+    }
+    __syncwarp();
+  }
+
+  // ========================================================================================
+  // Curvature-matched rho: rho_row = theta / (f' Sigma f), rho_u = theta_u / (Sigma_u)_aa where Sigma is the
+  // covariance-like forward recursion of the unconstrained LQ problem (Sigma+ = Acl Sigma Acl' + B S^-1 B').
+  // ========================================================================================
+  __device__ void node_cov(int kp, real w, real* Sg) {
+    real lin[M::NLIN], K[NU * NX], Si[NU * NU];
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) K[i] = F(F_K + i, kp);
+    {
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < NU; ++a)
+#pragma unroll
+        for (int b2 = a; b2 < NU; ++b2) {
+          const real v = F(F_SI + (q++), kp);
+          Si[a * NU + b2] = v;
+          Si[b2 * NU + a] = v;
+        }
+    }
+    const real rho_max = 1.0e9 * w;
+    {
+      const real fx = F(F_FC, kp), fy = F(F_FC + 1, kp);
+      const real q0 = fx * fx * Sg[0] + 2.0 * fx * fy * Sg[1] + fy * fy * Sg[NX + 1];
+      F(F_RHO, kp) = (q0 > 1e-12) ? fmin(P.theta / q0, rho_max) : 0.0;
+#pragma unroll
+      for (int j = 1; j < NR; ++j) {
+        real q = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int i2 = 0; i2 < NX; ++i2) q += P.rf[j - 1][i] * P.rf[j - 1][i2] * Sg[i * NX + i2];
+        F(F_RHO + j, kp) = (q > 1e-12) ? fmin(P.theta / q, rho_max) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      real var = Si[a * NU + a];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        real ks = 0.0;
+#pragma unroll
+        for (int i2 = 0; i2 < NX; ++i2) ks += K[a * NX + i2] * Sg[i2 * NX + i];
+        var += ks * K[a * NX + i];
+      }
+      F(F_RHO + NR + a, kp) = fmin(P.theta_u / var, rho_max);
+    }
+    // Sigma+ = Acl Sigma Acl' + B Si B',  Acl v = A v - B (K v)
+    real T[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      real kv[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        real v = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v += K[a * NX + j] * Sg[i * NX + j];
+        kv[a] = -v;
+      }
+      M::mulA(P, lin, Sg + i * NX, T + i * NX);
+      M::addBu(P, lin, kv, T + i * NX);
+    }
+    real Bd[NX * NU];
+    M::denseB(P, lin, Bd);
+    real Sn[NX * NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      real col[NX], o[NX], kv[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) col[i] = T[i * NX + j];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        real v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) v += K[a * NX + i] * col[i];
+        kv[a] = -v;
+      }
+      M::mulA(P, lin, col, o);
+      M::addBu(P, lin, kv, o);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Sn[i * NX + j] = o[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        real v = 0.0;
+#pragma unroll
+        for (int a = 0; a < NU; ++a)
+#pragma unroll
+          for (int b2 = 0; b2 < NU; ++b2) v += Bd[i * NU + a] * Si[a * NU + b2] * Bd[j * NU + b2];
+        Sn[i * NX + j] += v;
+      }
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Sg[i * NX + j] = 0.5 * (Sn[i * NX + j] + Sn[j * NX + i]);
+  }
+
+  __device__ void choose_rho() {
+    if (lane == 0) {
+      real Sg[NX * NX];
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) Sg[i] = 0.0;
+      node_cov(kp_of(0, 0), 1.0, Sg);
+      pack_sym(Sg, EX);
+    }
+    __syncwarp();
+    for (int d = 1; d <= P.NB; ++d) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+        real Sg[NX * NX];
+        unpack_sym(EX + (size_t)NS * bmpc_parent(P, b, d), Sg);
+        const real w = Wb[b];
+        for (int t = 0; t < P.N; ++t) node_cov(kp_of(b, t), w, Sg);
+        pack_sym(Sg, EX + (size_t)NS * b);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ========================================================================================
+  // Vector sweeps (the hot loop): backward for the feed-forward terms, forward for (x,u)
+  // ========================================================================================
+  __device__ __forceinline__ void bw_step(int kp, real* pn) {
+    real lin[M::NLIN], g[NX], r[NU], kff[NU];
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) g[i] = pn[i] + F(F_H0 + i, kp);
+    M::mulBT(P, lin, g, r);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) r[a] += F(F_UQ + a, kp);
+    {
+      real Si[NSU];
+#pragma unroll
+      for (int q = 0; q < NSU; ++q) Si[q] = F(F_SI + q, kp);
+      if constexpr (NU == 2) {
+        kff[0] = -(Si[0] * r[0] + Si[1] * r[1]);
+        kff[1] = -(Si[1] * r[0] + Si[2] * r[1]);
+      } else {
+        kff[0] = -(Si[0] * r[0] + Si[1] * r[1] + Si[2] * r[2]);
+        kff[1] = -(Si[1] * r[0] + Si[3] * r[1] + Si[4] * r[2]);
+        kff[2] = -(Si[2] * r[0] + Si[4] * r[1] + Si[5] * r[2]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = kff[a];
+    real p[NX];
+    M::mulAT(P, lin, g, p);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      real v = p[i] + F(F_XQ + i, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) v -= F(F_K + a * NX + i, kp) * r[a];
+      pn[i] = v;
+    }
+  }
+
+  __device__ void backward() {
+    for (int d = P.NB; d >= 1; --d) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+        real pn[NX];
+        if (d == P.NB) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) pn[i] = 0.0;   // terminal node: no linear term (MPC_branch.py:1094)
+        } else {
+          const int fc = bmpc_first_child(P, b, d);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) pn[i] = EX[(size_t)NS * fc + i];
+          for (int c = 1; c < P.m; ++c)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) pn[i] += EX[(size_t)NS * (fc + c) + i];
+        }
+        const int kp0 = kp_of(b, 0);
+        for (int t = P.N - 1; t >= 0; --t) bw_step(kp0 + t, pn);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) EX[(size_t)NS * b + i] = pn[i];
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      real pn[NX];
+      const int fc = bmpc_first_child(P, 0, 0);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) pn[i] = EX[(size_t)NS * fc + i];
+      for (int c = 1; c < P.m; ++c)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) pn[i] += EX[(size_t)NS * (fc + c) + i];
+      bw_step(kp_of(0, 0), pn);
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void fw_step(int kp, real* x) {
+    real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
+#pragma unroll
+    for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      real v = F(F_UQ + a, kp);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v -= F(F_K + a * NX + i, kp) * x[i];
+      u[a] = v;
+      F(F_UQ + a, kp) = v;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = x[i];
+    M::mulA(P, lin, x, xn);
+    M::addBu(P, lin, u, xn);
+    M::addC(cc, xn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xn[i];
+  }
+
+  __device__ void forward() {
+    if (lane == 0) {
+      real x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = P.x0[(size_t)prob * NX + i];
+      fw_step(kp_of(0, 0), x);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) EXX[i] = x[i];
+    }
+    __syncwarp();
+    for (int d = 1; d <= P.NB; ++d) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+        real x[NX];
+        const int pa = bmpc_parent(P, b, d);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = EXX[(size_t)NX * pa + i];
+        const int kp0 = kp_of(b, 0);
+        for (int t = 0; t < P.N; ++t) fw_step(kp0 + t, x);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) EXX[(size_t)NX * b + i] = x[i];
+      }
+      __syncwarp();
+    }
+  }
+
+  // ========================================================================================
+  // Row phase (node-parallel): ADMM z/y update through the single Moreau variable s, residuals, and
+  // the linear terms of the next KKT solve.
+  // ========================================================================================
+  __device__ __forceinline__ real row_value(int kp, int j, const real* x) {
+    if (j == 0) return F(F_FC, kp) * x[0] + F(F_FC + 1, kp) * x[1];
+    real v = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v += P.rf[j - 1][i] * x[i];
+    return v;
+  }
+  __device__ __forceinline__ void row_bounds(int kp, int j, real& lo, real& hi) {
+    if (j == 0) { lo = -1e300; hi = F(F_HC, kp); } else { lo = P.rlo[j - 1]; hi = P.rhi[j - 1]; }
+  }
+  __device__ __forceinline__ void add_row_grad(int kp, int j, real gcoef, real* qx) {
+    if (j == 0) {
+      qx[0] += F(F_FC, kp) * gcoef;
+      qx[1] += F(F_FC + 1, kp) * gcoef;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) qx[i] += P.rf[j - 1][i] * gcoef;
+    }
+  }
+
+  // update=false: only assemble q~ from the current s (start / after a failed polish)
+  // returns max(primal residual, dual residual) over this lane's nodes
+  __device__ real admm_rows(bool update) {
+    real res = 0.0;
+    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wb[b];
+      const real lam = P.lam_lin * w;
+      real x[NX], u[NU], qx[NX], qu[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = F(F_Q + i, kp); }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) { u[a] = F(F_UQ + a, kp); qu[a] = (k == 0) ? rlin : 0.0; }
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const real rho = F(F_RHO + j, kp);
+        if (rho > 0.0) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real thr = lam / rho;
+          real s = F(F_S + j, kp);
+          real v = prox_range(s, lo, hi, thr);
+          if (update) {
+            const real fx = row_value(kp, j, x);
+            const real sn = P.alpha * fx + (1.0 - P.alpha) * v + (s - v);
+            const real vn = prox_range(sn, lo, hi, thr);
+            res = fmax(res, fmax(fabs(fx - vn), fabs(vn - v) * rho / fmax(w, 1e-300) * 1e-3));
+            F(F_S + j, kp) = sn;
+            s = sn;
+            v = vn;
+          }
+          add_row_grad(kp, j, -rho * (2.0 * v - s), qx);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real rho = F(F_RHO + NR + a, kp);
+        real s = F(F_SU + a, kp);
+        real v = fmin(fmax(s, P.ulo[a]), P.uhi[a]);
+        if (update) {
+          const real sn = P.alpha * u[a] + (1.0 - P.alpha) * v + (s - v);
+          const real vn = fmin(fmax(sn, P.ulo[a]), P.uhi[a]);
+          res = fmax(res, fmax(fabs(u[a] - vn), fabs(vn - v) * rho / fmax(w, 1e-300) * 1e-3));
+          F(F_SU + a, kp) = sn;
+          s = sn;
+          v = vn;
+        }
+        qu[a] -= rho * (2.0 * v - s);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = qx[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
+    }
+    __syncwarp();
+    return res;
+  }
+
+  // ========================================================================================
+  // Active-set polish
+  // ========================================================================================
+  __device__ void polish_guess() {
+    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real lam = P.lam_lin * Wb[b];
+      int code = 0;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const real rho = F(F_RHO + j, kp);
+        int cj = ROW_IGNORED;
+        real y = 0.0;
+        if (rho > 0.0) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real thr = lam / rho;
+          const real s = F(F_S + j, kp);
+          if (s > hi + thr) cj = ROW_UP_LIN;
+          else if (s > hi) { cj = ROW_UP_KINK; y = fmin(rho * (s - hi), lam); }
+          else if (s >= lo) cj = ROW_INACTIVE;
+          else if (s >= lo - thr) { cj = ROW_LO_KINK; y = fmax(rho * (s - lo), -lam); }
+          else cj = ROW_LO_LIN;
+        }
+        code |= cj << (3 * j);
+        F(F_Y + j, kp) = y;
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real rho = F(F_RHO + NR + a, kp);
+        const real s = F(F_SU + a, kp);
+        int ca = IN_FREE;
+        real y = 0.0;
+        if (s > P.uhi[a]) { ca = IN_AT_HI; y = rho * (s - P.uhi[a]); }
+        else if (s < P.ulo[a]) { ca = IN_AT_LO; y = rho * (s - P.ulo[a]); }
+        code |= ca << (3 * NR + 2 * a);
+        F(F_Y + NR + a, kp) = y;
+      }
+      st[kp] = code;
+    }
+    __syncwarp();
+  }
+
+  __device__ void polish_assemble() {
+    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wb[b];
+      const real lam = P.lam_lin * w;
+      const int code = st[kp];
+      real qx[NX], qu[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) qx[i] = F(F_Q + i, kp);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const int cj = (code >> (3 * j)) & 7;
+        real lo, hi;
+        row_bounds(kp, j, lo, hi);
+        real g = 0.0;
+        if (cj == ROW_UP_LIN) g = lam;
+        else if (cj == ROW_LO_LIN) g = -lam;
+        else if (cj == ROW_UP_KINK) g = F(F_Y + j, kp) - big_row(kp, j, w) * hi;
+        else if (cj == ROW_LO_KINK) g = F(F_Y + j, kp) - big_row(kp, j, w) * lo;
+        if (g != 0.0) add_row_grad(kp, j, g, qx);
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const int ca = (code >> (3 * NR + 2 * a)) & 3;
+        real g = (k == 0) ? rlin : 0.0;
+        if (ca == IN_AT_HI) g += F(F_Y + NR + a, kp) - big_in(kp, a, w) * P.uhi[a];
+        else if (ca == IN_AT_LO) g += F(F_Y + NR + a, kp) - big_in(kp, a, w) * P.ulo[a];
+        qu[a] = g;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = qx[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
+    }
+    __syncwarp();
+  }
+
+  // multiplier (augmented-Lagrangian) update on the guessed-active rows; returns this lane's max residual
+  __device__ real polish_multipliers() {
+    real res = 0.0;
+    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wb[b];
+      const int code = st[kp];
+      real x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const int cj = (code >> (3 * j)) & 7;
+        if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real r = row_value(kp, j, x) - (cj == ROW_UP_KINK ? hi : lo);
+          F(F_Y + j, kp) += big_row(kp, j, w) * r;
+          res = fmax(res, fabs(r));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const int ca = (code >> (3 * NR + 2 * a)) & 3;
+        if (ca != IN_FREE) {
+          const real r = F(F_UQ + a, kp) - (ca == IN_AT_HI ? P.uhi[a] : P.ulo[a]);
+          F(F_Y + NR + a, kp) += big_in(kp, a, w) * r;
+          res = fmax(res, fabs(r));
+        }
+      }
+    }
+    __syncwarp();
+    return res;
+  }
+
+  // primal-dual active-set update from the last equality-constrained solve; returns #changes of this lane
+  __device__ int polish_update_sets() {
+    int changes = 0;
+    const real tol = 1e-7;
+    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wb[b];
+      const real lam = P.lam_lin * w;
+      const real ytol = 1e-9 * lam;
+      const int code = st[kp];
+      int ncode = 0;
+      real x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const int cj = (code >> (3 * j)) & 7;
+        int nj = cj;
+        if (cj != ROW_IGNORED) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real fx = row_value(kp, j, x);
+          const real y = F(F_Y + j, kp);
+          if (cj == ROW_INACTIVE) {
+            if (fx > hi + tol) { nj = ROW_UP_KINK; F(F_Y + j, kp) = 0.0; }
+            else if (fx < lo - tol) { nj = ROW_LO_KINK; F(F_Y + j, kp) = 0.0; }
+          } else if (cj == ROW_UP_KINK) {
+            if (y < -ytol) { nj = ROW_INACTIVE; F(F_Y + j, kp) = 0.0; }
+            else if (y > lam + ytol) { nj = ROW_UP_LIN; F(F_Y + j, kp) = 0.0; }
+          } else if (cj == ROW_LO_KINK) {
+            if (y > ytol) { nj = ROW_INACTIVE; F(F_Y + j, kp) = 0.0; }
+            else if (y < -lam - ytol) { nj = ROW_LO_LIN; F(F_Y + j, kp) = 0.0; }
+          } else if (cj == ROW_UP_LIN) {
+            if (fx < hi - tol) { nj = ROW_UP_KINK; F(F_Y + j, kp) = lam; }
+          } else if (cj == ROW_LO_LIN) {
+            if (fx > lo + tol) { nj = ROW_LO_KINK; F(F_Y + j, kp) = -lam; }
+          }
+        }
+        changes += (nj != cj);
+        ncode |= nj << (3 * j);
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const int ca = (code >> (3 * NR + 2 * a)) & 3;
+        int na = ca;
+        const real u = F(F_UQ + a, kp);
+        const real y = F(F_Y + NR + a, kp);
+        const real utol = 1e-9 * w;
+        if (ca == IN_FREE) {
+          if (u > P.uhi[a] + tol) { na = IN_AT_HI; F(F_Y + NR + a, kp) = 0.0; }
+          else if (u < P.ulo[a] - tol) { na = IN_AT_LO; F(F_Y + NR + a, kp) = 0.0; }
+        } else if (ca == IN_AT_HI) {
+          if (y < -utol) { na = IN_FREE; F(F_Y + NR + a, kp) = 0.0; }
+        } else {
+          if (y > utol) { na = IN_FREE; F(F_Y + NR + a, kp) = 0.0; }
+        }
+        changes += (na != ca);
+        ncode |= na << (3 * NR + 2 * a);
+      }
+      st[kp] = ncode;
+    }
+    __syncwarp();
+    return changes;
+  }
+
+  // returns true when the guessed active set was verified (then XQ/UQ hold the optimal x,u)
+  __device__ bool polish(int& nfact) {
+    polish_guess();
+    for (int pass = 0; pass < P.polish_passes; ++pass) {
+      factorize(FACT_POLISH);
+      ++nfact;
+      real res = 1.0;
+      for (int al = 0; al < 12; ++al) {
+        polish_assemble();
+        backward();
+        forward();
+        res = warp_max(polish_multipliers());
+        if (res < 1e-9) break;
+      }
+      const int changes = warp_sum_int(polish_update_sets());
+      if (!(res < 1e-7)) return false;          // stiff solve did not settle (also catches NaN)
+      if (changes == 0) return true;
+    }
+    return false;
+  }
+
+  // ========================================================================================
+  // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
+  // ========================================================================================
+  __device__ real emit_node(int b, int t, int kp, real w, real* x, real* uLin) {
+    const int k = bmpc_ndu(P, b) + t;
+    real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
+#pragma unroll
+    for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) u[a] = fmin(fmax(F(F_UQ + a, kp), P.ulo[a]), P.uhi[a]);
+    // objective (slacks eliminated)
+    real J = 0.0;
+    const real qs = 2.0 * w * (1.0 + P.dq_scale);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      real a = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) a += P.Q[i * NX + j] * x[j];
+      J += 0.5 * qs * x[i] * a + F(F_Q + i, kp) * x[i];
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      real v = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < NU; ++b2) v += P.R[a * NU + b2] * u[b2];
+      J += w * u[a] * v + ((k == 0) ? rlin * u[a] : 0.0);
+    }
+    const real lam = P.lam_lin * w;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      real lo, hi;
+      row_bounds(kp, j, lo, hi);
+      const real fx = row_value(kp, j, x);
+      J += lam * (fmax(fx - hi, 0.0) + fmax(lo - fx, 0.0));
+    }
+    if (P.out.uPred) {
+      real* o = P.out.uPred + ((size_t)prob * P.totalu + k) * NU;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) o[a] = u[a];
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) uLin[(size_t)k * NU + a] = u[a];
+    if (k == P.totalu - 1) {
+#pragma unroll
+      for (int a = 0; a < NU; ++a) uLin[(size_t)(k + 1) * NU + a] = u[a];   // uLin gets the last row twice (:1229)
+    }
+    if (k == 0) {
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        P.oldin[(size_t)prob * NU + a] = u[a];
+        if (P.out.u0) P.out.u0[(size_t)prob * NU + a] = u[a];
+      }
+    }
+    M::mulA(P, lin, x, xn);
+    M::addBu(P, lin, u, xn);
+    M::addC(cc, xn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xn[i];
+    return J;
+  }
+
+  __device__ real finish() {
+    real J = 0.0;
+    real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
+    real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.totalx * NX : nullptr;
+    if (lane == 0) {
+      real x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = P.x0[(size_t)prob * NX + i];
+      if (xP) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xP[i] = x[i];
+      }
+      J += emit_node(0, 0, kp_of(0, 0), 1.0, x, uLin);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) EXX[i] = x[i];
+    }
+    __syncwarp();
+    for (int d = 1; d <= P.NB; ++d) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+        real x[NX];
+        const int pa = bmpc_parent(P, b, d);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = EXX[(size_t)NX * pa + i];
+        const real w = Wb[b];
+        const int kx = bmpc_ndx(P, b);
+        for (int t = 0; t < P.N; ++t) {
+          if (xP) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xP[(size_t)(kx + t) * NX + i] = x[i];
+          }
+          J += emit_node(b, t, kp_of(b, t), w, x, uLin);
+        }
+        if (d == P.NB) {
+          if (xP) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xP[(size_t)(kx + P.N) * NX + i] = x[i];
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            real a = 0.0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a += P.Qf[i * NX + j] * x[j];
+            J += w * x[i] * a;   // terminal x' (w Qf) x, no linear term (:1094)
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) EXX[(size_t)NX * b + i] = x[i];
+      }
+      __syncwarp();
+    }
+    return warp_sum(J);
+  }
+
+  // ========================================================================================
+  __device__ void solve(int prob_) {
+    prob = prob_;
+    polpar = P.polpar ? P.polpar + (size_t)prob * P.m * 4 : nullptr;
+    expand_tree();
+    int nfact = 0, iters = 0, status = BMPC_STATUS_MAXITER;
+    factorize(FACT_FREE);
+    choose_rho();
+    factorize(FACT_ADMM);
+    nfact += 2;
+    admm_rows(false);
+    int next_polish = P.polish_first;
+    bool have_xu = false;
+    while (iters < P.max_iter) {
+      backward();
+      forward();
+      ++iters;
+      const real res = warp_max(admm_rows(true));
+      have_xu = false;
+      const bool conv = res < P.eps_abs;
+      if (iters >= next_polish || conv) {
+        next_polish = iters + P.polish_every;
+        if (polish(nfact)) {
+          status = BMPC_STATUS_POLISHED;
+          have_xu = true;
+          break;
+        }
+        if (conv) { status = BMPC_STATUS_CONVERGED; }
+        factorize(FACT_ADMM);
+        ++nfact;
+        admm_rows(false);
+        if (conv) break;
+      }
+    }
+    if (!have_xu) {
+      // XQ/UQ hold q~: one more KKT solve gives the (x,u) of the final ADMM state
+      backward();
+      forward();
+    }
+    const real J = finish();
+    if (lane == 0) {
+      const bool bad = !(J == J) || fabs(J) > 1e300;
+      if (P.out.status) P.out.status[prob] = bad ? BMPC_STATUS_NUMERIC : status;
+      if (P.out.iters) P.out.iters[prob] = iters;
+      if (P.out.nfact) P.out.nfact[prob] = nfact;
+      if (P.out.objective) P.out.objective[prob] = J;
+      P.started[prob] = 1;
+    }
+    __syncwarp();
+  }
+};
+
+template <class M, int NR, bool GWS>
+__global__ void __launch_bounds__(256) bmpc_solve_kernel(const KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  real* slab;
+  if (GWS) {
+    slab = P.gws + (size_t)(blockIdx.x * wpb + warp) * P.slab_reals;
+  } else {
+    slab = reinterpret_cast<real*>(smem_raw) + (size_t)warp * P.slab_reals;
+  }
+  Solver<M, NR> S(P, slab, lane);
+  for (;;) {
+    int prob = 0;
+    if (lane == 0) prob = atomicAdd(P.counter, 1);
+    prob = __shfl_sync(FULL_MASK, prob, 0);
+    if (prob >= P.count) break;
+    S.solve(prob);
+  }
+}

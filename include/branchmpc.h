@@ -1,0 +1,195 @@
+/*
+ * branchmpc.h - C ABI of libbranchmpc.so: batched Branch-MPC solves on one B200 (sm_100a).
+ *
+ * The reference (Gavinli-lgf/belief-planning) has no FFI layer: its boundary is the duck-typed
+ * Python pair  PredictiveModel + BranchMPC.solve(x, z, xRef)  (MPC_branch.py:883, :1171;
+ * highway_branch_dyn.py:264).  This library is what a ctypes binding under that interface calls
+ * (see INTEGRATION.md).  One call solves `count` independent scenario-tree MPC problems.
+ *
+ * Conventions
+ *  - every data pointer passed to bmpc_solve() is a DEVICE pointer owned by the caller
+ *    (PyTorch allocates); the library borrows it for the duration of the call;
+ *    bmpc_solve_host() is the same call on HOST buffers (copies included);
+ *  - all floating point data is IEEE float64, row-major, batch index outermost;
+ *  - functions return 0 on success or a negative BMPC_E_* code; nothing throws or aborts across
+ *    the ABI; per-problem solver status is an OUTPUT, not an error;
+ *  - a handle is bound to one device and is not thread-safe; work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream) and the call returns
+ *    without synchronising.
+ */
+#ifndef BRANCHMPC_H_
+#define BRANCHMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMPC_VERSION 100
+
+#define BMPC_MAX_N 4          /* state dimension supported by this build            */
+#define BMPC_MAX_D 3          /* input dimension                                    */
+#define BMPC_MAX_POLICIES 4   /* branching factor m                                 */
+#define BMPC_MAX_ROWS 4       /* two-sided soft state rows (besides the collision row) */
+#define BMPC_MAX_NB 3         /* branching depth                                    */
+
+/* model kinds: which closed-form predictive model the kernels evaluate */
+#define BMPC_MODEL_HIGHWAY 0   /* highway_branch_dyn.PredictiveModel   (n=4, d=2) */
+#define BMPC_MODEL_QUADRUPED 1 /* quadruped_branch_dyn.PredictiveModel (n=3, d=3) */
+
+/* controller kinds */
+#define BMPC_CTRL_BRANCH 0 /* MPC_branch.BranchMPC (effective, second definition, :881) */
+#define BMPC_CTRL_PROX 1   /* MPC_branch.BranchMPCProx (:82)                             */
+#define BMPC_CTRL_ROBUST 2 /* MPC_branch.robustMPC (:1275)                               */
+
+/* backup-policy kinds (symbolic branch of each reference policy) */
+#define BMPC_POLICY_MAINTAIN 0 /* highway_branch_dyn.backup_maintain        :54  */
+#define BMPC_POLICY_BRAKE 1    /* highway_branch_dyn.backup_brake           :108 */
+#define BMPC_POLICY_LC 2       /* highway_branch_dyn.backup_lc              :136, param = target state */
+#define BMPC_POLICY_TRACKV 3   /* highway_branch_dyn.backup_maintain_trackV :80,  param[0] = v0 */
+#define BMPC_POLICY_FORWARD 4  /* quadruped_branch_dyn.backup_forward       :34,  param[0] = v0 */
+#define BMPC_POLICY_STOP 5     /* quadruped_branch_dyn.backup_stop          :46  */
+
+/* error codes */
+#define BMPC_OK 0
+#define BMPC_E_INVALID (-1)     /* bad argument / unsupported configuration        */
+#define BMPC_E_CUDA (-2)        /* a CUDA runtime call failed (see bmpc_last_error) */
+#define BMPC_E_CAPACITY (-3)    /* count exceeds the handle's batch capacity        */
+#define BMPC_E_UNSUPPORTED (-4) /* valid in the reference, not built yet            */
+
+/* per-problem solver status (bmpc_outputs.status) */
+#define BMPC_STATUS_POLISHED 0  /* active set verified: exact optimum of the QP (to round-off)   */
+#define BMPC_STATUS_CONVERGED 1 /* ADMM residuals below tolerance, polish not verified           */
+#define BMPC_STATUS_MAXITER 2   /* iteration cap reached; best iterate returned                  */
+#define BMPC_STATUS_NUMERIC 3   /* non-finite data met; previous plan kept (reference: feasible=0) */
+
+typedef struct bmpc_config {
+  int32_t model;      /* BMPC_MODEL_*  */
+  int32_t controller; /* BMPC_CTRL_*   */
+  int32_t n, d;       /* state / input dimension (PredictiveModel.n, .d)               */
+  int32_t N;          /* steps per branch      (PredictiveModel.N, main_branch.py:24)   */
+  int32_t NB;         /* branching depth       (BranchMPCParams.NB, main_branch.py:30)  */
+  int32_t m;          /* number of backup policies = len(backupcons)                    */
+  double dt;
+  int32_t policy_kind[BMPC_MAX_POLICIES];
+  double policy_param[BMPC_MAX_POLICIES][4]; /* defaults; per-problem override in bmpc_solve */
+
+  /* cost, BranchMPCParams (MPC_branch.py:27-54), row-major */
+  double Q[BMPC_MAX_N * BMPC_MAX_N];
+  double Qf[BMPC_MAX_N * BMPC_MAX_N];
+  double R[BMPC_MAX_D * BMPC_MAX_D];
+  double dR[BMPC_MAX_D];
+  double Qslack[2]; /* [quadratic, linear] as the code uses them (:1105-1106); quadratic must be 0 */
+
+  /* soft state rows lo <= f'x <= hi (Fx x <= bx with opposite rows paired), weight Qslack[1]*w */
+  int32_t n_rows;
+  double row_f[BMPC_MAX_ROWS][BMPC_MAX_N];
+  double row_lo[BMPC_MAX_ROWS]; /* -inf allowed */
+  double row_hi[BMPC_MAX_ROWS]; /* +inf allowed */
+  /* hard input box (Fu u <= bu) */
+  double u_lo[BMPC_MAX_D];
+  double u_hi[BMPC_MAX_D];
+
+  /* model constants: Branch_constants / Quad_constants (utils.py:25-59) */
+  double veh_L, veh_W; /* highway: L, W                                               */
+  double Kpsi;         /* highway: heading gain of maintain/brake                     */
+  double s1;           /* branching-probability sharpness                             */
+  double lane_lo, lane_hi; /* highway model lane boundary LB (highway_branch_dyn.py:279) */
+  double quad_margin;  /* quadruped: (L1+L2)/2 + col_tol                              */
+
+  /* solver knobs (0 = library default) */
+  int32_t max_iter;       /* ADMM iteration cap (default 600)                         */
+  int32_t polish_first;   /* first polish attempt after this many iterations (25)     */
+  int32_t polish_every;   /* then every this many iterations (25)                     */
+  int32_t polish_passes;  /* active-set passes per attempt (4)                        */
+  double alpha;           /* over-relaxation (1.6)                                    */
+  double theta, theta_u;  /* curvature-matched rho scale for state rows / inputs (1)  */
+  double eps_abs;         /* ADMM residual tolerance for STATUS_CONVERGED (1e-5)      */
+
+  int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */
+  int32_t device;         /* CUDA device ordinal                                      */
+  int32_t reserved[8];
+} bmpc_config;
+
+/* Output device pointers; any may be NULL to skip that output. */
+typedef struct bmpc_outputs {
+  double* u0;        /* [count][d]            first applied input  (mpc.uPred[0])           */
+  double* uPred;     /* [count][totalu][d]    unpackSolution, MPC_branch.py:1226            */
+  double* xPred;     /* [count][totalx][n]    unpackSolution, MPC_branch.py:1225            */
+  double* xLin;      /* [count][totalu][n]    linearisation states per input node (xtraj)   */
+  double* zPred;     /* [count][totalu][n]    obstacle prediction per input node (ztraj)    */
+  double* branch_w;  /* [count][nbranch]      branch weights w                               */
+  double* branch_p;  /* [count][nbranch][m]   child probabilities of non-leaf branches       */
+  double* objective; /* [count]               QP objective (1/2 z'Pz + q'z, slacks eliminated) */
+  int32_t* status;   /* [count]               BMPC_STATUS_*                                  */
+  int32_t* iters;    /* [count]               ADMM iterations used                           */
+  int32_t* nfact;    /* [count]               Riccati factorisations used                    */
+} bmpc_outputs;
+
+typedef struct bmpc_handle bmpc_handle;
+
+int bmpc_version(void);
+
+/* Create a solver for one configuration.  Allocates the persistent per-episode state
+ * (warm-start inputs uLin, arg-max child per branch, OldInput) for batch_capacity episodes. */
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out);
+int bmpc_destroy(bmpc_handle* h);
+
+/* Forget the persistent state of the given episode slots (NULL = all): their next solve is a
+ * first solve (inittree: zero inputs, MPC_branch.py:932-957). */
+int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count);
+
+/* Tree numbering tables (BFS order, MPC_branch.py:928-981).  Each array has bmpc_num_branches()
+ * entries; NULL pointers are skipped.  Host pointers. */
+int bmpc_num_branches(const bmpc_handle* h);
+int bmpc_total_x(const bmpc_handle* h);
+int bmpc_total_u(const bmpc_handle* h);
+int bmpc_get_topology(const bmpc_handle* h, int32_t* ndx, int32_t* ndu, int32_t* depth, int32_t* parent);
+
+/* One MPC step for episodes 0..count-1 (episode i uses persistent slot i).
+ *   x0, z0, xref : [count][n] device float64   (solve(x, z, xRef), MPC_branch.py:1171)
+ *   policy_params: [count][m][4] device float64 or NULL (per-episode lane-change target etc.;
+ *                  the reference rebuilds its model for this, highway_branch_dyn.py:331)       */
+int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+               const double* policy_params, int64_t count, const bmpc_outputs* out, void* stream);
+
+/* Same step on HOST buffers: copies inputs to the device, solves, copies every non-NULL output
+ * back and synchronises.  `out` holds HOST pointers here. */
+int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                    const double* policy_params, int64_t count, const bmpc_outputs* out);
+
+/* Persistent state access for tests / checkpointing (device or host pointers, see `on_host`).
+ *   uLin [count][totalu+1][d], pbest [count][nbranch] (int32), old_input [count][d], started [count] (int32) */
+int bmpc_get_state(bmpc_handle* h, double* uLin, int32_t* pbest, double* old_input, int32_t* started,
+                   int64_t count, int on_host);
+int bmpc_set_state(bmpc_handle* h, const double* uLin, const int32_t* pbest, const double* old_input,
+                   const int32_t* started, int64_t count, int on_host);
+
+/* Model functions evaluated on the device for a batch of points (parity tests of rows M1-M5):
+ *   dyn_linearization: A [count][n][n], B [count][n][d], C [count][n], xp [count][n]
+ *   zpred            : [count][N][m*n]
+ *   branch_eval p    : [count][m]
+ *   col_eval         : hlin [count], dh [count][n]
+ * Device pointers; NULL outputs are skipped. */
+int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const double* u, const double* policy_params,
+                    int64_t count, double* A, double* B, double* C, double* xp, double* zpred, double* p,
+                    double* hlin, double* dh, void* stream);
+
+/* Kernel launch accounting since creation (for bench.py's gpu_launches). */
+int64_t bmpc_launch_count(const bmpc_handle* h);
+
+/* Measured FP64 FMA throughput of this GPU in TFLOP/s (a dependent-chain-free DFMA loop over all
+ * SMs; used as the roofline denominator by bench.py). Returns < 0 on error. */
+double bmpc_measure_fp64_peak(int device, int iters);
+
+/* Time of the last bmpc_solve kernel in milliseconds measured with CUDA events on its stream
+ * (valid after the stream has been synchronised). */
+float bmpc_last_kernel_ms(bmpc_handle* h);
+
+const char* bmpc_last_error(const bmpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRANCHMPC_H_ */

@@ -151,13 +151,14 @@ def solve_qp_ipm(P, q, A, l, u, tol=1e-10, max_iter=200, prox=1e-7):
     return z, ydual, it
 
 
-def polish(P, q, A, l, u, z, ydual, delta=1e-9, refine=8, act_tol=1e-6):
+def polish(P, q, A, l, u, z, ydual, delta=1e-9, refine=8, act_tol=1e-6, max_passes=12):
     """Active-set polish of an interior-point answer (same idea as OSQP's polish step).
 
     Rows whose dual is clearly non-zero (and equalities) are imposed as equalities; the
-    regularised KKT system is solved with iterative refinement.  Returns (z, y, ok) where ok
-    says the polished point passed the primal/dual sign checks; callers fall back to the
-    unpolished point otherwise.
+    regularised KKT system is solved with iterative refinement.  Rows that come back with a
+    wrong-sign multiplier are released and violated rows are added (a few active-set passes
+    starting from the interior-point guess).  Returns (z, y, ok); ok means primal feasible to
+    1e-9 with correctly signed multipliers, i.e. the point is the exact optimum.
     """
     P = sp.csc_matrix(P)
     Pu = sp.triu(P, format="csc")
@@ -170,24 +171,32 @@ def polish(P, q, A, l, u, z, ydual, delta=1e-9, refine=8, act_tol=1e-6):
     scale = max(1.0, np.abs(ydual).max())
     act_u = (~eq) & (ydual > act_tol * scale)
     act_l = (~eq) & (ydual < -act_tol * scale)
-    rows = np.where(eq | act_u | act_l)[0]
-    Aa = A[rows]
-    ba = np.where(act_l[rows], l[rows], u[rows])
-    ma = Aa.shape[0]
-    K = sp.bmat([[P + delta * sp.eye(n), Aa.T], [Aa, -delta * sp.eye(ma)]], format="csc")
-    lu = spla.splu(K)
-    Kexact = sp.bmat([[P, Aa.T], [Aa, None]], format="csr")
-    rhs = np.concatenate([-q, ba])
-    sol = lu.solve(rhs)
-    for _ in range(refine):
-        sol = sol + lu.solve(rhs - Kexact @ sol)
-    zp = sol[:n]
-    yp = np.zeros(A.shape[0])
-    yp[rows] = sol[n:]
-    Az = A @ zp
-    feas = max(np.max(np.maximum(Az - u, 0.0)), np.max(np.maximum(l - Az, 0.0)))
-    sign_ok = np.all(yp[act_u] >= -1e-7 * scale) and np.all(yp[act_l] <= 1e-7 * scale)
-    ok = bool(feas < 1e-8 and sign_ok)
+    zp, yp, ok = z, ydual, False
+    for _ in range(max_passes):
+        rows = np.where(eq | act_u | act_l)[0]
+        Aa = A[rows]
+        ba = np.where(act_l[rows], l[rows], u[rows])
+        ma = Aa.shape[0]
+        K = sp.bmat([[P + delta * sp.eye(n), Aa.T], [Aa, -delta * sp.eye(ma)]], format="csc")
+        lu = spla.splu(K)
+        Kexact = sp.bmat([[P, Aa.T], [Aa, None]], format="csr")
+        rhs = np.concatenate([-q, ba])
+        sol = lu.solve(rhs)
+        for _r in range(refine):
+            sol = sol + lu.solve(rhs - Kexact @ sol)
+        zp = sol[:n]
+        yp = np.zeros(A.shape[0])
+        yp[rows] = sol[n:]
+        Az = A @ zp
+        viol_u = (~eq) & (~act_u) & (Az - u > 1e-9)
+        viol_l = (~eq) & (~act_l) & (l - Az > 1e-9)
+        bad_u = act_u & (yp < 0.0)
+        bad_l = act_l & (yp > 0.0)
+        if not (viol_u.any() or viol_l.any() or bad_u.any() or bad_l.any()):
+            ok = True
+            break
+        act_u = (act_u & ~bad_u) | viol_u
+        act_l = (act_l & ~bad_l) | viol_l
     return zp, yp, ok
 
 
