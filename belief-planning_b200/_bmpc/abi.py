@@ -1,0 +1,101 @@
+"""ctypes mirror of include/branchmpc.h and the loader of libbranchmpc.so.
+
+There is no CPU fallback: if the CUDA library is missing or cannot be loaded, `load_library()` raises.
+"""
+import ctypes as C
+import os
+
+MAX_N, MAX_D, MAX_POLICIES, MAX_ROWS, MAX_NB = 4, 3, 4, 4, 3
+
+MODEL_HIGHWAY, MODEL_QUADRUPED = 0, 1
+CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST = 0, 1, 2
+POLICY_MAINTAIN, POLICY_BRAKE, POLICY_LC, POLICY_TRACKV, POLICY_FORWARD, POLICY_STOP = range(6)
+STATUS_POLISHED, STATUS_CONVERGED, STATUS_MAXITER, STATUS_NUMERIC = range(4)
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
+
+_dbl = C.c_double
+_i32 = C.c_int32
+
+
+class Config(C.Structure):
+    """struct bmpc_config"""
+    _fields_ = [
+        ("model", _i32), ("controller", _i32), ("n", _i32), ("d", _i32), ("N", _i32), ("NB", _i32), ("m", _i32),
+        ("dt", _dbl),
+        ("policy_kind", _i32 * MAX_POLICIES),
+        ("policy_param", (_dbl * 4) * MAX_POLICIES),
+        ("Q", _dbl * (MAX_N * MAX_N)), ("Qf", _dbl * (MAX_N * MAX_N)), ("R", _dbl * (MAX_D * MAX_D)),
+        ("dR", _dbl * MAX_D), ("Qslack", _dbl * 2),
+        ("n_rows", _i32),
+        ("row_f", (_dbl * MAX_N) * MAX_ROWS), ("row_lo", _dbl * MAX_ROWS), ("row_hi", _dbl * MAX_ROWS),
+        ("u_lo", _dbl * MAX_D), ("u_hi", _dbl * MAX_D),
+        ("veh_L", _dbl), ("veh_W", _dbl), ("Kpsi", _dbl), ("s1", _dbl), ("lane_lo", _dbl), ("lane_hi", _dbl),
+        ("quad_margin", _dbl),
+        ("max_iter", _i32), ("polish_first", _i32), ("polish_every", _i32), ("polish_passes", _i32),
+        ("polish_al_iters", _i32), ("warm_polish", _i32),
+        ("alpha", _dbl), ("theta", _dbl), ("theta_u", _dbl), ("eps_abs", _dbl), ("polish_big", _dbl),
+        ("polish_mult", _dbl),
+        ("batch_capacity", _i32), ("device", _i32), ("reserved", _i32 * 8),
+    ]
+
+
+_pd = C.POINTER(_dbl)
+_pi = C.POINTER(_i32)
+
+
+class Outputs(C.Structure):
+    """struct bmpc_outputs (device pointers for bmpc_solve, host pointers for bmpc_solve_host)"""
+    _fields_ = [("u0", C.c_void_p), ("uPred", C.c_void_p), ("xPred", C.c_void_p), ("xLin", C.c_void_p),
+                ("zPred", C.c_void_p), ("branch_w", C.c_void_p), ("branch_p", C.c_void_p), ("objective", C.c_void_p),
+                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p)]
+
+
+OUTPUT_NAMES = [f[0] for f in Outputs._fields_]
+
+# every symbol include/branchmpc.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("bmpc_version", C.c_int, []),
+    ("bmpc_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    ("bmpc_destroy", C.c_int, [C.c_void_p]),
+    ("bmpc_reset", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int64]),
+    ("bmpc_num_branches", C.c_int, [C.c_void_p]),
+    ("bmpc_total_x", C.c_int, [C.c_void_p]),
+    ("bmpc_total_u", C.c_int, [C.c_void_p]),
+    ("bmpc_get_topology", C.c_int, [C.c_void_p, _pi, _pi, _pi, _pi]),
+    ("bmpc_solve", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                             C.POINTER(Outputs), C.c_void_p]),
+    ("bmpc_solve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.POINTER(Outputs)]),
+    ("bmpc_get_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    ("bmpc_set_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    ("bmpc_eval_model", C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 8 + [C.c_void_p]),
+    ("bmpc_launch_count", C.c_int64, [C.c_void_p]),
+    ("bmpc_measure_fp64_peak", C.c_double, [C.c_int, C.c_int]),
+    ("bmpc_last_kernel_ms", C.c_float, [C.c_void_p]),
+    ("bmpc_last_error", C.c_char_p, [C.c_void_p]),
+]
+
+LIB_NAME = "libbranchmpc.so"
+_lib = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), LIB_NAME)
+
+
+def load_library():
+    """dlopen the in-tree CUDA library and bind every declared symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError("%s is not built (run `python -c 'import __graft_entry__ as g; g.build()'` at the repo "
+                           "root); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

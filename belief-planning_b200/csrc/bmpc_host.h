@@ -1,0 +1,116 @@
+// Host-side translation of a bmpc_config into the kernel parameter block: validation, tree numbering
+// (MPC_branch.py:928-981 in closed form) and solver defaults.  Shared by the CUDA library (bmpc_api.cu)
+// and the single-lane host build used by the CPU tests (tests/hostsim).
+#pragma once
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "bmpc_params.h"
+
+namespace bmpc {
+
+inline int model_dims(int model, int* n, int* d) {
+  if (model == BMPC_MODEL_HIGHWAY) { *n = 4; *d = 2; return 0; }
+  if (model == BMPC_MODEL_QUADRUPED) { *n = 3; *d = 3; return 0; }
+  return -1;
+}
+
+// Fills every field of KParams that does not depend on a particular call.  Returns BMPC_OK or an error code with
+// a message in `err`.
+inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
+  KParams P;
+  memset(&P, 0, sizeof(P));
+  int n = 0, d = 0;
+  if (model_dims(c.model, &n, &d) != 0) { *err = "unknown model kind"; return BMPC_E_INVALID; }
+  if (c.n != n || c.d != d) { *err = "n/d do not match the model kind"; return BMPC_E_INVALID; }
+  if (c.N < 2 || c.N > 64) { *err = "N must be in [2, 64]"; return BMPC_E_INVALID; }
+  if (c.NB < 1 || c.NB > BMPC_MAX_NB) { *err = "NB must be in [1, BMPC_MAX_NB]"; return BMPC_E_INVALID; }
+  if (c.m < 1 || c.m > BMPC_MAX_POLICIES) { *err = "m must be in [1, BMPC_MAX_POLICIES]"; return BMPC_E_INVALID; }
+  if (!(c.dt > 0.0)) { *err = "dt must be positive"; return BMPC_E_INVALID; }
+  if (c.n_rows < 0 || c.n_rows > BMPC_MAX_ROWS) { *err = "n_rows out of range"; return BMPC_E_INVALID; }
+  if (c.controller != BMPC_CTRL_BRANCH) {
+    *err = "controller kind not built yet (BRANCH only)";
+    return BMPC_E_UNSUPPORTED;
+  }
+  if (c.Qslack[0] != 0.0) { *err = "quadratic slack weight Qslack[0] must be 0 (the reference uses 0)"; return BMPC_E_UNSUPPORTED; }
+  if (!(c.Qslack[1] > 0.0)) { *err = "linear slack weight Qslack[1] must be positive"; return BMPC_E_INVALID; }
+  for (int i = 0; i < c.m; ++i) {
+    const int k = c.policy_kind[i];
+    const bool hw = (k == BMPC_POLICY_MAINTAIN || k == BMPC_POLICY_BRAKE || k == BMPC_POLICY_LC || k == BMPC_POLICY_TRACKV);
+    const bool qd = (k == BMPC_POLICY_FORWARD || k == BMPC_POLICY_STOP);
+    if ((c.model == BMPC_MODEL_HIGHWAY && !hw) || (c.model == BMPC_MODEL_QUADRUPED && !qd)) {
+      *err = "policy kind does not belong to the model";
+      return BMPC_E_INVALID;
+    }
+  }
+  for (int a = 0; a < d; ++a) {
+    if (!(c.u_lo[a] <= c.u_hi[a])) { *err = "empty input box"; return BMPC_E_INVALID; }
+    if (!(c.R[a * d + a] > 0.0)) { *err = "R must have a positive diagonal"; return BMPC_E_INVALID; }
+  }
+  P.m = c.m;
+  P.NB = c.NB;
+  P.N = c.N;
+  int pw = 1, off = 0;
+  for (int k = 0; k <= c.NB; ++k) {
+    P.pw[k] = pw;
+    P.off[k] = off;
+    off += pw;
+    pw *= c.m;
+  }
+  P.off[c.NB + 1] = off;
+  P.nbranch = off;
+  P.totalu = 1 + c.N * (P.nbranch - 1);
+  P.totalx = P.totalu + P.pw[c.NB];
+  P.nup = P.totalu + P.nbranch;
+  P.dt = c.dt;
+  P.veh_L = c.veh_L;
+  P.veh_W = c.veh_W;
+  P.Kpsi = c.Kpsi;
+  P.s1 = c.s1;
+  P.lane_lo = c.lane_lo;
+  P.lane_hi = c.lane_hi;
+  P.quad_margin = c.quad_margin;
+  for (int i = 0; i < BMPC_MAX_POLICIES; ++i) {
+    P.pol_kind[i] = c.policy_kind[i];
+    for (int k = 0; k < 4; ++k) P.pol_par[i][k] = c.policy_param[i][k];
+  }
+  P.ctrl = c.controller;
+  for (int i = 0; i < n * n; ++i) { P.Q[i] = c.Q[i]; P.Qf[i] = c.Qf[i]; }
+  for (int i = 0; i < d * d; ++i) P.R[i] = c.R[i];
+  for (int i = 0; i < d; ++i) { P.dR[i] = c.dR[i]; P.ulo[i] = c.u_lo[i]; P.uhi[i] = c.u_hi[i]; }
+  P.dq_scale = (c.controller == BMPC_CTRL_PROX) ? 3.0 : 0.5;   // MPC_branch.py:271 / :1070
+  P.lam_lin = c.Qslack[1];
+  P.nrows = c.n_rows;
+  for (int j = 0; j < c.n_rows; ++j) {
+    for (int i = 0; i < n; ++i) P.rf[j][i] = c.row_f[j][i];
+    P.rlo[j] = isfinite(c.row_lo[j]) ? c.row_lo[j] : -1.0e300;
+    P.rhi[j] = isfinite(c.row_hi[j]) ? c.row_hi[j] : 1.0e300;
+    if (!(P.rlo[j] <= P.rhi[j])) { *err = "empty state row range"; return BMPC_E_INVALID; }
+  }
+  P.max_iter = c.max_iter > 0 ? c.max_iter : 400;
+  P.polish_first = c.polish_first > 0 ? c.polish_first : 30;
+  P.polish_every = c.polish_every > 0 ? c.polish_every : 20;
+  P.polish_passes = c.polish_passes > 0 ? c.polish_passes : 8;
+  P.polish_al_iters = c.polish_al_iters > 0 ? c.polish_al_iters : 12;
+  P.warm_polish = c.warm_polish;
+  P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
+  P.theta = c.theta > 0.0 ? c.theta : 1.0;
+  P.theta_u = c.theta_u > 0.0 ? c.theta_u : 1.0;
+  P.eps_abs = c.eps_abs > 0.0 ? c.eps_abs : 1.0e-6;
+  P.polish_big = c.polish_big > 0.0 ? c.polish_big : 1.0e4;
+  P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e4;
+  *out = P;
+  return BMPC_OK;
+}
+
+// (model, number of soft rows incl. the collision row) -> which Solver instantiation runs
+inline bool supported_instance(int model, int n_rows) {
+  if (model == BMPC_MODEL_HIGHWAY) return n_rows >= 0 && n_rows <= 2;
+  if (model == BMPC_MODEL_QUADRUPED) return n_rows == 0;
+  return false;
+}
+
+}  // namespace bmpc

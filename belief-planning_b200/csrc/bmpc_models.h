@@ -2,15 +2,15 @@
 // The reference builds these as CasADi graphs and differentiates them automatically
 // (highway_branch_dyn.py:363-398, quadruped_branch_dyn.py:218-248); here they are written out.
 #pragma once
-#include "bmpc_common.cuh"
+#include "bmpc_params.h"
 
 // softmin/softmax accumulators with a running shift: sum(exp(-g v) v)/sum(exp(-g v)) is invariant to
 // subtracting a constant from the exponent, so the shifted form equals the reference's unshifted one
 // (highway_branch_dyn.py:151-162) without its overflow.
 struct SoftMinAcc {
   real vmin, num, den, gamma;
-  __device__ SoftMinAcc(real g) : vmin(1e300), num(0), den(0), gamma(g) {}
-  __device__ void add(real v) {
+  BMPC_D SoftMinAcc(real g) : vmin(1e300), num(0), den(0), gamma(g) {}
+  BMPC_D void add(real v) {
     if (v < vmin) {
       const real sc = (den > 0) ? exp(-gamma * (vmin - v)) : 0.0;
       num *= sc;
@@ -21,11 +21,11 @@ struct SoftMinAcc {
     num += e * v;
     den += e;
   }
-  __device__ real value() const { return num / den; }
+  BMPC_D real value() const { return num / den; }
 };
 
 // (dx e^dx + dy e^dy)/(e^dx + e^dy) and partials; veh_col core (highway_branch_dyn.py:231-234)
-__device__ __forceinline__ void soft_box(real dx, real dy, real& h, real& gx, real& gy) {
+BMPC_D void soft_box(real dx, real dy, real& h, real& gx, real& gy) {
   const real mx = fmax(dx, dy);
   const real ex = exp(dx - mx), ey = exp(dy - mx);
   const real wx = ex / (ex + ey), wy = 1.0 - wx;
@@ -34,7 +34,7 @@ __device__ __forceinline__ void soft_box(real dx, real dy, real& h, real& gx, re
   gy = wy * (1.0 + dy - h);
 }
 
-__device__ __forceinline__ real sgn(real v) { return (v > 0) - (v < 0); }
+BMPC_D real sgn(real v) { return (v > 0) - (v < 0); }
 
 // ------------------------------------------------------------------------------------------
 // Highway: x = (x, y, v, psi), u = (a, r).   highway_branch_dyn.py
@@ -46,9 +46,9 @@ struct HighwayModel {
   static constexpr int NCC = 2;   // C has two non-zero entries
 
   // one Euler step of dubin (:17-34, :369)
-  __device__ static void step(const KParams& P, const real* x, const real* u, real* xn) {
+  BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) {
     real s, c;
-    sincos(x[3], &s, &c);
+    bmpc_sincos(x[3], &s, &c);
     xn[0] = x[0] + P.dt * (x[2] * c);
     xn[1] = x[1] + P.dt * (x[2] * s);
     xn[2] = x[2] + P.dt * u[0];
@@ -56,7 +56,7 @@ struct HighwayModel {
   }
 
   // symbolic branch of each backup policy (:54-148)
-  __device__ static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) {
+  BMPC_D static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) {
     switch (kind) {
       case BMPC_POLICY_MAINTAIN:
         u[0] = 0.0;
@@ -86,9 +86,9 @@ struct HighwayModel {
   }
 
   // dyn_linearization (:284-291): compressed A, C and the successor state
-  __device__ static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
+  BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
     real s, c;
-    sincos(x[3], &s, &c);
+    bmpc_sincos(x[3], &s, &c);
     const real dt = P.dt, v = x[2];
     lin[0] = dt * c;
     lin[1] = -dt * v * s;
@@ -103,38 +103,38 @@ struct HighwayModel {
     cc[1] = -dt * v * x[3] * c;
   }
 
-  __device__ __forceinline__ static void mulA(const KParams&, const real* lin, const real* x, real* y) {
+  BMPC_D static void mulA(const KParams&, const real* lin, const real* x, real* y) {
     y[0] = x[0] + lin[0] * x[2] + lin[1] * x[3];
     y[1] = x[1] + lin[2] * x[2] + lin[3] * x[3];
     y[2] = x[2];
     y[3] = x[3];
   }
-  __device__ __forceinline__ static void mulAT(const KParams&, const real* lin, const real* g, real* y) {
+  BMPC_D static void mulAT(const KParams&, const real* lin, const real* g, real* y) {
     y[0] = g[0];
     y[1] = g[1];
     y[2] = g[2] + lin[0] * g[0] + lin[2] * g[1];
     y[3] = g[3] + lin[1] * g[0] + lin[3] * g[1];
   }
   // y += B u ;  r = B' g   (B = dt [0;0;I2], constant)
-  __device__ __forceinline__ static void addBu(const KParams& P, const real*, const real* u, real* y) {
+  BMPC_D static void addBu(const KParams& P, const real*, const real* u, real* y) {
     y[2] += P.dt * u[0];
     y[3] += P.dt * u[1];
   }
-  __device__ __forceinline__ static void mulBT(const KParams& P, const real*, const real* g, real* r) {
+  BMPC_D static void mulBT(const KParams& P, const real*, const real* g, real* r) {
     r[0] = P.dt * g[2];
     r[1] = P.dt * g[3];
   }
-  __device__ __forceinline__ static void addC(const real* cc, real* y) {
+  BMPC_D static void addC(const real* cc, real* y) {
     y[0] += cc[0];
     y[1] += cc[1];
   }
-  __device__ __forceinline__ static void expandC(const real* cc, real* C) {
+  BMPC_D static void expandC(const real* cc, real* C) {
     C[0] = cc[0];
     C[1] = cc[1];
     C[2] = 0.0;
     C[3] = 0.0;
   }
-  __device__ static void denseA(const KParams&, const real* lin, real* A) {
+  BMPC_D static void denseA(const KParams&, const real* lin, real* A) {
     for (int i = 0; i < 16; ++i) A[i] = 0.0;
     A[0] = A[5] = A[10] = A[15] = 1.0;
     A[2] = lin[0];
@@ -142,14 +142,14 @@ struct HighwayModel {
     A[6] = lin[2];
     A[7] = lin[3];
   }
-  __device__ static void denseB(const KParams& P, const real*, real* B) {
+  BMPC_D static void denseB(const KParams& P, const real*, real* B) {
     for (int i = 0; i < 8; ++i) B[i] = 0.0;
     B[4] = P.dt;
     B[7] = P.dt;
   }
 
   // collision function h(x,z) with size [L+1, W+0.2] and its gradient in (x,y) (:223-235, :386, :392)
-  __device__ static void collision(const KParams& P, const real* x, const real* zxy, real& h, real& dhx, real& dhy) {
+  BMPC_D static void collision(const KParams& P, const real* x, const real* zxy, real& h, real& dhx, real& dhy) {
     const real ex = x[0] - zxy[0], ey = x[1] - zxy[1];
     real gx, gy;
     soft_box(fabs(ex) - (P.veh_L + 1.0), fabs(ey) - (P.veh_W + 0.2), h, gx, gy);
@@ -160,7 +160,7 @@ struct HighwayModel {
   // Safety value of one policy: BF_traj (:337-349) over the obstacle rollout under `kind` against
   // the ego rollout under policy 0; also returns the obstacle trajectory through `emit(t, z)`.
   template <class Emit>
-  __device__ static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
+  BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
                                        const real* xe0, const real* z0, real* zlast, Emit emit) {
     real xe[4] = {xe0[0], xe0[1], xe0[2], xe0[3]};
     real z[4] = {z0[0], z0[1], z0[2], z0[3]};
@@ -188,7 +188,7 @@ struct HighwayModel {
   }
 
   // un-normalised branch weight exp(s1 * softsat(hi, 1)) (:355-359); softsat(h,1) == sigmoid(h)
-  __device__ static real branch_weight(const KParams& P, real hi, real /*himax*/) {
+  BMPC_D static real branch_weight(const KParams& P, real hi, real /*himax*/) {
     return exp(P.s1 / (1.0 + exp(-hi)));
   }
   static constexpr bool kWeightNeedsMax = false;
@@ -203,21 +203,21 @@ struct QuadrupedModel {
   static constexpr int NLIN = 4;  // dt*cos, dt*sin, A[0][2], A[1][2]
   static constexpr int NCC = 2;
 
-  __device__ static void step(const KParams& P, const real* x, const real* u, real* xn) {
+  BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) {
     real s, c;
-    sincos(x[2], &s, &c);
+    bmpc_sincos(x[2], &s, &c);
     xn[0] = x[0] + P.dt * (u[0] * c - u[1] * s);
     xn[1] = x[1] + P.dt * (u[0] * s + u[1] * c);
     xn[2] = x[2] + P.dt * u[2];
   }
-  __device__ static void policy(const KParams&, int kind, const real* par, const real*, real* u) {
+  BMPC_D static void policy(const KParams&, int kind, const real* par, const real*, real* u) {
     u[0] = (kind == BMPC_POLICY_FORWARD) ? par[0] : 0.0;
     u[1] = 0.0;
     u[2] = 0.0;
   }
-  __device__ static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
+  BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
     real s, c;
-    sincos(x[2], &s, &c);
+    bmpc_sincos(x[2], &s, &c);
     const real dt = P.dt;
     lin[0] = dt * c;
     lin[1] = dt * s;
@@ -230,55 +230,55 @@ struct QuadrupedModel {
     cc[0] = -lin[2] * x[2];
     cc[1] = -lin[3] * x[2];
   }
-  __device__ __forceinline__ static void mulA(const KParams&, const real* lin, const real* x, real* y) {
+  BMPC_D static void mulA(const KParams&, const real* lin, const real* x, real* y) {
     y[0] = x[0] + lin[2] * x[2];
     y[1] = x[1] + lin[3] * x[2];
     y[2] = x[2];
   }
-  __device__ __forceinline__ static void mulAT(const KParams&, const real* lin, const real* g, real* y) {
+  BMPC_D static void mulAT(const KParams&, const real* lin, const real* g, real* y) {
     y[0] = g[0];
     y[1] = g[1];
     y[2] = g[2] + lin[2] * g[0] + lin[3] * g[1];
   }
-  __device__ __forceinline__ static void addBu(const KParams& P, const real* lin, const real* u, real* y) {
+  BMPC_D static void addBu(const KParams& P, const real* lin, const real* u, real* y) {
     y[0] += lin[0] * u[0] - lin[1] * u[1];
     y[1] += lin[1] * u[0] + lin[0] * u[1];
     y[2] += P.dt * u[2];
   }
-  __device__ __forceinline__ static void mulBT(const KParams& P, const real* lin, const real* g, real* r) {
+  BMPC_D static void mulBT(const KParams& P, const real* lin, const real* g, real* r) {
     r[0] = lin[0] * g[0] + lin[1] * g[1];
     r[1] = -lin[1] * g[0] + lin[0] * g[1];
     r[2] = P.dt * g[2];
   }
-  __device__ __forceinline__ static void addC(const real* cc, real* y) {
+  BMPC_D static void addC(const real* cc, real* y) {
     y[0] += cc[0];
     y[1] += cc[1];
   }
-  __device__ __forceinline__ static void expandC(const real* cc, real* C) {
+  BMPC_D static void expandC(const real* cc, real* C) {
     C[0] = cc[0];
     C[1] = cc[1];
     C[2] = 0.0;
   }
-  __device__ static void denseA(const KParams&, const real* lin, real* A) {
+  BMPC_D static void denseA(const KParams&, const real* lin, real* A) {
     for (int i = 0; i < 9; ++i) A[i] = 0.0;
     A[0] = A[4] = A[8] = 1.0;
     A[2] = lin[2];
     A[5] = lin[3];
   }
-  __device__ static void denseB(const KParams& P, const real* lin, real* B) {
+  BMPC_D static void denseB(const KParams& P, const real* lin, real* B) {
     B[0] = lin[0]; B[1] = -lin[1]; B[2] = 0.0;
     B[3] = lin[1]; B[4] = lin[0];  B[5] = 0.0;
     B[6] = 0.0;    B[7] = 0.0;     B[8] = P.dt;
   }
   // robot_col, symbolic branch: L1 distance minus margin (:135-145)
-  __device__ static void collision(const KParams& P, const real* x, const real* zxy, real& h, real& dhx, real& dhy) {
+  BMPC_D static void collision(const KParams& P, const real* x, const real* zxy, real& h, real& dhx, real& dhy) {
     const real ex = x[0] - zxy[0], ey = x[1] - zxy[1];
     h = fabs(ex) + fabs(ey) - P.quad_margin;
     dhx = sgn(ex);
     dhy = sgn(ey);
   }
   template <class Emit>
-  __device__ static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
+  BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
                                        const real* xe0, const real* z0, real* zlast, Emit emit) {
     real xe[3] = {xe0[0], xe0[1], xe0[2]};
     real z[3] = {z0[0], z0[1], z0[2]};
@@ -298,6 +298,6 @@ struct QuadrupedModel {
     return acc.value();
   }
   // exp(s1*hi), shifted by the group maximum (normalisation cancels the shift) (:211-216)
-  __device__ static real branch_weight(const KParams& P, real hi, real himax) { return exp(P.s1 * (hi - himax)); }
+  BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return exp(P.s1 * (hi - himax)); }
   static constexpr bool kWeightNeedsMax = true;
 };

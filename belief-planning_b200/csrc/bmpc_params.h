@@ -1,17 +1,10 @@
-// Shared declarations for libbranchmpc.so (sm_100a).  See include/branchmpc.h for the ABI.
+// Kernel parameter block of libbranchmpc (passed by value; fits the 4 KB kernel-parameter space) and the
+// closed-form tree numbering of MPC_branch.py:928-981.  See include/branchmpc.h for the ABI.
 #pragma once
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdint.h>
+#include "bmpc_portable.h"
 
 #include "branchmpc.h"
 
-typedef double real;
-
-#define BMPC_WARP 32
-#define BMPC_BIG_PENALTY 1.0e4 /* stiff penalty (times branch weight) on guessed-active rows in the polish */
-
-// Everything a kernel needs, passed by value (fits the 4 KB kernel-parameter space).
 struct KParams {
   // ---- tree topology (BFS numbering of MPC_branch.py:928-981; all closed form) ----
   int m, NB, N;
@@ -32,8 +25,8 @@ struct KParams {
   real rf[BMPC_MAX_ROWS][BMPC_MAX_N], rlo[BMPC_MAX_ROWS], rhi[BMPC_MAX_ROWS];
   real ulo[BMPC_MAX_D], uhi[BMPC_MAX_D];
   // ---- solver ----
-  int max_iter, polish_first, polish_every, polish_passes;
-  real alpha, theta, theta_u, eps_abs;
+  int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, warm_polish;
+  real alpha, theta, theta_u, eps_abs, polish_big, polish_mult;
   // ---- batch ----
   int count;
   const real* x0;
@@ -50,15 +43,15 @@ struct KParams {
   size_t slab_reals;            // reals per problem slab
 };
 
-__host__ __device__ inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }
-__host__ __device__ inline int bmpc_ndx(const KParams& P, int b) {
-  const int ol = P.off[P.NB];
+BMPC_HD inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }
+BMPC_HD inline int bmpc_ndx(const KParams& P, int b) {
+  const int ol = P.off[P.NB];   // first leaf branch
   return b < ol ? bmpc_ndu(P, b) : 1 + P.N * (ol - 1) + (P.N + 1) * (b - ol);
 }
-__host__ __device__ inline int bmpc_depth(const KParams& P, int b) {
+BMPC_HD inline int bmpc_depth(const KParams& P, int b) {
   int d = 0;
   while (b >= P.off[d + 1]) ++d;
   return d;
 }
-__host__ __device__ inline int bmpc_parent(const KParams& P, int b, int d) { return P.off[d - 1] + (b - P.off[d]) / P.m; }
-__host__ __device__ inline int bmpc_first_child(const KParams& P, int b, int d) { return P.off[d + 1] + (b - P.off[d]) * P.m; }
+BMPC_HD inline int bmpc_parent(const KParams& P, int b, int d) { return P.off[d - 1] + (b - P.off[d]) / P.m; }
+BMPC_HD inline int bmpc_first_child(const KParams& P, int b, int d) { return P.off[d + 1] + (b - P.off[d]) * P.m; }

@@ -1,43 +1,32 @@
-// Warp-per-problem tree-QP solver: ADMM whose KKT step is a Riccati sweep over the branch tree,
-// finished by an active-set polish.  One warp owns one scenario-tree MPC problem; the per-node
-// data lives in that warp's shared-memory slab (field-major, one pad slot per branch so the lanes
-// of a sweep hit distinct banks); lanes are the parallel branches of a tree level during sweeps and
-// the nodes during the row phase.  Replaces buildCost + buildEqConstr + buildIneqConstr +
-// osqp_solve_qp + unpackSolution of the reference (MPC_branch.py:984-1274) and the per-node CasADi
-// calls of inittree/updatetree (:928-981, :1024-1061).
+// Warp-per-problem tree-QP solver: ADMM whose KKT step is a Riccati sweep over the branch tree, finished by a
+// primal-dual active-set polish that certifies the exact optimum.  One warp owns one scenario-tree MPC problem; the
+// per-node data lives in that warp's shared-memory slab (field-major, one pad slot per branch so that the lanes of a
+// sweep hit distinct banks); lanes are the parallel branches of a tree level during sweeps and the nodes during the
+// row phase.  Replaces buildCost + buildEqConstr + buildIneqConstr + osqp_solve_qp + unpackSolution of the reference
+// (MPC_branch.py:984-1274) and the per-node CasADi calls of inittree/updatetree (:928-981, :1024-1061).
+//
+// The QP is solved in its slack-free exact-penalty form: the reference's slack variables
+// s >= 0 with linear cost lam = Qslack[1]*w are eliminated, leaving lam*max(0, f'x - hi) per soft row, whose prox is
+// closed form.  Opposite rows of Fx are paired into one two-sided row lo <= f'x <= hi.
+//
+// ADMM bookkeeping: per row only the scaled Moreau variable sh = rho*(v + y/rho) is stored; the multiplier is
+//   y(sh) = clamp(sh - rho*hi, 0, lam)  above,  clamp(sh - rho*lo, -lam, 0)  below,  0 inside,
+// and rho*v = sh - y, so no division appears in the iteration.
 #pragma once
-#include "bmpc_models.cuh"
-
-#define FULL_MASK 0xffffffffu
-
-__device__ __forceinline__ real warp_max(real v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
-}
-__device__ __forceinline__ real warp_sum(real v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
-  return v;
-}
-__device__ __forceinline__ int warp_sum_int(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
-  return v;
-}
-
-// prox of lam*dist(., [lo,hi]) with threshold thr = lam/rho
-__device__ __forceinline__ real prox_range(real s, real lo, real hi, real thr) {
-  if (s > hi + thr) return s - thr;
-  if (s > hi) return hi;
-  if (s >= lo) return s;
-  if (s >= lo - thr) return lo;
-  return s + thr;
-}
+#include "bmpc_models.h"
 
 enum { ROW_INACTIVE = 0, ROW_UP_KINK = 1, ROW_UP_LIN = 2, ROW_LO_KINK = 3, ROW_LO_LIN = 4, ROW_IGNORED = 7 };
 enum { IN_FREE = 0, IN_AT_HI = 1, IN_AT_LO = 2 };
 enum { FACT_ADMM = 0, FACT_FREE = 1, FACT_POLISH = 2 };
+
+#define BMPC_NOLO (-1.0e300)
+
+// multiplier of a two-sided soft row from the scaled Moreau variable (rlo = rho*lo, rhi = rho*hi)
+BMPC_D real row_dual(real sh, real rlo, real rhi, real lam) {
+  if (sh > rhi) return fmin(sh - rhi, lam);
+  if (sh < rlo) return fmax(sh - rlo, -lam);
+  return 0.0;
+}
 
 template <class M, int NR>
 struct Solver {
@@ -48,21 +37,21 @@ struct Solver {
   static constexpr int F_LIN = 0;
   static constexpr int F_CC = F_LIN + M::NLIN;
   static constexpr int F_Q = F_CC + M::NCC;
-  static constexpr int F_FC = F_Q + NX;      // collision row f (x,y components); holds obstacle (x,y) before setup
+  static constexpr int F_FC = F_Q + NX;      // collision row f (x,y components); holds the obstacle (x,y) before setup
   static constexpr int F_HC = F_FC + 2;      // collision row upper bound
   static constexpr int F_RHO = F_HC + 1;     // rho of the NR soft rows then of the NU inputs
   static constexpr int F_K = F_RHO + NR + NU;
   static constexpr int F_SI = F_K + NU * NX; // S^-1, packed upper triangle
   static constexpr int F_H0 = F_SI + NSU;    // P+ C
-  static constexpr int F_S = F_H0 + NX;      // ADMM state s = v^ + y/rho per soft row
+  static constexpr int F_S = F_H0 + NX;      // ADMM state: scaled Moreau variable per soft row
   static constexpr int F_SU = F_S + NR;      // same for the inputs
   static constexpr int F_XQ = F_SU + NU;     // x after a forward sweep / q~x before a backward sweep
-  static constexpr int F_UQ = F_XQ + NX;     // u or kff / q~u
+  static constexpr int F_UQ = F_XQ + NX;     // u (kff between the sweeps) / q~u before a backward sweep
   static constexpr int F_Y = F_UQ + NU;      // polish multipliers (rows then inputs)
   static constexpr int NF = F_Y + NR + NU;
   static constexpr int BR = 1 + NS + 3 * NX; // per-branch reals: w, exchange(NS), x last, z last, x after last
 
-  __host__ __device__ static size_t slab_reals(int nup, int nbranch) {
+  BMPC_HD static size_t slab_reals(int nup, int nbranch) {
     return (size_t)NF * nup + (size_t)(nup + 1) / 2 + (size_t)BR * nbranch;
   }
 
@@ -78,29 +67,30 @@ struct Solver {
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
 
-  __device__ Solver(const KParams& P_, real* slab, int lane_) : P(P_), ws(slab), lane(lane_), nup(P_.nup) {
+  BMPC_D Solver(const KParams& P_, real* slab, int lane_) : P(P_), ws(slab), lane(lane_), nup(P_.nup) {
     st = reinterpret_cast<int*>(ws + (size_t)NF * nup);
     Wb = ws + (size_t)NF * nup + (nup + 1) / 2;
     EX = Wb + P.nbranch;
     EXL = EX + (size_t)NS * P.nbranch;
     EXZ = EXL + (size_t)NX * P.nbranch;
     EXX = EXZ + (size_t)NX * P.nbranch;
+    prob = 0;
+    rlin = 0.0;
+    polpar = nullptr;
   }
 
-  __device__ __forceinline__ real& F(int field, int kp) { return ws[(size_t)field * nup + kp]; }
-  __device__ __forceinline__ int kp_of(int b, int t) const { return bmpc_ndu(P, b) + t + b; }
-  __device__ __forceinline__ void node_of(int k, int& b, int& t) const {
+  BMPC_D real& F(int field, int kp) { return ws[(size_t)field * nup + kp]; }
+  BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(P, b) + t + b; }
+  BMPC_D void node_of(int k, int& b, int& t) const {
     if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / P.N; t = (k - 1) % P.N; }
   }
-  __device__ __forceinline__ const real* pol_par(int i) const {
-    return polpar ? polpar + 4 * i : P.pol_par[i];
-  }
+  BMPC_D const real* pol_par(int i) const { return polpar ? polpar + 4 * i : P.pol_par[i]; }
 
   // ========================================================================================
   // Tree expansion: obstacle rollouts, branch probabilities/weights, ego linearisation rollouts,
-  // per-node linearisation + collision linearisation + cost vectors   (kernels K1-K3)
+  // per-node linearisation + collision linearisation + cost vectors   (kernels K1-K3 of SURVEY.md)
   // ========================================================================================
-  __device__ void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn) {
+  BMPC_D void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn) {
     const int kp = kp_of(b, t);
     real lin[M::NLIN], cc[M::NCC];
     M::linearize(P, xbar, ubar, lin, cc, xn);
@@ -109,6 +99,7 @@ struct Solver {
 #pragma unroll
     for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
     const real* xref = P.xref + (size_t)prob * NX;
+    // linear state cost -2 w (xRef' Q° + xbar' dQ): Q° = Qf on the last node of a leaf branch of BranchMPC (:1095)
     const real* Ql = (leaf_last && P.ctrl == BMPC_CTRL_BRANCH) ? P.Qf : P.Q;
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
@@ -120,6 +111,7 @@ struct Solver {
       }
       F(F_Q + j, kp) = -2.0 * w * (a + P.dq_scale * c);
     }
+    // col_eval (:1114-1168): row -dh x - s <= h - dh xbar
     real zxy[2] = {F(F_FC, kp), F(F_FC + 1, kp)};
     real h, dhx, dhy;
     M::collision(P, xbar, zxy, h, dhx, dhy);
@@ -128,17 +120,17 @@ struct Solver {
     F(F_FC, kp) = fx;
     F(F_FC + 1, kp) = fy;
     F(F_HC, kp) = hi0;
-    // ADMM start: rows at the linearisation point, projected on their bounds
+    // ADMM start (unscaled, multiplied by rho in choose_rho): rows at the linearisation point, projected on their bounds
     F(F_S, kp) = fmin(fx * xbar[0] + fy * xbar[1], hi0);
 #pragma unroll
     for (int j = 1; j < NR; ++j) {
       real v = 0.0;
 #pragma unroll
       for (int i = 0; i < NX; ++i) v += P.rf[j - 1][i] * xbar[i];
-      F(F_S + j, kp) = fmin(fmax(v, P.rlo[j - 1]), P.rhi[j - 1]);
+      F(F_S + j, kp) = bmpc_clamp(v, P.rlo[j - 1], P.rhi[j - 1]);
     }
 #pragma unroll
-    for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = fmin(fmax(ubar[a], P.ulo[a]), P.uhi[a]);
+    for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ubar[a], P.ulo[a], P.uhi[a]);
     if (P.out.xLin) {
       real* o = P.out.xLin + ((size_t)prob * P.totalu + (bmpc_ndu(P, b) + t)) * NX;
 #pragma unroll
@@ -146,7 +138,7 @@ struct Solver {
     }
   }
 
-  __device__ void expand_tree() {
+  BMPC_DN void expand_tree() {
     const int started = P.started[prob];
     const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     int* pbest = P.pbest + (size_t)prob * P.nbranch;
@@ -156,6 +148,7 @@ struct Solver {
       real ub[NU], xb[NX], xn[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) xb[i] = x0[i];
+      // root input: previous first input of the most likely child (updatetree :1029-1031); zero on the first solve
       const int best = started ? pbest[0] : 0;
       const int kbest = bmpc_ndu(P, bmpc_first_child(P, 0, 0) + best);
 #pragma unroll
@@ -177,68 +170,62 @@ struct Solver {
         EXX[i] = xn[i];
       }
     }
-    __syncwarp();
+    lanes_sync();
     const int m = P.m;
-    const int chunk = (BMPC_WARP / m) * m;
     for (int d = 0; d < P.NB; ++d) {
-      // (a) obstacle rollouts under each policy + branch probabilities  (zpred_eval, branch_eval)
+      // (a) obstacle rollouts under each policy + safety value of each (zpred_eval, branch_eval); lanes = (branch, policy)
       const int cnt = P.pw[d] * m;
-      for (int base = 0; base < cnt; base += chunk) {
-        const int idx = base + lane;
-        const bool act = lane < chunk && idx < cnt;
-        const int b = P.off[d] + (act ? idx / m : 0);
-        const int i = act ? idx % m : 0;
+      for (int idx = lane; idx < cnt; idx += BMPC_LANES) {
+        const int b = P.off[d] + idx / m;
+        const int i = idx % m;
         const int c = bmpc_first_child(P, b, d) + i;
-        real hi = 0.0;
-        if (act) {
-          real zl[NX];
-          const int kc = bmpc_ndu(P, c);
-          const int kpc = kp_of(c, 0);
-          real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NX : nullptr;
-          hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXL + (size_t)NX * b,
-                                EXZ + (size_t)NX * b, zl, [&](int t, const real* z) {
-                                  F(F_FC, kpc + t) = z[0];
-                                  F(F_FC + 1, kpc + t) = z[1];
-                                  if (zout) {
+        real zl[NX];
+        const int kc = bmpc_ndu(P, c);
+        const int kpc = kp_of(c, 0);
+        real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NX : nullptr;
+        const real hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXL + (size_t)NX * b,
+                                         EXZ + (size_t)NX * b, zl, [&](int t, const real* z) {
+                                           F(F_FC, kpc + t) = z[0];
+                                           F(F_FC + 1, kpc + t) = z[1];
+                                           if (zout) {
 #pragma unroll
-                                    for (int q = 0; q < NX; ++q) zout[t * NX + q] = z[q];
-                                  }
-                                });
+                                             for (int q = 0; q < NX; ++q) zout[t * NX + q] = z[q];
+                                           }
+                                         });
 #pragma unroll
-          for (int q = 0; q < NX; ++q) EXZ[(size_t)NX * c + q] = zl[q];
-        }
-        const int g0 = (lane / m) * m;
+        for (int q = 0; q < NX; ++q) EXZ[(size_t)NX * c + q] = zl[q];
+        EX[(size_t)NS * c] = hi;   // exchange slot: safety value of child c
+      }
+      lanes_sync();
+      // (a') probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+        const int fc = bmpc_first_child(P, b, d);
         real himax = -1e300;
-        if (M::kWeightNeedsMax) {
-          for (int j = 0; j < m; ++j) himax = fmax(himax, __shfl_sync(FULL_MASK, hi, (g0 + j) & 31));
-        }
-        const real wgt = M::branch_weight(P, hi, himax);
+        for (int j = 0; j < m; ++j) himax = fmax(himax, EX[(size_t)NS * (fc + j)]);
         real sum = 0.0;
-        for (int j = 0; j < m; ++j) sum += __shfl_sync(FULL_MASK, wgt, (g0 + j) & 31);
-        const real p = wgt / sum;
+        for (int j = 0; j < m; ++j) sum += M::branch_weight(P, EX[(size_t)NS * (fc + j)], himax);
         int best = 0;
         real pb = -1.0;
         for (int j = 0; j < m; ++j) {
-          const real pj = __shfl_sync(FULL_MASK, p, (g0 + j) & 31);
-          if (pj > pb) { pb = pj; best = j; }
+          const real p = M::branch_weight(P, EX[(size_t)NS * (fc + j)], himax) / sum;
+          Wb[fc + j] = Wb[b] * p;
+          if (P.out.branch_p) P.out.branch_p[((size_t)prob * P.nbranch + b) * m + j] = p;
+          if (p > pb) { pb = p; best = j; }
         }
-        if (act) {
-          Wb[c] = Wb[b] * p;
-          if (P.out.branch_p) P.out.branch_p[((size_t)prob * P.nbranch + b) * m + i] = p;
-          if (i == 0) pbest[b] = best;   // read (old value) only before this point, see (b) below
-        }
+        // pbest[b] (old value) was consumed when b's own trajectory was shifted, one level up (or at the root above)
+        EX[(size_t)NS * b + 1] = (real)best;
       }
-      __syncwarp();
+      lanes_sync();
       // (b) ego linearisation trajectory of every child branch: time-shifted previous inputs
       //     (updatetree :1025-1033), nonlinear rollout + per-node linearisation (:1048-1059)
-      for (int c = P.off[d + 1] + lane; c < P.off[d + 2]; c += BMPC_WARP) {
+      for (int c = P.off[d + 1] + lane; c < P.off[d + 2]; c += BMPC_LANES) {
         const int b = bmpc_parent(P, c, d + 1);
         const bool leaf = (d + 1 == P.NB);
         const real w = Wb[c];
         const int kc = bmpc_ndu(P, c);
         int klast;
         if (leaf) {
-          klast = kc + P.N - 1;
+          klast = kc + P.N - 1;   // repeat the shifted last input (:1033)
         } else {
           klast = bmpc_ndu(P, bmpc_first_child(P, c, d + 1) + (started ? pbest[c] : 0));
         }
@@ -260,22 +247,23 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXX[(size_t)NX * c + i] = xb[i];
       }
-      __syncwarp();
+      lanes_sync();
+      // commit the new arg-max children of this level (their old values are no longer needed)
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EX[(size_t)NS * b + 1];
+      lanes_sync();
     }
     if (P.out.branch_w) {
-      for (int b = lane; b < P.nbranch; b += BMPC_WARP) P.out.branch_w[(size_t)prob * P.nbranch + b] = Wb[b];
+      for (int b = lane; b < P.nbranch; b += BMPC_LANES) P.out.branch_w[(size_t)prob * P.nbranch + b] = Wb[b];
     }
     rlin = 0.0;
-    if (started) {
 #pragma unroll
-      for (int a = 0; a < NU; ++a) rlin += -2.0 * P.oldin[(size_t)prob * NU + a] * P.dR[a];
-    }
+    for (int a = 0; a < NU; ++a) rlin += -2.0 * P.oldin[(size_t)prob * NU + a] * P.dR[a];
   }
 
   // ========================================================================================
   // Riccati factorisation over the tree
   // ========================================================================================
-  __device__ __forceinline__ void unpack_sym(const real* src, real* Pm) {
+  BMPC_D void unpack_sym(const real* src, real* Pm) {
     int q = 0;
 #pragma unroll
     for (int i = 0; i < NX; ++i)
@@ -286,7 +274,7 @@ struct Solver {
         ++q;
       }
   }
-  __device__ __forceinline__ void pack_sym(const real* Pm, real* dst) {
+  BMPC_D void pack_sym(const real* Pm, real* dst) {
     int q = 0;
 #pragma unroll
     for (int i = 0; i < NX; ++i)
@@ -294,7 +282,7 @@ struct Solver {
       for (int j = i; j < NX; ++j) dst[q++] = Pm[i * NX + j];
   }
 
-  __device__ static void invert_spd(const real* S, real* Si) {
+  BMPC_D static void invert_spd(const real* S, real* Si) {
     if constexpr (NU == 2) {
       const real det = S[0] * S[3] - S[1] * S[2];
       const real id = 1.0 / det;
@@ -320,17 +308,17 @@ struct Solver {
     }
   }
 
-  // Stiff penalty of a guessed-active row in the polish: at least BMPC_BIG_PENALTY*w and at least 100x the
-  // row's reduced stiffness (rho/theta), so every augmented-Lagrangian step contracts by <= ~1e-2.
-  __device__ __forceinline__ real big_row(int kp, int j, real w) {
-    return fmin(fmax(BMPC_BIG_PENALTY * w, 100.0 * F(F_RHO + j, kp) / P.theta), 1.0e8 * w);
+  // Stiff penalty of a guessed-active row in the polish: polish_mult times the row's curvature-matched stiffness
+  // (rho/theta = 1/(f' Sigma f)), at least polish_big*w, so that every augmented-Lagrangian step contracts strongly.
+  BMPC_D real big_row(int kp, int j, real w) {
+    return fmin(fmax(P.polish_big * w, P.polish_mult * F(F_RHO + j, kp) / P.theta), 1.0e12 * w);
   }
-  __device__ __forceinline__ real big_in(int kp, int a, real w) {
-    return fmin(fmax(BMPC_BIG_PENALTY * w, 100.0 * F(F_RHO + NR + a, kp) / P.theta_u), 1.0e8 * w);
+  BMPC_D real big_in(int kp, int a, real w) {
+    return fmin(fmax(P.polish_big * w, P.polish_mult * F(F_RHO + NR + a, kp) / P.theta_u), 1.0e12 * w);
   }
 
   // penalties of the node's soft rows and inputs for the requested factorisation
-  __device__ __forceinline__ void penalties(int kp, real w, int mode, real* pr, real* pu) {
+  BMPC_D void penalties(int kp, real w, int mode, real* pr, real* pu) {
     if (mode == FACT_ADMM) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) pr[j] = F(F_RHO + j, kp);
@@ -358,7 +346,7 @@ struct Solver {
 
   // one backward Riccati step; Pn (full NX x NX, symmetric) is the successor value Hessian on entry
   // and this node's on exit
-  __device__ void node_factor(int kp, real w, real* Pn, int mode) {
+  BMPC_D void node_factor(int kp, real w, real* Pn, int mode) {
     real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -403,7 +391,7 @@ struct Solver {
         for (int i = 0; i < NX; ++i) col[i] = PB[i * NU + b2];
         M::mulBT(P, lin, col, g2);
 #pragma unroll
-        for (int a = 0; a < NU; ++a) S[a * NU + b2] = g2[a] + 2.0 * w * 0.5 * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
+        for (int a = 0; a < NU; ++a) S[a * NU + b2] = g2[a] + w * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) S[a * NU + a] += pu[a];
@@ -430,7 +418,7 @@ struct Solver {
       }
     // P = Q~ + A' T - G' K
     real Pnew[NX * NX];
-    const real qs = 2.0 * w * (1.0 + P.dq_scale);
+    const real qs = w * (1.0 + P.dq_scale);
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
       real col[NX], o[NX];
@@ -439,13 +427,13 @@ struct Solver {
       M::mulAT(P, lin, col, o);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        real v = o[i] + qs * 0.5 * (P.Q[i * NX + j] + P.Q[j * NX + i]);
+        real v = o[i] + qs * (P.Q[i * NX + j] + P.Q[j * NX + i]);
 #pragma unroll
         for (int a = 0; a < NU; ++a) v -= G[a * NX + i] * K[a * NX + j];
         Pnew[i * NX + j] = v;
       }
     }
-    // soft-row penalties: collision row touches (x,y) only
+    // soft-row penalties: the collision row touches (x,y) only
     {
       const real fx = F(F_FC, kp), fy = F(F_FC + 1, kp);
       Pnew[0] += pr[0] * fx * fx;
@@ -465,51 +453,51 @@ struct Solver {
       for (int j = 0; j < NX; ++j) Pn[i * NX + j] = 0.5 * (Pnew[i * NX + j] + Pnew[j * NX + i]);
   }
 
-  __device__ void factorize(int mode) {
+  BMPC_D void sum_children(int b, int d, real* Pn) {
+    const int fc = bmpc_first_child(P, b, d);
+    unpack_sym(EX + (size_t)NS * fc, Pn);
+    for (int c = 1; c < P.m; ++c) {
+      real Pc[NX * NX];
+      unpack_sym(EX + (size_t)NS * (fc + c), Pc);
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) Pn[i] += Pc[i];
+    }
+  }
+
+  BMPC_DN void factorize(int mode) {
     for (int d = P.NB; d >= 1; --d) {
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         const real w = Wb[b];
         real Pn[NX * NX];
         if (d == P.NB) {
+          // terminal node: x' (w Qf) x in the reference's H, doubled by H <- 2H (:1094, :1112)
 #pragma unroll
           for (int i = 0; i < NX; ++i)
 #pragma unroll
             for (int j = 0; j < NX; ++j) Pn[i * NX + j] = w * (P.Qf[i * NX + j] + P.Qf[j * NX + i]);
         } else {
-          const int fc = bmpc_first_child(P, b, d);
-          unpack_sym(EX + (size_t)NS * fc, Pn);
-          for (int c = 1; c < P.m; ++c) {
-            real Pc[NX * NX];
-            unpack_sym(EX + (size_t)NS * (fc + c), Pc);
-#pragma unroll
-            for (int i = 0; i < NX * NX; ++i) Pn[i] += Pc[i];
-          }
+          sum_children(b, d, Pn);
         }
         for (int t = P.N - 1; t >= 0; --t) node_factor(kp_of(b, t), w, Pn, mode);
         pack_sym(Pn, EX + (size_t)NS * b);
       }
-      __syncwarp();
+      lanes_sync();
     }
     if (lane == 0) {
       real Pn[NX * NX];
-      const int fc = bmpc_first_child(P, 0, 0);
-      unpack_sym(EX + (size_t)NS * fc, Pn);
-      for (int c = 1; c < P.m; ++c) {
-        real Pc[NX * NX];
-        unpack_sym(EX + (size_t)NS * (fc + c), Pc);
-#pragma unroll
-        for (int i = 0; i < NX * NX; ++i) Pn[i] += Pc[i];
-      }
+      sum_children(0, 0, Pn);
       node_factor(kp_of(0, 0), 1.0, Pn, mode);
     }
-    __syncwarp();
+    lanes_sync();
   }
 
   // ========================================================================================
   // Curvature-matched rho: rho_row = theta / (f' Sigma f), rho_u = theta_u / (Sigma_u)_aa where Sigma is the
-  // covariance-like forward recursion of the unconstrained LQ problem (Sigma+ = Acl Sigma Acl' + B S^-1 B').
+  // covariance-like forward recursion of the unconstrained LQ problem (Sigma+ = Acl Sigma Acl' + B S^-1 B'),
+  // i.e. the diagonal of F H^-1 F' restricted to the dynamics: a Jacobi preconditioner of the ADMM dual problem.
+  // Also scales the ADMM start written by node_setup (sh = rho * v).
   // ========================================================================================
-  __device__ void node_cov(int kp, real w, real* Sg) {
+  BMPC_D void node_cov(int kp, real w, real* Sg) {
     real lin[M::NLIN], K[NU * NX], Si[NU * NU];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -530,7 +518,9 @@ struct Solver {
     {
       const real fx = F(F_FC, kp), fy = F(F_FC + 1, kp);
       const real q0 = fx * fx * Sg[0] + 2.0 * fx * fy * Sg[1] + fy * fy * Sg[NX + 1];
-      F(F_RHO, kp) = (q0 > 1e-12) ? fmin(P.theta / q0, rho_max) : 0.0;
+      const real r0 = (q0 > 1e-12) ? fmin(P.theta / q0, rho_max) : 0.0;
+      F(F_RHO, kp) = r0;
+      F(F_S, kp) *= r0;
 #pragma unroll
       for (int j = 1; j < NR; ++j) {
         real q = 0.0;
@@ -538,7 +528,9 @@ struct Solver {
         for (int i = 0; i < NX; ++i)
 #pragma unroll
           for (int i2 = 0; i2 < NX; ++i2) q += P.rf[j - 1][i] * P.rf[j - 1][i2] * Sg[i * NX + i2];
-        F(F_RHO + j, kp) = (q > 1e-12) ? fmin(P.theta / q, rho_max) : 0.0;
+        const real rj = (q > 1e-12) ? fmin(P.theta / q, rho_max) : 0.0;
+        F(F_RHO + j, kp) = rj;
+        F(F_S + j, kp) *= rj;
       }
     }
 #pragma unroll
@@ -551,7 +543,9 @@ struct Solver {
         for (int i2 = 0; i2 < NX; ++i2) ks += K[a * NX + i2] * Sg[i2 * NX + i];
         var += ks * K[a * NX + i];
       }
-      F(F_RHO + NR + a, kp) = fmin(P.theta_u / var, rho_max);
+      const real ra = fmin(P.theta_u / var, rho_max);
+      F(F_RHO + NR + a, kp) = ra;
+      F(F_SU + a, kp) *= ra;
     }
     // Sigma+ = Acl Sigma Acl' + B Si B',  Acl v = A v - B (K v)
     real T[NX * NX];
@@ -605,7 +599,7 @@ struct Solver {
       for (int j = 0; j < NX; ++j) Sg[i * NX + j] = 0.5 * (Sn[i * NX + j] + Sn[j * NX + i]);
   }
 
-  __device__ void choose_rho() {
+  BMPC_DN void choose_rho() {
     if (lane == 0) {
       real Sg[NX * NX];
 #pragma unroll
@@ -613,23 +607,23 @@ struct Solver {
       node_cov(kp_of(0, 0), 1.0, Sg);
       pack_sym(Sg, EX);
     }
-    __syncwarp();
+    lanes_sync();
     for (int d = 1; d <= P.NB; ++d) {
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real Sg[NX * NX];
         unpack_sym(EX + (size_t)NS * bmpc_parent(P, b, d), Sg);
         const real w = Wb[b];
         for (int t = 0; t < P.N; ++t) node_cov(kp_of(b, t), w, Sg);
         pack_sym(Sg, EX + (size_t)NS * b);
       }
-      __syncwarp();
+      lanes_sync();
     }
   }
 
   // ========================================================================================
   // Vector sweeps (the hot loop): backward for the feed-forward terms, forward for (x,u)
   // ========================================================================================
-  __device__ __forceinline__ void bw_step(int kp, real* pn) {
+  BMPC_D void bw_step(int kp, real* pn) {
     real lin[M::NLIN], g[NX], r[NU], kff[NU];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -664,9 +658,9 @@ struct Solver {
     }
   }
 
-  __device__ void backward() {
+  BMPC_DN void backward() {
     for (int d = P.NB; d >= 1; --d) {
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real pn[NX];
         if (d == P.NB) {
 #pragma unroll
@@ -684,7 +678,7 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EX[(size_t)NS * b + i] = pn[i];
       }
-      __syncwarp();
+      lanes_sync();
     }
     if (lane == 0) {
       real pn[NX];
@@ -696,10 +690,10 @@ struct Solver {
         for (int i = 0; i < NX; ++i) pn[i] += EX[(size_t)NS * (fc + c) + i];
       bw_step(kp_of(0, 0), pn);
     }
-    __syncwarp();
+    lanes_sync();
   }
 
-  __device__ __forceinline__ void fw_step(int kp, real* x) {
+  BMPC_D void fw_step(int kp, real* x) {
     real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -722,7 +716,7 @@ struct Solver {
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
   }
 
-  __device__ void forward() {
+  BMPC_DN void forward() {
     if (lane == 0) {
       real x[NX];
 #pragma unroll
@@ -731,9 +725,9 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < NX; ++i) EXX[i] = x[i];
     }
-    __syncwarp();
+    lanes_sync();
     for (int d = 1; d <= P.NB; ++d) {
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
         const int pa = bmpc_parent(P, b, d);
 #pragma unroll
@@ -743,25 +737,25 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXX[(size_t)NX * b + i] = x[i];
       }
-      __syncwarp();
+      lanes_sync();
     }
   }
 
   // ========================================================================================
-  // Row phase (node-parallel): ADMM z/y update through the single Moreau variable s, residuals, and
+  // Row phase (node-parallel): ADMM z/y update through the scaled Moreau variable, residuals, and
   // the linear terms of the next KKT solve.
   // ========================================================================================
-  __device__ __forceinline__ real row_value(int kp, int j, const real* x) {
+  BMPC_D real row_value(int kp, int j, const real* x) {
     if (j == 0) return F(F_FC, kp) * x[0] + F(F_FC + 1, kp) * x[1];
     real v = 0.0;
 #pragma unroll
     for (int i = 0; i < NX; ++i) v += P.rf[j - 1][i] * x[i];
     return v;
   }
-  __device__ __forceinline__ void row_bounds(int kp, int j, real& lo, real& hi) {
-    if (j == 0) { lo = -1e300; hi = F(F_HC, kp); } else { lo = P.rlo[j - 1]; hi = P.rhi[j - 1]; }
+  BMPC_D void row_bounds(int kp, int j, real& lo, real& hi) {
+    if (j == 0) { lo = BMPC_NOLO; hi = F(F_HC, kp); } else { lo = P.rlo[j - 1]; hi = P.rhi[j - 1]; }
   }
-  __device__ __forceinline__ void add_row_grad(int kp, int j, real gcoef, real* qx) {
+  BMPC_D void add_row_grad(int kp, int j, real gcoef, real* qx) {
     if (j == 0) {
       qx[0] += F(F_FC, kp) * gcoef;
       qx[1] += F(F_FC + 1, kp) * gcoef;
@@ -771,11 +765,12 @@ struct Solver {
     }
   }
 
-  // update=false: only assemble q~ from the current s (start / after a failed polish)
-  // returns max(primal residual, dual residual) over this lane's nodes
-  __device__ real admm_rows(bool update) {
+  // update=false: only assemble q~ from the current state (start / after a failed polish)
+  // check=true : also return max(primal residual, scaled dual residual) over this lane's nodes
+  template <bool UPDATE, bool CHECK>
+  BMPC_D real admm_rows() {
     real res = 0.0;
-    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -792,50 +787,56 @@ struct Solver {
         if (rho > 0.0) {
           real lo, hi;
           row_bounds(kp, j, lo, hi);
-          const real thr = lam / rho;
-          real s = F(F_S + j, kp);
-          real v = prox_range(s, lo, hi, thr);
-          if (update) {
-            const real fx = row_value(kp, j, x);
-            const real sn = P.alpha * fx + (1.0 - P.alpha) * v + (s - v);
-            const real vn = prox_range(sn, lo, hi, thr);
-            res = fmax(res, fmax(fabs(fx - vn), fabs(vn - v) * rho / fmax(w, 1e-300) * 1e-3));
-            F(F_S + j, kp) = sn;
-            s = sn;
-            v = vn;
+          const real rlo = rho * lo, rhi = rho * hi;
+          real sh = F(F_S + j, kp);
+          real y = row_dual(sh, rlo, rhi, lam);
+          if (UPDATE) {
+            const real rfx = rho * row_value(kp, j, x);
+            const real rv = sh - y;
+            const real shn = P.alpha * rfx + (1.0 - P.alpha) * rv + y;
+            const real yn = row_dual(shn, rlo, rhi, lam);
+            if (CHECK) {
+              const real rvn = shn - yn;
+              res = fmax(res, fmax(fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
+            }
+            F(F_S + j, kp) = shn;
+            sh = shn;
+            y = yn;
           }
-          add_row_grad(kp, j, -rho * (2.0 * v - s), qx);
+          add_row_grad(kp, j, -(sh - 2.0 * y), qx);
         }
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         const real rho = F(F_RHO + NR + a, kp);
-        real s = F(F_SU + a, kp);
-        real v = fmin(fmax(s, P.ulo[a]), P.uhi[a]);
-        if (update) {
-          const real sn = P.alpha * u[a] + (1.0 - P.alpha) * v + (s - v);
-          const real vn = fmin(fmax(sn, P.ulo[a]), P.uhi[a]);
-          res = fmax(res, fmax(fabs(u[a] - vn), fabs(vn - v) * rho / fmax(w, 1e-300) * 1e-3));
-          F(F_SU + a, kp) = sn;
-          s = sn;
-          v = vn;
+        real sh = F(F_SU + a, kp);
+        real rv = bmpc_clamp(sh, rho * P.ulo[a], rho * P.uhi[a]);
+        if (UPDATE) {
+          const real ru = rho * u[a];
+          const real shn = P.alpha * ru + (1.0 - P.alpha) * rv + (sh - rv);
+          const real rvn = bmpc_clamp(shn, rho * P.ulo[a], rho * P.uhi[a]);
+          if (CHECK) res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
+          F(F_SU + a, kp) = shn;
+          sh = shn;
+          rv = rvn;
         }
-        qu[a] -= rho * (2.0 * v - s);
+        qu[a] -= 2.0 * rv - sh;
       }
 #pragma unroll
       for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = qx[i];
 #pragma unroll
       for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
     }
-    __syncwarp();
+    lanes_sync();
     return res;
   }
 
   // ========================================================================================
-  // Active-set polish
+  // Active-set polish (primal-dual active set on the exact-penalty QP; equalities of a guessed set are
+  // imposed by a stiff penalty + augmented-Lagrangian refinement so that the same tree Riccati solves them)
   // ========================================================================================
-  __device__ void polish_guess() {
-    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+  BMPC_DN void polish_guess() {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -849,12 +850,12 @@ struct Solver {
         if (rho > 0.0) {
           real lo, hi;
           row_bounds(kp, j, lo, hi);
-          const real thr = lam / rho;
-          const real s = F(F_S + j, kp);
-          if (s > hi + thr) cj = ROW_UP_LIN;
-          else if (s > hi) { cj = ROW_UP_KINK; y = fmin(rho * (s - hi), lam); }
-          else if (s >= lo) cj = ROW_INACTIVE;
-          else if (s >= lo - thr) { cj = ROW_LO_KINK; y = fmax(rho * (s - lo), -lam); }
+          const real sh = F(F_S + j, kp);
+          const real rlo = rho * lo, rhi = rho * hi;
+          if (sh > rhi + lam) cj = ROW_UP_LIN;
+          else if (sh > rhi) { cj = ROW_UP_KINK; y = sh - rhi; }
+          else if (sh >= rlo) cj = ROW_INACTIVE;
+          else if (sh >= rlo - lam) { cj = ROW_LO_KINK; y = sh - rlo; }
           else cj = ROW_LO_LIN;
         }
         code |= cj << (3 * j);
@@ -863,21 +864,21 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         const real rho = F(F_RHO + NR + a, kp);
-        const real s = F(F_SU + a, kp);
+        const real sh = F(F_SU + a, kp);
         int ca = IN_FREE;
         real y = 0.0;
-        if (s > P.uhi[a]) { ca = IN_AT_HI; y = rho * (s - P.uhi[a]); }
-        else if (s < P.ulo[a]) { ca = IN_AT_LO; y = rho * (s - P.ulo[a]); }
+        if (sh > rho * P.uhi[a]) { ca = IN_AT_HI; y = sh - rho * P.uhi[a]; }
+        else if (sh < rho * P.ulo[a]) { ca = IN_AT_LO; y = sh - rho * P.ulo[a]; }
         code |= ca << (3 * NR + 2 * a);
         F(F_Y + NR + a, kp) = y;
       }
       st[kp] = code;
     }
-    __syncwarp();
+    lanes_sync();
   }
 
-  __device__ void polish_assemble() {
-    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+  BMPC_DN void polish_assemble() {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -912,13 +913,13 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
     }
-    __syncwarp();
+    lanes_sync();
   }
 
   // multiplier (augmented-Lagrangian) update on the guessed-active rows; returns this lane's max residual
-  __device__ real polish_multipliers() {
+  BMPC_DN real polish_multipliers() {
     real res = 0.0;
-    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -948,15 +949,15 @@ struct Solver {
         }
       }
     }
-    __syncwarp();
+    lanes_sync();
     return res;
   }
 
   // primal-dual active-set update from the last equality-constrained solve; returns #changes of this lane
-  __device__ int polish_update_sets() {
+  BMPC_DN int polish_update_sets() {
     int changes = 0;
     const real tol = 1e-7;
-    for (int k = lane; k < P.totalu; k += BMPC_WARP) {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1015,25 +1016,25 @@ struct Solver {
       }
       st[kp] = ncode;
     }
-    __syncwarp();
+    lanes_sync();
     return changes;
   }
 
   // returns true when the guessed active set was verified (then XQ/UQ hold the optimal x,u)
-  __device__ bool polish(int& nfact) {
+  BMPC_DN bool polish(int& nfact) {
     polish_guess();
     for (int pass = 0; pass < P.polish_passes; ++pass) {
       factorize(FACT_POLISH);
       ++nfact;
       real res = 1.0;
-      for (int al = 0; al < 12; ++al) {
+      for (int al = 0; al < P.polish_al_iters; ++al) {
         polish_assemble();
         backward();
         forward();
-        res = warp_max(polish_multipliers());
+        res = lanes_max(polish_multipliers());
         if (res < 1e-9) break;
       }
-      const int changes = warp_sum_int(polish_update_sets());
+      const int changes = lanes_sum_int(polish_update_sets());
       if (!(res < 1e-7)) return false;          // stiff solve did not settle (also catches NaN)
       if (changes == 0) return true;
     }
@@ -1043,7 +1044,7 @@ struct Solver {
   // ========================================================================================
   // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
   // ========================================================================================
-  __device__ real emit_node(int b, int t, int kp, real w, real* x, real* uLin) {
+  BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin) {
     const int k = bmpc_ndu(P, b) + t;
     real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
 #pragma unroll
@@ -1051,16 +1052,16 @@ struct Solver {
 #pragma unroll
     for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) u[a] = fmin(fmax(F(F_UQ + a, kp), P.ulo[a]), P.uhi[a]);
+    for (int a = 0; a < NU; ++a) u[a] = bmpc_clamp(F(F_UQ + a, kp), P.ulo[a], P.uhi[a]);
     // objective (slacks eliminated)
     real J = 0.0;
-    const real qs = 2.0 * w * (1.0 + P.dq_scale);
+    const real qs = w * (1.0 + P.dq_scale);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       real a = 0.0;
 #pragma unroll
       for (int j = 0; j < NX; ++j) a += P.Q[i * NX + j] * x[j];
-      J += 0.5 * qs * x[i] * a + F(F_Q + i, kp) * x[i];
+      J += qs * x[i] * a + F(F_Q + i, kp) * x[i];
     }
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
@@ -1103,7 +1104,7 @@ struct Solver {
     return J;
   }
 
-  __device__ real finish() {
+  BMPC_DN real finish() {
     real J = 0.0;
     real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.totalx * NX : nullptr;
@@ -1119,9 +1120,9 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < NX; ++i) EXX[i] = x[i];
     }
-    __syncwarp();
+    lanes_sync();
     for (int d = 1; d <= P.NB; ++d) {
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_WARP) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
         const int pa = bmpc_parent(P, b, d);
 #pragma unroll
@@ -1151,13 +1152,29 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXX[(size_t)NX * b + i] = x[i];
       }
-      __syncwarp();
+      lanes_sync();
     }
-    return warp_sum(J);
+    return lanes_sum(J);
+  }
+
+  // any non-finite input left by the last forward sweep?
+  BMPC_DN bool solution_is_finite() {
+    int bad = 0;
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real v = F(F_UQ + a, kp);
+        bad |= !(fabs(v) < 1e300);
+      }
+    }
+    return lanes_or_int(bad) == 0;
   }
 
   // ========================================================================================
-  __device__ void solve(int prob_) {
+  BMPC_D void solve(int prob_) {
     prob = prob_;
     polpar = P.polpar ? P.polpar + (size_t)prob * P.m * 4 : nullptr;
     expand_tree();
@@ -1166,15 +1183,17 @@ struct Solver {
     choose_rho();
     factorize(FACT_ADMM);
     nfact += 2;
-    admm_rows(false);
+    admm_rows<false, false>();
     int next_polish = P.polish_first;
     bool have_xu = false;
     while (iters < P.max_iter) {
       backward();
       forward();
       ++iters;
-      const real res = warp_max(admm_rows(true));
-      have_xu = false;
+      const bool check = (iters >= next_polish) || (iters % 10 == 0);
+      real res = 1e300;
+      if (check) res = lanes_max(admm_rows<true, true>());
+      else admm_rows<true, false>();
       const bool conv = res < P.eps_abs;
       if (iters >= next_polish || conv) {
         next_polish = iters + P.polish_every;
@@ -1183,10 +1202,10 @@ struct Solver {
           have_xu = true;
           break;
         }
-        if (conv) { status = BMPC_STATUS_CONVERGED; }
+        if (conv) status = BMPC_STATUS_CONVERGED;
         factorize(FACT_ADMM);
         ++nfact;
-        admm_rows(false);
+        admm_rows<false, false>();
         if (conv) break;
       }
     }
@@ -1195,37 +1214,21 @@ struct Solver {
       backward();
       forward();
     }
-    const real J = finish();
+    if (solution_is_finite()) {
+      const real J = finish();
+      if (lane == 0) {
+        if (P.out.status) P.out.status[prob] = status;
+        if (P.out.objective) P.out.objective[prob] = J;
+        P.started[prob] = 1;
+      }
+    } else if (lane == 0) {
+      // the reference keeps its previous plan when the solver fails (MPC_branch.py:1224): outputs and warm start untouched
+      if (P.out.status) P.out.status[prob] = BMPC_STATUS_NUMERIC;
+    }
     if (lane == 0) {
-      const bool bad = !(J == J) || fabs(J) > 1e300;
-      if (P.out.status) P.out.status[prob] = bad ? BMPC_STATUS_NUMERIC : status;
       if (P.out.iters) P.out.iters[prob] = iters;
       if (P.out.nfact) P.out.nfact[prob] = nfact;
-      if (P.out.objective) P.out.objective[prob] = J;
-      P.started[prob] = 1;
     }
-    __syncwarp();
+    lanes_sync();
   }
 };
-
-template <class M, int NR, bool GWS>
-__global__ void __launch_bounds__(256) bmpc_solve_kernel(const KParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  real* slab;
-  if (GWS) {
-    slab = P.gws + (size_t)(blockIdx.x * wpb + warp) * P.slab_reals;
-  } else {
-    slab = reinterpret_cast<real*>(smem_raw) + (size_t)warp * P.slab_reals;
-  }
-  Solver<M, NR> S(P, slab, lane);
-  for (;;) {
-    int prob = 0;
-    if (lane == 0) prob = atomicAdd(P.counter, 1);
-    prob = __shfl_sync(FULL_MASK, prob, 0);
-    if (prob >= P.count) break;
-    S.solve(prob);
-  }
-}

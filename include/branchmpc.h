@@ -99,13 +99,17 @@ typedef struct bmpc_config {
   double quad_margin;  /* quadruped: (L1+L2)/2 + col_tol                              */
 
   /* solver knobs (0 = library default) */
-  int32_t max_iter;       /* ADMM iteration cap (default 600)                         */
-  int32_t polish_first;   /* first polish attempt after this many iterations (25)     */
-  int32_t polish_every;   /* then every this many iterations (25)                     */
-  int32_t polish_passes;  /* active-set passes per attempt (4)                        */
-  double alpha;           /* over-relaxation (1.6)                                    */
-  double theta, theta_u;  /* curvature-matched rho scale for state rows / inputs (1)  */
-  double eps_abs;         /* ADMM residual tolerance for STATUS_CONVERGED (1e-5)      */
+  int32_t max_iter;        /* ADMM iteration cap (default 400)                                   */
+  int32_t polish_first;    /* first polish attempt after this many iterations (30)               */
+  int32_t polish_every;    /* then every this many iterations (20)                               */
+  int32_t polish_passes;   /* active-set passes per polish attempt (8)                           */
+  int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (12)                     */
+  int32_t warm_polish;     /* 1: on warm solves try a polish before the first ADMM iteration     */
+  double alpha;            /* over-relaxation (1.6)                                              */
+  double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */
+  double eps_abs;          /* ADMM residual tolerance for STATUS_CONVERGED (1e-6)                */
+  double polish_big;       /* lower bound of the stiff penalty, times branch weight (1e4)        */
+  double polish_mult;      /* stiff penalty = polish_mult x curvature-matched stiffness (1e4)    */
 
   int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */
   int32_t device;         /* CUDA device ordinal                                      */

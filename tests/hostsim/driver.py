@@ -1,0 +1,87 @@
+"""TEST INFRASTRUCTURE: ctypes driver of the single-lane host build of the solver text (tests/hostsim/hostsim.cpp).
+
+Used by the CPU tests to check the device algorithm against the oracle without a GPU; the product package never
+imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+PKG = os.path.join(ROOT, "belief-planning_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+from _bmpc import abi  # noqa: E402
+
+SO = os.path.join(HERE, "libbmpc_hostsim.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))
+                                                  if f.endswith(".h")] + [os.path.join(ROOT, "include", "branchmpc.h")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
+        return SO
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(PKG, "csrc"), srcs[0], "-o", SO]
+    subprocess.check_call(cmd)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.hostsim_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HostSim:
+    """Batched solver with persistent warm-start state, host arrays only."""
+
+    def __init__(self, cfg, capacity):
+        self.cfg = cfg
+        nb, tx, tu = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = lib().hostsim_sizes(C.byref(cfg), C.byref(nb), C.byref(tx), C.byref(tu))
+        if rc != 0:
+            raise RuntimeError("hostsim_sizes: %d %s" % (rc, lib().hostsim_last_error().decode()))
+        self.nbranch, self.totalx, self.totalu = nb.value, tx.value, tu.value
+        self.cap = capacity
+        self.uLin = np.zeros((capacity, self.totalu + 1, cfg.d))
+        self.pbest = np.zeros((capacity, self.nbranch), dtype=np.int32)
+        self.oldin = np.zeros((capacity, cfg.d))
+        self.started = np.zeros(capacity, dtype=np.int32)
+
+    def solve(self, x0, z0, xref, policy_params=None):
+        cfg = self.cfg
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=float)
+        z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=float)
+        xref = np.ascontiguousarray(np.atleast_2d(xref), dtype=float)
+        B = x0.shape[0]
+        assert B <= self.cap
+        pp = None if policy_params is None else np.ascontiguousarray(policy_params, dtype=float).reshape(B, cfg.m, 4)
+        res = {
+            "u0": np.zeros((B, cfg.d)), "uPred": np.zeros((B, self.totalu, cfg.d)),
+            "xPred": np.zeros((B, self.totalx, cfg.n)), "xLin": np.zeros((B, self.totalu, cfg.n)),
+            "zPred": np.zeros((B, self.totalu, cfg.n)), "branch_w": np.zeros((B, self.nbranch)),
+            "branch_p": np.full((B, self.nbranch, cfg.m), np.nan), "objective": np.zeros(B),
+            "status": np.full(B, -1, dtype=np.int32), "iters": np.zeros(B, dtype=np.int32),
+            "nfact": np.zeros(B, dtype=np.int32),
+        }
+        out = abi.Outputs(**{k: _ptr(v) for k, v in res.items()})
+        rc = lib().hostsim_solve(C.byref(cfg), _ptr(x0), _ptr(z0), _ptr(xref), _ptr(pp), C.c_int64(B), _ptr(self.uLin),
+                                 _ptr(self.pbest), _ptr(self.oldin), _ptr(self.started), C.byref(out))
+        if rc != 0:
+            raise RuntimeError("hostsim_solve: %d %s" % (rc, lib().hostsim_last_error().decode()))
+        return res

@@ -1,0 +1,67 @@
+// TEST INFRASTRUCTURE (never shipped, never loaded by the product package): the solver text of
+// belief-planning_b200/csrc/bmpc_solver.h compiled by g++ as a single-lane host program, so that the CPU test
+// suite can check the device ALGORITHM (tree expansion, Riccati/ADMM, polish, outputs, warm-start state) against
+// the oracle without a GPU.  The CUDA library builds the same headers with 32 lanes per problem.
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
+
+#include "bmpc_host.h"
+#include "bmpc_solver.h"
+
+namespace {
+template <class M, int NR>
+void run(KParams& P) {
+  P.slab_reals = Solver<M, NR>::slab_reals(P.nup, P.nbranch);
+  std::vector<real> slab(P.slab_reals, 0.0);
+  Solver<M, NR> S(P, slab.data(), 0);
+  for (int i = 0; i < P.count; ++i) S.solve(i);
+}
+std::string g_err;
+}  // namespace
+
+extern "C" {
+
+const char* hostsim_last_error(void) { return g_err.c_str(); }
+
+int hostsim_sizes(const bmpc_config* cfg, int32_t* nbranch, int32_t* totalx, int32_t* totalu) {
+  KParams P;
+  const int rc = bmpc::make_params(*cfg, &P, &g_err);
+  if (rc != BMPC_OK) return rc;
+  *nbranch = P.nbranch;
+  *totalx = P.totalx;
+  *totalu = P.totalu;
+  return BMPC_OK;
+}
+
+// All pointers are HOST pointers; uLin/pbest/oldin/started are the persistent state (caller-owned here).
+int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, const double* xref,
+                  const double* policy_params, int64_t count, double* uLin, int32_t* pbest, double* oldin,
+                  int32_t* started, const bmpc_outputs* out) {
+  KParams P;
+  const int rc = bmpc::make_params(*cfg, &P, &g_err);
+  if (rc != BMPC_OK) return rc;
+  if (!bmpc::supported_instance(cfg->model, cfg->n_rows)) { g_err = "unsupported (model, n_rows)"; return BMPC_E_UNSUPPORTED; }
+  P.count = (int)count;
+  P.x0 = x0;
+  P.z0 = z0;
+  P.xref = xref;
+  P.polpar = policy_params;
+  P.uLin = uLin;
+  P.pbest = pbest;
+  P.oldin = oldin;
+  P.started = started;
+  P.out = *out;
+  if (cfg->model == BMPC_MODEL_HIGHWAY) {
+    switch (cfg->n_rows) {
+      case 0: run<HighwayModel, 1>(P); break;
+      case 1: run<HighwayModel, 2>(P); break;
+      default: run<HighwayModel, 3>(P); break;
+    }
+  } else {
+    run<QuadrupedModel, 1>(P);
+  }
+  return BMPC_OK;
+}
+}
