@@ -1,0 +1,176 @@
+"""Batched Branch-MPC solver handle: thousands of independent scenario-tree problems per call on one B200.
+
+PyTorch is used only to own device memory and to name the CUDA stream; all arithmetic happens inside
+libbranchmpc.so (csrc/), reached through the C ABI of include/branchmpc.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_OUT_SHAPES = {
+    "u0": lambda s: (s.cfg.d,), "uPred": lambda s: (s.totalu, s.cfg.d), "xPred": lambda s: (s.totalx, s.cfg.n),
+    "xLin": lambda s: (s.totalu, s.cfg.n), "zPred": lambda s: (s.totalu, s.cfg.n), "branch_w": lambda s: (s.nbranch,),
+    "branch_p": lambda s: (s.nbranch, s.cfg.m), "objective": lambda s: (), "status": lambda s: (),
+    "iters": lambda s: (), "nfact": lambda s: (),
+}
+_INT_OUTPUTS = ("status", "iters", "nfact")
+LIGHT_OUTPUTS = ("u0", "objective", "status", "iters", "nfact")
+
+
+class BmpcError(RuntimeError):
+    pass
+
+
+class BatchedBranchMPC:
+    """One libbranchmpc handle (one device, one configuration, `batch_capacity` persistent episode slots)."""
+
+    def __init__(self, cfg):
+        self.lib = abi.load_library()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.bmpc_create(C.byref(cfg), C.byref(h))
+        if rc != abi.OK:
+            raise BmpcError("bmpc_create failed (%d): %s" % (rc, self.lib.bmpc_last_error(None).decode()))
+        self.h = h
+        self.nbranch = self.lib.bmpc_num_branches(h)
+        self.totalx = self.lib.bmpc_total_x(h)
+        self.totalu = self.lib.bmpc_total_u(h)
+        self.capacity = cfg.batch_capacity
+        self._dev_out = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bmpc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != abi.OK:
+            raise BmpcError("%s failed (%d): %s" % (what, rc, self.lib.bmpc_last_error(self.h).decode()))
+
+    # -- topology ------------------------------------------------------------------------------------------
+    def topology(self):
+        """(id, depth, ndx, ndu, parent) rows in BFS order, the numbering of MPC_branch.py:928-981."""
+        arr = [np.zeros(self.nbranch, dtype=np.int32) for _ in range(4)]
+        ptr = [a.ctypes.data_as(C.POINTER(C.c_int32)) for a in arr]
+        self._check(self.lib.bmpc_get_topology(self.h, *ptr), "bmpc_get_topology")
+        ndx, ndu, depth, parent = arr
+        return np.column_stack([np.arange(self.nbranch), depth, ndx, ndu, parent]).astype(np.int64)
+
+    def reset(self, episode_ids=None):
+        if episode_ids is None:
+            self._check(self.lib.bmpc_reset(self.h, None, 0), "bmpc_reset")
+        else:
+            ids = np.ascontiguousarray(episode_ids, dtype=np.int64)
+            self._check(self.lib.bmpc_reset(self.h, ids.ctypes.data_as(C.POINTER(C.c_int64)), len(ids)), "bmpc_reset")
+
+    # -- device path -----------------------------------------------------------------------------------------
+    def device_outputs(self, count, names):
+        import torch
+        dev = torch.device("cuda", self.cfg.device)
+        key = (count, tuple(names))
+        if key not in self._dev_out:
+            bufs = {}
+            for k in names:
+                dt = torch.int32 if k in _INT_OUTPUTS else torch.float64
+                bufs[k] = torch.empty((count,) + _OUT_SHAPES[k](self), dtype=dt, device=dev)
+            self._dev_out = {key: bufs}          # keep only the latest shape
+        return self._dev_out[key]
+
+    def solve(self, x0, z0, xref, policy_params=None, outputs=LIGHT_OUTPUTS, stream=None):
+        """x0, z0, xref: CUDA float64 tensors (count, n).  Returns a dict of CUDA tensors (reused between calls).
+        Asynchronous: the kernel is enqueued on `stream` (default: torch's current stream)."""
+        import torch
+        count = x0.shape[0]
+        for t in (x0, z0, xref):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.shape == (count, self.cfg.n)):
+                raise ValueError("inputs must be contiguous CUDA float64 tensors of shape (count, n)")
+        pp = None
+        if policy_params is not None:
+            if not (policy_params.is_cuda and policy_params.dtype == torch.float64 and policy_params.is_contiguous()
+                    and policy_params.numel() == count * self.cfg.m * 4):
+                raise ValueError("policy_params must be a contiguous CUDA float64 tensor of (count, m, 4)")
+            pp = policy_params.data_ptr()
+        bufs = self.device_outputs(count, outputs)
+        if "branch_p" in bufs:
+            bufs["branch_p"].fill_(float("nan"))
+        out = abi.Outputs(**{k: bufs[k].data_ptr() for k in bufs})
+        if stream is None:
+            stream = torch.cuda.current_stream(x0.device).cuda_stream
+        self._check(self.lib.bmpc_solve(self.h, x0.data_ptr(), z0.data_ptr(), xref.data_ptr(), pp, count,
+                                        C.byref(out), C.c_void_p(stream)), "bmpc_solve")
+        return bufs
+
+    # -- host path (the call the drop-in classes make) ---------------------------------------------------------
+    def solve_host(self, x0, z0, xref, policy_params=None, outputs=tuple(abi.OUTPUT_NAMES)):
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=np.float64)
+        xref = np.ascontiguousarray(np.atleast_2d(xref), dtype=np.float64)
+        count = x0.shape[0]
+        if x0.shape != (count, self.cfg.n) or z0.shape != x0.shape or xref.shape != x0.shape:
+            raise ValueError("x0, z0, xref must have shape (count, n)")
+        pp = None
+        if policy_params is not None:
+            pp = np.ascontiguousarray(policy_params, dtype=np.float64).reshape(count, self.cfg.m, 4)
+        res = {}
+        for k in outputs:
+            dt = np.int32 if k in _INT_OUTPUTS else np.float64
+            res[k] = np.empty((count,) + _OUT_SHAPES[k](self), dtype=dt)
+        out = abi.Outputs(**{k: v.ctypes.data for k, v in res.items()})
+        self._check(self.lib.bmpc_solve_host(self.h, x0.ctypes.data, z0.ctypes.data, xref.ctypes.data,
+                                             None if pp is None else pp.ctypes.data, count, C.byref(out)),
+                    "bmpc_solve_host")
+        return res
+
+    # -- persistent state ---------------------------------------------------------------------------------------
+    def get_state(self, count=None):
+        count = self.capacity if count is None else count
+        st = {"uLin": np.empty((count, self.totalu + 1, self.cfg.d)), "pbest": np.empty((count, self.nbranch), np.int32),
+              "old_input": np.empty((count, self.cfg.d)), "started": np.empty(count, np.int32)}
+        self._check(self.lib.bmpc_get_state(self.h, st["uLin"].ctypes.data, st["pbest"].ctypes.data,
+                                            st["old_input"].ctypes.data, st["started"].ctypes.data, count, 1),
+                    "bmpc_get_state")
+        return st
+
+    def set_state(self, st):
+        count = st["uLin"].shape[0]
+        arrs = [np.ascontiguousarray(st["uLin"], np.float64), np.ascontiguousarray(st["pbest"], np.int32),
+                np.ascontiguousarray(st["old_input"], np.float64), np.ascontiguousarray(st["started"], np.int32)]
+        self._check(self.lib.bmpc_set_state(self.h, *[a.ctypes.data for a in arrs], count, 1), "bmpc_set_state")
+
+    # -- model functions (parity of rows M1-M5) -------------------------------------------------------------------
+    def eval_model(self, x, z, u, policy_params=None):
+        import torch
+        dev = torch.device("cuda", self.cfg.device)
+        n, d, m, N = self.cfg.n, self.cfg.d, self.cfg.m, self.cfg.N
+        tx = torch.as_tensor(np.ascontiguousarray(x, np.float64), device=dev)
+        tz = torch.as_tensor(np.ascontiguousarray(z, np.float64), device=dev)
+        tu = torch.as_tensor(np.ascontiguousarray(u, np.float64), device=dev)
+        K = tx.shape[0]
+        pp = None
+        if policy_params is not None:
+            pp = torch.as_tensor(np.ascontiguousarray(policy_params, np.float64).reshape(K, m, 4), device=dev)
+        o = {"A": (K, n, n), "B": (K, n, d), "C": (K, n), "xp": (K, n), "zpred": (K, N, m * n), "p": (K, m), "hlin": (K,),
+             "dh": (K, n)}
+        t = {k: torch.zeros(s, dtype=torch.float64, device=dev) for k, s in o.items()}
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self.lib.bmpc_eval_model(self.h, tx.data_ptr(), tz.data_ptr(), tu.data_ptr(),
+                                             None if pp is None else pp.data_ptr(), K, t["A"].data_ptr(),
+                                             t["B"].data_ptr(), t["C"].data_ptr(), t["xp"].data_ptr(),
+                                             t["zpred"].data_ptr(), t["p"].data_ptr(), t["hlin"].data_ptr(),
+                                             t["dh"].data_ptr(), C.c_void_p(stream)), "bmpc_eval_model")
+        torch.cuda.synchronize(dev)
+        return {k: v.cpu().numpy() for k, v in t.items()}
+
+    def last_kernel_ms(self):
+        return float(self.lib.bmpc_last_kernel_ms(self.h))
+
+    def launch_count(self):
+        return int(self.lib.bmpc_launch_count(self.h))

@@ -1,0 +1,56 @@
+"""Seeded synthetic scenario batches; distributions anchored on the reference environments' initial
+conditions and respawn windows (Highway_env_branch.py:67, Highway_env.py:225, quadruped_env.py:58).
+
+Host-side numpy only: the arrays are handed to the library as float64 (device copies are made by the caller).
+"""
+import numpy as np
+
+from . import abi, config
+
+LANE_W = 3.6
+
+
+def highway_batch(count, seed=1237, n_lanes=4):
+    """Returns x0, z0, xref (count,4) and per-episode policy parameters (count,3,4) for [maintain, brake, lc]."""
+    rng = np.random.default_rng(seed)
+    lane_e = rng.integers(0, n_lanes, count)
+    lane_o = rng.integers(0, n_lanes, count)
+    x0 = np.column_stack([np.zeros(count), 1.8 + LANE_W * lane_e + rng.normal(0, 0.3, count), rng.uniform(15, 25, count),
+                          np.clip(rng.normal(0, 0.03, count), -0.2, 0.2)])
+    z0 = np.column_stack([rng.uniform(-15, 25, count), 1.8 + LANE_W * lane_o + rng.normal(0, 0.3, count),
+                          rng.uniform(15, 25, count), rng.normal(0, 0.03, count)])
+    xref = np.column_stack([np.zeros(count), 1.8 + LANE_W * lane_e, z0[:, 2] + rng.uniform(-3, 3, count), np.zeros(count)])
+    # lane-change target of the obstacle: an adjacent lane (Highway_env_branch.py:96-118 picks it per step)
+    step = np.where(lane_o == 0, 1, np.where(lane_o == n_lanes - 1, -1, rng.choice([-1, 1], count)))
+    tgt = np.column_stack([np.zeros(count), 1.8 + LANE_W * (lane_o + step), z0[:, 2], np.zeros(count)])
+    pp = np.zeros((count, 3, 4))
+    pp[:, 2, :] = tgt
+    return x0, z0, xref, pp
+
+
+def highway_policies(names=("maintain", "brake", "lc"), lc_target=(0.5, 1.8, 15.0, 0.0), v0=20.0):
+    table = {"maintain": (abi.POLICY_MAINTAIN, [0, 0, 0, 0]), "brake": (abi.POLICY_BRAKE, [0, 0, 0, 0]),
+             "lc": (abi.POLICY_LC, list(lc_target)), "trackv": (abi.POLICY_TRACKV, [v0, 0, 0, 0])}
+    return [table[n] for n in names]
+
+
+def highway_config(policies=("maintain", "brake", "lc"), NB=2, N=8, lc_target=(0.5, 1.8, 15.0, 0.0), am=6.0, rm=0.3,
+                   N_lane=4, W=2.5, L=4.0, batch_capacity=1, device=0, **knobs):
+    """main_branch.py:24-48 + Init_MPC.initBranchMPC (:40-72) as a bmpc_config."""
+    spec = config.highway_spec(N, 0.1, highway_policies(policies, lc_target), L, W, 0.1, 2.0)
+    Fx = np.array([[0., 1., 0., 0.], [0., -1., 0., 0.], [0., 0., 0., 1.], [0., 0., 0., -1.]])
+    bx = np.array([N_lane * LANE_W - W / 2, -W / 2, 0.25, 0.25])
+    Fu = np.kron(np.eye(2), np.array([1., -1.])).T
+    bu = np.array([am, am, rm, rm])
+    return config.make_config(spec, 4, 2, N, NB, np.diag([0., 3., 3., 10.]), np.diag([1., 100.]), Fx, bx, Fu, bu,
+                              np.array([0., 300.]), batch_capacity=batch_capacity, device=device, **knobs)
+
+
+def euler_highway(x, u, dt=0.1):
+    """vehicle plant (Highway_env_branch.py:39-41), batched."""
+    out = np.array(x, dtype=float, copy=True)
+    out[:, 0] += dt * x[:, 2] * np.cos(x[:, 3])
+    out[:, 1] += dt * x[:, 2] * np.sin(x[:, 3])
+    out[:, 2] += dt * u[:, 0]
+    out[:, 3] += dt * u[:, 1]
+    return out

@@ -1,0 +1,471 @@
+// libbranchmpc.so: C ABI (include/branchmpc.h) over the sm_100a kernels.  Nothing here throws or aborts across the
+// ABI; every failure is an integer code plus a message in bmpc_last_error().
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bmpc_host.h"
+#include "bmpc_solver.h"
+
+// ------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------
+
+// Persistent warps: every warp pulls problem indices from a global counter and solves them one at a time in its
+// own slab (shared memory when it fits, global/L2 otherwise).
+template <class M, int NR, bool GWS>
+__global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  real* slab;
+  if (GWS) {
+    slab = P.gws + (size_t)blockIdx.x * P.slab_reals;
+  } else {
+    slab = reinterpret_cast<real*>(smem_raw);
+  }
+  Solver<M, NR> S(P, slab, lane);
+  for (;;) {
+    int prob = 0;
+    if (lane == 0) prob = atomicAdd(P.counter, 1);
+    prob = __shfl_sync(BMPC_FULL_MASK, prob, 0);
+    if (prob >= P.count) break;
+    S.solve(prob);
+  }
+}
+
+// Point-wise model functions for the parity tests of rows M1-M5 (one thread per point).
+struct EvalArgs {
+  const real *x, *z, *u, *polpar;
+  real *A, *B, *C, *xp, *zpred, *p, *hlin, *dh;
+  int count;
+};
+
+template <class M>
+__global__ void bmpc_eval_kernel(const __grid_constant__ KParams P, const EvalArgs a) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count) return;
+  const real* x = a.x + (size_t)i * NX;
+  if (a.u && (a.A || a.B || a.C || a.xp)) {
+    const real* u = a.u + (size_t)i * NU;
+    real lin[M::NLIN], cc[M::NCC], xn[NX];
+    M::linearize(P, x, u, lin, cc, xn);
+    if (a.A) M::denseA(P, lin, a.A + (size_t)i * NX * NX);
+    if (a.B) M::denseB(P, lin, a.B + (size_t)i * NX * NU);
+    if (a.C) M::expandC(cc, a.C + (size_t)i * NX);
+    if (a.xp)
+      for (int q = 0; q < NX; ++q) a.xp[(size_t)i * NX + q] = xn[q];
+  }
+  if (a.z && (a.hlin || a.dh)) {
+    const real* z = a.z + (size_t)i * NX;
+    real h, dhx, dhy;
+    M::collision(P, x, z, h, dhx, dhy);
+    if (a.hlin) a.hlin[i] = h - (dhx * x[0] + dhy * x[1]);
+    if (a.dh) {
+      for (int q = 0; q < NX; ++q) a.dh[(size_t)i * NX + q] = 0.0;
+      a.dh[(size_t)i * NX] = dhx;
+      a.dh[(size_t)i * NX + 1] = dhy;
+    }
+  }
+  if (a.z && (a.zpred || a.p)) {
+    const real* z = a.z + (size_t)i * NX;
+    real hi[BMPC_MAX_POLICIES];
+    real himax = -1e300;
+    for (int k = 0; k < P.m; ++k) {
+      const real* par = a.polpar ? a.polpar + ((size_t)i * P.m + k) * 4 : P.pol_par[k];
+      const real* par0 = a.polpar ? a.polpar + ((size_t)i * P.m) * 4 : P.pol_par[0];
+      real zl[NX];
+      real* zo = a.zpred ? a.zpred + (size_t)i * P.N * P.m * NX : nullptr;
+      hi[k] = M::policy_safety(P, P.pol_kind[k], par, P.pol_kind[0], par0, x, z, zl, [&](int t, const real* zz) {
+        if (zo)
+          for (int q = 0; q < NX; ++q) zo[((size_t)t * P.m + k) * NX + q] = zz[q];
+      });
+      himax = fmax(himax, hi[k]);
+    }
+    if (a.p) {
+      real sum = 0.0;
+      for (int k = 0; k < P.m; ++k) sum += M::branch_weight(P, hi[k], himax);
+      for (int k = 0; k < P.m; ++k) a.p[(size_t)i * P.m + k] = M::branch_weight(P, hi[k], himax) / sum;
+    }
+  }
+}
+
+// Dependent-chain-free DFMA loop: 8 independent accumulators per thread.
+__global__ void bmpc_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------------------
+struct bmpc_handle {
+  bmpc_config cfg;
+  KParams P;            // call-independent part
+  int device = 0;
+  int num_sms = 0;
+  size_t slab_bytes = 0;
+  bool use_gws = false;
+  int grid = 0;         // persistent warps (= blocks)
+  // persistent per-episode state
+  real* uLin = nullptr;
+  int* pbest = nullptr;
+  real* oldin = nullptr;
+  int* started = nullptr;
+  int* counter = nullptr;
+  real* gws = nullptr;
+  // staging for bmpc_solve_host
+  real* stage_in = nullptr;   // x0 | z0 | xref | polpar
+  void* stage_out = nullptr;
+  size_t stage_out_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int64_t launches = 0;
+  std::string err;
+};
+
+static std::string g_create_error;
+
+#define BMPC_CK(h, call)                                                                           \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return BMPC_E_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+template <class M, int NR>
+static int configure_instance(bmpc_handle* h) {
+  using S = Solver<M, NR>;
+  h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
+  h->slab_bytes = h->P.slab_reals * sizeof(real);
+  int max_optin = 0;
+  BMPC_CK(h, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  h->use_gws = h->slab_bytes > (size_t)max_optin;
+  int per_sm = 0;
+  if (!h->use_gws) {
+    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)h->slab_bytes));
+    BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bmpc_solve_kernel<M, NR, false>, 32, h->slab_bytes));
+  } else {
+    BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bmpc_solve_kernel<M, NR, true>, 32, 0));
+    if (per_sm > 8) per_sm = 8;   // keep the global slabs of the resident warps inside L2
+  }
+  if (per_sm < 1) { h->err = "kernel does not fit on an SM"; return BMPC_E_CUDA; }
+  h->grid = per_sm * h->num_sms;
+  return BMPC_OK;
+}
+
+template <class M, int NR>
+static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStream_t s) {
+  if (h->use_gws) {
+    bmpc_solve_kernel<M, NR, true><<<grid, 32, 0, s>>>(P);
+  } else {
+    bmpc_solve_kernel<M, NR, false><<<grid, 32, h->slab_bytes, s>>>(P);
+  }
+  BMPC_CK(h, cudaGetLastError());
+  return BMPC_OK;
+}
+
+#define BMPC_DISPATCH(h, fn, ...)                                                        \
+  ((h)->cfg.model == BMPC_MODEL_HIGHWAY                                                  \
+       ? ((h)->cfg.n_rows == 0 ? fn<HighwayModel, 1>(__VA_ARGS__)                        \
+                               : (h)->cfg.n_rows == 1 ? fn<HighwayModel, 2>(__VA_ARGS__) \
+                                                      : fn<HighwayModel, 3>(__VA_ARGS__)) \
+       : fn<QuadrupedModel, 1>(__VA_ARGS__))
+
+static void free_handle(bmpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->uLin);
+  cudaFree(h->pbest);
+  cudaFree(h->oldin);
+  cudaFree(h->started);
+  cudaFree(h->counter);
+  cudaFree(h->gws);
+  cudaFree(h->stage_in);
+  cudaFree(h->stage_out);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
+  h->cfg = *cfg;
+  int rc = bmpc::make_params(*cfg, &h->P, &h->err);
+  if (rc != BMPC_OK) return rc;
+  if (!bmpc::supported_instance(cfg->model, cfg->n_rows)) {
+    h->err = "no kernel instance for this (model, n_rows)";
+    return BMPC_E_UNSUPPORTED;
+  }
+  if (cfg->batch_capacity < 1) { h->err = "batch_capacity must be >= 1"; return BMPC_E_INVALID; }
+  h->device = cfg->device;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  BMPC_CK(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  rc = BMPC_DISPATCH(h, configure_instance, h);
+  if (rc != BMPC_OK) return rc;
+  const size_t cap = (size_t)cfg->batch_capacity;
+  const KParams& P = h->P;
+  BMPC_CK(h, cudaMalloc(&h->uLin, cap * (P.totalu + 1) * cfg->d * sizeof(real)));
+  BMPC_CK(h, cudaMalloc(&h->pbest, cap * P.nbranch * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->oldin, cap * cfg->d * sizeof(real)));
+  BMPC_CK(h, cudaMalloc(&h->started, cap * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
+  if (h->use_gws) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->slab_bytes));
+  BMPC_CK(h, cudaEventCreate(&h->ev0));
+  BMPC_CK(h, cudaEventCreate(&h->ev1));
+  return bmpc_reset(h, nullptr, 0);
+}
+
+extern "C" {
+
+int bmpc_version(void) { return BMPC_VERSION; }
+
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return BMPC_E_INVALID; }
+  *out = nullptr;
+  bmpc_handle* h = new (std::nothrow) bmpc_handle();
+  if (!h) { g_create_error = "out of host memory"; return BMPC_E_INVALID; }
+  const int rc = create_impl(cfg, h);
+  if (rc != BMPC_OK) {
+    g_create_error = h->err;
+    free_handle(h);
+    return rc;
+  }
+  *out = h;
+  return BMPC_OK;
+}
+
+int bmpc_destroy(bmpc_handle* h) {
+  free_handle(h);
+  return BMPC_OK;
+}
+
+int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count) {
+  if (!h) return BMPC_E_INVALID;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  const KParams& P = h->P;
+  const size_t cap = (size_t)h->cfg.batch_capacity;
+  const size_t ulin_row = (size_t)(P.totalu + 1) * h->cfg.d * sizeof(real);
+  if (!episode_ids) {
+    BMPC_CK(h, cudaMemset(h->uLin, 0, cap * ulin_row));
+    BMPC_CK(h, cudaMemset(h->pbest, 0, cap * P.nbranch * sizeof(int)));
+    BMPC_CK(h, cudaMemset(h->oldin, 0, cap * h->cfg.d * sizeof(real)));
+    BMPC_CK(h, cudaMemset(h->started, 0, cap * sizeof(int)));
+    return BMPC_OK;
+  }
+  for (int64_t i = 0; i < count; ++i) {
+    const int64_t e = episode_ids[i];
+    if (e < 0 || (size_t)e >= cap) { h->err = "episode id out of range"; return BMPC_E_INVALID; }
+    BMPC_CK(h, cudaMemset((char*)h->uLin + e * ulin_row, 0, ulin_row));
+    BMPC_CK(h, cudaMemset(h->pbest + e * P.nbranch, 0, P.nbranch * sizeof(int)));
+    BMPC_CK(h, cudaMemset(h->oldin + e * h->cfg.d, 0, h->cfg.d * sizeof(real)));
+    BMPC_CK(h, cudaMemset(h->started + e, 0, sizeof(int)));
+  }
+  return BMPC_OK;
+}
+
+int bmpc_num_branches(const bmpc_handle* h) { return h ? h->P.nbranch : BMPC_E_INVALID; }
+int bmpc_total_x(const bmpc_handle* h) { return h ? h->P.totalx : BMPC_E_INVALID; }
+int bmpc_total_u(const bmpc_handle* h) { return h ? h->P.totalu : BMPC_E_INVALID; }
+
+int bmpc_get_topology(const bmpc_handle* h, int32_t* ndx, int32_t* ndu, int32_t* depth, int32_t* parent) {
+  if (!h) return BMPC_E_INVALID;
+  const KParams& P = h->P;
+  for (int b = 0; b < P.nbranch; ++b) {
+    const int d = bmpc_depth(P, b);
+    if (ndx) ndx[b] = bmpc_ndx(P, b);
+    if (ndu) ndu[b] = bmpc_ndu(P, b);
+    if (depth) depth[b] = d;
+    if (parent) parent[b] = d == 0 ? -1 : bmpc_parent(P, b, d);
+  }
+  return BMPC_OK;
+}
+
+int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
+               int64_t count, const bmpc_outputs* out, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (!x0 || !z0 || !xref || !out || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
+  if (count == 0) return BMPC_OK;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  KParams P = h->P;
+  P.count = (int)count;
+  P.x0 = x0;
+  P.z0 = z0;
+  P.xref = xref;
+  P.polpar = policy_params;
+  P.uLin = h->uLin;
+  P.pbest = h->pbest;
+  P.oldin = h->oldin;
+  P.started = h->started;
+  P.out = *out;
+  P.counter = h->counter;
+  P.gws = h->gws;
+  BMPC_CK(h, cudaMemsetAsync(h->counter, 0, sizeof(int), s));
+  const int grid = (int)(count < h->grid ? count : h->grid);
+  BMPC_CK(h, cudaEventRecord(h->ev0, s));
+  const int rc = BMPC_DISPATCH(h, launch_instance, h, P, grid, s);
+  if (rc != BMPC_OK) return rc;
+  BMPC_CK(h, cudaEventRecord(h->ev1, s));
+  h->timed = true;
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                    const double* policy_params, int64_t count, const bmpc_outputs* out) {
+  if (!h) return BMPC_E_INVALID;
+  if (!x0 || !z0 || !xref || !out || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
+  if (count == 0) return BMPC_OK;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  const KParams& P = h->P;
+  const size_t cap = (size_t)h->cfg.batch_capacity, n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
+  if (!h->stage_in) BMPC_CK(h, cudaMalloc(&h->stage_in, cap * (3 * n + 4 * m) * sizeof(real)));
+  // device staging of every output, laid out back to back
+  const size_t sz[11] = {d * 8, (size_t)P.totalu * d * 8, (size_t)P.totalx * n * 8, (size_t)P.totalu * n * 8,
+                         (size_t)P.totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4};
+  void* const host[11] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
+                          out->branch_p, out->objective, out->status, out->iters, out->nfact};
+  size_t per = 0;
+  for (int i = 0; i < 11; ++i) per += sz[i];
+  if (!h->stage_out) {
+    h->stage_out_bytes = cap * per;
+    BMPC_CK(h, cudaMalloc(&h->stage_out, h->stage_out_bytes));
+  }
+  real* dx0 = h->stage_in;
+  real* dz0 = dx0 + cap * n;
+  real* dxr = dz0 + cap * n;
+  real* dpp = dxr + cap * n;
+  cudaStream_t s = 0;
+  BMPC_CK(h, cudaMemcpyAsync(dx0, x0, count * n * 8, cudaMemcpyHostToDevice, s));
+  BMPC_CK(h, cudaMemcpyAsync(dz0, z0, count * n * 8, cudaMemcpyHostToDevice, s));
+  BMPC_CK(h, cudaMemcpyAsync(dxr, xref, count * n * 8, cudaMemcpyHostToDevice, s));
+  if (policy_params) BMPC_CK(h, cudaMemcpyAsync(dpp, policy_params, count * m * 4 * 8, cudaMemcpyHostToDevice, s));
+  void* dev[11];
+  {
+    char* p = (char*)h->stage_out;
+    for (int i = 0; i < 11; ++i) {
+      dev[i] = host[i] ? p : nullptr;
+      p += cap * sz[i];
+    }
+  }
+  bmpc_outputs dout;
+  dout.u0 = (double*)dev[0];
+  dout.uPred = (double*)dev[1];
+  dout.xPred = (double*)dev[2];
+  dout.xLin = (double*)dev[3];
+  dout.zPred = (double*)dev[4];
+  dout.branch_w = (double*)dev[5];
+  dout.branch_p = (double*)dev[6];
+  dout.objective = (double*)dev[7];
+  dout.status = (int32_t*)dev[8];
+  dout.iters = (int32_t*)dev[9];
+  dout.nfact = (int32_t*)dev[10];
+  if (dev[6]) BMPC_CK(h, cudaMemsetAsync(dev[6], 0xff, count * sz[6], s));   // NaN pattern for leaf rows of branch_p
+  const int rc = bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
+  if (rc != BMPC_OK) return rc;
+  for (int i = 0; i < 11; ++i)
+    if (host[i]) BMPC_CK(h, cudaMemcpyAsync(host[i], dev[i], count * sz[i], cudaMemcpyDeviceToHost, s));
+  BMPC_CK(h, cudaStreamSynchronize(s));
+  return BMPC_OK;
+}
+
+int bmpc_get_state(bmpc_handle* h, double* uLin, int32_t* pbest, double* old_input, int32_t* started, int64_t count,
+                   int on_host) {
+  if (!h) return BMPC_E_INVALID;
+  if (count < 0 || count > h->cfg.batch_capacity) { h->err = "count out of range"; return BMPC_E_CAPACITY; }
+  BMPC_CK(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind k = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  const KParams& P = h->P;
+  if (uLin) BMPC_CK(h, cudaMemcpy(uLin, h->uLin, count * (P.totalu + 1) * h->cfg.d * sizeof(real), k));
+  if (pbest) BMPC_CK(h, cudaMemcpy(pbest, h->pbest, count * P.nbranch * sizeof(int), k));
+  if (old_input) BMPC_CK(h, cudaMemcpy(old_input, h->oldin, count * h->cfg.d * sizeof(real), k));
+  if (started) BMPC_CK(h, cudaMemcpy(started, h->started, count * sizeof(int), k));
+  return BMPC_OK;
+}
+
+int bmpc_set_state(bmpc_handle* h, const double* uLin, const int32_t* pbest, const double* old_input,
+                   const int32_t* started, int64_t count, int on_host) {
+  if (!h) return BMPC_E_INVALID;
+  if (count < 0 || count > h->cfg.batch_capacity) { h->err = "count out of range"; return BMPC_E_CAPACITY; }
+  BMPC_CK(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind k = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const KParams& P = h->P;
+  if (uLin) BMPC_CK(h, cudaMemcpy(h->uLin, uLin, count * (P.totalu + 1) * h->cfg.d * sizeof(real), k));
+  if (pbest) BMPC_CK(h, cudaMemcpy(h->pbest, pbest, count * P.nbranch * sizeof(int), k));
+  if (old_input) BMPC_CK(h, cudaMemcpy(h->oldin, old_input, count * h->cfg.d * sizeof(real), k));
+  if (started) BMPC_CK(h, cudaMemcpy(h->started, started, count * sizeof(int), k));
+  return BMPC_OK;
+}
+
+int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const double* u, const double* policy_params,
+                    int64_t count, double* A, double* B, double* C, double* xp, double* zpred, double* p, double* hlin,
+                    double* dh, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (!x || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (count == 0) return BMPC_OK;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  EvalArgs a{x, z, u, policy_params, A, B, C, xp, zpred, p, hlin, dh, (int)count};
+  const int threads = 128, blocks = (int)((count + threads - 1) / threads);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.model == BMPC_MODEL_HIGHWAY) bmpc_eval_kernel<HighwayModel><<<blocks, threads, 0, s>>>(h->P, a);
+  else bmpc_eval_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, a);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+
+double bmpc_measure_fp64_peak(int device, int iters) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1.0;
+  if (iters < 1) iters = 4096;
+  const int threads = 256, blocks = sms * 8;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)threads * blocks * sizeof(double)) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  bmpc_dfma_kernel<<<blocks, threads>>>(out, iters);   // warm-up
+  double best = -1.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    bmpc_dfma_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * threads * blocks / (ms * 1e-3) * 1e-12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+float bmpc_last_kernel_ms(bmpc_handle* h) {
+  if (!h || !h->timed) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+const char* bmpc_last_error(const bmpc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"
