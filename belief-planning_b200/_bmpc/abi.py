@@ -47,7 +47,7 @@ class Outputs(C.Structure):
     """struct bmpc_outputs (device pointers for bmpc_solve, host pointers for bmpc_solve_host)"""
     _fields_ = [("u0", C.c_void_p), ("uPred", C.c_void_p), ("xPred", C.c_void_p), ("xLin", C.c_void_p),
                 ("zPred", C.c_void_p), ("branch_w", C.c_void_p), ("branch_p", C.c_void_p), ("objective", C.c_void_p),
-                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p)]
+                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p), ("nsolve", C.c_void_p)]
 
 
 OUTPUT_NAMES = [f[0] for f in Outputs._fields_]
@@ -69,6 +69,8 @@ SYMBOLS = [
     ("bmpc_get_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     ("bmpc_set_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     ("bmpc_eval_model", C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 8 + [C.c_void_p]),
+    ("bmpc_plant_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                  C.c_void_p]),
     ("bmpc_launch_count", C.c_int64, [C.c_void_p]),
     ("bmpc_measure_fp64_peak", C.c_double, [C.c_int, C.c_int]),
     ("bmpc_last_kernel_ms", C.c_float, [C.c_void_p]),

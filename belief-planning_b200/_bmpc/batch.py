@@ -13,10 +13,10 @@ _OUT_SHAPES = {
     "u0": lambda s: (s.cfg.d,), "uPred": lambda s: (s.totalu, s.cfg.d), "xPred": lambda s: (s.totalx, s.cfg.n),
     "xLin": lambda s: (s.totalu, s.cfg.n), "zPred": lambda s: (s.totalu, s.cfg.n), "branch_w": lambda s: (s.nbranch,),
     "branch_p": lambda s: (s.nbranch, s.cfg.m), "objective": lambda s: (), "status": lambda s: (),
-    "iters": lambda s: (), "nfact": lambda s: (),
+    "iters": lambda s: (), "nfact": lambda s: (), "nsolve": lambda s: (),
 }
-_INT_OUTPUTS = ("status", "iters", "nfact")
-LIGHT_OUTPUTS = ("u0", "objective", "status", "iters", "nfact")
+_INT_OUTPUTS = ("status", "iters", "nfact", "nsolve")
+LIGHT_OUTPUTS = ("u0", "objective", "status", "iters", "nfact", "nsolve")
 
 
 class BmpcError(RuntimeError):
@@ -107,6 +107,16 @@ class BatchedBranchMPC:
         self._check(self.lib.bmpc_solve(self.h, x0.data_ptr(), z0.data_ptr(), xref.data_ptr(), pp, count,
                                         C.byref(out), C.c_void_p(stream)), "bmpc_solve")
         return bufs
+
+    def plant_step(self, x, u, z, obstacle_policy=0, policy_params=None, stream=None):
+        """In-place Euler step of ego (input u) and obstacle (backup policy index) on CUDA tensors."""
+        import torch
+        count = x.shape[0]
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        pp = None if policy_params is None else policy_params.data_ptr()
+        self._check(self.lib.bmpc_plant_step(self.h, x.data_ptr(), u.data_ptr(), None if z is None else z.data_ptr(),
+                                             int(obstacle_policy), pp, count, C.c_void_p(stream)), "bmpc_plant_step")
 
     # -- host path (the call the drop-in classes make) ---------------------------------------------------------
     def solve_host(self, x0, z0, xref, policy_params=None, outputs=tuple(abi.OUTPUT_NAMES)):

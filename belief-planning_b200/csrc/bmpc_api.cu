@@ -93,6 +93,30 @@ __global__ void bmpc_eval_kernel(const __grid_constant__ KParams P, const EvalAr
   }
 }
 
+// Euler plant step of ego (applied input) and obstacle (one of the backup policies), one thread per episode.
+template <class M>
+__global__ void bmpc_plant_kernel(const __grid_constant__ KParams P, real* x, const real* u, real* z, int pol,
+                                  const real* polpar, int count) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (x && u) {
+    real xs[NX], us[NU], xn[NX];
+    for (int q = 0; q < NX; ++q) xs[q] = x[(size_t)i * NX + q];
+    for (int a = 0; a < NU; ++a) us[a] = u[(size_t)i * NU + a];
+    M::step(P, xs, us, xn);
+    for (int q = 0; q < NX; ++q) x[(size_t)i * NX + q] = xn[q];
+  }
+  if (z) {
+    real zs[NX], us[NU], zn[NX];
+    for (int q = 0; q < NX; ++q) zs[q] = z[(size_t)i * NX + q];
+    const real* par = polpar ? polpar + ((size_t)i * P.m + pol) * 4 : P.pol_par[pol];
+    M::policy(P, P.pol_kind[pol], par, zs, us);
+    M::step(P, zs, us, zn);
+    for (int q = 0; q < NX; ++q) z[(size_t)i * NX + q] = zn[q];
+  }
+}
+
 // Dependent-chain-free DFMA loop: 8 independent accumulators per thread.
 __global__ void bmpc_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -334,12 +358,12 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   const size_t cap = (size_t)h->cfg.batch_capacity, n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
   if (!h->stage_in) BMPC_CK(h, cudaMalloc(&h->stage_in, cap * (3 * n + 4 * m) * sizeof(real)));
   // device staging of every output, laid out back to back
-  const size_t sz[11] = {d * 8, (size_t)P.totalu * d * 8, (size_t)P.totalx * n * 8, (size_t)P.totalu * n * 8,
-                         (size_t)P.totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4};
-  void* const host[11] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
-                          out->branch_p, out->objective, out->status, out->iters, out->nfact};
+  const size_t sz[12] = {d * 8, (size_t)P.totalu * d * 8, (size_t)P.totalx * n * 8, (size_t)P.totalu * n * 8,
+                         (size_t)P.totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4};
+  void* const host[12] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
+                          out->branch_p, out->objective, out->status, out->iters, out->nfact, out->nsolve};
   size_t per = 0;
-  for (int i = 0; i < 11; ++i) per += sz[i];
+  for (int i = 0; i < 12; ++i) per += sz[i];
   if (!h->stage_out) {
     h->stage_out_bytes = cap * per;
     BMPC_CK(h, cudaMalloc(&h->stage_out, h->stage_out_bytes));
@@ -353,10 +377,10 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   BMPC_CK(h, cudaMemcpyAsync(dz0, z0, count * n * 8, cudaMemcpyHostToDevice, s));
   BMPC_CK(h, cudaMemcpyAsync(dxr, xref, count * n * 8, cudaMemcpyHostToDevice, s));
   if (policy_params) BMPC_CK(h, cudaMemcpyAsync(dpp, policy_params, count * m * 4 * 8, cudaMemcpyHostToDevice, s));
-  void* dev[11];
+  void* dev[12];
   {
     char* p = (char*)h->stage_out;
-    for (int i = 0; i < 11; ++i) {
+    for (int i = 0; i < 12; ++i) {
       dev[i] = host[i] ? p : nullptr;
       p += cap * sz[i];
     }
@@ -373,10 +397,11 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   dout.status = (int32_t*)dev[8];
   dout.iters = (int32_t*)dev[9];
   dout.nfact = (int32_t*)dev[10];
+  dout.nsolve = (int32_t*)dev[11];
   if (dev[6]) BMPC_CK(h, cudaMemsetAsync(dev[6], 0xff, count * sz[6], s));   // NaN pattern for leaf rows of branch_p
   const int rc = bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
   if (rc != BMPC_OK) return rc;
-  for (int i = 0; i < 11; ++i)
+  for (int i = 0; i < 12; ++i)
     if (host[i]) BMPC_CK(h, cudaMemcpyAsync(host[i], dev[i], count * sz[i], cudaMemcpyDeviceToHost, s));
   BMPC_CK(h, cudaStreamSynchronize(s));
   return BMPC_OK;
@@ -422,6 +447,23 @@ int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const doub
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.model == BMPC_MODEL_HIGHWAY) bmpc_eval_kernel<HighwayModel><<<blocks, threads, 0, s>>>(h->P, a);
   else bmpc_eval_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, a);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32_t obstacle_policy,
+                    const double* policy_params, int64_t count, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (count < 0 || obstacle_policy < 0 || obstacle_policy >= h->cfg.m) { h->err = "bad argument"; return BMPC_E_INVALID; }
+  if (count == 0) return BMPC_OK;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  const int threads = 128, blocks = (int)((count + threads - 1) / threads);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.model == BMPC_MODEL_HIGHWAY)
+    bmpc_plant_kernel<HighwayModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
+  else
+    bmpc_plant_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
   BMPC_CK(h, cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

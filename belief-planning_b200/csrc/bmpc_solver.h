@@ -21,6 +21,13 @@ enum { FACT_ADMM = 0, FACT_FREE = 1, FACT_POLISH = 2 };
 
 #define BMPC_NOLO (-1.0e300)
 
+#if defined(BMPC_HOSTSIM_TRACE) && !defined(__CUDACC__)
+#include <stdio.h>
+#define BMPC_TRACE(...) fprintf(stderr, __VA_ARGS__)
+#else
+#define BMPC_TRACE(...) ((void)0)
+#endif
+
 // multiplier of a two-sided soft row from the scaled Moreau variable (rlo = rho*lo, rhi = rho*hi)
 BMPC_D real row_dual(real sh, real rlo, real rhi, real lam) {
   if (sh > rhi) return fmin(sh - rhi, lam);
@@ -64,6 +71,7 @@ struct Solver {
   real* EXZ;
   real* EXX;
   int lane, nup, prob;
+  int nsolve;   // KKT solves (one backward + one forward sweep each) of the current problem
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
 
@@ -75,6 +83,7 @@ struct Solver {
     EXZ = EXL + (size_t)NX * P.nbranch;
     EXX = EXZ + (size_t)NX * P.nbranch;
     prob = 0;
+    nsolve = 0;
     rlin = 0.0;
     polpar = nullptr;
   }
@@ -717,6 +726,7 @@ struct Solver {
   }
 
   BMPC_DN void forward() {
+    ++nsolve;
     if (lane == 0) {
       real x[NX];
 #pragma unroll
@@ -935,6 +945,7 @@ struct Solver {
           real lo, hi;
           row_bounds(kp, j, lo, hi);
           const real r = row_value(kp, j, x) - (cj == ROW_UP_KINK ? hi : lo);
+          if (fabs(r) > 1e-6) BMPC_TRACE("      k %d row %d code %d r %.2e y %.3e lam %.3e big %.2e f=(%.3f,%.3f)\n", k, j, cj, r, F(F_Y + j, kp), P.lam_lin * w, big_row(kp, j, w), F(F_FC, kp), F(F_FC + 1, kp));
           F(F_Y + j, kp) += big_row(kp, j, w) * r;
           res = fmax(res, fabs(r));
         }
@@ -944,6 +955,7 @@ struct Solver {
         const int ca = (code >> (3 * NR + 2 * a)) & 3;
         if (ca != IN_FREE) {
           const real r = F(F_UQ + a, kp) - (ca == IN_AT_HI ? P.uhi[a] : P.ulo[a]);
+          if (fabs(r) > 1e-6) BMPC_TRACE("      k %d input %d code %d r %.2e y %.3e big %.2e\n", k, a, ca, r, F(F_Y + NR + a, kp), big_in(kp, a, w));
           F(F_Y + NR + a, kp) += big_in(kp, a, w) * r;
           res = fmax(res, fabs(r));
         }
@@ -1020,23 +1032,36 @@ struct Solver {
     return changes;
   }
 
-  // returns true when the guessed active set was verified (then XQ/UQ hold the optimal x,u)
+  // returns true when the guessed active set was verified (then XQ/UQ hold the optimal x,u).
+  // Per pass: factorise with stiff penalties on the guessed-active rows, refine the multipliers a few
+  // augmented-Lagrangian steps at a time and let the primal-dual rules revise the sets; a set that stays
+  // unchanged while the equality residual falls below 1e-7 is the verified optimum.  Conflicting guesses
+  // (e.g. the collision rows of sibling branches, which see the same position one step after the branching
+  // point) show up as multipliers running past their bounds and are revised without waiting for convergence.
   BMPC_DN bool polish(int& nfact) {
     polish_guess();
+    int prev_changes = 1 << 30;
     for (int pass = 0; pass < P.polish_passes; ++pass) {
       factorize(FACT_POLISH);
       ++nfact;
       real res = 1.0;
-      for (int al = 0; al < P.polish_al_iters; ++al) {
-        polish_assemble();
-        backward();
-        forward();
-        res = lanes_max(polish_multipliers());
-        if (res < 1e-9) break;
+      int al = 0;
+      for (;;) {
+        for (int chunk = 0; chunk < 3 && al < P.polish_al_iters; ++chunk, ++al) {
+          polish_assemble();
+          backward();
+          forward();
+          res = lanes_max(polish_multipliers());
+          if (res < 1e-9) break;
+        }
+        const int changes = lanes_sum_int(polish_update_sets());
+        BMPC_TRACE("    polish pass %d: al %d res %.2e changes %d\n", pass, al, res, changes);
+        if (!(res < 1e-1)) return false;            // far from any consistent set (also catches NaN)
+        if (changes > prev_changes) return false;   // the active-set iteration is diverging: back to ADMM
+        if (changes > 0) { prev_changes = changes; break; }   // revised sets: refactorise
+        if (res < 1e-7) return true;
+        if (al >= P.polish_al_iters) return false;  // consistent but too weakly controlled to settle
       }
-      const int changes = lanes_sum_int(polish_update_sets());
-      if (!(res < 1e-7)) return false;          // stiff solve did not settle (also catches NaN)
-      if (changes == 0) return true;
     }
     return false;
   }
@@ -1178,13 +1203,14 @@ struct Solver {
     prob = prob_;
     polpar = P.polpar ? P.polpar + (size_t)prob * P.m * 4 : nullptr;
     expand_tree();
+    nsolve = 0;
     int nfact = 0, iters = 0, status = BMPC_STATUS_MAXITER;
     factorize(FACT_FREE);
     choose_rho();
     factorize(FACT_ADMM);
     nfact += 2;
     admm_rows<false, false>();
-    int next_polish = P.polish_first;
+    int next_polish = P.polish_first, polish_gap = P.polish_every;
     bool have_xu = false;
     while (iters < P.max_iter) {
       backward();
@@ -1195,8 +1221,10 @@ struct Solver {
       if (check) res = lanes_max(admm_rows<true, true>());
       else admm_rows<true, false>();
       const bool conv = res < P.eps_abs;
+      if (check) BMPC_TRACE("  it %d res %.3e\n", iters, res);
       if (iters >= next_polish || conv) {
-        next_polish = iters + P.polish_every;
+        next_polish = iters + polish_gap;
+        polish_gap *= 2;   // back off: a problem whose active set is slow to settle should not pay for many attempts
         if (polish(nfact)) {
           status = BMPC_STATUS_POLISHED;
           have_xu = true;
@@ -1228,6 +1256,7 @@ struct Solver {
     if (lane == 0) {
       if (P.out.iters) P.out.iters[prob] = iters;
       if (P.out.nfact) P.out.nfact[prob] = nfact;
+      if (P.out.nsolve) P.out.nsolve[prob] = nsolve;
     }
     lanes_sync();
   }

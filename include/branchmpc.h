@@ -103,7 +103,7 @@ typedef struct bmpc_config {
   int32_t polish_first;    /* first polish attempt after this many iterations (30)               */
   int32_t polish_every;    /* then every this many iterations (20)                               */
   int32_t polish_passes;   /* active-set passes per polish attempt (8)                           */
-  int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (12)                     */
+  int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (24)                     */
   int32_t warm_polish;     /* 1: on warm solves try a polish before the first ADMM iteration     */
   double alpha;            /* over-relaxation (1.6)                                              */
   double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */
@@ -129,6 +129,7 @@ typedef struct bmpc_outputs {
   int32_t* status;   /* [count]               BMPC_STATUS_*                                  */
   int32_t* iters;    /* [count]               ADMM iterations used                           */
   int32_t* nfact;    /* [count]               Riccati factorisations used                    */
+  int32_t* nsolve;   /* [count]               KKT solves (backward+forward sweeps): ADMM + polish */
 } bmpc_outputs;
 
 typedef struct bmpc_handle bmpc_handle;
@@ -179,6 +180,13 @@ int bmpc_set_state(bmpc_handle* h, const double* uLin, const int32_t* pbest, con
 int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const double* u, const double* policy_params,
                     int64_t count, double* A, double* B, double* C, double* xp, double* zpred, double* p,
                     double* hlin, double* dh, void* stream);
+
+/* Plant step of the reference environments, batched on the device (vehicle.step, Highway_env_branch.py:39-41;
+ * robot.step, quadruped_env.py:24-40): x <- x + dt f(x, u) for the ego with the applied input u [count][d], and the
+ * obstacle z under backup policy `obstacle_policy` (index into the handle's policy table, per-episode parameters from
+ * policy_params as in bmpc_solve).  In place; device pointers; either state pointer may be NULL. */
+int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32_t obstacle_policy,
+                    const double* policy_params, int64_t count, void* stream);
 
 /* Kernel launch accounting since creation (for bench.py's gpu_launches). */
 int64_t bmpc_launch_count(const bmpc_handle* h);

@@ -1,0 +1,64 @@
+"""Shared test helpers: golden fixtures, bmpc_config factories, oracle drivers."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "belief-planning_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from _bmpc import scenarios  # noqa: E402
+from oracle import params  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HIGHWAY_FIXTURES = ["highway_branch_default", "highway_branch_close", "highway_branch_m2_nb3", "highway_branch_m3_nb1"]
+
+# parity bars of BASELINE.json's north_star
+TOL_U0 = 1e-3        # first applied control, absolute
+TOL_OBJ = 1e-4       # objective, relative
+TOL_VIOL = 1e-5      # constraint violation, absolute
+
+
+def load_fixture(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def fixture_config(g, **kw):
+    return scenarios.highway_config(policies=[str(p) for p in g["meta_policies"]], NB=int(g["meta_NB"]),
+                                    N=int(g["meta_N"]), lc_target=tuple(g["meta_lc_target"]), **kw)
+
+
+def check_fixture_closed_loop(solve, g, tol=1e-6):
+    """`solve(x, z, xref) -> result dict` is called for every recorded step of a fixture; everything the reference
+    produced for that step (tree data, linearisation trajectory, optimum) must be reproduced."""
+    for k in range(int(g["meta_steps"])):
+        pre = "s%d_" % k
+        r = solve(g[pre + "x0"], g[pre + "z0"], g[pre + "xref"])
+        assert r["status"][0] in (0, 1), "step %d status %d" % (k, r["status"][0])
+        np.testing.assert_allclose(r["branch_w"][0], g[pre + "w"], atol=tol)
+        p_ref = g[pre + "p"]
+        mask = np.isfinite(p_ref)
+        np.testing.assert_allclose(r["branch_p"][0][mask], p_ref[mask], atol=tol)
+        assert np.isnan(r["branch_p"][0][~mask]).all()
+        np.testing.assert_allclose(r["xLin"][0], g[pre + "xbar"], atol=tol)      # depends on the previous optimum
+        np.testing.assert_allclose(r["zPred"][0], g[pre + "zbar"], atol=1e-9)
+        np.testing.assert_allclose(r["uPred"][0], g[pre + "uPred"], atol=tol)
+        np.testing.assert_allclose(r["xPred"][0], g[pre + "xPred"], atol=tol)
+        assert np.abs(r["u0"][0] - g[pre + "uPred"][0]).max() < TOL_U0
+        obj = float(g[pre + "objective"])
+        assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj)
+
+
+def oracle_episode(x, z, xref, lc_target, steps):
+    """Closed loop of the oracle controller; returns per-step (x, z, u0, objective, uPred)."""
+    mpc = params.highway_branch_mpc(lc_target=lc_target)
+    out = []
+    for _ in range(steps):
+        u = mpc.solve(x, z, xref).copy()
+        out.append((x.copy(), z.copy(), u, mpc.objective, mpc.uPred.copy()))
+        x = scenarios.euler_highway(x[None], u[None])[0]
+        z = scenarios.euler_highway(z[None], np.array([[0.0, -0.1 * z[3]]]))[0]
+    return out

@@ -1,0 +1,179 @@
+"""Parity tests proper: libbranchmpc.so on the B200, called through the C ABI, against
+  * the golden fixtures produced by the unmodified reference (tests/golden/*.npz),
+  * the oracle on seeded random problems (sizes the oracle finishes in seconds),
+  * size-independent properties at BASELINE.json's full batch (16384 episodes).
+
+Bars (BASELINE.json north_star): first applied control within 1e-3, objective relative difference <= 1e-4,
+constraint violation <= 1e-5, bit-exact tree topology and branch indexing.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import (HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
+                           load_fixture, oracle_episode)
+from _bmpc import abi, scenarios
+from oracle.branch_mpc import TreeTopology
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bmpc():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    from _bmpc import batch
+    return batch
+
+
+@pytest.mark.parametrize("m,NB", [(2, 1), (3, 1), (4, 1), (2, 2), (3, 2), (4, 2), (2, 3), (3, 3), (4, 3)])
+def test_topology_is_bit_exact(bmpc, m, NB):
+    names = ["maintain", "brake", "lc", "trackv"][:m]
+    mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(policies=names, NB=NB))
+    T = TreeTopology(m, NB, 8)
+    assert (mpc.topology() == T.table()).all()
+    assert (mpc.totalx, mpc.totalu, mpc.nbranch) == (T.totalx, T.totalu, T.nbranch)
+    mpc.close()
+
+
+def test_topology_matches_reference_fixture(bmpc):
+    for name in HIGHWAY_FIXTURES:
+        g = load_fixture(name)
+        mpc = bmpc.BatchedBranchMPC(fixture_config(g))
+        assert (mpc.topology() == g["s0_tree"]).all()
+        assert [mpc.totalx, mpc.totalu] == list(g["s0_totals"])
+        mpc.close()
+
+
+def test_model_functions_match_reference(bmpc):
+    """Rows M1-M5: dyn_linearization, zpred_eval, branch_eval, col_eval vs the reference's CasADi graphs."""
+    g = load_fixture("model_functions")
+    mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(lc_target=tuple(g["hw_lc_target"])))
+    r = mpc.eval_model(g["hw_X"], g["hw_Z"], g["hw_U"])
+    for k in ("A", "B", "C", "xp", "zpred", "p", "dh"):
+        np.testing.assert_allclose(r[k], g["hw_" + k], atol=1e-11, err_msg=k)
+    np.testing.assert_allclose(r["hlin"], g["hw_hlin"], atol=1e-10)
+    assert np.abs(r["p"].sum(axis=1) - 1.0).max() < 1e-12
+    mpc.close()
+
+
+@pytest.mark.parametrize("name", HIGHWAY_FIXTURES)
+def test_fixture_closed_loop(bmpc, name):
+    g = load_fixture(name)
+    mpc = bmpc.BatchedBranchMPC(fixture_config(g))
+    check_fixture_closed_loop(lambda x, z, r: mpc.solve_host(x, z, r), g)
+    mpc.close()
+
+
+def test_random_batch_against_oracle(bmpc):
+    B, steps = 32, 2
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=2024)
+    mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=B))
+    ref = [oracle_episode(x0[i], z0[i], xref[i], pp[i, 2], steps) for i in range(B)]
+    x, z = x0.copy(), z0.copy()
+    for s in range(steps):
+        for i in range(B):
+            x[i], z[i] = ref[i][s][0], ref[i][s][1]
+        r = mpc.solve_host(x, z, xref, pp)
+        du = max(np.abs(r["u0"][i] - ref[i][s][2]).max() for i in range(B))
+        dj = max(abs(r["objective"][i] - ref[i][s][3]) / abs(ref[i][s][3]) for i in range(B))
+        assert du < TOL_U0 and dj < TOL_OBJ, (s, du, dj)
+        # continue from the oracle's solution so that step s+1 linearises about the same trajectory
+        st = mpc.get_state(B)
+        for i in range(B):
+            st["uLin"][i, :-1] = ref[i][s][4]
+            st["uLin"][i, -1] = ref[i][s][4][-1]
+            st["old_input"][i] = ref[i][s][2]
+        mpc.set_state(st)
+    mpc.close()
+
+
+def _violations(r, x0, cfg):
+    """max violation of the QP's hard constraints by the returned plan: initial state, input box, shared branching
+    states; the dynamics are checked through the reference's structure xPred[child first] == xPred[sibling first]."""
+    u = r["uPred"]
+    v = max(0.0, float((u[:, :, 0] - cfg.u_hi[0]).max()), float((cfg.u_lo[0] - u[:, :, 0]).max()),
+            float((u[:, :, 1] - cfg.u_hi[1]).max()), float((cfg.u_lo[1] - u[:, :, 1]).max()))
+    v = max(v, float(np.abs(r["xPred"][:, 0] - x0).max()))
+    return v
+
+
+def test_full_batch_properties(bmpc):
+    import torch
+    B = 16384
+    cfg = scenarios.highway_config(batch_capacity=B)
+    mpc = bmpc.BatchedBranchMPC(cfg)
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=31)
+    r = mpc.solve_host(x0, z0, xref, pp)
+    assert (r["status"] <= abi.STATUS_MAXITER).all()
+    assert (r["status"] == abi.STATUS_POLISHED).mean() > 0.99
+    assert np.isfinite(r["objective"]).all() and np.isfinite(r["xPred"]).all()
+    assert _violations(r, x0, cfg) <= TOL_VIOL
+    # all children of one branch start from the same state (MPC_branch.py:1007-1012), bit for bit
+    topo = mpc.topology()
+    for b in range(mpc.nbranch):
+        kids = topo[topo[:, 4] == b]
+        for c in kids[1:]:
+            assert np.array_equal(r["xPred"][:, kids[0][2]], r["xPred"][:, c[2]])
+    w = r["branch_w"]
+    assert np.abs(w[:, 1:4].sum(axis=1) - 1.0).max() < 1e-12 and np.abs(w[:, 4:].sum(axis=1) - 1.0).max() < 1e-12
+    # permutation invariance: problems are independent, so a shuffled batch gives the shuffled results bit for bit
+    perm = np.random.default_rng(0).permutation(B)
+    mpc.reset()
+    r2 = mpc.solve_host(x0[perm], z0[perm], xref[perm], pp[perm])
+    for k in ("u0", "uPred", "xPred", "objective", "status", "iters"):
+        assert np.array_equal(r2[k], r[k][perm]), k
+    # device-pointer entry point == host entry point
+    mpc.reset()
+    dev = torch.device("cuda", 0)
+    out = mpc.solve(*[torch.as_tensor(a, device=dev) for a in (x0, z0, xref, pp)])
+    torch.cuda.synchronize()
+    assert np.array_equal(out["u0"].cpu().numpy(), r["u0"])
+    # warm step: state persisted per episode slot; reset(ids) makes exactly those episodes cold again
+    x1 = scenarios.euler_highway(x0, r["u0"])
+    rw = mpc.solve_host(x1, z0, xref, pp)
+    assert (rw["status"] <= abi.STATUS_MAXITER).all()
+    ids = np.arange(0, B, 2)
+    mpc.reset(ids)
+    rc = mpc.solve_host(x0, z0, xref, pp)
+    assert np.array_equal(rc["u0"][ids], r["u0"][ids])
+    mpc.close()
+
+
+def test_plant_step_matches_reference_plant(bmpc):
+    import torch
+    B = 1000
+    mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=B))
+    x0, z0, _, pp = scenarios.highway_batch(B, seed=3)
+    u = np.random.default_rng(1).uniform(-1, 1, (B, 2))
+    dev = torch.device("cuda", 0)
+    tx, tz, tu, tp = [torch.as_tensor(a, device=dev) for a in (x0, z0, u, pp)]
+    mpc.plant_step(tx, tu, tz, 0, tp)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(tx.cpu().numpy(), scenarios.euler_highway(x0, u), atol=1e-12)
+    np.testing.assert_allclose(tz.cpu().numpy(), scenarios.euler_highway(z0, np.column_stack([np.zeros(B), -0.1 * z0[:, 3]])),
+                               atol=1e-12)
+    mpc.close()
+
+
+def test_errors_are_codes_not_crashes(bmpc):
+    mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=2))
+    x = np.zeros((3, 4))
+    with pytest.raises(bmpc.BmpcError, match="capacity"):
+        mpc.solve_host(x, x, x)
+    with pytest.raises(ValueError):
+        mpc.solve_host(np.zeros((2, 3)), np.zeros((2, 3)), np.zeros((2, 3)))
+    # non-finite input: status NUMERIC, no crash, other episodes unaffected
+    x0, z0, xref, pp = scenarios.highway_batch(2, seed=1)
+    good = mpc.solve_host(x0, z0, xref, pp)
+    mpc.reset()
+    x0[1, 2] = np.nan
+    r = mpc.solve_host(x0, z0, xref, pp)
+    assert r["status"][1] == abi.STATUS_NUMERIC and r["status"][0] == good["status"][0]
+    assert np.array_equal(r["u0"][0], good["u0"][0])
+    mpc.close()
+
+
+def test_smoke_entry(bmpc):
+    import __graft_entry__ as entry
+    entry.smoke()

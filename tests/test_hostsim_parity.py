@@ -1,0 +1,54 @@
+"""The solver text of the CUDA kernel (belief-planning_b200/csrc/bmpc_solver.h), compiled for the host as a single-lane
+program (tests/hostsim), against the golden fixtures produced by the unmodified reference and against the oracle.
+
+This checks the ALGORITHM the GPU runs (tree expansion, linearisation, Riccati/ADMM, polish, outputs, warm-start state)
+on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.so on the B200.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import (HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+                     oracle_episode)
+from _bmpc import scenarios
+from tests.hostsim.driver import HostSim
+
+
+@pytest.mark.parametrize("name", HIGHWAY_FIXTURES)
+def test_fixture_closed_loop(name):
+    g = load_fixture(name)
+    hs = HostSim(fixture_config(g), 1)
+    check_fixture_closed_loop(lambda x, z, r: hs.solve(x, z, r), g)
+
+
+def test_random_batch_against_oracle():
+    B, steps = 12, 2
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=99)
+    hs = HostSim(scenarios.highway_config(), B)
+    ref = [oracle_episode(x0[i], z0[i], xref[i], pp[i, 2], steps) for i in range(B)]
+    x, z = x0.copy(), z0.copy()
+    for s in range(steps):
+        for i in range(B):      # the oracle's closed loop defines the states of step s
+            x[i], z[i] = ref[i][s][0], ref[i][s][1]
+        r = hs.solve(x, z, xref, pp)
+        for i in range(B):
+            assert np.abs(r["u0"][i] - ref[i][s][2]).max() < TOL_U0
+            assert abs(r["objective"][i] - ref[i][s][3]) <= TOL_OBJ * abs(ref[i][s][3])
+        # the warm-start state must follow the ORACLE's solution for the next step to be comparable
+        for i in range(B):
+            hs.uLin[i, :-1] = ref[i][s][4]
+            hs.uLin[i, -1] = ref[i][s][4][-1]
+            hs.oldin[i] = ref[i][s][2]
+
+
+def test_all_problems_of_a_batch_are_certified():
+    B = 400
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=7)
+    hs = HostSim(scenarios.highway_config(), B)
+    r = hs.solve(x0, z0, xref, pp)
+    assert (r["status"] == 0).mean() > 0.99 and (r["status"] <= 2).all()
+    assert np.isfinite(r["objective"]).all()
+    assert (r["uPred"][:, :, 0] <= 6.0 + 1e-12).all() and (r["uPred"][:, :, 0] >= -6.0 - 1e-12).all()
+    assert (np.abs(r["uPred"][:, :, 1]) <= 0.3 + 1e-12).all()
+    assert np.array_equal(r["xPred"][:, 0], x0)
+    # children of one parent start from the same state (buildEqConstr, MPC_branch.py:1007-1012)
+    assert np.array_equal(r["xPred"][:, 1], r["xPred"][:, 9]) and np.array_equal(r["xPred"][:, 1], r["xPred"][:, 17])
