@@ -91,10 +91,11 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
     if (!(P.rlo[j] <= P.rhi[j])) { *err = "empty state row range"; return BMPC_E_INVALID; }
   }
   P.max_iter = c.max_iter > 0 ? c.max_iter : 400;
-  P.polish_first = c.polish_first > 0 ? c.polish_first : 30;
-  P.polish_every = c.polish_every > 0 ? c.polish_every : 20;
+  P.polish_first = c.polish_first > 0 ? c.polish_first : 10;
+  P.polish_every = c.polish_every > 0 ? c.polish_every : 10;
   P.polish_passes = c.polish_passes > 0 ? c.polish_passes : 8;
   P.polish_al_iters = c.polish_al_iters > 0 ? c.polish_al_iters : 24;
+  P.polish_careful = c.polish_careful > 0 ? c.polish_careful : (c.polish_careful < 0 ? 0 : 12);
   P.warm_polish = c.warm_polish;
   P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
   P.theta = c.theta > 0.0 ? c.theta : 1.0;

@@ -946,7 +946,8 @@ struct Solver {
           row_bounds(kp, j, lo, hi);
           const real r = row_value(kp, j, x) - (cj == ROW_UP_KINK ? hi : lo);
           if (fabs(r) > 1e-6) BMPC_TRACE("      k %d row %d code %d r %.2e y %.3e lam %.3e big %.2e f=(%.3f,%.3f)\n", k, j, cj, r, F(F_Y + j, kp), P.lam_lin * w, big_row(kp, j, w), F(F_FC, kp), F(F_FC + 1, kp));
-          F(F_Y + j, kp) += big_row(kp, j, w) * r;
+          const real yn = F(F_Y + j, kp) + big_row(kp, j, w) * r;
+          F(F_Y + j, kp) = yn;
           res = fmax(res, fabs(r));
         }
       }
@@ -965,9 +966,14 @@ struct Solver {
     return res;
   }
 
-  // primal-dual active-set update from the last equality-constrained solve; returns #changes of this lane
-  BMPC_DN int polish_update_sets() {
+  // Primal-dual active-set update from the last equality-constrained solve.  Every candidate change carries a score in
+  // multiplier units (primal violations are scaled by the row's curvature-matched stiffness), and only candidates
+  // with score >= thresh are applied; score_max returns the largest score seen (for the one-change-at-a-time mode).
+  // restricted=true (stalled refinement): only kink rows whose multiplier is out of range by more than the last
+  // multiplier step are revised; everything else is left for a settled solve.
+  BMPC_DN int polish_update_sets(bool restricted, real thresh, bool apply, real& score_max) {
     int changes = 0;
+    real smax = 0.0;
     const real tol = 1e-7;
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
@@ -985,50 +991,81 @@ struct Solver {
       for (int j = 0; j < NR; ++j) {
         const int cj = (code >> (3 * j)) & 7;
         int nj = cj;
+        real ynew = 0.0, score = 0.0;
         if (cj != ROW_IGNORED) {
           real lo, hi;
           row_bounds(kp, j, lo, hi);
           const real fx = row_value(kp, j, x);
           const real y = F(F_Y + j, kp);
-          if (cj == ROW_INACTIVE) {
-            if (fx > hi + tol) { nj = ROW_UP_KINK; F(F_Y + j, kp) = 0.0; }
-            else if (fx < lo - tol) { nj = ROW_LO_KINK; F(F_Y + j, kp) = 0.0; }
+          const real stiff = F(F_RHO + j, kp) / P.theta;
+          if (restricted) {
+            if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) {
+              const real m2 = 2.0 * big_row(kp, j, w) * fabs(fx - (cj == ROW_UP_KINK ? hi : lo));
+              const real ys = (cj == ROW_UP_KINK) ? y : -y;     // in [0, lam] when consistent
+              if (ys + m2 < -ytol) { nj = ROW_INACTIVE; score = -ys; }
+              else if (ys - m2 > lam + ytol) { nj = (cj == ROW_UP_KINK) ? ROW_UP_LIN : ROW_LO_LIN; score = ys - lam; }
+            }
+          } else if (cj == ROW_INACTIVE) {
+            if (fx > hi + tol) { nj = ROW_UP_KINK; score = stiff * (fx - hi); }
+            else if (fx < lo - tol) { nj = ROW_LO_KINK; score = stiff * (lo - fx); }
           } else if (cj == ROW_UP_KINK) {
-            if (y < -ytol) { nj = ROW_INACTIVE; F(F_Y + j, kp) = 0.0; }
-            else if (y > lam + ytol) { nj = ROW_UP_LIN; F(F_Y + j, kp) = 0.0; }
+            if (y < -ytol) { nj = ROW_INACTIVE; score = -y; }
+            else if (y > lam + ytol) { nj = ROW_UP_LIN; score = y - lam; }
           } else if (cj == ROW_LO_KINK) {
-            if (y > ytol) { nj = ROW_INACTIVE; F(F_Y + j, kp) = 0.0; }
-            else if (y < -lam - ytol) { nj = ROW_LO_LIN; F(F_Y + j, kp) = 0.0; }
+            if (y > ytol) { nj = ROW_INACTIVE; score = y; }
+            else if (y < -lam - ytol) { nj = ROW_LO_LIN; score = -y - lam; }
           } else if (cj == ROW_UP_LIN) {
-            if (fx < hi - tol) { nj = ROW_UP_KINK; F(F_Y + j, kp) = lam; }
+            if (fx < hi - tol) { nj = ROW_UP_KINK; ynew = lam; score = stiff * (hi - fx); }
           } else if (cj == ROW_LO_LIN) {
-            if (fx > lo + tol) { nj = ROW_LO_KINK; F(F_Y + j, kp) = -lam; }
+            if (fx > lo + tol) { nj = ROW_LO_KINK; ynew = -lam; score = stiff * (fx - lo); }
           }
         }
-        changes += (nj != cj);
+        if (nj != cj) {
+          smax = fmax(smax, score);
+          if (apply && score >= thresh) {
+            BMPC_TRACE("        k %d row %d: %d -> %d score %.3e\n", k, j, cj, nj, score);
+            F(F_Y + j, kp) = ynew;
+            ++changes;
+          } else {
+            nj = cj;
+          }
+        }
         ncode |= nj << (3 * j);
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         const int ca = (code >> (3 * NR + 2 * a)) & 3;
         int na = ca;
+        real score = 0.0;
         const real u = F(F_UQ + a, kp);
         const real y = F(F_Y + NR + a, kp);
         const real utol = 1e-9 * w;
-        if (ca == IN_FREE) {
-          if (u > P.uhi[a] + tol) { na = IN_AT_HI; F(F_Y + NR + a, kp) = 0.0; }
-          else if (u < P.ulo[a] - tol) { na = IN_AT_LO; F(F_Y + NR + a, kp) = 0.0; }
+        const real stiff = F(F_RHO + NR + a, kp) / P.theta_u;
+        if (restricted) {
+        } else if (ca == IN_FREE) {
+          if (u > P.uhi[a] + tol) { na = IN_AT_HI; score = stiff * (u - P.uhi[a]); }
+          else if (u < P.ulo[a] - tol) { na = IN_AT_LO; score = stiff * (P.ulo[a] - u); }
         } else if (ca == IN_AT_HI) {
-          if (y < -utol) { na = IN_FREE; F(F_Y + NR + a, kp) = 0.0; }
+          if (y < -utol) { na = IN_FREE; score = -y; }
         } else {
-          if (y > utol) { na = IN_FREE; F(F_Y + NR + a, kp) = 0.0; }
+          if (y > utol) { na = IN_FREE; score = y; }
         }
-        changes += (na != ca);
+        if (na != ca) {
+          smax = fmax(smax, score);
+          if (apply && score >= thresh) {
+            BMPC_TRACE("        k %d input %d: %d -> %d score %.3e\n", k, a, ca, na, score);
+            F(F_Y + NR + a, kp) = 0.0;
+            ++changes;
+          } else {
+            na = ca;
+          }
+        }
         ncode |= na << (3 * NR + 2 * a);
       }
-      st[kp] = ncode;
+      if (apply) st[kp] = ncode;
     }
     lanes_sync();
+    score_max = smax;
     return changes;
   }
 
@@ -1038,29 +1075,51 @@ struct Solver {
   // unchanged while the equality residual falls below 1e-7 is the verified optimum.  Conflicting guesses
   // (e.g. the collision rows of sibling branches, which see the same position one step after the branching
   // point) show up as multipliers running past their bounds and are revised without waiting for convergence.
-  BMPC_DN bool polish(int& nfact) {
+  BMPC_DN bool polish(int& nfact, bool allow_careful) {
     polish_guess();
     int prev_changes = 1 << 30;
-    for (int pass = 0; pass < P.polish_passes; ++pass) {
+    bool careful = false;
+    const int max_passes = P.polish_passes + P.polish_careful;
+    for (int pass = 0; pass < max_passes; ++pass) {
+      if (!careful && pass >= P.polish_passes) return false;
       factorize(FACT_POLISH);
       ++nfact;
-      real res = 1.0;
+      real res = 1.0, prev = 1e300;
+      bool stalled = false;
       int al = 0;
-      for (;;) {
-        for (int chunk = 0; chunk < 3 && al < P.polish_al_iters; ++chunk, ++al) {
-          polish_assemble();
-          backward();
-          forward();
-          res = lanes_max(polish_multipliers());
-          if (res < 1e-9) break;
+      for (; al < P.polish_al_iters; ++al) {
+        polish_assemble();
+        backward();
+        forward();
+        res = lanes_max(polish_multipliers());
+        if (res < 1e-9) break;
+        if (al >= 3 && res > 0.5 * prev) { stalled = true; break; }   // not contracting: conflicting or very weak set
+        prev = res;
+      }
+      const bool settled = res < 1e-7;
+      if (!(res < 1e-1)) return false;              // far from any consistent set (also catches NaN)
+      // Set decisions need multipliers that are accurate (error ~ penalty x residual); a stalled refinement only
+      // revises kink rows whose multipliers have plainly left their range.
+      real smax = 0.0;
+      int changes;
+      if (careful && settled) {
+        // one change at a time (the classical active-set rule): the most violated condition only
+        polish_update_sets(false, 0.0, false, smax);
+        smax = lanes_max(smax);
+        changes = lanes_sum_int(polish_update_sets(false, smax * (1.0 - 1e-12), true, smax));
+      } else {
+        changes = lanes_sum_int(polish_update_sets(!settled, -1.0, true, smax));
+      }
+      BMPC_TRACE("    polish pass %d: al %d res %.2e stalled %d careful %d changes %d\n", pass, al, res, (int)stalled,
+                 (int)careful, changes);
+      if (changes == 0) return settled;
+      if (settled && !careful) {
+        // the all-at-once primal-dual iteration is not contracting: fall back to one change per pass
+        if (changes > prev_changes) {
+          if (!allow_careful || P.polish_careful <= 0) return false;
+          careful = true;
         }
-        const int changes = lanes_sum_int(polish_update_sets());
-        BMPC_TRACE("    polish pass %d: al %d res %.2e changes %d\n", pass, al, res, changes);
-        if (!(res < 1e-1)) return false;            // far from any consistent set (also catches NaN)
-        if (changes > prev_changes) return false;   // the active-set iteration is diverging: back to ADMM
-        if (changes > 0) { prev_changes = changes; break; }   // revised sets: refactorise
-        if (res < 1e-7) return true;
-        if (al >= P.polish_al_iters) return false;  // consistent but too weakly controlled to settle
+        prev_changes = changes;
       }
     }
     return false;
@@ -1225,7 +1284,7 @@ struct Solver {
       if (iters >= next_polish || conv) {
         next_polish = iters + polish_gap;
         polish_gap *= 2;   // back off: a problem whose active set is slow to settle should not pay for many attempts
-        if (polish(nfact)) {
+        if (polish(nfact, iters >= 4 * P.polish_first)) {
           status = BMPC_STATUS_POLISHED;
           have_xu = true;
           break;

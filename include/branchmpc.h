@@ -100,10 +100,11 @@ typedef struct bmpc_config {
 
   /* solver knobs (0 = library default) */
   int32_t max_iter;        /* ADMM iteration cap (default 400)                                   */
-  int32_t polish_first;    /* first polish attempt after this many iterations (30)               */
-  int32_t polish_every;    /* then every this many iterations (20)                               */
+  int32_t polish_first;    /* first polish attempt after this many iterations (10)               */
+  int32_t polish_every;    /* then this many later, doubling after each failed attempt (10)                          */
   int32_t polish_passes;   /* active-set passes per polish attempt (8)                           */
   int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (24)                     */
+  int32_t polish_careful;  /* extra one-change-at-a-time passes when the set iteration cycles (12; <0 = off) */
   int32_t warm_polish;     /* 1: on warm solves try a polish before the first ADMM iteration     */
   double alpha;            /* over-relaxation (1.6)                                              */
   double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */
