@@ -54,3 +54,38 @@ def euler_highway(x, u, dt=0.1):
     out[:, 2] += dt * u[:, 0]
     out[:, 3] += dt * u[:, 1]
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# quadruped (main_quadruped.py:14-41, Init_MPC.initquadBranchMPC :74-94)
+# ------------------------------------------------------------------------------------------------------------
+def quadruped_config(NB=2, N=25, v0=0.2, vxm=0.2, vym=0.1, rm=0.5, batch_capacity=1, device=0,
+                     controller=abi.CTRL_PROX, **knobs):
+    pol = [(abi.POLICY_FORWARD, [v0, 0, 0, 0]), (abi.POLICY_STOP, [0, 0, 0, 0])]
+    spec = config.quadruped_spec(N, 0.2, pol, 0.5, 1.0, 0.2, 2.0)
+    Fu = np.kron(np.eye(3), np.array([1., -1.])).T
+    bu = np.array([vxm, 0., vym, vym, rm, rm])
+    return config.make_config(spec, 3, 3, N, NB, np.eye(3), np.diag([1., 100., 1.]), np.empty((0, 3)), np.empty(0), Fu, bu,
+                              np.array([0., 300.]), controller=controller, dR=np.array([0.9, 5., 1.]),
+                              batch_capacity=batch_capacity, device=device, **knobs)
+
+
+def quadruped_batch(count, seed=1238, goal=(5.0, -3.0, 0.0)):
+    """ego near the origin, obstacle 1-4 m away at a random bearing (quadruped_env.py:58), goal as xRef."""
+    rng = np.random.default_rng(seed)
+    x0 = np.column_stack([rng.uniform(-1, 1, count), rng.uniform(-1, 1, count), rng.uniform(-np.pi, np.pi, count)])
+    dist, bearing = rng.uniform(1, 4, count), rng.uniform(-np.pi, np.pi, count)
+    z0 = np.column_stack([x0[:, 0] + dist * np.cos(bearing), x0[:, 1] + dist * np.sin(bearing),
+                          rng.uniform(-np.pi, np.pi, count)])
+    xref = np.tile(np.asarray(goal, dtype=float), (count, 1))
+    return x0, z0, xref
+
+
+def euler_quadruped(x, u, dt=0.2):
+    """robot plant (quadruped_env.py:24-40), batched."""
+    out = np.array(x, dtype=float, copy=True)
+    c, s = np.cos(x[:, 2]), np.sin(x[:, 2])
+    out[:, 0] += dt * (u[:, 0] * c - u[:, 1] * s)
+    out[:, 1] += dt * (u[:, 0] * s + u[:, 1] * c)
+    out[:, 2] += dt * u[:, 2]
+    return out

@@ -200,12 +200,17 @@ static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStrea
   return BMPC_OK;
 }
 
-#define BMPC_DISPATCH(h, fn, ...)                                                        \
+#define BMPC_DISPATCH_M(h, fn, HW, QD, ...)                                              \
   ((h)->cfg.model == BMPC_MODEL_HIGHWAY                                                  \
-       ? ((h)->cfg.n_rows == 0 ? fn<HighwayModel, 1>(__VA_ARGS__)                        \
-                               : (h)->cfg.n_rows == 1 ? fn<HighwayModel, 2>(__VA_ARGS__) \
-                                                      : fn<HighwayModel, 3>(__VA_ARGS__)) \
-       : fn<QuadrupedModel, 1>(__VA_ARGS__))
+       ? ((h)->cfg.n_rows == 0 ? fn<HW, 1>(__VA_ARGS__)                                  \
+                               : (h)->cfg.n_rows == 1 ? fn<HW, 2>(__VA_ARGS__)           \
+                                                      : fn<HW, 3>(__VA_ARGS__))          \
+       : fn<QD, 1>(__VA_ARGS__))
+// BranchMPCProx carries the previous input through the Riccati state (RateAug); BranchMPC does not need to.
+#define BMPC_DISPATCH(h, fn, ...)                                                                       \
+  ((h)->cfg.controller == BMPC_CTRL_PROX                                                                \
+       ? BMPC_DISPATCH_M(h, fn, RateAug<HighwayModel>, RateAug<QuadrupedModel>, __VA_ARGS__)            \
+       : BMPC_DISPATCH_M(h, fn, HighwayModel, QuadrupedModel, __VA_ARGS__))
 
 static void free_handle(bmpc_handle* h) {
   if (!h) return;

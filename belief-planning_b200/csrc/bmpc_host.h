@@ -31,8 +31,8 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   if (c.m < 1 || c.m > BMPC_MAX_POLICIES) { *err = "m must be in [1, BMPC_MAX_POLICIES]"; return BMPC_E_INVALID; }
   if (!(c.dt > 0.0)) { *err = "dt must be positive"; return BMPC_E_INVALID; }
   if (c.n_rows < 0 || c.n_rows > BMPC_MAX_ROWS) { *err = "n_rows out of range"; return BMPC_E_INVALID; }
-  if (c.controller != BMPC_CTRL_BRANCH) {
-    *err = "controller kind not built yet (BRANCH only)";
+  if (c.controller != BMPC_CTRL_BRANCH && c.controller != BMPC_CTRL_PROX) {
+    *err = "controller kind not built yet (BRANCH and PROX only)";
     return BMPC_E_UNSUPPORTED;
   }
   if (c.Qslack[0] != 0.0) { *err = "quadratic slack weight Qslack[0] must be 0 (the reference uses 0)"; return BMPC_E_UNSUPPORTED; }
@@ -103,6 +103,8 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.eps_abs = c.eps_abs > 0.0 ? c.eps_abs : 1.0e-6;
   P.polish_big = c.polish_big > 0.0 ? c.polish_big : 1.0e4;
   P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e4;
+  P.rho_u_feedback = 1.0;
+  P.rebalance = c.reserved[0] == 1 ? 0 : 1;   // experimental switch
   *out = P;
   return BMPC_OK;
 }

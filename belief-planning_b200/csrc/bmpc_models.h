@@ -40,7 +40,9 @@ BMPC_D real sgn(real v) { return (v > 0) - (v < 0); }
 // Highway: x = (x, y, v, psi), u = (a, r).   highway_branch_dyn.py
 // ------------------------------------------------------------------------------------------
 struct HighwayModel {
-  static constexpr int NX = 4;
+  static constexpr int NX = 4;    // Riccati state dimension
+  static constexpr int NXP = 4;   // physical state dimension
+  static constexpr bool RATE = false;
   static constexpr int NU = 2;
   static constexpr int NLIN = 4;  // dt*cos, -dt*v*sin, dt*sin, dt*v*cos  (the four non-trivial entries of A)
   static constexpr int NCC = 2;   // C has two non-zero entries
@@ -199,6 +201,8 @@ struct HighwayModel {
 // ------------------------------------------------------------------------------------------
 struct QuadrupedModel {
   static constexpr int NX = 3;
+  static constexpr int NXP = 3;
+  static constexpr bool RATE = false;
   static constexpr int NU = 3;
   static constexpr int NLIN = 4;  // dt*cos, dt*sin, A[0][2], A[1][2]
   static constexpr int NCC = 2;
@@ -300,4 +304,73 @@ struct QuadrupedModel {
   // exp(s1*hi), shifted by the group maximum (normalisation cancels the shift) (:211-216)
   BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return exp(P.s1 * (hi - himax)); }
   static constexpr bool kWeightNeedsMax = true;
+};
+
+// ------------------------------------------------------------------------------------------
+// Input-rate costs (BranchMPCProx, MPC_branch.py:280-297) couple consecutive inputs.  The Riccati recursion carries the
+// previous input as extra state: xi = (x, v), v_{k+1} = u_k, i.e. A~ = [A 0; 0 0], B~ = [B; I], C~ = [C; 0].  This
+// wrapper presents a physical model M in that augmented form; everything that concerns the physical state (rollouts,
+// collision, policies, linearisation data) is forwarded unchanged.
+// ------------------------------------------------------------------------------------------
+template <class M>
+struct RateAug {
+  static constexpr int NXP = M::NXP;
+  static constexpr int NU = M::NU;
+  static constexpr int NX = M::NXP + M::NU;
+  static constexpr int NLIN = M::NLIN;
+  static constexpr int NCC = M::NCC;
+  static constexpr bool RATE = true;
+
+  BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) { M::step(P, x, u, xn); }
+  BMPC_D static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) { M::policy(P, kind, par, x, u); }
+  BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
+    M::linearize(P, x, u, lin, cc, xn);
+  }
+  BMPC_D static void mulA(const KParams& P, const real* lin, const real* x, real* y) {
+    M::mulA(P, lin, x, y);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) y[NXP + a] = 0.0;
+  }
+  BMPC_D static void mulAT(const KParams& P, const real* lin, const real* g, real* y) {
+    M::mulAT(P, lin, g, y);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) y[NXP + a] = 0.0;
+  }
+  BMPC_D static void addBu(const KParams& P, const real* lin, const real* u, real* y) {
+    M::addBu(P, lin, u, y);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) y[NXP + a] += u[a];
+  }
+  BMPC_D static void mulBT(const KParams& P, const real* lin, const real* g, real* r) {
+    M::mulBT(P, lin, g, r);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) r[a] += g[NXP + a];
+  }
+  BMPC_D static void addC(const real* cc, real* y) { M::addC(cc, y); }
+  BMPC_D static void expandC(const real* cc, real* C) {
+    M::expandC(cc, C);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) C[NXP + a] = 0.0;
+  }
+  BMPC_D static void denseA(const KParams& P, const real* lin, real* A) { M::denseA(P, lin, A); }   // physical block only
+  BMPC_D static void denseB(const KParams& P, const real* lin, real* B) {
+    real Bp[NXP * NU];
+    M::denseB(P, lin, Bp);
+#pragma unroll
+    for (int i = 0; i < NXP * NU; ++i) B[i] = Bp[i];
+#pragma unroll
+    for (int a = 0; a < NU; ++a)
+#pragma unroll
+      for (int b = 0; b < NU; ++b) B[(NXP + a) * NU + b] = (a == b) ? 1.0 : 0.0;
+  }
+  BMPC_D static void collision(const KParams& P, const real* x, const real* zxy, real& h, real& dhx, real& dhy) {
+    M::collision(P, x, zxy, h, dhx, dhy);
+  }
+  template <class Emit>
+  BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
+                                   const real* xe0, const real* z0, real* zlast, Emit emit) {
+    return M::policy_safety(P, kind, par, kind0, par0, xe0, z0, zlast, emit);
+  }
+  BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return M::branch_weight(P, hi, himax); }
+  static constexpr bool kWeightNeedsMax = M::kWeightNeedsMax;
 };

@@ -25,8 +25,8 @@ struct KParams {
   real rf[BMPC_MAX_ROWS][BMPC_MAX_N], rlo[BMPC_MAX_ROWS], rhi[BMPC_MAX_ROWS];
   real ulo[BMPC_MAX_D], uhi[BMPC_MAX_D];
   // ---- solver ----
-  int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish;
-  real alpha, theta, theta_u, eps_abs, polish_big, polish_mult;
+  int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance;
+  real alpha, theta, theta_u, eps_abs, polish_big, polish_mult, rho_u_feedback;
   // ---- batch ----
   int count;
   const real* x0;

@@ -37,14 +37,16 @@ BMPC_D real row_dual(real sh, real rlo, real rhi, real lam) {
 
 template <class M, int NR>
 struct Solver {
-  static constexpr int NX = M::NX, NU = M::NU;
+  static constexpr int NX = M::NX, NU = M::NU;   // Riccati state (physical, or physical + previous input) / input
+  static constexpr int NXP = M::NXP;             // physical state dimension
+  static constexpr bool RATE = M::RATE;          // input-rate costs carried through the augmented state
   static constexpr int NS = NX * (NX + 1) / 2;
   static constexpr int NSU = NU * (NU + 1) / 2;
   // field offsets (each field is one real per padded node)
   static constexpr int F_LIN = 0;
   static constexpr int F_CC = F_LIN + M::NLIN;
   static constexpr int F_Q = F_CC + M::NCC;
-  static constexpr int F_FC = F_Q + NX;      // collision row f (x,y components); holds the obstacle (x,y) before setup
+  static constexpr int F_FC = F_Q + NXP;     // collision row f (x,y components); holds the obstacle (x,y) before setup
   static constexpr int F_HC = F_FC + 2;      // collision row upper bound
   static constexpr int F_RHO = F_HC + 1;     // rho of the NR soft rows then of the NU inputs
   static constexpr int F_K = F_RHO + NR + NU;
@@ -71,6 +73,7 @@ struct Solver {
   real* EXZ;
   real* EXX;
   int lane, nup, prob;
+  real gap_r, stp_r, gap_u, stp_u;   // last residual check: max primal gap |f'x - v| and max step |v+ - v| (rows / inputs)
   int nsolve;   // KKT solves (one backward + one forward sweep each) of the current problem
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
@@ -107,16 +110,16 @@ struct Solver {
     for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
 #pragma unroll
     for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
-    const real* xref = P.xref + (size_t)prob * NX;
+    const real* xref = P.xref + (size_t)prob * NXP;
     // linear state cost -2 w (xRef' Q° + xbar' dQ): Q° = Qf on the last node of a leaf branch of BranchMPC (:1095)
     const real* Ql = (leaf_last && P.ctrl == BMPC_CTRL_BRANCH) ? P.Qf : P.Q;
 #pragma unroll
-    for (int j = 0; j < NX; ++j) {
+    for (int j = 0; j < NXP; ++j) {
       real a = 0.0, c = 0.0;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        a += xref[i] * Ql[i * NX + j];
-        c += xbar[i] * P.Q[i * NX + j];
+      for (int i = 0; i < NXP; ++i) {
+        a += xref[i] * Ql[i * NXP + j];
+        c += xbar[i] * P.Q[i * NXP + j];
       }
       F(F_Q + j, kp) = -2.0 * w * (a + P.dq_scale * c);
     }
@@ -135,15 +138,15 @@ struct Solver {
     for (int j = 1; j < NR; ++j) {
       real v = 0.0;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v += P.rf[j - 1][i] * xbar[i];
+      for (int i = 0; i < NXP; ++i) v += P.rf[j - 1][i] * xbar[i];
       F(F_S + j, kp) = bmpc_clamp(v, P.rlo[j - 1], P.rhi[j - 1]);
     }
 #pragma unroll
     for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ubar[a], P.ulo[a], P.uhi[a]);
     if (P.out.xLin) {
-      real* o = P.out.xLin + ((size_t)prob * P.totalu + (bmpc_ndu(P, b) + t)) * NX;
+      real* o = P.out.xLin + ((size_t)prob * P.totalu + (bmpc_ndu(P, b) + t)) * NXP;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) o[i] = xbar[i];
+      for (int i = 0; i < NXP; ++i) o[i] = xbar[i];
     }
   }
 
@@ -151,12 +154,12 @@ struct Solver {
     const int started = P.started[prob];
     const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     int* pbest = P.pbest + (size_t)prob * P.nbranch;
-    const real* x0 = P.x0 + (size_t)prob * NX;
-    const real* z0 = P.z0 + (size_t)prob * NX;
+    const real* x0 = P.x0 + (size_t)prob * NXP;
+    const real* z0 = P.z0 + (size_t)prob * NXP;
     if (lane == 0) {
-      real ub[NU], xb[NX], xn[NX];
+      real ub[NU], xb[NXP], xn[NXP];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) xb[i] = x0[i];
+      for (int i = 0; i < NXP; ++i) xb[i] = x0[i];
       // root input: previous first input of the most likely child (updatetree :1029-1031); zero on the first solve
       const int best = started ? pbest[0] : 0;
       const int kbest = bmpc_ndu(P, bmpc_first_child(P, 0, 0) + best);
@@ -167,13 +170,13 @@ struct Solver {
       F(F_FC + 1, kp) = z0[1];
       Wb[0] = 1.0;
       if (P.out.zPred) {
-        real* o = P.out.zPred + (size_t)prob * P.totalu * NX;
+        real* o = P.out.zPred + (size_t)prob * P.totalu * NXP;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) o[i] = z0[i];
+        for (int i = 0; i < NXP; ++i) o[i] = z0[i];
       }
       node_setup(0, 0, xb, ub, 1.0, false, xn);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
+      for (int i = 0; i < NXP; ++i) {
         EXL[i] = xb[i];
         EXZ[i] = z0[i];
         EXX[i] = xn[i];
@@ -188,21 +191,21 @@ struct Solver {
         const int b = P.off[d] + idx / m;
         const int i = idx % m;
         const int c = bmpc_first_child(P, b, d) + i;
-        real zl[NX];
+        real zl[NXP];
         const int kc = bmpc_ndu(P, c);
         const int kpc = kp_of(c, 0);
-        real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NX : nullptr;
+        real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NXP : nullptr;
         const real hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXL + (size_t)NX * b,
                                          EXZ + (size_t)NX * b, zl, [&](int t, const real* z) {
                                            F(F_FC, kpc + t) = z[0];
                                            F(F_FC + 1, kpc + t) = z[1];
                                            if (zout) {
 #pragma unroll
-                                             for (int q = 0; q < NX; ++q) zout[t * NX + q] = z[q];
+                                             for (int q = 0; q < NXP; ++q) zout[t * NXP + q] = z[q];
                                            }
                                          });
 #pragma unroll
-        for (int q = 0; q < NX; ++q) EXZ[(size_t)NX * c + q] = zl[q];
+        for (int q = 0; q < NXP; ++q) EXZ[(size_t)NX * c + q] = zl[q];
         EX[(size_t)NS * c] = hi;   // exchange slot: safety value of child c
       }
       lanes_sync();
@@ -238,23 +241,23 @@ struct Solver {
         } else {
           klast = bmpc_ndu(P, bmpc_first_child(P, c, d + 1) + (started ? pbest[c] : 0));
         }
-        real xb[NX], xn[NX], ub[NU];
+        real xb[NXP], xn[NXP], ub[NU];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) xb[i] = EXX[(size_t)NX * b + i];
+        for (int i = 0; i < NXP; ++i) xb[i] = EXX[(size_t)NX * b + i];
         for (int t = 0; t < P.N; ++t) {
           const int ksrc = (t < P.N - 1) ? kc + t + 1 : klast;
 #pragma unroll
           for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[ksrc * NU + a] : 0.0;
           if (t == P.N - 1) {
 #pragma unroll
-            for (int i = 0; i < NX; ++i) EXL[(size_t)NX * c + i] = xb[i];
+            for (int i = 0; i < NXP; ++i) EXL[(size_t)NX * c + i] = xb[i];
           }
           node_setup(c, t, xb, ub, w, leaf && t == P.N - 1, xn);
 #pragma unroll
-          for (int i = 0; i < NX; ++i) xb[i] = xn[i];
+          for (int i = 0; i < NXP; ++i) xb[i] = xn[i];
         }
 #pragma unroll
-        for (int i = 0; i < NX; ++i) EXX[(size_t)NX * c + i] = xb[i];
+        for (int i = 0; i < NXP; ++i) EXX[(size_t)NX * c + i] = xb[i];
       }
       lanes_sync();
       // commit the new arg-max children of this level (their old values are no longer needed)
@@ -317,15 +320,18 @@ struct Solver {
     }
   }
 
+  // fixed-input helpers of the polish: value of input a when the active-set code pins it to a bound, else 0
+  BMPC_D real pinned_value(int code, int a) {
+    const int ca = (code >> (3 * NR + 2 * a)) & 3;
+    return ca == IN_AT_HI ? P.uhi[a] : (ca == IN_AT_LO ? P.ulo[a] : 0.0);
+  }
+  BMPC_D bool pinned(int code, int a) { return ((code >> (3 * NR + 2 * a)) & 3) != IN_FREE; }
+
   // Stiff penalty of a guessed-active row in the polish: polish_mult times the row's curvature-matched stiffness
   // (rho/theta = 1/(f' Sigma f)), at least polish_big*w, so that every augmented-Lagrangian step contracts strongly.
   BMPC_D real big_row(int kp, int j, real w) {
     return fmin(fmax(P.polish_big * w, P.polish_mult * F(F_RHO + j, kp) / P.theta), 1.0e12 * w);
   }
-  BMPC_D real big_in(int kp, int a, real w) {
-    return fmin(fmax(P.polish_big * w, P.polish_mult * F(F_RHO + NR + a, kp) / P.theta_u), 1.0e12 * w);
-  }
-
   // penalties of the node's soft rows and inputs for the requested factorisation
   BMPC_D void penalties(int kp, real w, int mode, real* pr, real* pu) {
     if (mode == FACT_ADMM) {
@@ -348,14 +354,16 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         const int ca = (code >> (3 * NR + 2 * a)) & 3;
-        pu[a] = (ca != IN_FREE) ? big_in(kp, a, w) : 0.0;
+        pu[a] = 0.0;   // inputs at a bound are eliminated exactly (see node_factor), not penalised
       }
     }
   }
 
   // one backward Riccati step; Pn (full NX x NX, symmetric) is the successor value Hessian on entry
   // and this node's on exit
-  BMPC_D void node_factor(int kp, real w, real* Pn, int mode) {
+  // rate = weight of the input-rate pair (previous input, this input), sig = 0 where the reference drops the pair's
+  // own-input term (leaf last node, MPC_branch.py:303), root = the root-input quirks apply (:311-312)
+  BMPC_D void node_factor(int kp, real w, real* Pn, int mode, real rate, real sig, bool root) {
     real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -363,10 +371,17 @@ struct Solver {
     for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
     real pr[NR], pu[NU];
     penalties(kp, w, mode, pr, pu);
-    // h0 = P+ C
+    // h0 = P+ C  (polish: C + B u_pinned, the inputs held at their bounds act as a known offset of the dynamics)
+    const int pcode = (mode == FACT_POLISH) ? st[kp] : 0;
     {
       real C[NX];
       M::expandC(cc, C);
+      if (mode == FACT_POLISH) {
+        real up[NU];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) up[a] = pinned_value(pcode, a);
+        M::addBu(P, lin, up, C);
+      }
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         real a = 0.0;
@@ -404,9 +419,38 @@ struct Solver {
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) S[a * NU + a] += pu[a];
+      if (RATE) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a) S[a * NU + a] += 2.0 * rate * sig * P.dR[a];
+        if (root) {
+          // Hu[0:d,0:d] += dR broadcasts the vector over the rows (:312); OSQP keeps the upper triangle
+#pragma unroll
+          for (int a = 0; a < NU; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < NU; ++b2) S[a * NU + b2] += 2.0 * P.dR[a > b2 ? a : b2];
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) G[a * NX + NXP + a] += -2.0 * rate * P.dR[a];   // cross term previous input x input
+      }
     }
     real Si[NU * NU];
+    if (mode == FACT_POLISH) {
+      // inverse on the free inputs only: pinned rows/columns are cut out (K and kff vanish there)
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        if (pinned(pcode, a)) {
+#pragma unroll
+          for (int b2 = 0; b2 < NU; ++b2) { S[a * NU + b2] = 0.0; S[b2 * NU + a] = 0.0; }
+          S[a * NU + a] = 1.0;
+        }
+      }
+    }
     invert_spd(S, Si);
+    if (mode == FACT_POLISH) {
+#pragma unroll
+      for (int a = 0; a < NU; ++a)
+        if (pinned(pcode, a)) Si[a * NU + a] = 0.0;
+    }
     {
       int q = 0;
 #pragma unroll
@@ -436,7 +480,9 @@ struct Solver {
       M::mulAT(P, lin, col, o);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        real v = o[i] + qs * (P.Q[i * NX + j] + P.Q[j * NX + i]);
+        real v = o[i];
+        if (i < NXP && j < NXP) v += qs * (P.Q[i * NXP + j] + P.Q[j * NXP + i]);
+        if (RATE && i == j && i >= NXP) v += 2.0 * rate * P.dR[i - NXP];
 #pragma unroll
         for (int a = 0; a < NU; ++a) v -= G[a * NX + i] * K[a * NX + j];
         Pnew[i * NX + j] = v;
@@ -452,9 +498,9 @@ struct Solver {
 #pragma unroll
       for (int j = 1; j < NR; ++j)
 #pragma unroll
-        for (int i = 0; i < NX; ++i)
+        for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NX; ++i2) Pnew[i * NX + i2] += pr[j] * P.rf[j - 1][i] * P.rf[j - 1][i2];
+          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * P.rf[j - 1][i] * P.rf[j - 1][i2];
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i)
@@ -483,11 +529,13 @@ struct Solver {
 #pragma unroll
           for (int i = 0; i < NX; ++i)
 #pragma unroll
-            for (int j = 0; j < NX; ++j) Pn[i * NX + j] = w * (P.Qf[i * NX + j] + P.Qf[j * NX + i]);
+            for (int j = 0; j < NX; ++j)
+              Pn[i * NX + j] = (i < NXP && j < NXP) ? w * (P.Qf[i * NXP + j] + P.Qf[j * NXP + i]) : 0.0;
         } else {
           sum_children(b, d, Pn);
         }
-        for (int t = P.N - 1; t >= 0; --t) node_factor(kp_of(b, t), w, Pn, mode);
+        for (int t = P.N - 1; t >= 0; --t)
+          node_factor(kp_of(b, t), w, Pn, mode, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0, false);
         pack_sym(Pn, EX + (size_t)NS * b);
       }
       lanes_sync();
@@ -495,7 +543,7 @@ struct Solver {
     if (lane == 0) {
       real Pn[NX * NX];
       sum_children(0, 0, Pn);
-      node_factor(kp_of(0, 0), 1.0, Pn, mode);
+      node_factor(kp_of(0, 0), 1.0, Pn, mode, 0.0, 1.0, true);
     }
     lanes_sync();
   }
@@ -534,9 +582,9 @@ struct Solver {
       for (int j = 1; j < NR; ++j) {
         real q = 0.0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i)
+        for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NX; ++i2) q += P.rf[j - 1][i] * P.rf[j - 1][i2] * Sg[i * NX + i2];
+          for (int i2 = 0; i2 < NXP; ++i2) q += P.rf[j - 1][i] * P.rf[j - 1][i2] * Sg[i * NX + i2];
         const real rj = (q > 1e-12) ? fmin(P.theta / q, rho_max) : 0.0;
         F(F_RHO + j, kp) = rj;
         F(F_S + j, kp) *= rj;
@@ -550,7 +598,7 @@ struct Solver {
         real ks = 0.0;
 #pragma unroll
         for (int i2 = 0; i2 < NX; ++i2) ks += K[a * NX + i2] * Sg[i2 * NX + i];
-        var += ks * K[a * NX + i];
+        var += P.rho_u_feedback * ks * K[a * NX + i];
       }
       const real ra = fmin(P.theta_u / var, rho_max);
       F(F_RHO + NR + a, kp) = ra;
@@ -673,7 +721,19 @@ struct Solver {
         real pn[NX];
         if (d == P.NB) {
 #pragma unroll
-          for (int i = 0; i < NX; ++i) pn[i] = 0.0;   // terminal node: no linear term (MPC_branch.py:1094)
+          for (int i = 0; i < NX; ++i) pn[i] = 0.0;   // BranchMPC terminal node: no linear term (MPC_branch.py:1094)
+          if (P.ctrl == BMPC_CTRL_PROX) {
+            // BranchMPCProx: -2 w xRef' Qf (:308)
+            const real* xref = P.xref + (size_t)prob * NXP;
+            const real w = Wb[b];
+#pragma unroll
+            for (int j = 0; j < NXP; ++j) {
+              real a = 0.0;
+#pragma unroll
+              for (int i = 0; i < NXP; ++i) a += xref[i] * P.Qf[i * NXP + j];
+              pn[j] = -2.0 * w * a;
+            }
+          }
         } else {
           const int fc = bmpc_first_child(P, b, d);
 #pragma unroll
@@ -730,7 +790,7 @@ struct Solver {
     if (lane == 0) {
       real x[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = P.x0[(size_t)prob * NX + i];
+      for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
       fw_step(kp_of(0, 0), x);
 #pragma unroll
       for (int i = 0; i < NX; ++i) EXX[i] = x[i];
@@ -759,7 +819,7 @@ struct Solver {
     if (j == 0) return F(F_FC, kp) * x[0] + F(F_FC + 1, kp) * x[1];
     real v = 0.0;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) v += P.rf[j - 1][i] * x[i];
+    for (int i = 0; i < NXP; ++i) v += P.rf[j - 1][i] * x[i];
     return v;
   }
   BMPC_D void row_bounds(int kp, int j, real& lo, real& hi) {
@@ -771,7 +831,7 @@ struct Solver {
       qx[1] += F(F_FC + 1, kp) * gcoef;
     } else {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) qx[i] += P.rf[j - 1][i] * gcoef;
+      for (int i = 0; i < NXP; ++i) qx[i] += P.rf[j - 1][i] * gcoef;
     }
   }
 
@@ -780,6 +840,7 @@ struct Solver {
   template <bool UPDATE, bool CHECK>
   BMPC_D real admm_rows() {
     real res = 0.0;
+    if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; }
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -788,7 +849,7 @@ struct Solver {
       const real lam = P.lam_lin * w;
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = F(F_Q + i, kp); }
+      for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0; }
 #pragma unroll
       for (int a = 0; a < NU; ++a) { u[a] = F(F_UQ + a, kp); qu[a] = (k == 0) ? rlin : 0.0; }
 #pragma unroll
@@ -808,6 +869,9 @@ struct Solver {
             if (CHECK) {
               const real rvn = shn - yn;
               res = fmax(res, fmax(fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
+              gap_r = fmax(gap_r, fabs(rfx - rvn) / rho);
+              stp_r = fmax(stp_r, fabs(rvn - rv) / rho);
+              if (fabs(rfx - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [row] k %d j %d rho %.3e prim %.3e dual %.3e fx %.4f hi %.4f w %.3e\n", k, j, rho, fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w), rfx / rho, hi, w);
             }
             F(F_S + j, kp) = shn;
             sh = shn;
@@ -825,7 +889,12 @@ struct Solver {
           const real ru = rho * u[a];
           const real shn = P.alpha * ru + (1.0 - P.alpha) * rv + (sh - rv);
           const real rvn = bmpc_clamp(shn, rho * P.ulo[a], rho * P.uhi[a]);
-          if (CHECK) res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
+          if (CHECK) {
+            res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
+            gap_u = fmax(gap_u, fabs(ru - rvn) / rho);
+            stp_u = fmax(stp_u, fabs(rvn - rv) / rho);
+            if (fabs(ru - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [in] k %d a %d rho %.3e prim %.3e dual %.3e u %.4f w %.3e\n", k, a, rho, fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w), u[a], w);
+          }
           F(F_SU + a, kp) = shn;
           sh = shn;
           rv = rvn;
@@ -839,6 +908,50 @@ struct Solver {
     }
     lanes_sync();
     return res;
+  }
+
+  // Residual balancing (Boyd et al. 2011, 3.4.1) on top of the curvature-matched rho: with rho in matched units the
+  // primal gap |f'x - v| and the step |v+ - v| are commensurable; when one dominates, the whole group (state rows /
+  // inputs) is rescaled.  The ADMM state (v, y) is kept: sh' = s (sh - y) + y.  The caller refactorises.
+  BMPC_DN bool rebalance_rho() {
+    const real gr = lanes_max(gap_r), sr = lanes_max(stp_r), gu = lanes_max(gap_u), su = lanes_max(stp_u);
+    real fr = sqrt(gr / fmax(sr, 1e-30)), fu = sqrt(gu / fmax(su, 1e-30));
+    fr = (gr > 1e-9 || sr > 1e-9) ? bmpc_clamp(fr, 0.2, 5.0) : 1.0;
+    fu = (gu > 1e-9 || su > 1e-9) ? bmpc_clamp(fu, 0.2, 5.0) : 1.0;
+    if (fr > 0.5 && fr < 2.0) fr = 1.0;
+    if (fu > 0.5 && fu < 2.0) fu = 1.0;
+    BMPC_TRACE("    rebalance: rows gap %.2e step %.2e -> x%.2f   inputs gap %.2e step %.2e -> x%.2f\n", gr, sr, fr, gu, su, fu);
+    if (fr == 1.0 && fu == 1.0) return false;
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real lam = P.lam_lin * Wb[b];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const real rho = F(F_RHO + j, kp);
+        if (rho > 0.0 && fr != 1.0) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real sh = F(F_S + j, kp);
+          const real y = row_dual(sh, rho * lo, rho * hi, lam);
+          F(F_S + j, kp) = fr * (sh - y) + y;
+          F(F_RHO + j, kp) = fr * rho;
+        }
+      }
+      if (fu != 1.0) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          const real rho = F(F_RHO + NR + a, kp);
+          const real sh = F(F_SU + a, kp);
+          const real rv = bmpc_clamp(sh, rho * P.ulo[a], rho * P.uhi[a]);
+          F(F_SU + a, kp) = fu * rv + (sh - rv);
+          F(F_RHO + NR + a, kp) = fu * rho;
+        }
+      }
+    }
+    lanes_sync();
+    return true;
   }
 
   // ========================================================================================
@@ -897,7 +1010,7 @@ struct Solver {
       const int code = st[kp];
       real qx[NX], qu[NU];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) qx[i] = F(F_Q + i, kp);
+      for (int i = 0; i < NX; ++i) qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int cj = (code >> (3 * j)) & 7;
@@ -910,13 +1023,24 @@ struct Solver {
         else if (cj == ROW_LO_KINK) g = F(F_Y + j, kp) - big_row(kp, j, w) * lo;
         if (g != 0.0) add_row_grad(kp, j, g, qx);
       }
+      // u = u_pinned + delta: the stage terms that couple delta (and the previous input) with the pinned part
+      real up[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) { up[a] = pinned_value(code, a); qu[a] = (k == 0) ? rlin : 0.0; }
+      const real rate = (k == 0) ? 0.0 : w;
+      const real sig = (b >= P.off[P.NB] && t == P.N - 1) ? 0.0 : 1.0;
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        const int ca = (code >> (3 * NR + 2 * a)) & 3;
-        real g = (k == 0) ? rlin : 0.0;
-        if (ca == IN_AT_HI) g += F(F_Y + NR + a, kp) - big_in(kp, a, w) * P.uhi[a];
-        else if (ca == IN_AT_LO) g += F(F_Y + NR + a, kp) - big_in(kp, a, w) * P.ulo[a];
-        qu[a] = g;
+#pragma unroll
+        for (int b2 = 0; b2 < NU; ++b2) {
+          real r2 = w * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
+          if (RATE && k == 0) r2 += 2.0 * P.dR[a > b2 ? a : b2];
+          qu[a] += r2 * up[b2];
+        }
+        if (RATE) {
+          qu[a] += 2.0 * rate * sig * P.dR[a] * up[a];
+          qx[NXP + (RATE ? a : 0)] += -2.0 * rate * P.dR[a] * up[a];
+        }
       }
 #pragma unroll
       for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = qx[i];
@@ -951,19 +1075,134 @@ struct Solver {
           res = fmax(res, fabs(r));
         }
       }
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        const int ca = (code >> (3 * NR + 2 * a)) & 3;
-        if (ca != IN_FREE) {
-          const real r = F(F_UQ + a, kp) - (ca == IN_AT_HI ? P.uhi[a] : P.ulo[a]);
-          if (fabs(r) > 1e-6) BMPC_TRACE("      k %d input %d code %d r %.2e y %.3e big %.2e\n", k, a, ca, r, F(F_Y + NR + a, kp), big_in(kp, a, w));
-          F(F_Y + NR + a, kp) += big_in(kp, a, w) * r;
-          res = fmax(res, fabs(r));
-        }
-      }
     }
     lanes_sync();
     return res;
+  }
+
+  // pinned inputs take their bound value after the backward sweep (their gain rows and feed-forward are zero)
+  BMPC_DN void polish_inject() {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const int code = st[kp];
+#pragma unroll
+      for (int a = 0; a < NU; ++a)
+        if (pinned(code, a)) F(F_UQ + a, kp) = pinned_value(code, a);
+    }
+    lanes_sync();
+  }
+
+  // Adjoint (costate) sweep of the equality-constrained solution in XQ/UQ: lam_k = dstage/dxi + A~' lam_{k+1}.  The
+  // multiplier of a pinned input is minus the Lagrangian gradient with respect to it; for the free inputs that
+  // gradient is zero (stationarity), whose largest violation is returned as a certificate.
+  BMPC_D real adjoint_step(int k, int b, int t, int kp, real w, real* lam) {
+    real lin[M::NLIN], x[NX], u[NU], gu[NU], st_x[NX];
+#pragma unroll
+    for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
+    const int code = st[kp];
+    const real rate = (k == 0) ? 0.0 : w;
+    const real sig = (b >= P.off[P.NB] && t == P.N - 1) ? 0.0 : 1.0;
+    M::mulBT(P, lin, lam, gu);
+    real viol = 0.0;
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      real g = gu[a] + ((k == 0) ? rlin : 0.0);
+#pragma unroll
+      for (int b2 = 0; b2 < NU; ++b2) {
+        real r2 = w * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
+        if (RATE && k == 0) r2 += 2.0 * P.dR[a > b2 ? a : b2];
+        g += r2 * u[b2];
+      }
+      if (RATE) g += 2.0 * rate * P.dR[a] * (sig * u[a] - x[NXP + (RATE ? a : 0)]);
+      if (pinned(code, a)) F(F_Y + NR + a, kp) = -g;
+      else viol = fmax(viol, fabs(g));
+    }
+    const real qs = w * (1.0 + P.dq_scale);
+    const real lamw = P.lam_lin * w;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      real v = 0.0;
+      if (i < NXP) {
+        v = F(F_Q + (i < NXP ? i : 0), kp);
+#pragma unroll
+        for (int j = 0; j < NXP; ++j) v += qs * (P.Q[(i < NXP ? i : 0) * NXP + j] + P.Q[j * NXP + (i < NXP ? i : 0)]) * x[j];
+      } else if (RATE) {
+        v = 2.0 * rate * P.dR[i - NXP] * (x[i] - u[i - NXP]);
+      }
+      st_x[i] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      const int cj = (code >> (3 * j)) & 7;
+      real g = 0.0;
+      if (cj == ROW_UP_LIN) g = lamw;
+      else if (cj == ROW_LO_LIN) g = -lamw;
+      else if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) g = F(F_Y + j, kp);
+      if (g != 0.0) add_row_grad(kp, j, g, st_x);
+    }
+    real al[NX];
+    M::mulAT(P, lin, lam, al);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) lam[i] = st_x[i] + al[i];
+    return viol;
+  }
+
+  BMPC_DN real polish_adjoint() {
+    real viol = 0.0;
+    for (int d = P.NB; d >= 1; --d) {
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+        const real w = Wb[b];
+        real lam[NX];
+        if (d == P.NB) {
+          // terminal costate: 2 w Qf x_T (BranchMPCProx: - 2 w Qf' xRef as well); x_T was left in EXX by forward()
+          const real* xT = EXX + (size_t)NX * b;
+          const real* xref = P.xref + (size_t)prob * NXP;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            real v = 0.0;
+            if (i < NXP) {
+#pragma unroll
+              for (int j = 0; j < NXP; ++j) {
+                v += w * (P.Qf[(i < NXP ? i : 0) * NXP + j] + P.Qf[j * NXP + (i < NXP ? i : 0)]) * xT[j];
+                if (P.ctrl == BMPC_CTRL_PROX) v -= 2.0 * w * P.Qf[j * NXP + (i < NXP ? i : 0)] * xref[j];
+              }
+            }
+            lam[i] = v;
+          }
+        } else {
+          const int fc = bmpc_first_child(P, b, d);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) lam[i] = EX[(size_t)NS * fc + i];
+          for (int c = 1; c < P.m; ++c)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) lam[i] += EX[(size_t)NS * (fc + c) + i];
+        }
+        const int kp0 = kp_of(b, 0);
+        const int k0 = bmpc_ndu(P, b);
+        for (int t = P.N - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(k0 + t, b, t, kp0 + t, w, lam));
+#pragma unroll
+        for (int i = 0; i < NX; ++i) EX[(size_t)NS * b + i] = lam[i];
+      }
+      lanes_sync();
+    }
+    if (lane == 0) {
+      real lam[NX];
+      const int fc = bmpc_first_child(P, 0, 0);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) lam[i] = EX[(size_t)NS * fc + i];
+      for (int c = 1; c < P.m; ++c)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam[i] += EX[(size_t)NS * (fc + c) + i];
+      viol = fmax(viol, adjoint_step(0, 0, 0, kp_of(0, 0), 1.0, lam));
+    }
+    lanes_sync();
+    return viol;
   }
 
   // Primal-dual active-set update from the last equality-constrained solve.  Every candidate change carries a score in
@@ -1090,6 +1329,7 @@ struct Solver {
       for (; al < P.polish_al_iters; ++al) {
         polish_assemble();
         backward();
+        polish_inject();
         forward();
         res = lanes_max(polish_multipliers());
         if (res < 1e-9) break;
@@ -1097,7 +1337,10 @@ struct Solver {
         prev = res;
       }
       const bool settled = res < 1e-7;
-      if (!(res < 1e-1)) return false;              // far from any consistent set (also catches NaN)
+      if (!(res < 1e30)) return false;              // non-finite data
+      const real stat = lanes_max(polish_adjoint());   // multipliers of the pinned inputs + stationarity certificate
+      BMPC_TRACE("    stationarity of the free inputs: %.2e\n", stat);
+      (void)stat;
       // Set decisions need multipliers that are accurate (error ~ penalty x residual); a stalled refinement only
       // revises kink rows whose multipliers have plainly left their range.
       real smax = 0.0;
@@ -1128,7 +1371,7 @@ struct Solver {
   // ========================================================================================
   // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
   // ========================================================================================
-  BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin) {
+  BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin, real rate, real sig) {
     const int k = bmpc_ndu(P, b) + t;
     real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
 #pragma unroll
@@ -1141,11 +1384,25 @@ struct Solver {
     real J = 0.0;
     const real qs = w * (1.0 + P.dq_scale);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) {
+    for (int i = 0; i < NXP; ++i) {
       real a = 0.0;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) a += P.Q[i * NX + j] * x[j];
+      for (int j = 0; j < NXP; ++j) a += P.Q[i * NXP + j] * x[j];
       J += qs * x[i] * a + F(F_Q + i, kp) * x[i];
+    }
+    if (RATE) {
+      // input-rate pair (previous input v = x[NXP..], this input u): rate [v'dR v - 2 v'dR u + sig u'dR u]
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real v = x[NXP + (RATE ? a : 0)];
+        J += rate * P.dR[a] * (v * v - 2.0 * v * u[a] + sig * u[a] * u[a]);
+      }
+      if (k == 0) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a)
+#pragma unroll
+          for (int b2 = 0; b2 < NU; ++b2) J += P.dR[a > b2 ? a : b2] * u[a] * u[b2];   // root quirk (:312)
+      }
     }
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
@@ -1191,16 +1448,16 @@ struct Solver {
   BMPC_DN real finish() {
     real J = 0.0;
     real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
-    real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.totalx * NX : nullptr;
+    real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.totalx * NXP : nullptr;
     if (lane == 0) {
       real x[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = P.x0[(size_t)prob * NX + i];
+      for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
       if (xP) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) xP[i] = x[i];
+        for (int i = 0; i < NXP; ++i) xP[i] = x[i];
       }
-      J += emit_node(0, 0, kp_of(0, 0), 1.0, x, uLin);
+      J += emit_node(0, 0, kp_of(0, 0), 1.0, x, uLin, 0.0, 1.0);
 #pragma unroll
       for (int i = 0; i < NX; ++i) EXX[i] = x[i];
     }
@@ -1216,21 +1473,26 @@ struct Solver {
         for (int t = 0; t < P.N; ++t) {
           if (xP) {
 #pragma unroll
-            for (int i = 0; i < NX; ++i) xP[(size_t)(kx + t) * NX + i] = x[i];
+            for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + t) * NXP + i] = x[i];
           }
-          J += emit_node(b, t, kp_of(b, t), w, x, uLin);
+          J += emit_node(b, t, kp_of(b, t), w, x, uLin, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0);
         }
         if (d == P.NB) {
           if (xP) {
 #pragma unroll
-            for (int i = 0; i < NX; ++i) xP[(size_t)(kx + P.N) * NX + i] = x[i];
+            for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + P.N) * NXP + i] = x[i];
           }
+          const real* xref = P.xref + (size_t)prob * NXP;
 #pragma unroll
-          for (int i = 0; i < NX; ++i) {
-            real a = 0.0;
+          for (int i = 0; i < NXP; ++i) {
+            real a = 0.0, c = 0.0;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) a += P.Qf[i * NX + j] * x[j];
-            J += w * x[i] * a;   // terminal x' (w Qf) x, no linear term (:1094)
+            for (int j = 0; j < NXP; ++j) {
+              a += P.Qf[i * NXP + j] * x[j];
+              c += P.Qf[j * NXP + i] * xref[j];
+            }
+            // terminal x' (w Qf) x; BranchMPC has no linear term there (:1094), BranchMPCProx has -2 w xRef' Qf (:308)
+            J += w * x[i] * a - ((P.ctrl == BMPC_CTRL_PROX) ? 2.0 * w * c * x[i] : 0.0);
           }
         }
 #pragma unroll
@@ -1290,6 +1552,7 @@ struct Solver {
           break;
         }
         if (conv) status = BMPC_STATUS_CONVERGED;
+        if (!conv && P.rebalance) rebalance_rho();
         factorize(FACT_ADMM);
         ++nfact;
         admm_rows<false, false>();

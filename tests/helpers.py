@@ -31,6 +31,10 @@ def fixture_config(g, **kw):
                                     N=int(g["meta_N"]), lc_target=tuple(g["meta_lc_target"]), **kw)
 
 
+def quadruped_fixture_config(g, **kw):
+    return scenarios.quadruped_config(NB=int(g["meta_NB"]), N=int(g["meta_N"]), v0=float(g["meta_v0"]), **kw)
+
+
 def check_fixture_closed_loop(solve, g, tol=1e-6):
     """`solve(x, z, xref) -> result dict` is called for every recorded step of a fixture; everything the reference
     produced for that step (tree data, linearisation trajectory, optimum) must be reproduced."""

@@ -53,14 +53,15 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   P.oldin = oldin;
   P.started = started;
   P.out = *out;
+  const bool prox = cfg->controller == BMPC_CTRL_PROX;
   if (cfg->model == BMPC_MODEL_HIGHWAY) {
     switch (cfg->n_rows) {
-      case 0: run<HighwayModel, 1>(P); break;
-      case 1: run<HighwayModel, 2>(P); break;
-      default: run<HighwayModel, 3>(P); break;
+      case 0: prox ? run<RateAug<HighwayModel>, 1>(P) : run<HighwayModel, 1>(P); break;
+      case 1: prox ? run<RateAug<HighwayModel>, 2>(P) : run<HighwayModel, 2>(P); break;
+      default: prox ? run<RateAug<HighwayModel>, 3>(P) : run<HighwayModel, 3>(P); break;
     }
   } else {
-    run<QuadrupedModel, 1>(P);
+    prox ? run<RateAug<QuadrupedModel>, 1>(P) : run<QuadrupedModel, 1>(P);
   }
   return BMPC_OK;
 }

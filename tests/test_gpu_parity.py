@@ -9,7 +9,7 @@ constraint violation <= 1e-5, bit-exact tree topology and branch indexing.
 import numpy as np
 import pytest
 
-from tests.helpers import (HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
+from tests.helpers import (quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
                            load_fixture, oracle_episode)
 from _bmpc import abi, scenarios
 from oracle.branch_mpc import TreeTopology
@@ -62,6 +62,24 @@ def test_fixture_closed_loop(bmpc, name):
     g = load_fixture(name)
     mpc = bmpc.BatchedBranchMPC(fixture_config(g))
     check_fixture_closed_loop(lambda x, z, r: mpc.solve_host(x, z, r), g)
+    mpc.close()
+
+
+def test_quadruped_prox_fixture_closed_loop(bmpc):
+    g = load_fixture("quadruped_prox_default")
+    mpc = bmpc.BatchedBranchMPC(quadruped_fixture_config(g))
+    assert (mpc.topology() == g["s0_tree"]).all() and [mpc.totalx, mpc.totalu] == list(g["s0_totals"])
+    check_fixture_closed_loop(lambda x, z, r: mpc.solve_host(x, z, r), g, tol=1e-5)
+    mpc.close()
+
+
+def test_quadruped_model_functions_match_reference(bmpc):
+    g = load_fixture("model_functions")
+    mpc = bmpc.BatchedBranchMPC(scenarios.quadruped_config())
+    r = mpc.eval_model(g["qd_X"], g["qd_Z"], g["qd_U"])
+    for k in ("A", "B", "C", "xp", "zpred", "p", "dh"):
+        np.testing.assert_allclose(r[k], g["qd_" + k], atol=1e-11, err_msg=k)
+    np.testing.assert_allclose(r["hlin"], g["qd_hlin"], atol=1e-10)
     mpc.close()
 
 

@@ -7,7 +7,7 @@ on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.
 import numpy as np
 import pytest
 
-from tests.helpers import (HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+from tests.helpers import (quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
                      oracle_episode)
 from _bmpc import scenarios
 from tests.hostsim.driver import HostSim
@@ -18,6 +18,14 @@ def test_fixture_closed_loop(name):
     g = load_fixture(name)
     hs = HostSim(fixture_config(g), 1)
     check_fixture_closed_loop(lambda x, z, r: hs.solve(x, z, r), g)
+
+
+def test_quadruped_prox_fixture_closed_loop():
+    """BranchMPCProx on the quadruped model (main_quadruped.py): input-rate costs through the augmented state."""
+    g = load_fixture("quadruped_prox_default")
+    hs = HostSim(quadruped_fixture_config(g), 1)
+    assert [hs.totalx, hs.totalu] == list(g["s0_totals"])
+    check_fixture_closed_loop(lambda x, z, r: hs.solve(x, z, r), g, tol=1e-5)
 
 
 def test_random_batch_against_oracle():
