@@ -11,6 +11,7 @@ MODEL_HIGHWAY, MODEL_QUADRUPED = 0, 1
 CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST = 0, 1, 2
 POLICY_MAINTAIN, POLICY_BRAKE, POLICY_LC, POLICY_TRACKV, POLICY_FORWARD, POLICY_STOP = range(6)
 STATUS_POLISHED, STATUS_CONVERGED, STATUS_MAXITER, STATUS_NUMERIC = range(4)
+SLAB_AUTO, SLAB_SHARED, SLAB_SPLIT, SLAB_GLOBAL = range(4)
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
 
 _dbl = C.c_double
@@ -35,7 +36,7 @@ class Config(C.Structure):
         ("polish_al_iters", _i32), ("polish_careful", _i32), ("warm_polish", _i32),
         ("alpha", _dbl), ("theta", _dbl), ("theta_u", _dbl), ("eps_abs", _dbl), ("polish_big", _dbl),
         ("polish_mult", _dbl),
-        ("batch_capacity", _i32), ("device", _i32), ("reserved", _i32 * 8),
+        ("slab_mode", _i32), ("batch_capacity", _i32), ("device", _i32), ("reserved", _i32 * 8),
     ]
 
 
@@ -47,7 +48,7 @@ class Outputs(C.Structure):
     """struct bmpc_outputs (device pointers for bmpc_solve, host pointers for bmpc_solve_host)"""
     _fields_ = [("u0", C.c_void_p), ("uPred", C.c_void_p), ("xPred", C.c_void_p), ("xLin", C.c_void_p),
                 ("zPred", C.c_void_p), ("branch_w", C.c_void_p), ("branch_p", C.c_void_p), ("objective", C.c_void_p),
-                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p), ("nsolve", C.c_void_p)]
+                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p), ("nsolve", C.c_void_p), ("cycles", C.c_void_p)]
 
 
 OUTPUT_NAMES = [f[0] for f in Outputs._fields_]
@@ -71,6 +72,7 @@ SYMBOLS = [
     ("bmpc_eval_model", C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 8 + [C.c_void_p]),
     ("bmpc_plant_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                   C.c_void_p]),
+    ("bmpc_get_launch_info", C.c_int, [C.c_void_p, _pi, _pi, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("bmpc_launch_count", C.c_int64, [C.c_void_p]),
     ("bmpc_measure_fp64_peak", C.c_double, [C.c_int, C.c_int]),
     ("bmpc_last_kernel_ms", C.c_float, [C.c_void_p]),

@@ -13,7 +13,7 @@ _OUT_SHAPES = {
     "u0": lambda s: (s.cfg.d,), "uPred": lambda s: (s.totalu, s.cfg.d), "xPred": lambda s: (s.totalx, s.cfg.n),
     "xLin": lambda s: (s.totalu, s.cfg.n), "zPred": lambda s: (s.totalu, s.cfg.n), "branch_w": lambda s: (s.nbranch,),
     "branch_p": lambda s: (s.nbranch, s.cfg.m), "objective": lambda s: (), "status": lambda s: (),
-    "iters": lambda s: (), "nfact": lambda s: (), "nsolve": lambda s: (),
+    "iters": lambda s: (), "nfact": lambda s: (), "nsolve": lambda s: (), "cycles": lambda s: (),
 }
 _INT_OUTPUTS = ("status", "iters", "nfact", "nsolve")
 LIGHT_OUTPUTS = ("u0", "objective", "status", "iters", "nfact", "nsolve")
@@ -79,7 +79,7 @@ class BatchedBranchMPC:
         if key not in self._dev_out:
             bufs = {}
             for k in names:
-                dt = torch.int32 if k in _INT_OUTPUTS else torch.float64
+                dt = torch.int64 if k == "cycles" else (torch.int32 if k in _INT_OUTPUTS else torch.float64)
                 bufs[k] = torch.empty((count,) + _OUT_SHAPES[k](self), dtype=dt, device=dev)
             self._dev_out = {key: bufs}          # keep only the latest shape
         return self._dev_out[key]
@@ -131,7 +131,7 @@ class BatchedBranchMPC:
             pp = np.ascontiguousarray(policy_params, dtype=np.float64).reshape(count, self.cfg.m, 4)
         res = {}
         for k in outputs:
-            dt = np.int32 if k in _INT_OUTPUTS else np.float64
+            dt = np.int64 if k == "cycles" else (np.int32 if k in _INT_OUTPUTS else np.float64)
             res[k] = np.empty((count,) + _OUT_SHAPES[k](self), dtype=dt)
         out = abi.Outputs(**{k: v.ctypes.data for k, v in res.items()})
         self._check(self.lib.bmpc_solve_host(self.h, x0.ctypes.data, z0.ctypes.data, xref.ctypes.data,
@@ -178,6 +178,13 @@ class BatchedBranchMPC:
                                              t["dh"].data_ptr(), C.c_void_p(stream)), "bmpc_eval_model")
         torch.cuda.synchronize(dev)
         return {k: v.cpu().numpy() for k, v in t.items()}
+
+    def launch_info(self):
+        mode, warps, smem, gl = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        self._check(self.lib.bmpc_get_launch_info(self.h, C.byref(mode), C.byref(warps), C.byref(smem), C.byref(gl)),
+                    "bmpc_get_launch_info")
+        return {"slab_mode": ["auto", "shared", "split", "global"][mode.value], "warps": warps.value,
+                "smem_bytes_per_warp": smem.value, "global_bytes_per_warp": gl.value}
 
     def last_kernel_ms(self):
         return float(self.lib.bmpc_last_kernel_ms(self.h))

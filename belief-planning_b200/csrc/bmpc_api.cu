@@ -16,17 +16,22 @@
 
 // Persistent warps: every warp pulls problem indices from a global counter and solves them one at a time in its
 // own slab (shared memory when it fits, global/L2 otherwise).
-template <class M, int NR, bool GWS>
+// MODE = BMPC_SLAB_SHARED (whole slab in shared memory), BMPC_SLAB_SPLIT (iterate fields in shared memory, factor fields
+// in this warp's global region, which stays L2-resident), BMPC_SLAB_GLOBAL (everything in the global region).
+template <class M, int NR, int MODE>
 __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
+  constexpr bool SPLIT = (MODE == BMPC_SLAB_SPLIT);
   real* slab;
-  if (GWS) {
+  real* factor = nullptr;
+  if (MODE == BMPC_SLAB_GLOBAL) {
     slab = P.gws + (size_t)blockIdx.x * P.slab_reals;
   } else {
     slab = reinterpret_cast<real*>(smem_raw);
+    if (SPLIT) factor = P.gws + (size_t)blockIdx.x * P.factor_reals;
   }
-  Solver<M, NR> S(P, slab, lane);
+  Solver<M, NR, SPLIT> S(P, slab, factor, lane);
   for (;;) {
     int prob = 0;
     if (lane == 0) prob = atomicAdd(P.counter, 1);
@@ -137,7 +142,8 @@ struct bmpc_handle {
   int device = 0;
   int num_sms = 0;
   size_t slab_bytes = 0;
-  bool use_gws = false;
+  int mode = BMPC_SLAB_SHARED;   // resolved BMPC_SLAB_* placement
+  size_t gws_bytes_per_warp = 0;
   int grid = 0;         // persistent warps (= blocks)
   // persistent per-episode state
   real* uLin = nullptr;
@@ -167,34 +173,69 @@ static std::string g_create_error;
     }                                                                                              \
   } while (0)
 
+template <class M, int NR, int MODE>
+static int try_mode(bmpc_handle* h, int max_optin, int* per_sm) {
+  using S = Solver<M, NR, MODE == BMPC_SLAB_SPLIT>;
+  const size_t slab = S::slab_reals(h->P.nup, h->P.nbranch) * sizeof(real);
+  const size_t smem = (MODE == BMPC_SLAB_GLOBAL) ? 0 : slab;
+  *per_sm = 0;
+  if (smem > (size_t)max_optin) return BMPC_OK;   // does not fit: caller falls through to the next mode
+  if (smem > 0)
+    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE>, 32, smem));
+  return BMPC_OK;
+}
+
 template <class M, int NR>
 static int configure_instance(bmpc_handle* h) {
-  using S = Solver<M, NR>;
-  h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
-  h->slab_bytes = h->P.slab_reals * sizeof(real);
   int max_optin = 0;
   BMPC_CK(h, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  h->use_gws = h->slab_bytes > (size_t)max_optin;
-  int per_sm = 0;
-  if (!h->use_gws) {
-    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)h->slab_bytes));
-    BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bmpc_solve_kernel<M, NR, false>, 32, h->slab_bytes));
-  } else {
-    BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bmpc_solve_kernel<M, NR, true>, 32, 0));
-    if (per_sm > 8) per_sm = 8;   // keep the global slabs of the resident warps inside L2
+  int want = h->cfg.slab_mode;
+  if (want == BMPC_SLAB_AUTO) want = BMPC_SLAB_SPLIT;
+  int per_sm = 0, rc = BMPC_OK;
+  h->mode = 0;
+  if (want == BMPC_SLAB_SHARED) {
+    rc = try_mode<M, NR, BMPC_SLAB_SHARED>(h, max_optin, &per_sm);
+    if (rc != BMPC_OK) return rc;
+    if (per_sm > 0) h->mode = BMPC_SLAB_SHARED;
   }
-  if (per_sm < 1) { h->err = "kernel does not fit on an SM"; return BMPC_E_CUDA; }
+  if (h->mode == 0 && want != BMPC_SLAB_GLOBAL) {
+    rc = try_mode<M, NR, BMPC_SLAB_SPLIT>(h, max_optin, &per_sm);
+    if (rc != BMPC_OK) return rc;
+    if (per_sm > 0) h->mode = BMPC_SLAB_SPLIT;
+  }
+  if (h->mode == 0) {
+    rc = try_mode<M, NR, BMPC_SLAB_GLOBAL>(h, max_optin, &per_sm);
+    if (rc != BMPC_OK) return rc;
+    if (per_sm > 8) per_sm = 8;   // keep the global slabs of the resident warps inside L2
+    if (per_sm > 0) h->mode = BMPC_SLAB_GLOBAL;
+  }
+  if (per_sm < 1 || h->mode == 0) { h->err = "kernel does not fit on an SM"; return BMPC_E_CUDA; }
+  if (h->cfg.reserved[1] > 0 && per_sm > h->cfg.reserved[1]) per_sm = h->cfg.reserved[1];   // occupancy cap (experiments)
   h->grid = per_sm * h->num_sms;
+  if (h->mode == BMPC_SLAB_SPLIT) {
+    using S = Solver<M, NR, true>;
+    h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
+    h->P.factor_reals = S::factor_reals(h->P.nup);
+    h->gws_bytes_per_warp = h->P.factor_reals * sizeof(real);
+  } else {
+    using S = Solver<M, NR, false>;
+    h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
+    h->P.factor_reals = 0;
+    h->gws_bytes_per_warp = (h->mode == BMPC_SLAB_GLOBAL) ? h->P.slab_reals * sizeof(real) : 0;
+  }
+  h->slab_bytes = (h->mode == BMPC_SLAB_GLOBAL) ? 0 : h->P.slab_reals * sizeof(real);
   return BMPC_OK;
 }
 
 template <class M, int NR>
 static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStream_t s) {
-  if (h->use_gws) {
-    bmpc_solve_kernel<M, NR, true><<<grid, 32, 0, s>>>(P);
+  if (h->mode == BMPC_SLAB_SHARED) {
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED><<<grid, 32, h->slab_bytes, s>>>(P);
+  } else if (h->mode == BMPC_SLAB_SPLIT) {
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT><<<grid, 32, h->slab_bytes, s>>>(P);
   } else {
-    bmpc_solve_kernel<M, NR, false><<<grid, 32, h->slab_bytes, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL><<<grid, 32, 0, s>>>(P);
   }
   BMPC_CK(h, cudaGetLastError());
   return BMPC_OK;
@@ -249,7 +290,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->oldin, cap * cfg->d * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->started, cap * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
-  if (h->use_gws) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->slab_bytes));
+  if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
   BMPC_CK(h, cudaEventCreate(&h->ev1));
   return bmpc_reset(h, nullptr, 0);
@@ -363,12 +404,12 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   const size_t cap = (size_t)h->cfg.batch_capacity, n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
   if (!h->stage_in) BMPC_CK(h, cudaMalloc(&h->stage_in, cap * (3 * n + 4 * m) * sizeof(real)));
   // device staging of every output, laid out back to back
-  const size_t sz[12] = {d * 8, (size_t)P.totalu * d * 8, (size_t)P.totalx * n * 8, (size_t)P.totalu * n * 8,
-                         (size_t)P.totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4};
-  void* const host[12] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
-                          out->branch_p, out->objective, out->status, out->iters, out->nfact, out->nsolve};
+  const size_t sz[13] = {d * 8, (size_t)P.totalu * d * 8, (size_t)P.totalx * n * 8, (size_t)P.totalu * n * 8,
+                         (size_t)P.totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8};
+  void* const host[13] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
+                          out->branch_p, out->objective, out->status, out->iters, out->nfact, out->nsolve, out->cycles};
   size_t per = 0;
-  for (int i = 0; i < 12; ++i) per += sz[i];
+  for (int i = 0; i < 13; ++i) per += sz[i];
   if (!h->stage_out) {
     h->stage_out_bytes = cap * per;
     BMPC_CK(h, cudaMalloc(&h->stage_out, h->stage_out_bytes));
@@ -382,10 +423,10 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   BMPC_CK(h, cudaMemcpyAsync(dz0, z0, count * n * 8, cudaMemcpyHostToDevice, s));
   BMPC_CK(h, cudaMemcpyAsync(dxr, xref, count * n * 8, cudaMemcpyHostToDevice, s));
   if (policy_params) BMPC_CK(h, cudaMemcpyAsync(dpp, policy_params, count * m * 4 * 8, cudaMemcpyHostToDevice, s));
-  void* dev[12];
+  void* dev[13];
   {
     char* p = (char*)h->stage_out;
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 13; ++i) {
       dev[i] = host[i] ? p : nullptr;
       p += cap * sz[i];
     }
@@ -403,10 +444,11 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   dout.iters = (int32_t*)dev[9];
   dout.nfact = (int32_t*)dev[10];
   dout.nsolve = (int32_t*)dev[11];
+  dout.cycles = (int64_t*)dev[12];
   if (dev[6]) BMPC_CK(h, cudaMemsetAsync(dev[6], 0xff, count * sz[6], s));   // NaN pattern for leaf rows of branch_p
   const int rc = bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
   if (rc != BMPC_OK) return rc;
-  for (int i = 0; i < 12; ++i)
+  for (int i = 0; i < 13; ++i)
     if (host[i]) BMPC_CK(h, cudaMemcpyAsync(host[i], dev[i], count * sz[i], cudaMemcpyDeviceToHost, s));
   BMPC_CK(h, cudaStreamSynchronize(s));
   return BMPC_OK;
@@ -471,6 +513,16 @@ int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32
     bmpc_plant_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
   BMPC_CK(h, cudaGetLastError());
   h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warps, int64_t* smem_bytes,
+                         int64_t* global_bytes_per_warp) {
+  if (!h) return BMPC_E_INVALID;
+  if (slab_mode) *slab_mode = h->mode;
+  if (warps) *warps = h->grid;
+  if (smem_bytes) *smem_bytes = (int64_t)h->slab_bytes;
+  if (global_bytes_per_warp) *global_bytes_per_warp = (int64_t)h->gws_bytes_per_warp;
   return BMPC_OK;
 }
 

@@ -41,6 +41,7 @@ struct KParams {
   int* counter;                 // work queue head
   real* gws;                    // global workspace (only when the per-problem slab does not fit shared memory)
   size_t slab_reals;            // reals per problem slab
+  size_t factor_reals;          // reals of the per-warp factor-field region (split placement)
 };
 
 BMPC_HD inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }

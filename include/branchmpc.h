@@ -51,6 +51,12 @@ extern "C" {
 #define BMPC_POLICY_FORWARD 4  /* quadruped_branch_dyn.backup_forward       :34,  param[0] = v0 */
 #define BMPC_POLICY_STOP 5     /* quadruped_branch_dyn.backup_stop          :46  */
 
+/* working-set placement (bmpc_config.slab_mode) */
+#define BMPC_SLAB_AUTO 0
+#define BMPC_SLAB_SHARED 1 /* everything in shared memory (falls back to GLOBAL when it does not fit) */
+#define BMPC_SLAB_SPLIT 2  /* iterate fields in shared memory, factor fields in a per-warp L2-resident region */
+#define BMPC_SLAB_GLOBAL 3 /* everything in global memory */
+
 /* error codes */
 #define BMPC_OK 0
 #define BMPC_E_INVALID (-1)     /* bad argument / unsupported configuration        */
@@ -112,6 +118,7 @@ typedef struct bmpc_config {
   double polish_big;       /* lower bound of the stiff penalty, times branch weight (1e4)        */
   double polish_mult;      /* stiff penalty = polish_mult x curvature-matched stiffness (1e4)    */
 
+  int32_t slab_mode;      /* BMPC_SLAB_*: where a problem's working set lives (0 = library picks) */
   int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */
   int32_t device;         /* CUDA device ordinal                                      */
   int32_t reserved[8];
@@ -131,6 +138,7 @@ typedef struct bmpc_outputs {
   int32_t* iters;    /* [count]               ADMM iterations used                           */
   int32_t* nfact;    /* [count]               Riccati factorisations used                    */
   int32_t* nsolve;   /* [count]               KKT solves (backward+forward sweeps): ADMM + polish */
+  int64_t* cycles;   /* [count]               SM clock cycles the owning warp spent on the problem */
 } bmpc_outputs;
 
 typedef struct bmpc_handle bmpc_handle;
@@ -188,6 +196,11 @@ int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const doub
  * policy_params as in bmpc_solve).  In place; device pointers; either state pointer may be NULL. */
 int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32_t obstacle_policy,
                     const double* policy_params, int64_t count, void* stream);
+
+/* How the solve kernel is launched for this handle: resolved BMPC_SLAB_* placement, number of persistent warps
+ * (= thread blocks of 32), dynamic shared memory per warp, bytes of the per-warp global region. */
+int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warps, int64_t* smem_bytes,
+                         int64_t* global_bytes_per_warp);
 
 /* Kernel launch accounting since creation (for bench.py's gpu_launches). */
 int64_t bmpc_launch_count(const bmpc_handle* h);

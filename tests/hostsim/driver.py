@@ -77,7 +77,7 @@ class HostSim:
             "zPred": np.zeros((B, self.totalu, cfg.n)), "branch_w": np.zeros((B, self.nbranch)),
             "branch_p": np.full((B, self.nbranch, cfg.m), np.nan), "objective": np.zeros(B),
             "status": np.full(B, -1, dtype=np.int32), "iters": np.zeros(B, dtype=np.int32),
-            "nfact": np.zeros(B, dtype=np.int32), "nsolve": np.zeros(B, dtype=np.int32),
+            "nfact": np.zeros(B, dtype=np.int32), "nsolve": np.zeros(B, dtype=np.int32), "cycles": np.zeros(B, dtype=np.int64),
         }
         out = abi.Outputs(**{k: _ptr(v) for k, v in res.items()})
         rc = lib().hostsim_solve(C.byref(cfg), _ptr(x0), _ptr(z0), _ptr(xref), _ptr(pp), C.c_int64(B), _ptr(self.uLin),

@@ -11,12 +11,18 @@
 #include "bmpc_solver.h"
 
 namespace {
+bool g_split = false;
+template <class M, int NR, bool SPLIT>
+void run_layout(KParams& P) {
+  using S = Solver<M, NR, SPLIT>;
+  P.slab_reals = S::slab_reals(P.nup, P.nbranch);
+  std::vector<real> slab(P.slab_reals, 0.0), factor(S::factor_reals(P.nup) + 2, 0.0);
+  S solver(P, slab.data(), factor.data(), 0);
+  for (int i = 0; i < P.count; ++i) solver.solve(i);
+}
 template <class M, int NR>
 void run(KParams& P) {
-  P.slab_reals = Solver<M, NR>::slab_reals(P.nup, P.nbranch);
-  std::vector<real> slab(P.slab_reals, 0.0);
-  Solver<M, NR> S(P, slab.data(), 0);
-  for (int i = 0; i < P.count; ++i) S.solve(i);
+  if (g_split) run_layout<M, NR, true>(P); else run_layout<M, NR, false>(P);
 }
 std::string g_err;
 }  // namespace
@@ -43,6 +49,7 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   const int rc = bmpc::make_params(*cfg, &P, &g_err);
   if (rc != BMPC_OK) return rc;
   if (!bmpc::supported_instance(cfg->model, cfg->n_rows)) { g_err = "unsupported (model, n_rows)"; return BMPC_E_UNSUPPORTED; }
+  g_split = cfg->slab_mode == BMPC_SLAB_SPLIT;
   P.count = (int)count;
   P.x0 = x0;
   P.z0 = z0;
