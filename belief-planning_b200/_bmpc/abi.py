@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("veh_L", _dbl), ("veh_W", _dbl), ("Kpsi", _dbl), ("s1", _dbl), ("lane_lo", _dbl), ("lane_hi", _dbl),
         ("quad_margin", _dbl),
         ("max_iter", _i32), ("polish_first", _i32), ("polish_every", _i32), ("polish_passes", _i32),
-        ("polish_al_iters", _i32), ("polish_careful", _i32), ("warm_polish", _i32),
+        ("polish_al_iters", _i32), ("polish_careful", _i32), ("warm_polish", _i32), ("rho_refresh", _i32),
         ("alpha", _dbl), ("theta", _dbl), ("theta_u", _dbl), ("eps_abs", _dbl), ("polish_big", _dbl),
         ("polish_mult", _dbl),
         ("slab_mode", _i32), ("batch_capacity", _i32), ("device", _i32), ("reserved", _i32 * 8),

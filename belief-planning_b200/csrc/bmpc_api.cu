@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   constexpr bool SPLIT = (MODE == BMPC_SLAB_SPLIT);
+  (void)smem_raw;
   real* slab;
   real* factor = nullptr;
   if (MODE == BMPC_SLAB_GLOBAL) {
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ 
     slab = reinterpret_cast<real*>(smem_raw);
     if (SPLIT) factor = P.gws + (size_t)blockIdx.x * P.factor_reals;
   }
-  Solver<M, NR, SPLIT> S(P, slab, factor, lane);
+  Solver<M, NR, MODE> S(P, slab, factor, lane);
   for (;;) {
     int prob = 0;
     if (lane == 0) prob = atomicAdd(P.counter, 1);
@@ -150,6 +151,10 @@ struct bmpc_handle {
   int* pbest = nullptr;
   real* oldin = nullptr;
   int* started = nullptr;
+  // solver caches (not part of the reference-visible state): rho of the last refresh, active set of the last optimum
+  real* rho_cache = nullptr;
+  int* code_cache = nullptr;
+  int* cache_state = nullptr;
   int* counter = nullptr;
   real* gws = nullptr;
   // staging for bmpc_solve_host
@@ -175,7 +180,7 @@ static std::string g_create_error;
 
 template <class M, int NR, int MODE>
 static int try_mode(bmpc_handle* h, int max_optin, int* per_sm) {
-  using S = Solver<M, NR, MODE == BMPC_SLAB_SPLIT>;
+  using S = Solver<M, NR, MODE>;
   const size_t slab = S::slab_reals(h->P.nup, h->P.nbranch) * sizeof(real);
   const size_t smem = (MODE == BMPC_SLAB_GLOBAL) ? 0 : slab;
   *per_sm = 0;
@@ -214,12 +219,12 @@ static int configure_instance(bmpc_handle* h) {
   if (h->cfg.reserved[1] > 0 && per_sm > h->cfg.reserved[1]) per_sm = h->cfg.reserved[1];   // occupancy cap (experiments)
   h->grid = per_sm * h->num_sms;
   if (h->mode == BMPC_SLAB_SPLIT) {
-    using S = Solver<M, NR, true>;
+    using S = Solver<M, NR, BMPC_SLAB_SPLIT>;
     h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
     h->P.factor_reals = S::factor_reals(h->P.nup);
     h->gws_bytes_per_warp = h->P.factor_reals * sizeof(real);
   } else {
-    using S = Solver<M, NR, false>;
+    using S = Solver<M, NR, BMPC_SLAB_GLOBAL>;
     h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
     h->P.factor_reals = 0;
     h->gws_bytes_per_warp = (h->mode == BMPC_SLAB_GLOBAL) ? h->P.slab_reals * sizeof(real) : 0;
@@ -260,6 +265,9 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->pbest);
   cudaFree(h->oldin);
   cudaFree(h->started);
+  cudaFree(h->rho_cache);
+  cudaFree(h->code_cache);
+  cudaFree(h->cache_state);
   cudaFree(h->counter);
   cudaFree(h->gws);
   cudaFree(h->stage_in);
@@ -289,6 +297,9 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->pbest, cap * P.nbranch * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->oldin, cap * cfg->d * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->started, cap * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->rho_cache, cap * P.totalu * (BMPC_MAX_ROWS + 1 + BMPC_MAX_D) * sizeof(real)));
+  BMPC_CK(h, cudaMalloc(&h->code_cache, cap * P.totalu * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->cache_state, cap * 2 * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
   if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
@@ -331,6 +342,7 @@ int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count) {
     BMPC_CK(h, cudaMemset(h->pbest, 0, cap * P.nbranch * sizeof(int)));
     BMPC_CK(h, cudaMemset(h->oldin, 0, cap * h->cfg.d * sizeof(real)));
     BMPC_CK(h, cudaMemset(h->started, 0, cap * sizeof(int)));
+    BMPC_CK(h, cudaMemset(h->cache_state, 0xff, cap * 2 * sizeof(int)));
     return BMPC_OK;
   }
   for (int64_t i = 0; i < count; ++i) {
@@ -340,6 +352,7 @@ int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count) {
     BMPC_CK(h, cudaMemset(h->pbest + e * P.nbranch, 0, P.nbranch * sizeof(int)));
     BMPC_CK(h, cudaMemset(h->oldin + e * h->cfg.d, 0, h->cfg.d * sizeof(real)));
     BMPC_CK(h, cudaMemset(h->started + e, 0, sizeof(int)));
+    BMPC_CK(h, cudaMemset(h->cache_state + 2 * e, 0xff, 2 * sizeof(int)));
   }
   return BMPC_OK;
 }
@@ -379,6 +392,9 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.pbest = h->pbest;
   P.oldin = h->oldin;
   P.started = h->started;
+  P.rho_cache = h->rho_cache;
+  P.code_cache = h->code_cache;
+  P.cache_state = h->cache_state;
   P.out = *out;
   P.counter = h->counter;
   P.gws = h->gws;
@@ -479,6 +495,8 @@ int bmpc_set_state(bmpc_handle* h, const double* uLin, const int32_t* pbest, con
   if (pbest) BMPC_CK(h, cudaMemcpy(h->pbest, pbest, count * P.nbranch * sizeof(int), k));
   if (old_input) BMPC_CK(h, cudaMemcpy(h->oldin, old_input, count * h->cfg.d * sizeof(real), k));
   if (started) BMPC_CK(h, cudaMemcpy(h->started, started, count * sizeof(int), k));
+  // a caller-supplied warm start invalidates the solver's own caches for those episodes
+  BMPC_CK(h, cudaMemset(h->cache_state, 0xff, count * 2 * sizeof(int)));
   return BMPC_OK;
 }
 

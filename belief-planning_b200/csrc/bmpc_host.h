@@ -96,7 +96,9 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.polish_passes = c.polish_passes > 0 ? c.polish_passes : 8;
   P.polish_al_iters = c.polish_al_iters > 0 ? c.polish_al_iters : 24;
   P.polish_careful = c.polish_careful > 0 ? c.polish_careful : (c.polish_careful < 0 ? 0 : 12);
-  P.warm_polish = c.warm_polish;
+  P.warm_polish = c.warm_polish >= 0 ? 1 : 0;
+  P.warm_passes = c.warm_polish > 0 ? c.warm_polish : 3;
+  P.rho_refresh = c.rho_refresh > 0 ? c.rho_refresh : (c.rho_refresh < 0 ? 0 : 8);
   P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
   P.theta = c.theta > 0.0 ? c.theta : 1.0;
   P.theta_u = c.theta_u > 0.0 ? c.theta_u : 1.0;

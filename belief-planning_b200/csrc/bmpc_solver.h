@@ -35,12 +35,20 @@ BMPC_D real row_dual(real sh, real rlo, real rhi, real lam) {
   return 0.0;
 }
 
-// SPLIT = false: every field lives in one slab (shared memory when it fits, else global), field-major.
-// SPLIT = true : the factor fields (written by a factorisation, read-only during the ADMM sweeps) live in a per-warp
-//                global/L2 region, node-major so that one node's data is contiguous; only the iterate fields stay in
-//                shared memory.  That cuts the shared footprint ~3x and lets ~3x more warps be resident per SM.
-template <class M, int NR, bool SPLIT = false>
+// Working-set placement (MODE = BMPC_SLAB_*), all node-major (one node's fields are contiguous, so a node step
+// addresses them as base + immediate offset):
+//   SHARED: every field in the warp's shared-memory slab (record stride odd -> the lanes of a sweep and of the row
+//           phase hit distinct banks);
+//   SPLIT : the factor fields (written by a factorisation, read-only during the ADMM sweeps) in a per-warp global/L2
+//           region, the iterate fields in shared memory (~3x smaller shared footprint, ~3x more resident warps);
+//   GLOBAL: everything in the per-warp global region (trees too large for shared memory).
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) real bmpc_smem[];
+#endif
+
+template <class M, int NR, int MODE = BMPC_SLAB_SHARED>
 struct Solver {
+  static constexpr bool SPLIT = (MODE == BMPC_SLAB_SPLIT);
   static constexpr int NX = M::NX, NU = M::NU;   // Riccati state (physical, or physical + previous input) / input
   static constexpr int NXP = M::NXP;             // physical state dimension
   static constexpr bool RATE = M::RATE;          // input-rate costs carried through the augmented state
@@ -64,49 +72,59 @@ struct Solver {
   static constexpr int NF = F_Y + NR + NU;
   static constexpr int BR = 1 + NS + 3 * NX; // per-branch reals: w, exchange(NS), x last, z last, x after last
   static constexpr int NFA = F_S;                 // factor fields per node
-  static constexpr int NFAP = (NFA + 1) & ~1;     // ... padded to an even count (16-byte aligned node records)
+  static constexpr int NFAP = (NFA + 1) & ~1;     // ... padded to an even count (16-byte aligned records in global)
   static constexpr int NFW = SPLIT ? NF - NFA : NF;   // fields kept in the slab
+  static constexpr int NFWP = NFW | 1;                // slab record stride, odd (bank-conflict-free)
 
   BMPC_HD static size_t slab_reals(int nup, int nbranch) {
-    return (size_t)NFW * nup + (size_t)(nup + 1) / 2 + (size_t)BR * nbranch;
+    return (size_t)NFWP * nup + (size_t)(nup + 1) / 2 + (size_t)BR * nbranch;
   }
   BMPC_HD static size_t factor_reals(int nup) { return SPLIT ? (size_t)NFAP * nup : 0; }
 
   const KParams& P;
-  real* ws;
+  real* ws;     // slab base (shared memory is addressed through bmpc_smem on the device so that loads are LDS)
   real* fa;     // factor-field region (SPLIT only)
-  int* st;
-  real* Wb;
-  real* EX;
-  real* EXL;
-  real* EXZ;
-  real* EXX;
+  int oSt, oWb, oEX, oEXL, oEXZ, oEXX;   // offsets (in reals) of the per-branch arrays inside the slab
   int lane, nup, prob;
+  bool use_codes;   // this solve starts its polish from the cached active set of the previous step
   real gap_r, stp_r, gap_u, stp_u;   // last residual check: max primal gap |f'x - v| and max step |v+ - v| (rows / inputs)
   int nsolve;   // KKT solves (one backward + one forward sweep each) of the current problem
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
 
   BMPC_D Solver(const KParams& P_, real* slab, real* factor, int lane_) : P(P_), ws(slab), fa(factor), lane(lane_), nup(P_.nup) {
-    st = reinterpret_cast<int*>(ws + (size_t)NFW * nup);
-    Wb = ws + (size_t)NFW * nup + (nup + 1) / 2;
-    EX = Wb + P.nbranch;
-    EXL = EX + (size_t)NS * P.nbranch;
-    EXZ = EXL + (size_t)NX * P.nbranch;
-    EXX = EXZ + (size_t)NX * P.nbranch;
+    oSt = NFWP * nup;
+    oWb = oSt + (nup + 1) / 2;
+    oEX = oWb + P.nbranch;
+    oEXL = oEX + NS * P.nbranch;
+    oEXZ = oEXL + NX * P.nbranch;
+    oEXX = oEXZ + NX * P.nbranch;
     prob = 0;
+    use_codes = false;
     nsolve = 0;
     rlin = 0.0;
     polpar = nullptr;
   }
 
+  BMPC_D real* slab() {
+#if defined(__CUDA_ARCH__)
+    if (MODE != BMPC_SLAB_GLOBAL) return bmpc_smem;   // one warp per block: the slab starts at shared offset 0
+#endif
+    return ws;
+  }
   BMPC_D real& F(int field, int kp) {
     if (SPLIT) {
-      if (field < NFA) return fa[(size_t)kp * NFAP + field];
-      return ws[(size_t)(field - NFA) * nup + kp];
+      if (field < NFA) return fa[kp * NFAP + field];
+      return slab()[kp * NFWP + (field - NFA)];
     }
-    return ws[(size_t)field * nup + kp];
+    return slab()[kp * NFWP + field];
   }
+  BMPC_D int* stp() { return reinterpret_cast<int*>(slab() + oSt); }
+  BMPC_D real* Wbp() { return slab() + oWb; }
+  BMPC_D real* EXp() { return slab() + oEX; }
+  BMPC_D real* EXLp() { return slab() + oEXL; }
+  BMPC_D real* EXZp() { return slab() + oEXZ; }
+  BMPC_D real* EXXp() { return slab() + oEXX; }
   BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(P, b) + t + b; }
   BMPC_D void node_of(int k, int& b, int& t) const {
     if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / P.N; t = (k - 1) % P.N; }
@@ -169,6 +187,7 @@ struct Solver {
     const int started = P.started[prob];
     const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     int* pbest = P.pbest + (size_t)prob * P.nbranch;
+    const int* codes = P.code_cache + (size_t)prob * P.totalu;
     const real* x0 = P.x0 + (size_t)prob * NXP;
     const real* z0 = P.z0 + (size_t)prob * NXP;
     if (lane == 0) {
@@ -181,9 +200,10 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[kbest * NU + a] : 0.0;
       const int kp = kp_of(0, 0);
+      if (use_codes) stp()[kp] = codes[kbest];
       F(F_FC, kp) = z0[0];
       F(F_FC + 1, kp) = z0[1];
-      Wb[0] = 1.0;
+      Wbp()[0] = 1.0;
       if (P.out.zPred) {
         real* o = P.out.zPred + (size_t)prob * P.totalu * NXP;
 #pragma unroll
@@ -192,9 +212,9 @@ struct Solver {
       node_setup(0, 0, xb, ub, 1.0, false, xn);
 #pragma unroll
       for (int i = 0; i < NXP; ++i) {
-        EXL[i] = xb[i];
-        EXZ[i] = z0[i];
-        EXX[i] = xn[i];
+        EXLp()[i] = xb[i];
+        EXZp()[i] = z0[i];
+        EXXp()[i] = xn[i];
       }
     }
     lanes_sync();
@@ -210,8 +230,8 @@ struct Solver {
         const int kc = bmpc_ndu(P, c);
         const int kpc = kp_of(c, 0);
         real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NXP : nullptr;
-        const real hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXL + (size_t)NX * b,
-                                         EXZ + (size_t)NX * b, zl, [&](int t, const real* z) {
+        const real hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXLp() + NX * b,
+                                         EXZp() + NX * b, zl, [&](int t, const real* z) {
                                            F(F_FC, kpc + t) = z[0];
                                            F(F_FC + 1, kpc + t) = z[1];
                                            if (zout) {
@@ -220,27 +240,27 @@ struct Solver {
                                            }
                                          });
 #pragma unroll
-        for (int q = 0; q < NXP; ++q) EXZ[(size_t)NX * c + q] = zl[q];
-        EX[(size_t)NS * c] = hi;   // exchange slot: safety value of child c
+        for (int q = 0; q < NXP; ++q) EXZp()[NX * c + q] = zl[q];
+        EXp()[NS * c] = hi;   // exchange slot: safety value of child c
       }
       lanes_sync();
       // (a') probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         const int fc = bmpc_first_child(P, b, d);
         real himax = -1e300;
-        for (int j = 0; j < m; ++j) himax = fmax(himax, EX[(size_t)NS * (fc + j)]);
+        for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
         real sum = 0.0;
-        for (int j = 0; j < m; ++j) sum += M::branch_weight(P, EX[(size_t)NS * (fc + j)], himax);
+        for (int j = 0; j < m; ++j) sum += M::branch_weight(P, EXp()[NS * (fc + j)], himax);
         int best = 0;
         real pb = -1.0;
         for (int j = 0; j < m; ++j) {
-          const real p = M::branch_weight(P, EX[(size_t)NS * (fc + j)], himax) / sum;
-          Wb[fc + j] = Wb[b] * p;
+          const real p = M::branch_weight(P, EXp()[NS * (fc + j)], himax) / sum;
+          Wbp()[fc + j] = Wbp()[b] * p;
           if (P.out.branch_p) P.out.branch_p[((size_t)prob * P.nbranch + b) * m + j] = p;
           if (p > pb) { pb = p; best = j; }
         }
         // pbest[b] (old value) was consumed when b's own trajectory was shifted, one level up (or at the root above)
-        EX[(size_t)NS * b + 1] = (real)best;
+        EXp()[NS * b + 1] = (real)best;
       }
       lanes_sync();
       // (b) ego linearisation trajectory of every child branch: time-shifted previous inputs
@@ -248,7 +268,7 @@ struct Solver {
       for (int c = P.off[d + 1] + lane; c < P.off[d + 2]; c += BMPC_LANES) {
         const int b = bmpc_parent(P, c, d + 1);
         const bool leaf = (d + 1 == P.NB);
-        const real w = Wb[c];
+        const real w = Wbp()[c];
         const int kc = bmpc_ndu(P, c);
         int klast;
         if (leaf) {
@@ -258,29 +278,30 @@ struct Solver {
         }
         real xb[NXP], xn[NXP], ub[NU];
 #pragma unroll
-        for (int i = 0; i < NXP; ++i) xb[i] = EXX[(size_t)NX * b + i];
+        for (int i = 0; i < NXP; ++i) xb[i] = EXXp()[NX * b + i];
         for (int t = 0; t < P.N; ++t) {
           const int ksrc = (t < P.N - 1) ? kc + t + 1 : klast;
 #pragma unroll
           for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[ksrc * NU + a] : 0.0;
+          if (use_codes) stp()[kp_of(c, t)] = codes[ksrc];   // the active set shifts in time like the inputs
           if (t == P.N - 1) {
 #pragma unroll
-            for (int i = 0; i < NXP; ++i) EXL[(size_t)NX * c + i] = xb[i];
+            for (int i = 0; i < NXP; ++i) EXLp()[NX * c + i] = xb[i];
           }
           node_setup(c, t, xb, ub, w, leaf && t == P.N - 1, xn);
 #pragma unroll
           for (int i = 0; i < NXP; ++i) xb[i] = xn[i];
         }
 #pragma unroll
-        for (int i = 0; i < NXP; ++i) EXX[(size_t)NX * c + i] = xb[i];
+        for (int i = 0; i < NXP; ++i) EXXp()[NX * c + i] = xb[i];
       }
       lanes_sync();
       // commit the new arg-max children of this level (their old values are no longer needed)
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EX[(size_t)NS * b + 1];
+      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EXp()[NS * b + 1];
       lanes_sync();
     }
     if (P.out.branch_w) {
-      for (int b = lane; b < P.nbranch; b += BMPC_LANES) P.out.branch_w[(size_t)prob * P.nbranch + b] = Wb[b];
+      for (int b = lane; b < P.nbranch; b += BMPC_LANES) P.out.branch_w[(size_t)prob * P.nbranch + b] = Wbp()[b];
     }
     rlin = 0.0;
 #pragma unroll
@@ -360,7 +381,7 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) pu[a] = 0.0;
     } else {
-      const int code = st[kp];
+      const int code = stp()[kp];
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int cj = (code >> (3 * j)) & 7;
@@ -387,7 +408,7 @@ struct Solver {
     real pr[NR], pu[NU];
     penalties(kp, w, mode, pr, pu);
     // h0 = P+ C  (polish: C + B u_pinned, the inputs held at their bounds act as a known offset of the dynamics)
-    const int pcode = (mode == FACT_POLISH) ? st[kp] : 0;
+    const int pcode = (mode == FACT_POLISH) ? stp()[kp] : 0;
     {
       real C[NX];
       M::expandC(cc, C);
@@ -525,10 +546,10 @@ struct Solver {
 
   BMPC_D void sum_children(int b, int d, real* Pn) {
     const int fc = bmpc_first_child(P, b, d);
-    unpack_sym(EX + (size_t)NS * fc, Pn);
+    unpack_sym(EXp() + NS * fc, Pn);
     for (int c = 1; c < P.m; ++c) {
       real Pc[NX * NX];
-      unpack_sym(EX + (size_t)NS * (fc + c), Pc);
+      unpack_sym(EXp() + NS * (fc + c), Pc);
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) Pn[i] += Pc[i];
     }
@@ -537,7 +558,7 @@ struct Solver {
   BMPC_DN void factorize(int mode) {
     for (int d = P.NB; d >= 1; --d) {
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
-        const real w = Wb[b];
+        const real w = Wbp()[b];
         real Pn[NX * NX];
         if (d == P.NB) {
           // terminal node: x' (w Qf) x in the reference's H, doubled by H <- 2H (:1094, :1112)
@@ -551,7 +572,7 @@ struct Solver {
         }
         for (int t = P.N - 1; t >= 0; --t)
           node_factor(kp_of(b, t), w, Pn, mode, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0, false);
-        pack_sym(Pn, EX + (size_t)NS * b);
+        pack_sym(Pn, EXp() + NS * b);
       }
       lanes_sync();
     }
@@ -677,16 +698,16 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) Sg[i] = 0.0;
       node_cov(kp_of(0, 0), 1.0, Sg);
-      pack_sym(Sg, EX);
+      pack_sym(Sg, EXp());
     }
     lanes_sync();
     for (int d = 1; d <= P.NB; ++d) {
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real Sg[NX * NX];
-        unpack_sym(EX + (size_t)NS * bmpc_parent(P, b, d), Sg);
-        const real w = Wb[b];
+        unpack_sym(EXp() + NS * bmpc_parent(P, b, d), Sg);
+        const real w = Wbp()[b];
         for (int t = 0; t < P.N; ++t) node_cov(kp_of(b, t), w, Sg);
-        pack_sym(Sg, EX + (size_t)NS * b);
+        pack_sym(Sg, EXp() + NS * b);
       }
       lanes_sync();
     }
@@ -740,7 +761,7 @@ struct Solver {
           if (P.ctrl == BMPC_CTRL_PROX) {
             // BranchMPCProx: -2 w xRef' Qf (:308)
             const real* xref = P.xref + (size_t)prob * NXP;
-            const real w = Wb[b];
+            const real w = Wbp()[b];
 #pragma unroll
             for (int j = 0; j < NXP; ++j) {
               real a = 0.0;
@@ -752,15 +773,15 @@ struct Solver {
         } else {
           const int fc = bmpc_first_child(P, b, d);
 #pragma unroll
-          for (int i = 0; i < NX; ++i) pn[i] = EX[(size_t)NS * fc + i];
+          for (int i = 0; i < NX; ++i) pn[i] = EXp()[NS * fc + i];
           for (int c = 1; c < P.m; ++c)
 #pragma unroll
-            for (int i = 0; i < NX; ++i) pn[i] += EX[(size_t)NS * (fc + c) + i];
+            for (int i = 0; i < NX; ++i) pn[i] += EXp()[NS * (fc + c) + i];
         }
         const int kp0 = kp_of(b, 0);
         for (int t = P.N - 1; t >= 0; --t) bw_step(kp0 + t, pn);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) EX[(size_t)NS * b + i] = pn[i];
+        for (int i = 0; i < NX; ++i) EXp()[NS * b + i] = pn[i];
       }
       lanes_sync();
     }
@@ -768,10 +789,10 @@ struct Solver {
       real pn[NX];
       const int fc = bmpc_first_child(P, 0, 0);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) pn[i] = EX[(size_t)NS * fc + i];
+      for (int i = 0; i < NX; ++i) pn[i] = EXp()[NS * fc + i];
       for (int c = 1; c < P.m; ++c)
 #pragma unroll
-        for (int i = 0; i < NX; ++i) pn[i] += EX[(size_t)NS * (fc + c) + i];
+        for (int i = 0; i < NX; ++i) pn[i] += EXp()[NS * (fc + c) + i];
       bw_step(kp_of(0, 0), pn);
     }
     lanes_sync();
@@ -808,7 +829,7 @@ struct Solver {
       for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
       fw_step(kp_of(0, 0), x);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) EXX[i] = x[i];
+      for (int i = 0; i < NX; ++i) EXXp()[i] = x[i];
     }
     lanes_sync();
     for (int d = 1; d <= P.NB; ++d) {
@@ -816,11 +837,11 @@ struct Solver {
         real x[NX];
         const int pa = bmpc_parent(P, b, d);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = EXX[(size_t)NX * pa + i];
+        for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
         const int kp0 = kp_of(b, 0);
         for (int t = 0; t < P.N; ++t) fw_step(kp0 + t, x);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) EXX[(size_t)NX * b + i] = x[i];
+        for (int i = 0; i < NX; ++i) EXXp()[NX * b + i] = x[i];
       }
       lanes_sync();
     }
@@ -860,7 +881,7 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real w = Wb[b];
+      const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
@@ -925,6 +946,76 @@ struct Solver {
     return res;
   }
 
+  // rho cache: the curvature-matched rho changes slowly from one MPC step to the next, so warm solves reuse the
+  // values of the previous step (refreshed every P.rho_refresh solves) and skip the free factorisation + covariance sweep.
+  BMPC_DN void store_rho() {
+    real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+#pragma unroll
+      for (int j = 0; j < NR + NU; ++j) cache[(size_t)k * (NR + NU) + j] = F(F_RHO + j, kp);
+    }
+    lanes_sync();
+  }
+  BMPC_DN void load_rho() {
+    const real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const real r = cache[(size_t)k * (NR + NU) + j];
+        F(F_RHO + j, kp) = r;
+        F(F_S + j, kp) *= r;      // ADMM start written by node_setup, scaled as in choose_rho
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real r = cache[(size_t)k * (NR + NU) + NR + a];
+        F(F_RHO + NR + a, kp) = r;
+        F(F_SU + a, kp) *= r;
+      }
+    }
+    lanes_sync();
+  }
+  // shifted codes of the previous optimum -> a consistent starting guess for the polish (multipliers start at their
+  // natural values: 0 on kinks)
+  BMPC_DN void guess_from_codes() {
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const int code = stp()[kp];
+      int ncode = 0;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        int cj = (code >> (3 * j)) & 7;
+        if (!(F(F_RHO + j, kp) > 0.0)) cj = ROW_IGNORED;
+        else if (cj == ROW_IGNORED) cj = ROW_INACTIVE;
+        ncode |= cj << (3 * j);
+        F(F_Y + j, kp) = 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        ncode |= ((code >> (3 * NR + 2 * a)) & 3) << (3 * NR + 2 * a);
+        F(F_Y + NR + a, kp) = 0.0;
+      }
+      stp()[kp] = ncode;
+    }
+    lanes_sync();
+  }
+  BMPC_DN void store_codes() {
+    int* codes = P.code_cache + (size_t)prob * P.totalu;
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      codes[k] = stp()[kp_of(b, t)];
+    }
+    lanes_sync();
+  }
+
   // Residual balancing (Boyd et al. 2011, 3.4.1) on top of the curvature-matched rho: with rho in matched units the
   // primal gap |f'x - v| and the step |v+ - v| are commensurable; when one dominates, the whole group (state rows /
   // inputs) is rescaled.  The ADMM state (v, y) is kept: sh' = s (sh - y) + y.  The caller refactorises.
@@ -941,7 +1032,7 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real lam = P.lam_lin * Wb[b];
+      const real lam = P.lam_lin * Wbp()[b];
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const real rho = F(F_RHO + j, kp);
@@ -978,7 +1069,7 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real lam = P.lam_lin * Wb[b];
+      const real lam = P.lam_lin * Wbp()[b];
       int code = 0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
@@ -1010,7 +1101,7 @@ struct Solver {
         code |= ca << (3 * NR + 2 * a);
         F(F_Y + NR + a, kp) = y;
       }
-      st[kp] = code;
+      stp()[kp] = code;
     }
     lanes_sync();
   }
@@ -1020,9 +1111,9 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real w = Wb[b];
+      const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
-      const int code = st[kp];
+      const int code = stp()[kp];
       real qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0;
@@ -1072,8 +1163,8 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real w = Wb[b];
-      const int code = st[kp];
+      const real w = Wbp()[b];
+      const int code = stp()[kp];
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
@@ -1101,7 +1192,7 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const int code = st[kp];
+      const int code = stp()[kp];
 #pragma unroll
       for (int a = 0; a < NU; ++a)
         if (pinned(code, a)) F(F_UQ + a, kp) = pinned_value(code, a);
@@ -1120,7 +1211,7 @@ struct Solver {
     for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
 #pragma unroll
     for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
-    const int code = st[kp];
+    const int code = stp()[kp];
     const real rate = (k == 0) ? 0.0 : w;
     const real sig = (b >= P.off[P.NB] && t == P.N - 1) ? 0.0 : 1.0;
     M::mulBT(P, lin, lam, gu);
@@ -1172,11 +1263,11 @@ struct Solver {
     real viol = 0.0;
     for (int d = P.NB; d >= 1; --d) {
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
-        const real w = Wb[b];
+        const real w = Wbp()[b];
         real lam[NX];
         if (d == P.NB) {
-          // terminal costate: 2 w Qf x_T (BranchMPCProx: - 2 w Qf' xRef as well); x_T was left in EXX by forward()
-          const real* xT = EXX + (size_t)NX * b;
+          // terminal costate: 2 w Qf x_T (BranchMPCProx: - 2 w Qf' xRef as well); x_T was left in EXXp() by forward()
+          const real* xT = EXXp() + NX * b;
           const real* xref = P.xref + (size_t)prob * NXP;
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
@@ -1193,16 +1284,16 @@ struct Solver {
         } else {
           const int fc = bmpc_first_child(P, b, d);
 #pragma unroll
-          for (int i = 0; i < NX; ++i) lam[i] = EX[(size_t)NS * fc + i];
+          for (int i = 0; i < NX; ++i) lam[i] = EXp()[NS * fc + i];
           for (int c = 1; c < P.m; ++c)
 #pragma unroll
-            for (int i = 0; i < NX; ++i) lam[i] += EX[(size_t)NS * (fc + c) + i];
+            for (int i = 0; i < NX; ++i) lam[i] += EXp()[NS * (fc + c) + i];
         }
         const int kp0 = kp_of(b, 0);
         const int k0 = bmpc_ndu(P, b);
         for (int t = P.N - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(k0 + t, b, t, kp0 + t, w, lam));
 #pragma unroll
-        for (int i = 0; i < NX; ++i) EX[(size_t)NS * b + i] = lam[i];
+        for (int i = 0; i < NX; ++i) EXp()[NS * b + i] = lam[i];
       }
       lanes_sync();
     }
@@ -1210,10 +1301,10 @@ struct Solver {
       real lam[NX];
       const int fc = bmpc_first_child(P, 0, 0);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) lam[i] = EX[(size_t)NS * fc + i];
+      for (int i = 0; i < NX; ++i) lam[i] = EXp()[NS * fc + i];
       for (int c = 1; c < P.m; ++c)
 #pragma unroll
-        for (int i = 0; i < NX; ++i) lam[i] += EX[(size_t)NS * (fc + c) + i];
+        for (int i = 0; i < NX; ++i) lam[i] += EXp()[NS * (fc + c) + i];
       viol = fmax(viol, adjoint_step(0, 0, 0, kp_of(0, 0), 1.0, lam));
     }
     lanes_sync();
@@ -1233,10 +1324,10 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real w = Wb[b];
+      const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
       const real ytol = 1e-9 * lam;
-      const int code = st[kp];
+      const int code = stp()[kp];
       int ncode = 0;
       real x[NX];
 #pragma unroll
@@ -1316,7 +1407,7 @@ struct Solver {
         }
         ncode |= na << (3 * NR + 2 * a);
       }
-      if (apply) st[kp] = ncode;
+      if (apply) stp()[kp] = ncode;
     }
     lanes_sync();
     score_max = smax;
@@ -1329,13 +1420,14 @@ struct Solver {
   // unchanged while the equality residual falls below 1e-7 is the verified optimum.  Conflicting guesses
   // (e.g. the collision rows of sibling branches, which see the same position one step after the branching
   // point) show up as multipliers running past their bounds and are revised without waiting for convergence.
-  BMPC_DN bool polish(int& nfact, bool allow_careful) {
-    polish_guess();
+  BMPC_DN bool polish(int& nfact, bool allow_careful, bool from_admm_state) {
+    if (from_admm_state) polish_guess();
+    const int base_passes = from_admm_state ? P.polish_passes : P.warm_passes;
     int prev_changes = 1 << 30;
     bool careful = false;
-    const int max_passes = P.polish_passes + P.polish_careful;
+    const int max_passes = base_passes + P.polish_careful;
     for (int pass = 0; pass < max_passes; ++pass) {
-      if (!careful && pass >= P.polish_passes) return false;
+      if (!careful && pass >= base_passes) return false;
       factorize(FACT_POLISH);
       ++nfact;
       real res = 1.0, prev = 1e300;
@@ -1474,7 +1566,7 @@ struct Solver {
       }
       J += emit_node(0, 0, kp_of(0, 0), 1.0, x, uLin, 0.0, 1.0);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) EXX[i] = x[i];
+      for (int i = 0; i < NX; ++i) EXXp()[i] = x[i];
     }
     lanes_sync();
     for (int d = 1; d <= P.NB; ++d) {
@@ -1482,8 +1574,8 @@ struct Solver {
         real x[NX];
         const int pa = bmpc_parent(P, b, d);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = EXX[(size_t)NX * pa + i];
-        const real w = Wb[b];
+        for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
+        const real w = Wbp()[b];
         const int kx = bmpc_ndx(P, b);
         for (int t = 0; t < P.N; ++t) {
           if (xP) {
@@ -1511,7 +1603,7 @@ struct Solver {
           }
         }
 #pragma unroll
-        for (int i = 0; i < NX; ++i) EXX[(size_t)NX * b + i] = x[i];
+        for (int i = 0; i < NX; ++i) EXXp()[NX * b + i] = x[i];
       }
       lanes_sync();
     }
@@ -1541,17 +1633,37 @@ struct Solver {
 #endif
     prob = prob_;
     polpar = P.polpar ? P.polpar + (size_t)prob * P.m * 4 : nullptr;
+    const int warm = P.started[prob];
+    int* cstate = P.cache_state + (size_t)prob * 2;   // [0] age of the cached rho (-1: none), [1] cached codes valid
+    const bool reuse_rho = warm && P.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < P.rho_refresh;
+    use_codes = warm && P.warm_polish && cstate[1] == 1 && reuse_rho;
     expand_tree();
     nsolve = 0;
     int nfact = 0, iters = 0, status = BMPC_STATUS_MAXITER;
-    factorize(FACT_FREE);
-    choose_rho();
-    factorize(FACT_ADMM);
-    nfact += 2;
-    admm_rows<false, false>();
-    int next_polish = P.polish_first, polish_gap = P.polish_every;
     bool have_xu = false;
-    while (iters < P.max_iter) {
+    if (reuse_rho) {
+      load_rho();
+    } else {
+      factorize(FACT_FREE);
+      choose_rho();
+      store_rho();
+      ++nfact;
+    }
+    if (use_codes) {
+      // warm solve: the previous optimum's active set, shifted in time, is usually one or two changes away
+      guess_from_codes();
+      if (polish(nfact, false, false)) {
+        status = BMPC_STATUS_POLISHED;
+        have_xu = true;
+      }
+    }
+    int next_polish = P.polish_first, polish_gap = P.polish_every;
+    if (!have_xu) {
+      factorize(FACT_ADMM);
+      ++nfact;
+      admm_rows<false, false>();
+    }
+    while (!have_xu && iters < P.max_iter) {
       backward();
       forward();
       ++iters;
@@ -1564,7 +1676,7 @@ struct Solver {
       if (iters >= next_polish || conv) {
         next_polish = iters + polish_gap;
         polish_gap *= 2;   // back off: a problem whose active set is slow to settle should not pay for many attempts
-        if (polish(nfact, iters >= 4 * P.polish_first)) {
+        if (polish(nfact, iters >= 4 * P.polish_first, true)) {
           status = BMPC_STATUS_POLISHED;
           have_xu = true;
           break;
@@ -1584,10 +1696,13 @@ struct Solver {
     }
     if (solution_is_finite()) {
       const real J = finish();
+      if (status == BMPC_STATUS_POLISHED) store_codes();
       if (lane == 0) {
         if (P.out.status) P.out.status[prob] = status;
         if (P.out.objective) P.out.objective[prob] = J;
         P.started[prob] = 1;
+        cstate[0] = reuse_rho ? cstate[0] + 1 : 0;
+        cstate[1] = (status == BMPC_STATUS_POLISHED) ? 1 : 0;
       }
     } else if (lane == 0) {
       // the reference keeps its previous plan when the solver fails (MPC_branch.py:1224): outputs and warm start untouched

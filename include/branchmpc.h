@@ -111,7 +111,9 @@ typedef struct bmpc_config {
   int32_t polish_passes;   /* active-set passes per polish attempt (8)                           */
   int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (24)                     */
   int32_t polish_careful;  /* extra one-change-at-a-time passes when the set iteration cycles (12; <0 = off) */
-  int32_t warm_polish;     /* 1: on warm solves try a polish before the first ADMM iteration     */
+  int32_t warm_polish;     /* warm solves first try a polish from the previous optimum's shifted active set:
+                              number of active-set passes for that attempt (3; <0 = off)        */
+  int32_t rho_refresh;     /* warm solves reuse the cached rho for this many steps (8; <0 = recompute every solve)   */
   double alpha;            /* over-relaxation (1.6)                                              */
   double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */
   double eps_abs;          /* ADMM residual tolerance for STATUS_CONVERGED (1e-6)                */

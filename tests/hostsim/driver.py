@@ -62,6 +62,9 @@ class HostSim:
         self.pbest = np.zeros((capacity, self.nbranch), dtype=np.int32)
         self.oldin = np.zeros((capacity, cfg.d))
         self.started = np.zeros(capacity, dtype=np.int32)
+        self.rho_cache = np.zeros((capacity, self.totalu, abi.MAX_ROWS + 1 + abi.MAX_D))
+        self.code_cache = np.zeros((capacity, self.totalu), dtype=np.int32)
+        self.cache_state = np.full((capacity, 2), -1, dtype=np.int32)
 
     def solve(self, x0, z0, xref, policy_params=None):
         cfg = self.cfg
@@ -81,7 +84,8 @@ class HostSim:
         }
         out = abi.Outputs(**{k: _ptr(v) for k, v in res.items()})
         rc = lib().hostsim_solve(C.byref(cfg), _ptr(x0), _ptr(z0), _ptr(xref), _ptr(pp), C.c_int64(B), _ptr(self.uLin),
-                                 _ptr(self.pbest), _ptr(self.oldin), _ptr(self.started), C.byref(out))
+                                 _ptr(self.pbest), _ptr(self.oldin), _ptr(self.started), _ptr(self.rho_cache),
+                                 _ptr(self.code_cache), _ptr(self.cache_state), C.byref(out))
         if rc != 0:
             raise RuntimeError("hostsim_solve: %d %s" % (rc, lib().hostsim_last_error().decode()))
         return res

@@ -12,9 +12,9 @@
 
 namespace {
 bool g_split = false;
-template <class M, int NR, bool SPLIT>
+template <class M, int NR, int MODE>
 void run_layout(KParams& P) {
-  using S = Solver<M, NR, SPLIT>;
+  using S = Solver<M, NR, MODE>;
   P.slab_reals = S::slab_reals(P.nup, P.nbranch);
   std::vector<real> slab(P.slab_reals, 0.0), factor(S::factor_reals(P.nup) + 2, 0.0);
   S solver(P, slab.data(), factor.data(), 0);
@@ -22,7 +22,7 @@ void run_layout(KParams& P) {
 }
 template <class M, int NR>
 void run(KParams& P) {
-  if (g_split) run_layout<M, NR, true>(P); else run_layout<M, NR, false>(P);
+  if (g_split) run_layout<M, NR, BMPC_SLAB_SPLIT>(P); else run_layout<M, NR, BMPC_SLAB_SHARED>(P);
 }
 std::string g_err;
 }  // namespace
@@ -44,7 +44,8 @@ int hostsim_sizes(const bmpc_config* cfg, int32_t* nbranch, int32_t* totalx, int
 // All pointers are HOST pointers; uLin/pbest/oldin/started are the persistent state (caller-owned here).
 int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, const double* xref,
                   const double* policy_params, int64_t count, double* uLin, int32_t* pbest, double* oldin,
-                  int32_t* started, const bmpc_outputs* out) {
+                  int32_t* started, double* rho_cache, int32_t* code_cache, int32_t* cache_state,
+                  const bmpc_outputs* out) {
   KParams P;
   const int rc = bmpc::make_params(*cfg, &P, &g_err);
   if (rc != BMPC_OK) return rc;
@@ -59,6 +60,9 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   P.pbest = pbest;
   P.oldin = oldin;
   P.started = started;
+  P.rho_cache = rho_cache;
+  P.code_cache = code_cache;
+  P.cache_state = cache_state;
   P.out = *out;
   const bool prox = cfg->controller == BMPC_CTRL_PROX;
   if (cfg->model == BMPC_MODEL_HIGHWAY) {
