@@ -34,11 +34,37 @@ __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ 
   }
   Solver<M, NR, MODE> S(P, slab, factor, lane);
   for (;;) {
-    int prob = 0;
-    if (lane == 0) prob = atomicAdd(P.counter, 1);
-    prob = __shfl_sync(BMPC_FULL_MASK, prob, 0);
-    if (prob >= P.count) break;
-    S.solve(prob);
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(P.counter, 1);
+    idx = __shfl_sync(BMPC_FULL_MASK, idx, 0);
+    if (idx >= P.count) break;
+    S.solve(P.order ? P.order[idx] : idx);
+  }
+}
+
+// Longest-processing-time-first work order: episodes sorted by the cycles their previous solve took (descending,
+// 64 logarithmic buckets), so that the few expensive problems start first and overlap with the bulk instead of forming
+// the tail of the launch.  Single block; counting sort in shared memory.
+__global__ void __launch_bounds__(1024) bmpc_order_kernel(const int* __restrict__ cost, int count, int* __restrict__ order) {
+  __shared__ int hist[64];
+  __shared__ int start[64];
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int c = cost[i];
+    const int bkt = c <= 0 ? 0 : min(63, 2 * (31 - __clz(c)) + ((c >> max(0, 30 - __clz(c))) & 1));
+    atomicAdd(&hist[bkt], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 63; b >= 0; --b) { start[b] = acc; acc += hist[b]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int c = cost[i];
+    const int bkt = c <= 0 ? 0 : min(63, 2 * (31 - __clz(c)) + ((c >> max(0, 30 - __clz(c))) & 1));
+    order[atomicAdd(&start[bkt], 1)] = i;
   }
 }
 
@@ -155,6 +181,8 @@ struct bmpc_handle {
   real* rho_cache = nullptr;
   int* code_cache = nullptr;
   int* cache_state = nullptr;
+  int* cost = nullptr;    // cycles >> 10 of each episode's previous solve (0 = unknown)
+  int* order = nullptr;   // work order of the current launch
   int* counter = nullptr;
   real* gws = nullptr;
   // staging for bmpc_solve_host
@@ -268,6 +296,8 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->rho_cache);
   cudaFree(h->code_cache);
   cudaFree(h->cache_state);
+  cudaFree(h->cost);
+  cudaFree(h->order);
   cudaFree(h->counter);
   cudaFree(h->gws);
   cudaFree(h->stage_in);
@@ -300,6 +330,8 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->rho_cache, cap * P.totalu * (BMPC_MAX_ROWS + 1 + BMPC_MAX_D) * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->code_cache, cap * P.totalu * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->cache_state, cap * 2 * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->cost, cap * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->order, cap * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
   if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
@@ -343,6 +375,7 @@ int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count) {
     BMPC_CK(h, cudaMemset(h->oldin, 0, cap * h->cfg.d * sizeof(real)));
     BMPC_CK(h, cudaMemset(h->started, 0, cap * sizeof(int)));
     BMPC_CK(h, cudaMemset(h->cache_state, 0xff, cap * 2 * sizeof(int)));
+    BMPC_CK(h, cudaMemset(h->cost, 0, cap * sizeof(int)));
     return BMPC_OK;
   }
   for (int64_t i = 0; i < count; ++i) {
@@ -395,6 +428,14 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.rho_cache = h->rho_cache;
   P.code_cache = h->code_cache;
   P.cache_state = h->cache_state;
+  P.cost = h->cost;
+  P.order = nullptr;
+  if (count > h->grid && h->cfg.reserved[4] == 0) {
+    bmpc_order_kernel<<<1, 1024, 0, s>>>(h->cost, (int)count, h->order);
+    BMPC_CK(h, cudaGetLastError());
+    P.order = h->order;
+    h->launches += 1;
+  }
   P.out = *out;
   P.counter = h->counter;
   P.gws = h->gws;

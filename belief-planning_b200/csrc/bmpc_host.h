@@ -105,6 +105,9 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.eps_abs = c.eps_abs > 0.0 ? c.eps_abs : 1.0e-6;
   P.polish_big = c.polish_big > 0.0 ? c.polish_big : 1.0e4;
   P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e4;
+  P.check_every = 5;
+  P.polish_stable = c.reserved[2];
+  P.polish_force = c.reserved[3] > 0 ? c.reserved[3] : 80;
   P.rho_u_feedback = 1.0;
   P.rebalance = c.reserved[0] == 1 ? 0 : 1;   // experimental switch
   *out = P;

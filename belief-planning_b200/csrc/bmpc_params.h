@@ -25,7 +25,7 @@ struct KParams {
   real rf[BMPC_MAX_ROWS][BMPC_MAX_N], rlo[BMPC_MAX_ROWS], rhi[BMPC_MAX_ROWS];
   real ulo[BMPC_MAX_D], uhi[BMPC_MAX_D];
   // ---- solver ----
-  int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes;
+  int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes, check_every, polish_stable, polish_force;
   real alpha, theta, theta_u, eps_abs, polish_big, polish_mult, rho_u_feedback;
   // ---- batch ----
   int count;
@@ -41,6 +41,8 @@ struct KParams {
   int* code_cache;              // solver cache [cap][totalu]: active-set codes of the last certified optimum
   int* cache_state;             // solver cache [cap][2]: age of rho_cache (-1 none), code_cache valid
   bmpc_outputs out;
+  int* cost;                    // solver cache [cap]: cycles >> 10 of the previous solve (scheduling hint), may be null
+  const int* order;             // work order of this launch (longest expected first), or null = natural order
   int* counter;                 // work queue head
   real* gws;                    // global workspace (only when the per-problem slab does not fit shared memory)
   size_t slab_reals;            // reals per problem slab

@@ -88,6 +88,7 @@ struct Solver {
   int lane, nup, prob;
   bool use_codes;   // this solve starts its polish from the cached active set of the previous step
   real gap_r, stp_r, gap_u, stp_u;   // last residual check: max primal gap |f'x - v| and max step |v+ - v| (rows / inputs)
+  int set_changes;                   // last residual check: nodes whose implied active set differs from the previous check
   int nsolve;   // KKT solves (one backward + one forward sweep each) of the current problem
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
@@ -876,13 +877,14 @@ struct Solver {
   template <bool UPDATE, bool CHECK>
   BMPC_D real admm_rows() {
     real res = 0.0;
-    if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; }
+    if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; set_changes = 0; }
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
+      int ncode = 0;   // CHECK: the active set the ADMM state currently implies (compared with the previous check)
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0; }
@@ -907,6 +909,9 @@ struct Solver {
               res = fmax(res, fmax(fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
               gap_r = fmax(gap_r, fabs(rfx - rvn) / rho);
               stp_r = fmax(stp_r, fabs(rvn - rv) / rho);
+              const int cj = (shn > rhi + lam) ? ROW_UP_LIN : (shn > rhi) ? ROW_UP_KINK : (shn >= rlo) ? ROW_INACTIVE
+                             : (shn >= rlo - lam) ? ROW_LO_KINK : ROW_LO_LIN;
+              ncode |= cj << (3 * j);
               if (fabs(rfx - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [row] k %d j %d rho %.3e prim %.3e dual %.3e fx %.4f hi %.4f w %.3e\n", k, j, rho, fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w), rfx / rho, hi, w);
             }
             F(F_S + j, kp) = shn;
@@ -929,6 +934,7 @@ struct Solver {
             res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
             gap_u = fmax(gap_u, fabs(ru - rvn) / rho);
             stp_u = fmax(stp_u, fabs(rvn - rv) / rho);
+            ncode |= ((shn > rho * P.uhi[a]) ? IN_AT_HI : (shn < rho * P.ulo[a]) ? IN_AT_LO : IN_FREE) << (3 * NR + 2 * a);
             if (fabs(ru - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [in] k %d a %d rho %.3e prim %.3e dual %.3e u %.4f w %.3e\n", k, a, rho, fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w), u[a], w);
           }
           F(F_SU + a, kp) = shn;
@@ -941,6 +947,14 @@ struct Solver {
       for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = qx[i];
 #pragma unroll
       for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
+      if (UPDATE && CHECK) {
+        // rows without a penalty (rho = 0) stay "ignored"
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+          if (!(F(F_RHO + j, kp) > 0.0)) ncode |= ROW_IGNORED << (3 * j);
+        set_changes += (ncode != stp()[kp]);
+        stp()[kp] = ncode;
+      }
     }
     lanes_sync();
     return res;
@@ -1657,7 +1671,7 @@ struct Solver {
         have_xu = true;
       }
     }
-    int next_polish = P.polish_first, polish_gap = P.polish_every;
+    int next_polish = P.polish_first, polish_gap = P.polish_every, next_forced = P.polish_force;
     if (!have_xu) {
       factorize(FACT_ADMM);
       ++nfact;
@@ -1667,13 +1681,21 @@ struct Solver {
       backward();
       forward();
       ++iters;
-      const bool check = (iters >= next_polish) || (iters % 10 == 0);
+      const bool check = (iters % P.check_every == 0);
       real res = 1e300;
-      if (check) res = lanes_max(admm_rows<true, true>());
-      else admm_rows<true, false>();
+      int moved = 1 << 20;
+      if (check) {
+        res = lanes_max(admm_rows<true, true>());
+        moved = lanes_sum_int(set_changes);
+      } else {
+        admm_rows<true, false>();
+      }
       const bool conv = res < P.eps_abs;
-      if (check) BMPC_TRACE("  it %d res %.3e\n", iters, res);
-      if (iters >= next_polish || conv) {
+      if (check) BMPC_TRACE("  it %d res %.3e set changes %d\n", iters, res, moved);
+      // polish when the active set implied by the ADMM state has stopped moving (or, at the latest, every force_every)
+      const bool due = check && iters >= next_polish && (moved <= P.polish_stable || iters >= next_forced);
+      if (due || conv) {
+        next_forced = iters + P.polish_force;
         next_polish = iters + polish_gap;
         polish_gap *= 2;   // back off: a problem whose active set is slow to settle should not pay for many attempts
         if (polish(nfact, iters >= 4 * P.polish_first, true)) {
@@ -1714,6 +1736,7 @@ struct Solver {
       if (P.out.nsolve) P.out.nsolve[prob] = nsolve;
 #if defined(__CUDA_ARCH__)
       if (P.out.cycles) P.out.cycles[prob] = (int64_t)(clock64() - t_start);
+      if (P.cost) P.cost[prob] = (int)min((long long)0x7fffffff, (clock64() - t_start) >> 10);
 #else
       if (P.out.cycles) P.out.cycles[prob] = 0;
 #endif
