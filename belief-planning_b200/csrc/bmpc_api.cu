@@ -224,7 +224,7 @@ static int configure_instance(bmpc_handle* h) {
   int max_optin = 0;
   BMPC_CK(h, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   int want = h->cfg.slab_mode;
-  if (want == BMPC_SLAB_AUTO) want = BMPC_SLAB_SPLIT;
+  if (want == BMPC_SLAB_AUTO) want = BMPC_SLAB_SHARED;   // measured: the shared slab wins whenever it fits (profiles/)
   int per_sm = 0, rc = BMPC_OK;
   h->mode = 0;
   if (want == BMPC_SLAB_SHARED) {

@@ -321,6 +321,7 @@ def run_gpu(args):
                                   "flops_per_solve": flops_per_solve,
                                   "peak_source": "bmpc_measure_fp64_peak (DFMA loop, this GPU, this run)"}},
             "cpu_baseline": cpu, "latency": lat, "wall_s_timed_region": t_wall,
+            "step_ms": [round(v, 3) for v in step_ms], "launch": mpc.launch_info(),
         }
         print(json.dumps(line), flush=True)
     mpc.close()

@@ -24,7 +24,10 @@ x0, z0, xref, pp = scenarios.highway_batch(B)
 dev = torch.device("cuda", 0)
 tx, tz, tr, tp = [torch.as_tensor(a, device=dev) for a in (x0, z0, xref, pp)]
 outs = ("u0", "status", "iters", "nfact", "nsolve", "cycles")
-for s in range(4):
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if os.environ.get('FLUSH') else None
+for s in range(int(os.environ.get('STEPS', '4'))):
+    if flush is not None:
+        flush.zero_()
     out = mpc.solve(tx, tz, tr, tp, outputs=outs)
     torch.cuda.synchronize()
     ms = mpc.last_kernel_ms()
