@@ -181,7 +181,7 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from _bmpc import batch, scenarios
+    from _bmpc import batch, scenarios, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,10 +236,8 @@ def run_gpu(args):
     launches = mpc.launch_count() - launches0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in events]
     total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    # the only communication of the run: max over ranks of the timed region (NCCL all_reduce MAX of one scalar)
+    total_ms_max = shard.reduce_stats({"max_total_ms": total_ms}, device=dev)["max_total_ms"]
     value = world * B * K / (total_ms_max * 1e-3)
 
     it = torch.cat(stats["iters"]).double()
@@ -270,10 +268,8 @@ def run_gpu(args):
                 e2e_t += dt
             hx[:] = scenarios.euler_highway(hx, r["u0"])
             hz[:] = scenarios.euler_highway(hz, np.column_stack([np.zeros(B), -0.1 * hz[:, 3]]))
-        te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * K / float(te.item()), "unit": UNIT,
+        e2e_max = shard.reduce_stats({"max_e2e_s": e2e_t}, device=dev)["max_e2e_s"]
+        e2e = {"value": world * B * K / e2e_max, "unit": UNIT,
                "h2d_bytes_per_step": int(B * (3 * 4 + 3 * 4) * 8), "d2h_bytes_per_step": int(B * (2 * 8 + 8 + 4))}
     if rank == 0:
         # p50 latency of a single warm solve through the host API (batch of one)
