@@ -44,6 +44,14 @@ _pd = C.POINTER(_dbl)
 _pi = C.POINTER(_i32)
 
 
+class HmmParams(C.Structure):
+    """struct bmpc_hmm_params"""
+    _fields_ = [(k, _dbl) for k in ("Kpsi", "L", "W", "ylb", "yub", "col_alpha", "s1", "s2", "c2", "tran_diag")]
+
+
+HMM_MAINTAIN, HMM_BRAKE = 0, 1
+
+
 class Outputs(C.Structure):
     """struct bmpc_outputs (device pointers for bmpc_solve, host pointers for bmpc_solve_host)"""
     _fields_ = [("u0", C.c_void_p), ("uPred", C.c_void_p), ("xPred", C.c_void_p), ("xLin", C.c_void_p),
@@ -70,6 +78,13 @@ SYMBOLS = [
     ("bmpc_get_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     ("bmpc_set_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     ("bmpc_eval_model", C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 8 + [C.c_void_p]),
+    ("bmpc_hmm_backup_rollout", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _pi, C.c_int32, _dbl, _dbl, C.c_void_p,
+                                          C.c_int32, C.c_void_p]),
+    ("bmpc_hmm_rollout_sensitivity", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _pi, C.c_int32, _dbl, _dbl, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ("bmpc_hmm_belief_update", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                         C.POINTER(HmmParams), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p]),
     ("bmpc_plant_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                   C.c_void_p]),
     ("bmpc_get_launch_info", C.c_int, [C.c_void_p, _pi, _pi, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

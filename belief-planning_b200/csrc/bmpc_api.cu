@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "bmpc_hmm.cuh"
 #include "bmpc_host.h"
 #include "bmpc_solver.h"
 
@@ -583,6 +584,64 @@ int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warp
   if (smem_bytes) *smem_bytes = (int64_t)h->slab_bytes;
   if (global_bytes_per_warp) *global_bytes_per_warp = (int64_t)h->gws_bytes_per_warp;
   return BMPC_OK;
+}
+
+static int hmm_kinds_to_device(const int32_t* kinds, int m, int** dev) {
+  if (!kinds || m < 1 || m > BMPC_MAX_POLICIES) return BMPC_E_INVALID;
+  for (int j = 0; j < m; ++j)
+    if (kinds[j] != BMPC_HMM_MAINTAIN && kinds[j] != BMPC_HMM_BRAKE) return BMPC_E_INVALID;
+  if (cudaMalloc(dev, m * sizeof(int)) != cudaSuccess) return BMPC_E_CUDA;
+  if (cudaMemcpy(*dev, kinds, m * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(*dev); return BMPC_E_CUDA; }
+  return BMPC_OK;
+}
+
+int bmpc_hmm_backup_rollout(const double* x0, int64_t count, int32_t M, int32_t m, const int32_t* policy_kind, int32_t N,
+                            double dt, double Kpsi, double* xbackup, int32_t device, void* stream) {
+  if (!x0 || !xbackup || count < 0 || M < 1 || N < 1) { g_create_error = "bad argument"; return BMPC_E_INVALID; }
+  if (count == 0) return BMPC_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return BMPC_E_CUDA;
+  int* dk = nullptr;
+  const int rc = hmm_kinds_to_device(policy_kind, m, &dk);
+  if (rc != BMPC_OK) return rc;
+  const int64_t n = count * M * m;
+  hmm::rollout_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x0, (int)count, M, m, dk, N, dt, Kpsi, xbackup);
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(dk);
+  return e == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
+}
+
+int bmpc_hmm_rollout_sensitivity(const double* x0, int64_t count, int32_t m, const int32_t* policy_kind, int32_t steps,
+                                 double ts, double Kpsi, const double* f0, double* xx, double* QQ, double* Qt,
+                                 int32_t device, void* stream) {
+  if (!x0 || !f0 || !xx || !QQ || !Qt || count < 0 || steps < 1) { g_create_error = "bad argument"; return BMPC_E_INVALID; }
+  if (count == 0) return BMPC_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return BMPC_E_CUDA;
+  int* dk = nullptr;
+  const int rc = hmm_kinds_to_device(policy_kind, m, &dk);
+  if (rc != BMPC_OK) return rc;
+  const int64_t n = count * m;
+  hmm::sensitivity_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x0, (int)count, m, dk, steps, ts, Kpsi, f0,
+                                                                                     xx, QQ, Qt);
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(dk);
+  return e == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
+}
+
+int bmpc_hmm_belief_update(const double* ego, const double* xb, const double* b, const double* cbf, int64_t count,
+                           int32_t M, int32_t m, const bmpc_hmm_params* p, int32_t clip, double* h, double* H,
+                           double* b_next, int32_t device, void* stream) {
+  if (!ego || !xb || !b || !p || !b_next || count < 0 || M < 1 || m < 1 || m > BMPC_MAX_POLICIES) {
+    g_create_error = "bad argument";
+    return BMPC_E_INVALID;
+  }
+  if (count == 0) return BMPC_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return BMPC_E_CUDA;
+  const int64_t n = count * M;
+  hmm::belief_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ego, xb, b, cbf, (int)count, M, m, *p, clip, h, H,
+                                                                                b_next);
+  return cudaGetLastError() == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
 }
 
 int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }

@@ -192,6 +192,34 @@ int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const doub
                     int64_t count, double* A, double* B, double* C, double* xp, double* zpred, double* p,
                     double* hlin, double* dh, void* stream);
 
+/* ---- belief-state model (HMM_backup_dyn.py), rows H1/H2 of the hot-path table -------------------------------------
+ * Device pointers, float64; no handle needed (no persistent state).  Policies of that module: */
+#define BMPC_HMM_MAINTAIN 0 /* HMM_backup_dyn.backup_maintain :105 */
+#define BMPC_HMM_BRAKE 1    /* HMM_backup_dyn.backup_brake :107-109 (numeric softmax(-5, -v, 3)) */
+
+typedef struct bmpc_hmm_params {
+  double Kpsi, L, W, ylb, yub, col_alpha, s1, s2, c2, tran_diag; /* utils HMM/Branch constants */
+} bmpc_hmm_params;
+
+/* PredictiveModel.generate_backup_traj (:204-214): x0 [count][M][4] -> xbackup [count][M*m][N*4], row m*i+j = agent i
+ * under policy j, flattened component-major as casadi.reshape does.  policy_kind: m HOST ints. */
+int bmpc_hmm_backup_rollout(const double* x0, int64_t count, int32_t M, int32_t m, const int32_t* policy_kind, int32_t N,
+                            double dt, double Kpsi, double* xbackup, int32_t device, void* stream);
+
+/* module-level generate_backup_traj with sensitivity (:54-85): x0 [count][4]; outputs for every (point, policy):
+ * xx [count][m][steps][4], QQ [count][m][steps][16] (dx_t/dx_0), Qt [count][m][steps][4] (xdot - f0). f0: 4 device doubles. */
+int bmpc_hmm_rollout_sensitivity(const double* x0, int64_t count, int32_t m, const int32_t* policy_kind, int32_t steps,
+                                 double ts, double Kpsi, const double* f0, double* xx, double* QQ, double* Qt,
+                                 int32_t device, void* stream);
+
+/* belief transition (backup_trans :96-101 inside calc_xp_expr :249-257) and, when cbf != NULL, the environment's update
+ * (Highway_env.py:251-256): ego [count][4], xb [count][M][m][4] (backup state of every agent/policy at the evaluated
+ * time), b [count][M][m], cbf [count][M][m] or NULL.  clip=1: numeric veh_col (+-5 clip, :145-147), clip=0: symbolic.
+ * Outputs (NULL = skip): h [count][M][m], H [count][M][m][m], b_next [count][M][m]. */
+int bmpc_hmm_belief_update(const double* ego, const double* xb, const double* b, const double* cbf, int64_t count,
+                           int32_t M, int32_t m, const bmpc_hmm_params* p, int32_t clip, double* h, double* H,
+                           double* b_next, int32_t device, void* stream);
+
 /* Plant step of the reference environments, batched on the device (vehicle.step, Highway_env_branch.py:39-41;
  * robot.step, quadruped_env.py:24-40): x <- x + dt f(x, u) for the ego with the applied input u [count][d], and the
  * obstacle z under backup policy `obstacle_policy` (index into the handle's policy table, per-episode parameters from

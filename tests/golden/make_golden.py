@@ -216,8 +216,70 @@ def model_function_vectors():
     np.savez_compressed(os.path.join(HERE, "model_functions.npz"), **out)
 
 
+def hmm_vectors():
+    """Numeric functions of the reference's HMM_backup_dyn.py (belief-state model): backup rollouts with and without
+    the sensitivity matrix, belief transition, normalised collision function.  The module imports a name its `utils.py`
+    does not define (`HMM_constants`, HMM_backup_dyn.py:5); a dataclass with the fields the module reads is injected
+    before the import - the module's code is untouched."""
+    import dataclasses
+    print("hmm fixture")
+
+    @dataclasses.dataclass
+    class HMM_constants:
+        s1: float = None; s2: float = None; c2: float = None; tran_diag: float = None; alpha: float = None
+        R: float = None; am: float = None; rm: float = None; J_c: float = None; s_c: float = None
+        ylb: float = None; yub: float = None; W: float = None; L: float = None; col_alpha: float = None
+        Kpsi: float = None
+
+    with refenv.reference_imports():
+        rutils.HMM_constants = HMM_constants
+        import HMM_backup_dyn as hmm
+    cons = HMM_constants(s1=2, s2=3, c2=0.5, tran_diag=0.3, alpha=1, R=1.2, am=6.0, rm=0.3, J_c=20, s_c=1, ylb=0., yub=7.2,
+                         L=4, W=2.5, col_alpha=5, Kpsi=0.1)
+    rng = np.random.default_rng(777)
+    K, M, m, N, dt = 12, 2, 2, 10, 0.1
+    backupcons = [lambda s: hmm.backup_maintain(s, cons), lambda s: hmm.backup_brake(s, cons)]
+    X0 = np.stack([np.column_stack([rng.uniform(-10, 30, M), rng.uniform(0.5, 6.5, M), rng.uniform(8, 25, M),
+                                    rng.normal(0, 0.05, M)]) for _ in range(K)])
+    # the constructor builds symbolic graphs the casadi stand-in does not cover; the rollout METHOD is called unbound on a
+    # plain attribute holder (same code, HMM_backup_dyn.py:204-214)
+    import types
+    holder = types.SimpleNamespace(M=M, m=m, n=4, dt=dt, backupcons=backupcons)
+    XB = np.stack([np.array(hmm.PredictiveModel.generate_backup_traj(holder, X0[k], N)) for k in range(K)])   # (K, M*m, N*n)
+    # module-level rollout with sensitivity (HMM_backup_dyn.py:54-85): fixed number of steps
+    steps, ts = 6, 0.05
+    f0 = np.array([1.0, 0.0, 0.0, 0.0])
+    XX, QQ, QT = [], [], []
+    for k in range(K):
+        for j in range(m):
+            tt, xx, uu, Q, Qt = hmm.generate_backup_traj(X0[k, 0], backupcons[j], lambda s, t: t >= steps * ts - 1e-12, f0, ts=ts)
+            XX.append(np.array(xx)); QQ.append(np.array(Q)); QT.append(np.array(Qt))
+    # belief transition + input probability (HMM_backup_dyn.py:96-104) and the h used by the model (:255)
+    EGO = np.column_stack([rng.uniform(-5, 5, K), rng.uniform(0.5, 6.5, K), rng.uniform(10, 25, K), rng.normal(0, 0.05, K)])
+    H_all, h_all, bnext, bnext_env = [], [], [], []
+    Bm = rng.dirichlet(np.ones(m), size=(K, M))
+    CBF = rng.uniform(-1, 2, size=(K, M, m))
+    for k in range(K):
+        for i in range(M):
+            h = np.zeros(m)
+            for j in range(m):
+                xb = XB[k, m * i + j].reshape(N, 4, order="F")[3]                     # backup state after 4 steps
+                hc = float(hmm.veh_col(EGO[k], xb, [cons.L + 1, cons.W + 0.2]))
+                # symbolic (un-clipped) branch value equals the numeric one inside the +-5 clip range
+                h[j] = float(hmm.softmin(hc, float(hmm.lane_bdry_h(xb, cons.ylb, cons.yub)), cons.col_alpha))
+            H = np.array(hmm.backup_trans(h, cons))
+            bi = Bm[k, i] @ H
+            be = bi * np.array([hmm.backup_input_prob(CBF[k, i, j], cons) for j in range(m)])
+            H_all.append(H); h_all.append(h); bnext.append(bi); bnext_env.append(be / be.sum())
+    np.savez_compressed(os.path.join(HERE, "hmm_functions.npz"), X0=X0, XB=XB, N=np.array(N), dt=np.array(dt),
+                        sens_x=np.array(XX), sens_Q=np.array(QQ), sens_Qt=np.array(QT), sens_f0=f0, sens_ts=np.array(ts),
+                        sens_steps=np.array(steps), EGO=EGO, B=Bm, CBF=CBF, H=np.array(H_all).reshape(K, M, m, m),
+                        h=np.array(h_all).reshape(K, M, m), b_next=np.array(bnext).reshape(K, M, m),
+                        b_next_env=np.array(bnext_env).reshape(K, M, m), t_index=np.array(3))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "quad"]
+    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "quad", "hmm"]
     if "models" in which:
         model_function_vectors()
     if "hw_default" in which:
@@ -238,3 +300,5 @@ if __name__ == "__main__":
                     [0, 1.8, 20, 0], [5, 5.4, 20, 0], [0, 1.8, 26.5, 0], steps=3)
     if "quad" in which:
         run_quadruped("quadruped_prox_default", [0, 0, 0], [2, 0.3, np.pi], [5., 5., 0.], steps=3)
+    if "hmm" in which:
+        hmm_vectors()

@@ -338,6 +338,13 @@ def norm_1(x):
     return SX._wrap(e)
 
 
+def reshape(x, *shape):
+    """casadi.reshape is column-major (numeric inputs only here; used by HMM_backup_dyn.py:213)."""
+    if len(shape) == 1:
+        shape = tuple(shape[0])
+    return _np.reshape(_np.asarray(x, dtype=float), shape, order="F")
+
+
 def kron(a, b):
     a = _lift(a)._e
     b = _lift(b)._e
