@@ -171,6 +171,10 @@ class _BatchedController:
         branch's linearisation trajectory (MPC_branch.py:1231-1246)."""
         if self.uPred is None:
             raise RuntimeError("solve() has not been called")
+        if self.controller_kind == abi.CTRL_ROBUST:
+            # robustMPC.BT2array (:1385-1395): one ego trajectory; the obstacle tree is not returned by the kernel
+            pick = (lambda a: a[episode]) if np.ndim(self.uPred) == 3 else (lambda a: a)
+            return [pick(self.xPred)], [], [pick(self.uPred)], []
         batched = np.ndim(self.uPred) == 3
         sel = (lambda a: a[episode]) if batched else (lambda a: a)
         xbar, zbar, w = sel(self._xbar), sel(self.zPred), sel(self.branch_w)

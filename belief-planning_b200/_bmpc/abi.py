@@ -71,6 +71,7 @@ SYMBOLS = [
     ("bmpc_total_x", C.c_int, [C.c_void_p]),
     ("bmpc_total_u", C.c_int, [C.c_void_p]),
     ("bmpc_get_topology", C.c_int, [C.c_void_p, _pi, _pi, _pi, _pi]),
+    ("bmpc_ulin_rows", C.c_int, [C.c_void_p]),
     ("bmpc_solve", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                              C.POINTER(Outputs), C.c_void_p]),
     ("bmpc_solve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -37,6 +37,7 @@ class BatchedBranchMPC:
         self.nbranch = self.lib.bmpc_num_branches(h)
         self.totalx = self.lib.bmpc_total_x(h)
         self.totalu = self.lib.bmpc_total_u(h)
+        self.ulin_rows = self.lib.bmpc_ulin_rows(h)
         self.capacity = cfg.batch_capacity
         self._dev_out = {}
 
@@ -142,7 +143,7 @@ class BatchedBranchMPC:
     # -- persistent state ---------------------------------------------------------------------------------------
     def get_state(self, count=None):
         count = self.capacity if count is None else count
-        st = {"uLin": np.empty((count, self.totalu + 1, self.cfg.d)), "pbest": np.empty((count, self.nbranch), np.int32),
+        st = {"uLin": np.empty((count, self.ulin_rows, self.cfg.d)), "pbest": np.empty((count, self.nbranch), np.int32),
               "old_input": np.empty((count, self.cfg.d)), "started": np.empty(count, np.int32)}
         self._check(self.lib.bmpc_get_state(self.h, st["uLin"].ctypes.data, st["pbest"].ctypes.data,
                                             st["old_input"].ctypes.data, st["started"].ctypes.data, count, 1),

@@ -19,7 +19,7 @@
 // own slab (shared memory when it fits, global/L2 otherwise).
 // MODE = BMPC_SLAB_SHARED (whole slab in shared memory), BMPC_SLAB_SPLIT (iterate fields in shared memory, factor fields
 // in this warp's global region, which stays L2-resident), BMPC_SLAB_GLOBAL (everything in the global region).
-template <class M, int NR, int MODE>
+template <class M, int NR, int MODE, int NC = 1>
 __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ 
     slab = reinterpret_cast<real*>(smem_raw);
     if (SPLIT) factor = P.gws + (size_t)blockIdx.x * P.factor_reals;
   }
-  Solver<M, NR, MODE> S(P, slab, factor, lane);
+  Solver<M, NR, MODE, NC> S(P, slab, factor, lane);
   for (;;) {
     int idx = 0;
     if (lane == 0) idx = atomicAdd(P.counter, 1);
@@ -107,21 +107,21 @@ __global__ void bmpc_eval_kernel(const __grid_constant__ KParams P, const EvalAr
     const real* z = a.z + (size_t)i * NX;
     real hi[BMPC_MAX_POLICIES];
     real himax = -1e300;
-    for (int k = 0; k < P.m; ++k) {
-      const real* par = a.polpar ? a.polpar + ((size_t)i * P.m + k) * 4 : P.pol_par[k];
-      const real* par0 = a.polpar ? a.polpar + ((size_t)i * P.m) * 4 : P.pol_par[0];
+    for (int k = 0; k < P.zm; ++k) {
+      const real* par = a.polpar ? a.polpar + ((size_t)i * P.zm + k) * 4 : P.pol_par[k];
+      const real* par0 = a.polpar ? a.polpar + ((size_t)i * P.zm) * 4 : P.pol_par[0];
       real zl[NX];
-      real* zo = a.zpred ? a.zpred + (size_t)i * P.N * P.m * NX : nullptr;
-      hi[k] = M::policy_safety(P, P.pol_kind[k], par, P.pol_kind[0], par0, x, z, zl, [&](int t, const real* zz) {
+      real* zo = a.zpred ? a.zpred + (size_t)i * P.zN * P.zm * NX : nullptr;
+      hi[k] = M::policy_safety(P, P.pol_kind[k], par, P.pol_kind[0], par0, x, z, zl, P.zN, [&](int t, const real* zz) {
         if (zo)
-          for (int q = 0; q < NX; ++q) zo[((size_t)t * P.m + k) * NX + q] = zz[q];
+          for (int q = 0; q < NX; ++q) zo[((size_t)t * P.zm + k) * NX + q] = zz[q];
       });
       himax = fmax(himax, hi[k]);
     }
     if (a.p) {
       real sum = 0.0;
-      for (int k = 0; k < P.m; ++k) sum += M::branch_weight(P, hi[k], himax);
-      for (int k = 0; k < P.m; ++k) a.p[(size_t)i * P.m + k] = M::branch_weight(P, hi[k], himax) / sum;
+      for (int k = 0; k < P.zm; ++k) sum += M::branch_weight(P, hi[k], himax);
+      for (int k = 0; k < P.zm; ++k) a.p[(size_t)i * P.zm + k] = M::branch_weight(P, hi[k], himax) / sum;
     }
   }
 }
@@ -177,10 +177,11 @@ struct bmpc_handle {
   real* uLin = nullptr;
   int* pbest = nullptr;
   real* oldin = nullptr;
+  real* xprev = nullptr;   // robustMPC only: previous predicted states
   int* started = nullptr;
   // solver caches (not part of the reference-visible state): rho of the last refresh, active set of the last optimum
   real* rho_cache = nullptr;
-  int* code_cache = nullptr;
+  long long* code_cache = nullptr;
   int* cache_state = nullptr;
   int* cost = nullptr;    // cycles >> 10 of each episode's previous solve (0 = unknown)
   int* order = nullptr;   // work order of the current launch
@@ -207,20 +208,20 @@ static std::string g_create_error;
     }                                                                                              \
   } while (0)
 
-template <class M, int NR, int MODE>
+template <class M, int NR, int MODE, int NC>
 static int try_mode(bmpc_handle* h, int max_optin, int* per_sm) {
-  using S = Solver<M, NR, MODE>;
-  const size_t slab = S::slab_reals(h->P.nup, h->P.nbranch) * sizeof(real);
+  using S = Solver<M, NR, MODE, NC>;
+  const size_t slab = S::slab_reals(h->P.nup, h->P.nbx) * sizeof(real);
   const size_t smem = (MODE == BMPC_SLAB_GLOBAL) ? 0 : slab;
   *per_sm = 0;
   if (smem > (size_t)max_optin) return BMPC_OK;   // does not fit: caller falls through to the next mode
   if (smem > 0)
-    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE>, 32, smem));
+    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, MODE, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE, NC>, 32, smem));
   return BMPC_OK;
 }
 
-template <class M, int NR>
+template <class M, int NR, int NC = 1>
 static int configure_instance(bmpc_handle* h) {
   int max_optin = 0;
   BMPC_CK(h, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -229,17 +230,17 @@ static int configure_instance(bmpc_handle* h) {
   int per_sm = 0, rc = BMPC_OK;
   h->mode = 0;
   if (want == BMPC_SLAB_SHARED) {
-    rc = try_mode<M, NR, BMPC_SLAB_SHARED>(h, max_optin, &per_sm);
+    rc = try_mode<M, NR, BMPC_SLAB_SHARED, NC>(h, max_optin, &per_sm);
     if (rc != BMPC_OK) return rc;
     if (per_sm > 0) h->mode = BMPC_SLAB_SHARED;
   }
   if (h->mode == 0 && want != BMPC_SLAB_GLOBAL) {
-    rc = try_mode<M, NR, BMPC_SLAB_SPLIT>(h, max_optin, &per_sm);
+    rc = try_mode<M, NR, BMPC_SLAB_SPLIT, NC>(h, max_optin, &per_sm);
     if (rc != BMPC_OK) return rc;
     if (per_sm > 0) h->mode = BMPC_SLAB_SPLIT;
   }
   if (h->mode == 0) {
-    rc = try_mode<M, NR, BMPC_SLAB_GLOBAL>(h, max_optin, &per_sm);
+    rc = try_mode<M, NR, BMPC_SLAB_GLOBAL, NC>(h, max_optin, &per_sm);
     if (rc != BMPC_OK) return rc;
     if (per_sm > 8) per_sm = 8;   // keep the global slabs of the resident warps inside L2
     if (per_sm > 0) h->mode = BMPC_SLAB_GLOBAL;
@@ -248,13 +249,13 @@ static int configure_instance(bmpc_handle* h) {
   if (h->cfg.reserved[1] > 0 && per_sm > h->cfg.reserved[1]) per_sm = h->cfg.reserved[1];   // occupancy cap (experiments)
   h->grid = per_sm * h->num_sms;
   if (h->mode == BMPC_SLAB_SPLIT) {
-    using S = Solver<M, NR, BMPC_SLAB_SPLIT>;
-    h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
+    using S = Solver<M, NR, BMPC_SLAB_SPLIT, NC>;
+    h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbx);
     h->P.factor_reals = S::factor_reals(h->P.nup);
     h->gws_bytes_per_warp = h->P.factor_reals * sizeof(real);
   } else {
-    using S = Solver<M, NR, BMPC_SLAB_GLOBAL>;
-    h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbranch);
+    using S = Solver<M, NR, BMPC_SLAB_GLOBAL, NC>;
+    h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbx);
     h->P.factor_reals = 0;
     h->gws_bytes_per_warp = (h->mode == BMPC_SLAB_GLOBAL) ? h->P.slab_reals * sizeof(real) : 0;
   }
@@ -262,14 +263,14 @@ static int configure_instance(bmpc_handle* h) {
   return BMPC_OK;
 }
 
-template <class M, int NR>
+template <class M, int NR, int NC = 1>
 static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStream_t s) {
   if (h->mode == BMPC_SLAB_SHARED) {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED><<<grid, 32, h->slab_bytes, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, 32, h->slab_bytes, s>>>(P);
   } else if (h->mode == BMPC_SLAB_SPLIT) {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT><<<grid, 32, h->slab_bytes, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, 32, h->slab_bytes, s>>>(P);
   } else {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL><<<grid, 32, 0, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, 32, 0, s>>>(P);
   }
   BMPC_CK(h, cudaGetLastError());
   return BMPC_OK;
@@ -282,8 +283,10 @@ static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStrea
                                                       : fn<HW, 3>(__VA_ARGS__))          \
        : fn<QD, 1>(__VA_ARGS__))
 // BranchMPCProx carries the previous input through the Riccati state (RateAug); BranchMPC does not need to.
+// robustMPC: highway model, 2 state rows + up to 9 obstacle nodes per time slot
 #define BMPC_DISPATCH(h, fn, ...)                                                                       \
-  ((h)->cfg.controller == BMPC_CTRL_PROX                                                                \
+  ((h)->cfg.controller == BMPC_CTRL_ROBUST ? fn<HighwayModel, 11, 9>(__VA_ARGS__) :                     \
+   (h)->cfg.controller == BMPC_CTRL_PROX                                                                \
        ? BMPC_DISPATCH_M(h, fn, RateAug<HighwayModel>, RateAug<QuadrupedModel>, __VA_ARGS__)            \
        : BMPC_DISPATCH_M(h, fn, HighwayModel, QuadrupedModel, __VA_ARGS__))
 
@@ -293,6 +296,7 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->uLin);
   cudaFree(h->pbest);
   cudaFree(h->oldin);
+  cudaFree(h->xprev);
   cudaFree(h->started);
   cudaFree(h->rho_cache);
   cudaFree(h->code_cache);
@@ -312,8 +316,8 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   h->cfg = *cfg;
   int rc = bmpc::make_params(*cfg, &h->P, &h->err);
   if (rc != BMPC_OK) return rc;
-  if (!bmpc::supported_instance(cfg->model, cfg->n_rows)) {
-    h->err = "no kernel instance for this (model, n_rows)";
+  if (!bmpc::supported_instance(cfg->model, cfg->n_rows, cfg->controller, h->P.zpw[h->P.zNB])) {
+    h->err = "no kernel instance for this (model, n_rows, controller)";
     return BMPC_E_UNSUPPORTED;
   }
   if (cfg->batch_capacity < 1) { h->err = "batch_capacity must be >= 1"; return BMPC_E_INVALID; }
@@ -328,8 +332,9 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->pbest, cap * P.nbranch * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->oldin, cap * cfg->d * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->started, cap * sizeof(int)));
+  if (cfg->controller == BMPC_CTRL_ROBUST) BMPC_CK(h, cudaMalloc(&h->xprev, cap * P.pub_totalx * cfg->n * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->rho_cache, cap * P.totalu * (BMPC_MAX_ROWS + 1 + BMPC_MAX_D) * sizeof(real)));
-  BMPC_CK(h, cudaMalloc(&h->code_cache, cap * P.totalu * sizeof(int)));
+  BMPC_CK(h, cudaMalloc(&h->code_cache, cap * P.totalu * sizeof(long long)));
   BMPC_CK(h, cudaMalloc(&h->cache_state, cap * 2 * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->cost, cap * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->order, cap * sizeof(int)));
@@ -392,8 +397,10 @@ int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count) {
 }
 
 int bmpc_num_branches(const bmpc_handle* h) { return h ? h->P.nbranch : BMPC_E_INVALID; }
-int bmpc_total_x(const bmpc_handle* h) { return h ? h->P.totalx : BMPC_E_INVALID; }
-int bmpc_total_u(const bmpc_handle* h) { return h ? h->P.totalu : BMPC_E_INVALID; }
+int bmpc_total_x(const bmpc_handle* h) { return h ? h->P.pub_totalx : BMPC_E_INVALID; }
+int bmpc_total_u(const bmpc_handle* h) { return h ? h->P.pub_totalu : BMPC_E_INVALID; }
+
+int bmpc_ulin_rows(const bmpc_handle* h) { return h ? h->P.totalu + 1 : BMPC_E_INVALID; }
 
 int bmpc_get_topology(const bmpc_handle* h, int32_t* ndx, int32_t* ndu, int32_t* depth, int32_t* parent) {
   if (!h) return BMPC_E_INVALID;
@@ -425,6 +432,7 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.uLin = h->uLin;
   P.pbest = h->pbest;
   P.oldin = h->oldin;
+  P.xprev = h->xprev;
   P.started = h->started;
   P.rho_cache = h->rho_cache;
   P.code_cache = h->code_cache;
@@ -462,8 +470,8 @@ int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const do
   const size_t cap = (size_t)h->cfg.batch_capacity, n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
   if (!h->stage_in) BMPC_CK(h, cudaMalloc(&h->stage_in, cap * (3 * n + 4 * m) * sizeof(real)));
   // device staging of every output, laid out back to back
-  const size_t sz[13] = {d * 8, (size_t)P.totalu * d * 8, (size_t)P.totalx * n * 8, (size_t)P.totalu * n * 8,
-                         (size_t)P.totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8};
+  const size_t sz[13] = {d * 8, (size_t)P.pub_totalu * d * 8, (size_t)P.pub_totalx * n * 8, (size_t)P.pub_totalu * n * 8,
+                         (size_t)P.pub_totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8};
   void* const host[13] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
                           out->branch_p, out->objective, out->status, out->iters, out->nfact, out->nsolve, out->cycles};
   size_t per = 0;

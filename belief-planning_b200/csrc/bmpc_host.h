@@ -31,9 +31,14 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   if (c.m < 1 || c.m > BMPC_MAX_POLICIES) { *err = "m must be in [1, BMPC_MAX_POLICIES]"; return BMPC_E_INVALID; }
   if (!(c.dt > 0.0)) { *err = "dt must be positive"; return BMPC_E_INVALID; }
   if (c.n_rows < 0 || c.n_rows > BMPC_MAX_ROWS) { *err = "n_rows out of range"; return BMPC_E_INVALID; }
-  if (c.controller != BMPC_CTRL_BRANCH && c.controller != BMPC_CTRL_PROX) {
-    *err = "controller kind not built yet (BRANCH and PROX only)";
-    return BMPC_E_UNSUPPORTED;
+  if (c.controller != BMPC_CTRL_BRANCH && c.controller != BMPC_CTRL_PROX && c.controller != BMPC_CTRL_ROBUST) {
+    *err = "unknown controller kind";
+    return BMPC_E_INVALID;
+  }
+  const bool robust = c.controller == BMPC_CTRL_ROBUST;
+  if (robust) {
+    for (int a = 0; a < d; ++a)
+      if (c.dR[a] != 0.0) { *err = "robustMPC with input-rate costs (dR != 0) is not built"; return BMPC_E_UNSUPPORTED; }
   }
   if (c.Qslack[0] != 0.0) { *err = "quadratic slack weight Qslack[0] must be 0 (the reference uses 0)"; return BMPC_E_UNSUPPORTED; }
   if (!(c.Qslack[1] > 0.0)) { *err = "linear slack weight Qslack[1] must be positive"; return BMPC_E_INVALID; }
@@ -50,21 +55,41 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
     if (!(c.u_lo[a] <= c.u_hi[a])) { *err = "empty input box"; return BMPC_E_INVALID; }
     if (!(c.R[a * d + a] > 0.0)) { *err = "R must have a positive diagonal"; return BMPC_E_INVALID; }
   }
-  P.m = c.m;
-  P.NB = c.NB;
-  P.N = c.N;
+  // obstacle scenario tree
+  P.zm = c.m;
+  P.zNB = c.NB;
+  P.zN = c.N;
+  {
+    int pw = 1, off = 0;
+    for (int k = 0; k <= c.NB; ++k) {
+      P.zpw[k] = pw;
+      P.zoff[k] = off;
+      off += pw;
+      pw *= c.m;
+    }
+    P.zoff[c.NB + 1] = off;
+    P.znbranch = off;
+  }
+  // ego tree: the scenario tree itself, or (robustMPC, MPC_branch.py:1301-1302) one chain of N*NB+1 input nodes plus an
+  // internal dummy stage that carries the terminal state's cost and soft rows
+  P.m = robust ? 1 : c.m;
+  P.NB = robust ? 1 : c.NB;
+  P.N = robust ? c.N * c.NB + 1 : c.N;
   int pw = 1, off = 0;
-  for (int k = 0; k <= c.NB; ++k) {
+  for (int k = 0; k <= P.NB; ++k) {
     P.pw[k] = pw;
     P.off[k] = off;
     off += pw;
-    pw *= c.m;
+    pw *= P.m;
   }
-  P.off[c.NB + 1] = off;
+  P.off[P.NB + 1] = off;
   P.nbranch = off;
-  P.totalu = 1 + c.N * (P.nbranch - 1);
-  P.totalx = P.totalu + P.pw[c.NB];
+  P.totalu = 1 + P.N * (P.nbranch - 1);
+  P.totalx = robust ? P.totalu : P.totalu + P.pw[P.NB];
+  P.pub_totalu = robust ? P.totalu - 1 : P.totalu;
+  P.pub_totalx = P.totalx;
   P.nup = P.totalu + P.nbranch;
+  P.nbx = P.nbranch > P.znbranch ? P.nbranch : P.znbranch;
   P.dt = c.dt;
   P.veh_L = c.veh_L;
   P.veh_W = c.veh_W;
@@ -81,7 +106,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   for (int i = 0; i < n * n; ++i) { P.Q[i] = c.Q[i]; P.Qf[i] = c.Qf[i]; }
   for (int i = 0; i < d * d; ++i) P.R[i] = c.R[i];
   for (int i = 0; i < d; ++i) { P.dR[i] = c.dR[i]; P.ulo[i] = c.u_lo[i]; P.uhi[i] = c.u_hi[i]; }
-  P.dq_scale = (c.controller == BMPC_CTRL_PROX) ? 3.0 : 0.5;   // MPC_branch.py:271 / :1070
+  P.dq_scale = (c.controller == BMPC_CTRL_PROX) ? 3.0 : (robust ? 0.0 : 0.5);   // MPC_branch.py:271 / :1070 / none in robustMPC
   P.lam_lin = c.Qslack[1];
   P.nrows = c.n_rows;
   for (int j = 0; j < c.n_rows; ++j) {
@@ -115,7 +140,9 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
 }
 
 // (model, number of soft rows incl. the collision row) -> which Solver instantiation runs
-inline bool supported_instance(int model, int n_rows) {
+inline bool supported_instance(int model, int n_rows, int controller = BMPC_CTRL_BRANCH, int obstacle_leaves = 1) {
+  // robustMPC is instantiated for the highway model with the reference's two state rows and up to 9 obstacle nodes per slot
+  if (controller == BMPC_CTRL_ROBUST) return model == BMPC_MODEL_HIGHWAY && n_rows == 2 && obstacle_leaves <= 9;
   if (model == BMPC_MODEL_HIGHWAY) return n_rows >= 0 && n_rows <= 2;
   if (model == BMPC_MODEL_QUADRUPED) return n_rows == 0;
   return false;

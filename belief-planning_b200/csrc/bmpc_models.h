@@ -163,11 +163,11 @@ struct HighwayModel {
   // the ego rollout under policy 0; also returns the obstacle trajectory through `emit(t, z)`.
   template <class Emit>
   BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
-                                       const real* xe0, const real* z0, real* zlast, Emit emit) {
+                                       const real* xe0, const real* z0, real* zlast, int nsteps, Emit emit) {
     real xe[4] = {xe0[0], xe0[1], xe0[2], xe0[3]};
     real z[4] = {z0[0], z0[1], z0[2], z0[3]};
     SoftMinAcc acc(5.0);
-    for (int t = 0; t < P.N; ++t) {
+    for (int t = 0; t < nsteps; ++t) {
       real u[2], xn[4];
       policy(P, kind0, par0, xe, u);
       step(P, xe, u, xn);
@@ -283,11 +283,11 @@ struct QuadrupedModel {
   }
   template <class Emit>
   BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
-                                       const real* xe0, const real* z0, real* zlast, Emit emit) {
+                                       const real* xe0, const real* z0, real* zlast, int nsteps, Emit emit) {
     real xe[3] = {xe0[0], xe0[1], xe0[2]};
     real z[3] = {z0[0], z0[1], z0[2]};
     SoftMinAcc acc(5.0);
-    for (int t = 0; t < P.N; ++t) {
+    for (int t = 0; t < nsteps; ++t) {
       real u[3], xn[3];
       policy(P, kind0, par0, xe, u);
       step(P, xe, u, xn);
@@ -368,8 +368,8 @@ struct RateAug {
   }
   template <class Emit>
   BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
-                                   const real* xe0, const real* z0, real* zlast, Emit emit) {
-    return M::policy_safety(P, kind, par, kind0, par0, xe0, z0, zlast, emit);
+                                   const real* xe0, const real* z0, real* zlast, int nsteps, Emit emit) {
+    return M::policy_safety(P, kind, par, kind0, par0, xe0, z0, zlast, nsteps, emit);
   }
   BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return M::branch_weight(P, hi, himax); }
   static constexpr bool kWeightNeedsMax = M::kWeightNeedsMax;

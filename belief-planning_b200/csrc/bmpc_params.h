@@ -12,6 +12,11 @@ struct KParams {
   int nup;                      // padded node count = totalu + nbranch (one pad slot per branch)
   int off[BMPC_MAX_NB + 2];     // first branch id of each depth; off[NB+1] = nbranch
   int pw[BMPC_MAX_NB + 1];      // m^depth
+  // obstacle scenario tree (equal to the ego tree for the branch controllers; robustMPC plans one ego chain against it)
+  int zm, zNB, zN, znbranch;
+  int zoff[BMPC_MAX_NB + 2], zpw[BMPC_MAX_NB + 1];
+  int nbx;                      // branches the per-branch arrays of the slab are sized for = max(nbranch, znbranch)
+  int pub_totalu, pub_totalx;   // rows of uPred / xPred the caller sees (the robust chain carries one internal dummy stage)
   // ---- model ----
   real dt, veh_L, veh_W, Kpsi, s1, lane_lo, lane_hi, quad_margin;
   int pol_kind[BMPC_MAX_POLICIES];
@@ -36,9 +41,10 @@ struct KParams {
   real* uLin;                   // persistent [cap][totalu+1][d]
   int* pbest;                   // persistent [cap][nbranch]
   real* oldin;                  // persistent [cap][d]
+  real* xprev;                  // persistent [cap][pub_totalx][n]: previous predicted states (robustMPC's LTV shift), else null
   int* started;                 // persistent [cap]
   real* rho_cache;              // solver cache [cap][totalu][rows+inputs]: curvature-matched rho of the last refresh
-  int* code_cache;              // solver cache [cap][totalu]: active-set codes of the last certified optimum
+  long long* code_cache;              // solver cache [cap][totalu]: active-set codes of the last certified optimum
   int* cache_state;             // solver cache [cap][2]: age of rho_cache (-1 none), code_cache valid
   bmpc_outputs out;
   int* cost;                    // solver cache [cap]: cycles >> 10 of the previous solve (scheduling hint), may be null

@@ -18,6 +18,7 @@
 enum { ROW_INACTIVE = 0, ROW_UP_KINK = 1, ROW_UP_LIN = 2, ROW_LO_KINK = 3, ROW_LO_LIN = 4, ROW_IGNORED = 7 };
 enum { IN_FREE = 0, IN_AT_HI = 1, IN_AT_LO = 2 };
 enum { FACT_ADMM = 0, FACT_FREE = 1, FACT_POLISH = 2 };
+typedef long long code_t;   // per-node active-set code (see Solver::row_of / in_of)
 
 #define BMPC_NOLO (-1.0e300)
 
@@ -46,7 +47,9 @@ BMPC_D real row_dual(real sh, real rlo, real rhi, real lam) {
 extern __shared__ __align__(16) real bmpc_smem[];
 #endif
 
-template <class M, int NR, int MODE = BMPC_SLAB_SHARED>
+// NR = soft rows per node: NC collision rows (1 for the branch controllers; robustMPC has one per obstacle node of the
+// time slot, up to m^NB) followed by the two-sided state rows of the configuration.
+template <class M, int NR, int MODE = BMPC_SLAB_SHARED, int NC = 1>
 struct Solver {
   static constexpr bool SPLIT = (MODE == BMPC_SLAB_SPLIT);
   static constexpr int NX = M::NX, NU = M::NU;   // Riccati state (physical, or physical + previous input) / input
@@ -59,8 +62,8 @@ struct Solver {
   static constexpr int F_CC = F_LIN + M::NLIN;
   static constexpr int F_Q = F_CC + M::NCC;
   static constexpr int F_FC = F_Q + NXP;     // collision row f (x,y components); holds the obstacle (x,y) before setup
-  static constexpr int F_HC = F_FC + 2;      // collision row upper bound
-  static constexpr int F_RHO = F_HC + 1;     // rho of the NR soft rows then of the NU inputs
+  static constexpr int F_HC = F_FC + 2 * NC; // collision row upper bounds
+  static constexpr int F_RHO = F_HC + NC;    // rho of the NR soft rows then of the NU inputs
   static constexpr int F_K = F_RHO + NR + NU;
   static constexpr int F_SI = F_K + NU * NX; // S^-1, packed upper triangle
   static constexpr int F_H0 = F_SI + NSU;    // P+ C
@@ -76,8 +79,8 @@ struct Solver {
   static constexpr int NFW = SPLIT ? NF - NFA : NF;   // fields kept in the slab
   static constexpr int NFWP = NFW | 1;                // slab record stride, odd (bank-conflict-free)
 
-  BMPC_HD static size_t slab_reals(int nup, int nbranch) {
-    return (size_t)NFWP * nup + (size_t)(nup + 1) / 2 + (size_t)BR * nbranch;
+  BMPC_HD static size_t slab_reals(int nup, int nbranch) {   // nbranch = KParams::nbx
+    return (size_t)NFWP * nup + (size_t)nup + (size_t)BR * nbranch;
   }
   BMPC_HD static size_t factor_reals(int nup) { return SPLIT ? (size_t)NFAP * nup : 0; }
 
@@ -95,11 +98,11 @@ struct Solver {
 
   BMPC_D Solver(const KParams& P_, real* slab, real* factor, int lane_) : P(P_), ws(slab), fa(factor), lane(lane_), nup(P_.nup) {
     oSt = NFWP * nup;
-    oWb = oSt + (nup + 1) / 2;
-    oEX = oWb + P.nbranch;
-    oEXL = oEX + NS * P.nbranch;
-    oEXZ = oEXL + NX * P.nbranch;
-    oEXX = oEXZ + NX * P.nbranch;
+    oWb = oSt + nup;
+    oEX = oWb + P.nbx;
+    oEXL = oEX + NS * P.nbx;
+    oEXZ = oEXL + NX * P.nbx;
+    oEXX = oEXZ + NX * P.nbx;
     prob = 0;
     use_codes = false;
     nsolve = 0;
@@ -120,12 +123,19 @@ struct Solver {
     }
     return slab()[kp * NFWP + field];
   }
-  BMPC_D int* stp() { return reinterpret_cast<int*>(slab() + oSt); }
+  BMPC_D code_t* stp() { return reinterpret_cast<code_t*>(slab() + oSt); }
   BMPC_D real* Wbp() { return slab() + oWb; }
   BMPC_D real* EXp() { return slab() + oEX; }
   BMPC_D real* EXLp() { return slab() + oEXL; }
   BMPC_D real* EXZp() { return slab() + oEXZ; }
   BMPC_D real* EXXp() { return slab() + oEXX; }
+  // active-set code of a node: 3 bits per soft row, then 2 bits per input
+  BMPC_D static int row_of(code_t c, int j) { return (int)((c >> (3 * j)) & 7); }
+  BMPC_D static int in_of(code_t c, int a) { return (int)((c >> (3 * NR + 2 * a)) & 3); }
+  BMPC_D static code_t row_bits(int v, int j) { return (code_t)v << (3 * j); }
+  BMPC_D static code_t in_bits(int v, int a) { return (code_t)v << (3 * NR + 2 * a); }
+  static_assert(3 * NR + 2 * NU <= 62, "active-set code does not fit 64 bits");
+
   BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(P, b) + t + b; }
   BMPC_D void node_of(int k, int& b, int& t) const {
     if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / P.N; t = (k - 1) % P.N; }
@@ -136,7 +146,39 @@ struct Solver {
   // Tree expansion: obstacle rollouts, branch probabilities/weights, ego linearisation rollouts,
   // per-node linearisation + collision linearisation + cost vectors   (kernels K1-K3 of SURVEY.md)
   // ========================================================================================
-  BMPC_D void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn) {
+  // collision rows (col_eval, :1114-1168: -dh x - s <= h - dh xbar) against the `ncol` obstacle positions parked in the
+  // FC slots, and the ADMM start of every soft row (unscaled, multiplied by rho in choose_rho / load_rho): rows at the
+  // linearisation point, projected on their bounds
+  BMPC_D void rows_setup(int kp, const real* xbar, int ncol) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (j < ncol) {
+        real zxy[2] = {F(F_FC + 2 * j, kp), F(F_FC + 2 * j + 1, kp)};
+        real h, dhx, dhy;
+        M::collision(P, xbar, zxy, h, dhx, dhy);
+        const real fx = -dhx, fy = -dhy;
+        const real hi0 = h - (dhx * xbar[0] + dhy * xbar[1]);
+        F(F_FC + 2 * j, kp) = fx;
+        F(F_FC + 2 * j + 1, kp) = fy;
+        F(F_HC + j, kp) = hi0;
+        F(F_S + j, kp) = fmin(fx * xbar[0] + fy * xbar[1], hi0);
+      } else {
+        F(F_FC + 2 * j, kp) = 0.0;       // no obstacle in this slot: a zero row gets rho = 0 and is ignored
+        F(F_FC + 2 * j + 1, kp) = 0.0;
+        F(F_HC + j, kp) = 1.0e30;
+        F(F_S + j, kp) = 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = NC; j < NR; ++j) {
+      real v = 0.0;
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) v += P.rf[j - NC][i] * xbar[i];
+      F(F_S + j, kp) = bmpc_clamp(v, P.rlo[j - NC], P.rhi[j - NC]);
+    }
+  }
+
+  BMPC_D void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn, int ncol = 1) {
     const int kp = kp_of(b, t);
     real lin[M::NLIN], cc[M::NCC];
     M::linearize(P, xbar, ubar, lin, cc, xn);
@@ -157,24 +199,7 @@ struct Solver {
       }
       F(F_Q + j, kp) = -2.0 * w * (a + P.dq_scale * c);
     }
-    // col_eval (:1114-1168): row -dh x - s <= h - dh xbar
-    real zxy[2] = {F(F_FC, kp), F(F_FC + 1, kp)};
-    real h, dhx, dhy;
-    M::collision(P, xbar, zxy, h, dhx, dhy);
-    const real fx = -dhx, fy = -dhy;
-    const real hi0 = h - (dhx * xbar[0] + dhy * xbar[1]);
-    F(F_FC, kp) = fx;
-    F(F_FC + 1, kp) = fy;
-    F(F_HC, kp) = hi0;
-    // ADMM start (unscaled, multiplied by rho in choose_rho): rows at the linearisation point, projected on their bounds
-    F(F_S, kp) = fmin(fx * xbar[0] + fy * xbar[1], hi0);
-#pragma unroll
-    for (int j = 1; j < NR; ++j) {
-      real v = 0.0;
-#pragma unroll
-      for (int i = 0; i < NXP; ++i) v += P.rf[j - 1][i] * xbar[i];
-      F(F_S + j, kp) = bmpc_clamp(v, P.rlo[j - 1], P.rhi[j - 1]);
-    }
+    rows_setup(kp, xbar, ncol);
 #pragma unroll
     for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ubar[a], P.ulo[a], P.uhi[a]);
     if (P.out.xLin) {
@@ -188,7 +213,7 @@ struct Solver {
     const int started = P.started[prob];
     const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     int* pbest = P.pbest + (size_t)prob * P.nbranch;
-    const int* codes = P.code_cache + (size_t)prob * P.totalu;
+    const code_t* codes = P.code_cache + (size_t)prob * P.totalu;
     const real* x0 = P.x0 + (size_t)prob * NXP;
     const real* z0 = P.z0 + (size_t)prob * NXP;
     if (lane == 0) {
@@ -232,7 +257,7 @@ struct Solver {
         const int kpc = kp_of(c, 0);
         real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NXP : nullptr;
         const real hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXLp() + NX * b,
-                                         EXZp() + NX * b, zl, [&](int t, const real* z) {
+                                         EXZp() + NX * b, zl, P.N, [&](int t, const real* z) {
                                            F(F_FC, kpc + t) = z[0];
                                            F(F_FC + 1, kpc + t) = z[1];
                                            if (zout) {
@@ -309,6 +334,118 @@ struct Solver {
     for (int a = 0; a < NU; ++a) rlin += -2.0 * P.oldin[(size_t)prob * NU + a] * P.dR[a];
   }
 
+  // ----------------------------------------------------------------------------------------
+  // robustMPC (MPC_branch.py:1275-1595): ONE ego chain (root + N*NB input nodes + an internal dummy stage for the
+  // terminal state) against every obstacle node of the scenario tree.  Linearisation: zero-input nonlinear rollout on
+  // the first solve (get_xLin :1326-1335), afterwards the previous QP solution shifted by one step (:1429-1431; note that
+  // the shifted trajectory does NOT restart from the measured state).  Obstacle nodes are collected per time slot
+  // t = (depth-1) N + i + 1 in BFS order (:1336-1383); slot t gives node t its collision rows.
+  // ----------------------------------------------------------------------------------------
+  BMPC_DN void expand_chain() {
+    const int started = P.started[prob];
+    const int Nx = P.totalu, Nu = P.totalu - 1;   // states incl. the terminal one / real inputs
+    const real* uPrev = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
+    const real* xPrev = P.xprev + (size_t)prob * P.pub_totalx * NXP;
+    const code_t* codes = P.code_cache + (size_t)prob * P.totalu;
+    const real* x0 = P.x0 + (size_t)prob * NXP;
+    const real* z0 = P.z0 + (size_t)prob * NXP;
+    auto kp_chain = [&](int k) { return k == 0 ? kp_of(0, 0) : kp_of(1, k - 1); };
+    // 1. linearisation trajectory, parked in the sweep vectors
+    if (!started) {
+      if (lane == 0) {
+        real x[NXP], xn[NXP], u[NU];
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) x[i] = x0[i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) u[a] = 0.0;
+        for (int k = 0; k < Nx; ++k) {
+          const int kp = kp_chain(k);
+#pragma unroll
+          for (int i = 0; i < NXP; ++i) F(F_XQ + i, kp) = x[i];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = 0.0;
+          M::step(P, x, u, xn);
+#pragma unroll
+          for (int i = 0; i < NXP; ++i) x[i] = xn[i];
+        }
+      }
+    } else {
+      for (int k = lane; k < Nx; k += BMPC_LANES) {
+        const int kp = kp_chain(k);
+        const int kx = (k + 1 < Nx) ? k + 1 : Nx - 1;
+        const int ku = (k + 1 < Nu) ? k + 1 : Nu - 1;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) F(F_XQ + i, kp) = xPrev[(size_t)kx * NXP + i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = (k < Nu) ? uPrev[(size_t)ku * NU + a] : 0.0;
+        if (use_codes) stp()[kp] = codes[(k + 1 < Nu) ? k + 1 : k];
+      }
+    }
+    // 2. obstacle scenario tree -> collision-row slots of the chain nodes
+    if (lane == 0) {
+      const int kp = kp_chain(0);
+      F(F_FC, kp) = z0[0];
+      F(F_FC + 1, kp) = z0[1];
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) EXZp()[i] = z0[i];
+    }
+    lanes_sync();
+    const int m = P.zm;
+    for (int d = 0; d < P.zNB; ++d) {
+      const int cnt = P.zpw[d] * m;
+      for (int idx = lane; idx < cnt; idx += BMPC_LANES) {
+        const int b = P.zoff[d] + idx / m;
+        const int i = idx % m;
+        const int c = P.zoff[d + 1] + (b - P.zoff[d]) * m + i;
+        const int j = c - P.zoff[d + 1];                 // position inside the slot (BFS order)
+        real zl[NXP];
+        M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), x0, EXZp() + NX * b, zl, P.zN,
+                         [&](int t, const real* z) {
+                           const int kp = kp_chain(d * P.zN + t + 1);
+                           F(F_FC + 2 * (j < NC ? j : 0), kp) = z[0];
+                           F(F_FC + 2 * (j < NC ? j : 0) + 1, kp) = z[1];
+                         });
+#pragma unroll
+        for (int q = 0; q < NXP; ++q) EXZp()[NX * c + q] = zl[q];
+      }
+      lanes_sync();
+    }
+    // 3. per-node data: every node is linearised about its own (x, u) of the shifted trajectory - no rollout dependence
+    const real* xref = P.xref + (size_t)prob * NXP;
+    for (int k = lane; k < Nx; k += BMPC_LANES) {
+      const int kp = kp_chain(k);
+      real xb[NXP], ub[NU], xn[NXP], lin[M::NLIN], cc[M::NCC];
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) xb[i] = F(F_XQ + i, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) ub[a] = F(F_UQ + a, kp);
+      M::linearize(P, xb, ub, lin, cc, xn);
+#pragma unroll
+      for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
+#pragma unroll
+      for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
+      const real* Ql = (k == Nx - 1) ? P.Qf : P.Q;       // buildCost :1541-1556: q = -2 xRef' blockdiag(Q.., Qf)
+#pragma unroll
+      for (int jj = 0; jj < NXP; ++jj) {
+        real a = 0.0;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) a += xref[i] * Ql[i * NXP + jj];
+        F(F_Q + jj, kp) = -2.0 * a;
+      }
+      const int depth = (k == 0) ? 0 : (k - 1) / P.zN + 1;
+      const int ncol = (k <= P.zN * P.zNB) ? P.zpw[depth] : 0;   // the terminal state has state rows only (:1470-1482)
+      rows_setup(kp, xb, ncol);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ub[a], P.ulo[a], P.uhi[a]);
+    }
+    if (lane == 0) {
+      Wbp()[0] = 1.0;     // slack weights are not branch-weighted in robustMPC (:1562)
+      Wbp()[1] = 1.0;
+    }
+    rlin = 0.0;
+    lanes_sync();
+  }
+
   // ========================================================================================
   // Riccati factorisation over the tree
   // ========================================================================================
@@ -358,11 +495,11 @@ struct Solver {
   }
 
   // fixed-input helpers of the polish: value of input a when the active-set code pins it to a bound, else 0
-  BMPC_D real pinned_value(int code, int a) {
-    const int ca = (code >> (3 * NR + 2 * a)) & 3;
+  BMPC_D real pinned_value(code_t code, int a) {
+    const int ca = in_of(code, a);
     return ca == IN_AT_HI ? P.uhi[a] : (ca == IN_AT_LO ? P.ulo[a] : 0.0);
   }
-  BMPC_D bool pinned(int code, int a) { return ((code >> (3 * NR + 2 * a)) & 3) != IN_FREE; }
+  BMPC_D bool pinned(code_t code, int a) { return in_of(code, a) != IN_FREE; }
 
   // Stiff penalty of a guessed-active row in the polish: polish_mult times the row's curvature-matched stiffness
   // (rho/theta = 1/(f' Sigma f)), at least polish_big*w, so that every augmented-Lagrangian step contracts strongly.
@@ -382,15 +519,15 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) pu[a] = 0.0;
     } else {
-      const int code = stp()[kp];
+      const code_t code = stp()[kp];
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        const int cj = (code >> (3 * j)) & 7;
+        const int cj = row_of(code, j);
         pr[j] = (cj == ROW_UP_KINK || cj == ROW_LO_KINK) ? big_row(kp, j, w) : 0.0;
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        const int ca = (code >> (3 * NR + 2 * a)) & 3;
+        const int ca = in_of(code, a);
         pu[a] = 0.0;   // inputs at a bound are eliminated exactly (see node_factor), not penalised
       }
     }
@@ -400,7 +537,8 @@ struct Solver {
   // and this node's on exit
   // rate = weight of the input-rate pair (previous input, this input), sig = 0 where the reference drops the pair's
   // own-input term (leaf last node, MPC_branch.py:303), root = the root-input quirks apply (:311-312)
-  BMPC_D void node_factor(int kp, real w, real* Pn, int mode, real rate, real sig, bool root) {
+  BMPC_D void node_factor(int kp, real w, real* Pn, int mode, real rate, real sig, bool root, bool use_qf = false) {
+    const real* Qs = use_qf ? P.Qf : P.Q;   // robustMPC: the dummy stage carries the terminal cost Qf
     real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -409,7 +547,7 @@ struct Solver {
     real pr[NR], pu[NU];
     penalties(kp, w, mode, pr, pu);
     // h0 = P+ C  (polish: C + B u_pinned, the inputs held at their bounds act as a known offset of the dynamics)
-    const int pcode = (mode == FACT_POLISH) ? stp()[kp] : 0;
+    const code_t pcode = (mode == FACT_POLISH) ? stp()[kp] : 0;
     {
       real C[NX];
       M::expandC(cc, C);
@@ -518,7 +656,7 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         real v = o[i];
-        if (i < NXP && j < NXP) v += qs * (P.Q[i * NXP + j] + P.Q[j * NXP + i]);
+        if (i < NXP && j < NXP) v += qs * (Qs[i * NXP + j] + Qs[j * NXP + i]);
         if (RATE && i == j && i >= NXP) v += 2.0 * rate * P.dR[i - NXP];
 #pragma unroll
         for (int a = 0; a < NU; ++a) v -= G[a * NX + i] * K[a * NX + j];
@@ -527,17 +665,20 @@ struct Solver {
     }
     // soft-row penalties: the collision row touches (x,y) only
     {
-      const real fx = F(F_FC, kp), fy = F(F_FC + 1, kp);
-      Pnew[0] += pr[0] * fx * fx;
-      Pnew[1] += pr[0] * fx * fy;
-      Pnew[NX] += pr[0] * fx * fy;
-      Pnew[NX + 1] += pr[0] * fy * fy;
 #pragma unroll
-      for (int j = 1; j < NR; ++j)
+      for (int j = 0; j < NC; ++j) {
+        const real fx = F(F_FC + 2 * j, kp), fy = F(F_FC + 2 * j + 1, kp);
+        Pnew[0] += pr[j] * fx * fx;
+        Pnew[1] += pr[j] * fx * fy;
+        Pnew[NX] += pr[j] * fx * fy;
+        Pnew[NX + 1] += pr[j] * fy * fy;
+      }
+#pragma unroll
+      for (int j = NC; j < NR; ++j)
 #pragma unroll
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * P.rf[j - 1][i] * P.rf[j - 1][i2];
+          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * P.rf[j - NC][i] * P.rf[j - NC][i2];
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i)
@@ -567,12 +708,13 @@ struct Solver {
           for (int i = 0; i < NX; ++i)
 #pragma unroll
             for (int j = 0; j < NX; ++j)
-              Pn[i * NX + j] = (i < NXP && j < NXP) ? w * (P.Qf[i * NXP + j] + P.Qf[j * NXP + i]) : 0.0;
+              Pn[i * NX + j] = (i < NXP && j < NXP && P.ctrl != BMPC_CTRL_ROBUST) ? w * (P.Qf[i * NXP + j] + P.Qf[j * NXP + i]) : 0.0;
         } else {
           sum_children(b, d, Pn);
         }
         for (int t = P.N - 1; t >= 0; --t)
-          node_factor(kp_of(b, t), w, Pn, mode, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0, false);
+          node_factor(kp_of(b, t), w, Pn, mode, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0, false,
+                      P.ctrl == BMPC_CTRL_ROBUST && d == P.NB && t == P.N - 1);
         pack_sym(Pn, EXp() + NS * b);
       }
       lanes_sync();
@@ -610,18 +752,21 @@ struct Solver {
     }
     const real rho_max = 1.0e9 * w;
     {
-      const real fx = F(F_FC, kp), fy = F(F_FC + 1, kp);
-      const real q0 = fx * fx * Sg[0] + 2.0 * fx * fy * Sg[1] + fy * fy * Sg[NX + 1];
-      const real r0 = (q0 > 1e-12) ? fmin(P.theta / q0, rho_max) : 0.0;
-      F(F_RHO, kp) = r0;
-      F(F_S, kp) *= r0;
 #pragma unroll
-      for (int j = 1; j < NR; ++j) {
+      for (int j = 0; j < NC; ++j) {
+        const real fx = F(F_FC + 2 * j, kp), fy = F(F_FC + 2 * j + 1, kp);
+        const real q0 = fx * fx * Sg[0] + 2.0 * fx * fy * Sg[1] + fy * fy * Sg[NX + 1];
+        const real r0 = (q0 > 1e-12) ? fmin(P.theta / q0, rho_max) : 0.0;
+        F(F_RHO + j, kp) = r0;
+        F(F_S + j, kp) *= r0;
+      }
+#pragma unroll
+      for (int j = NC; j < NR; ++j) {
         real q = 0.0;
 #pragma unroll
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NXP; ++i2) q += P.rf[j - 1][i] * P.rf[j - 1][i2] * Sg[i * NX + i2];
+          for (int i2 = 0; i2 < NXP; ++i2) q += P.rf[j - NC][i] * P.rf[j - NC][i2] * Sg[i * NX + i2];
         const real rj = (q > 1e-12) ? fmin(P.theta / q, rho_max) : 0.0;
         F(F_RHO + j, kp) = rj;
         F(F_S + j, kp) *= rj;
@@ -853,22 +998,22 @@ struct Solver {
   // the linear terms of the next KKT solve.
   // ========================================================================================
   BMPC_D real row_value(int kp, int j, const real* x) {
-    if (j == 0) return F(F_FC, kp) * x[0] + F(F_FC + 1, kp) * x[1];
+    if (j < NC) return F(F_FC + 2 * j, kp) * x[0] + F(F_FC + 2 * j + 1, kp) * x[1];
     real v = 0.0;
 #pragma unroll
-    for (int i = 0; i < NXP; ++i) v += P.rf[j - 1][i] * x[i];
+    for (int i = 0; i < NXP; ++i) v += P.rf[j - NC][i] * x[i];
     return v;
   }
   BMPC_D void row_bounds(int kp, int j, real& lo, real& hi) {
-    if (j == 0) { lo = BMPC_NOLO; hi = F(F_HC, kp); } else { lo = P.rlo[j - 1]; hi = P.rhi[j - 1]; }
+    if (j < NC) { lo = BMPC_NOLO; hi = F(F_HC + j, kp); } else { lo = P.rlo[j - NC]; hi = P.rhi[j - NC]; }
   }
   BMPC_D void add_row_grad(int kp, int j, real gcoef, real* qx) {
-    if (j == 0) {
-      qx[0] += F(F_FC, kp) * gcoef;
-      qx[1] += F(F_FC + 1, kp) * gcoef;
+    if (j < NC) {
+      qx[0] += F(F_FC + 2 * j, kp) * gcoef;
+      qx[1] += F(F_FC + 2 * j + 1, kp) * gcoef;
     } else {
 #pragma unroll
-      for (int i = 0; i < NXP; ++i) qx[i] += P.rf[j - 1][i] * gcoef;
+      for (int i = 0; i < NXP; ++i) qx[i] += P.rf[j - NC][i] * gcoef;
     }
   }
 
@@ -884,7 +1029,7 @@ struct Solver {
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
-      int ncode = 0;   // CHECK: the active set the ADMM state currently implies (compared with the previous check)
+      code_t ncode = 0;   // CHECK: the active set the ADMM state currently implies (compared with the previous check)
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0; }
@@ -911,7 +1056,7 @@ struct Solver {
               stp_r = fmax(stp_r, fabs(rvn - rv) / rho);
               const int cj = (shn > rhi + lam) ? ROW_UP_LIN : (shn > rhi) ? ROW_UP_KINK : (shn >= rlo) ? ROW_INACTIVE
                              : (shn >= rlo - lam) ? ROW_LO_KINK : ROW_LO_LIN;
-              ncode |= cj << (3 * j);
+              ncode |= row_bits(cj, j);
               if (fabs(rfx - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [row] k %d j %d rho %.3e prim %.3e dual %.3e fx %.4f hi %.4f w %.3e\n", k, j, rho, fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w), rfx / rho, hi, w);
             }
             F(F_S + j, kp) = shn;
@@ -934,7 +1079,7 @@ struct Solver {
             res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
             gap_u = fmax(gap_u, fabs(ru - rvn) / rho);
             stp_u = fmax(stp_u, fabs(rvn - rv) / rho);
-            ncode |= ((shn > rho * P.uhi[a]) ? IN_AT_HI : (shn < rho * P.ulo[a]) ? IN_AT_LO : IN_FREE) << (3 * NR + 2 * a);
+            ncode |= in_bits((shn > rho * P.uhi[a]) ? IN_AT_HI : (shn < rho * P.ulo[a]) ? IN_AT_LO : IN_FREE, a);
             if (fabs(ru - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [in] k %d a %d rho %.3e prim %.3e dual %.3e u %.4f w %.3e\n", k, a, rho, fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w), u[a], w);
           }
           F(F_SU + a, kp) = shn;
@@ -951,7 +1096,7 @@ struct Solver {
         // rows without a penalty (rho = 0) stay "ignored"
 #pragma unroll
         for (int j = 0; j < NR; ++j)
-          if (!(F(F_RHO + j, kp) > 0.0)) ncode |= ROW_IGNORED << (3 * j);
+          if (!(F(F_RHO + j, kp) > 0.0)) ncode |= row_bits(ROW_IGNORED, j);
         set_changes += (ncode != stp()[kp]);
         stp()[kp] = ncode;
       }
@@ -1001,19 +1146,19 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const int code = stp()[kp];
-      int ncode = 0;
+      const code_t code = stp()[kp];
+      code_t ncode = 0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        int cj = (code >> (3 * j)) & 7;
+        int cj = row_of(code, j);
         if (!(F(F_RHO + j, kp) > 0.0)) cj = ROW_IGNORED;
         else if (cj == ROW_IGNORED) cj = ROW_INACTIVE;
-        ncode |= cj << (3 * j);
+        ncode |= row_bits(cj, j);
         F(F_Y + j, kp) = 0.0;
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        ncode |= ((code >> (3 * NR + 2 * a)) & 3) << (3 * NR + 2 * a);
+        ncode |= in_bits(in_of(code, a), a);
         F(F_Y + NR + a, kp) = 0.0;
       }
       stp()[kp] = ncode;
@@ -1021,7 +1166,7 @@ struct Solver {
     lanes_sync();
   }
   BMPC_DN void store_codes() {
-    int* codes = P.code_cache + (size_t)prob * P.totalu;
+    code_t* codes = P.code_cache + (size_t)prob * P.totalu;
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1084,7 +1229,7 @@ struct Solver {
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real lam = P.lam_lin * Wbp()[b];
-      int code = 0;
+      code_t code = 0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const real rho = F(F_RHO + j, kp);
@@ -1101,7 +1246,7 @@ struct Solver {
           else if (sh >= rlo - lam) { cj = ROW_LO_KINK; y = sh - rlo; }
           else cj = ROW_LO_LIN;
         }
-        code |= cj << (3 * j);
+        code |= row_bits(cj, j);
         F(F_Y + j, kp) = y;
       }
 #pragma unroll
@@ -1112,7 +1257,7 @@ struct Solver {
         real y = 0.0;
         if (sh > rho * P.uhi[a]) { ca = IN_AT_HI; y = sh - rho * P.uhi[a]; }
         else if (sh < rho * P.ulo[a]) { ca = IN_AT_LO; y = sh - rho * P.ulo[a]; }
-        code |= ca << (3 * NR + 2 * a);
+        code |= in_bits(ca, a);
         F(F_Y + NR + a, kp) = y;
       }
       stp()[kp] = code;
@@ -1127,13 +1272,13 @@ struct Solver {
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
-      const int code = stp()[kp];
+      const code_t code = stp()[kp];
       real qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        const int cj = (code >> (3 * j)) & 7;
+        const int cj = row_of(code, j);
         real lo, hi;
         row_bounds(kp, j, lo, hi);
         real g = 0.0;
@@ -1178,13 +1323,13 @@ struct Solver {
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
-      const int code = stp()[kp];
+      const code_t code = stp()[kp];
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        const int cj = (code >> (3 * j)) & 7;
+        const int cj = row_of(code, j);
         if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) {
           real lo, hi;
           row_bounds(kp, j, lo, hi);
@@ -1206,7 +1351,7 @@ struct Solver {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const int code = stp()[kp];
+      const code_t code = stp()[kp];
 #pragma unroll
       for (int a = 0; a < NU; ++a)
         if (pinned(code, a)) F(F_UQ + a, kp) = pinned_value(code, a);
@@ -1225,7 +1370,7 @@ struct Solver {
     for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
 #pragma unroll
     for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
-    const int code = stp()[kp];
+    const code_t code = stp()[kp];
     const real rate = (k == 0) ? 0.0 : w;
     const real sig = (b >= P.off[P.NB] && t == P.N - 1) ? 0.0 : 1.0;
     M::mulBT(P, lin, lam, gu);
@@ -1259,7 +1404,7 @@ struct Solver {
     }
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
-      const int cj = (code >> (3 * j)) & 7;
+      const int cj = row_of(code, j);
       real g = 0.0;
       if (cj == ROW_UP_LIN) g = lamw;
       else if (cj == ROW_LO_LIN) g = -lamw;
@@ -1341,14 +1486,14 @@ struct Solver {
       const real w = Wbp()[b];
       const real lam = P.lam_lin * w;
       const real ytol = 1e-9 * lam;
-      const int code = stp()[kp];
-      int ncode = 0;
+      const code_t code = stp()[kp];
+      code_t ncode = 0;
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        const int cj = (code >> (3 * j)) & 7;
+        const int cj = row_of(code, j);
         int nj = cj;
         real ynew = 0.0, score = 0.0;
         if (cj != ROW_IGNORED) {
@@ -1389,11 +1534,11 @@ struct Solver {
             nj = cj;
           }
         }
-        ncode |= nj << (3 * j);
+        ncode |= row_bits(nj, j);
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        const int ca = (code >> (3 * NR + 2 * a)) & 3;
+        const int ca = in_of(code, a);
         int na = ca;
         real score = 0.0;
         const real u = F(F_UQ + a, kp);
@@ -1419,7 +1564,7 @@ struct Solver {
             na = ca;
           }
         }
-        ncode |= na << (3 * NR + 2 * a);
+        ncode |= in_bits(na, a);
       }
       if (apply) stp()[kp] = ncode;
     }
@@ -1492,7 +1637,8 @@ struct Solver {
   // ========================================================================================
   // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
   // ========================================================================================
-  BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin, real rate, real sig) {
+  BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin, real rate, real sig, bool use_qf = false) {
+    const real* Qs = use_qf ? P.Qf : P.Q;
     const int k = bmpc_ndu(P, b) + t;
     real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
 #pragma unroll
@@ -1508,7 +1654,7 @@ struct Solver {
     for (int i = 0; i < NXP; ++i) {
       real a = 0.0;
 #pragma unroll
-      for (int j = 0; j < NXP; ++j) a += P.Q[i * NXP + j] * x[j];
+      for (int j = 0; j < NXP; ++j) a += Qs[i * NXP + j] * x[j];
       J += qs * x[i] * a + F(F_Q + i, kp) * x[i];
     }
     if (RATE) {
@@ -1540,8 +1686,8 @@ struct Solver {
       const real fx = row_value(kp, j, x);
       J += lam * (fmax(fx - hi, 0.0) + fmax(lo - fx, 0.0));
     }
-    if (P.out.uPred) {
-      real* o = P.out.uPred + ((size_t)prob * P.totalu + k) * NU;
+    if (P.out.uPred && k < P.pub_totalu) {
+      real* o = P.out.uPred + ((size_t)prob * P.pub_totalu + k) * NU;
 #pragma unroll
       for (int a = 0; a < NU; ++a) o[a] = u[a];
     }
@@ -1569,7 +1715,9 @@ struct Solver {
   BMPC_DN real finish() {
     real J = 0.0;
     real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
-    real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.totalx * NXP : nullptr;
+    real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.pub_totalx * NXP : nullptr;
+    real* xprev = P.xprev ? P.xprev + (size_t)prob * P.pub_totalx * NXP : nullptr;   // robustMPC's LTV shift source
+    const bool robust = P.ctrl == BMPC_CTRL_ROBUST;
     if (lane == 0) {
       real x[NX];
 #pragma unroll
@@ -1577,6 +1725,10 @@ struct Solver {
       if (xP) {
 #pragma unroll
         for (int i = 0; i < NXP; ++i) xP[i] = x[i];
+      }
+      if (xprev) {
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) xprev[i] = x[i];
       }
       J += emit_node(0, 0, kp_of(0, 0), 1.0, x, uLin, 0.0, 1.0);
 #pragma unroll
@@ -1596,9 +1748,14 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + t) * NXP + i] = x[i];
           }
-          J += emit_node(b, t, kp_of(b, t), w, x, uLin, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0);
+          if (xprev) {
+#pragma unroll
+            for (int i = 0; i < NXP; ++i) xprev[(size_t)(kx + t) * NXP + i] = x[i];
+          }
+          J += emit_node(b, t, kp_of(b, t), w, x, uLin, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0,
+                         robust && d == P.NB && t == P.N - 1);
         }
-        if (d == P.NB) {
+        if (d == P.NB && !robust) {
           if (xP) {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + P.N) * NXP + i] = x[i];
@@ -1646,12 +1803,13 @@ struct Solver {
     const long long t_start = clock64();
 #endif
     prob = prob_;
-    polpar = P.polpar ? P.polpar + (size_t)prob * P.m * 4 : nullptr;
+    polpar = P.polpar ? P.polpar + (size_t)prob * P.zm * 4 : nullptr;
     const int warm = P.started[prob];
     int* cstate = P.cache_state + (size_t)prob * 2;   // [0] age of the cached rho (-1: none), [1] cached codes valid
     const bool reuse_rho = warm && P.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < P.rho_refresh;
     use_codes = warm && P.warm_polish && cstate[1] == 1 && reuse_rho;
-    expand_tree();
+    if (P.ctrl == BMPC_CTRL_ROBUST) expand_chain();
+    else expand_tree();
     nsolve = 0;
     int nfact = 0, iters = 0, status = BMPC_STATUS_MAXITER;
     bool have_xu = false;

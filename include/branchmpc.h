@@ -41,7 +41,7 @@ extern "C" {
 /* controller kinds */
 #define BMPC_CTRL_BRANCH 0 /* MPC_branch.BranchMPC (effective, second definition, :881) */
 #define BMPC_CTRL_PROX 1   /* MPC_branch.BranchMPCProx (:82)                             */
-#define BMPC_CTRL_ROBUST 2 /* MPC_branch.robustMPC (:1275)                               */
+#define BMPC_CTRL_ROBUST 2 /* MPC_branch.robustMPC (:1275): total_u = N*NB+1, total_x = N*NB+2; xLin/zPred outputs unused */
 
 /* backup-policy kinds (symbolic branch of each reference policy) */
 #define BMPC_POLICY_MAINTAIN 0 /* highway_branch_dyn.backup_maintain        :54  */
@@ -162,6 +162,9 @@ int bmpc_num_branches(const bmpc_handle* h);
 int bmpc_total_x(const bmpc_handle* h);
 int bmpc_total_u(const bmpc_handle* h);
 int bmpc_get_topology(const bmpc_handle* h, int32_t* ndx, int32_t* ndu, int32_t* depth, int32_t* parent);
+/* rows of the persistent uLin array per episode (bmpc_get_state / bmpc_set_state): total_u + 1, or total_u + 2 for
+ * robustMPC, whose chain carries one internal stage for the terminal state */
+int bmpc_ulin_rows(const bmpc_handle* h);
 
 /* One MPC step for episodes 0..count-1 (episode i uses persistent slot i).
  *   x0, z0, xref : [count][n] device float64   (solve(x, z, xRef), MPC_branch.py:1171)

@@ -53,3 +53,11 @@ def quadruped_mpc_params(vxm=0.2, vym=0.1, rm=0.5):
 def quadruped_prox_mpc(NB=2, N=25, xRef=(5., 5., 0.)):
     model = quadruped_model(N=N)
     return BranchMPCOracle(model, NB, xRef=np.asarray(xRef, dtype=float), variant="prox", **quadruped_mpc_params())
+
+
+def highway_robust_mpc(policies=None, NB=2, N=8, lc_target=(0.5, 1.8, 15.0, 0.0), xRef=None, N_lane=4):
+    from .robust_mpc import RobustMPCOracle
+    model = highway_model(policies, N=N, lc_target=lc_target)
+    par = highway_mpc_params(N_lane=N_lane)
+    xRef = np.asarray(lc_target if xRef is None else xRef, dtype=float)
+    return RobustMPCOracle(model, NB, xRef=xRef, **par)

@@ -124,7 +124,14 @@ def solve_qp_ipm(P, q, A, l, u, tol=1e-10, max_iter=200, prox=1e-7):
         if max(np.abs(rd).max() / scale, np.abs(rp_e).max() if me else 0.0,
                np.abs(rp_i).max() if mi else 0.0) < tol and mu < tol:
             break
-        dz, dy, ds, dl = solve_newton(rd, rp_e, rp_i, s * lam)
+        # Near the optimum the barrier system becomes numerically singular; the last good iterate is then handed to
+        # `polish`, which computes the exact optimum on the identified active set.
+        try:
+            dz, dy, ds, dl = solve_newton(rd, rp_e, rp_i, s * lam)
+        except RuntimeError:
+            break
+        if not (np.isfinite(dz).all() and np.isfinite(dl).all()):
+            break
 
         def step(v, dv):
             neg = dv < 0
@@ -133,7 +140,12 @@ def solve_qp_ipm(P, q, A, l, u, tol=1e-10, max_iter=200, prox=1e-7):
         mu_aff = ((s + a_aff * ds) @ (lam + a_aff * dl)) / max(mi, 1)
         sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
         rc = s * lam + ds * dl - sigma * mu
-        dz, dy, ds, dl = solve_newton(rd, rp_e, rp_i, rc)
+        try:
+            dz, dy, ds, dl = solve_newton(rd, rp_e, rp_i, rc)
+        except RuntimeError:
+            break
+        if not (np.isfinite(dz).all() and np.isfinite(dl).all()):
+            break
         a = min(step(s, ds), step(lam, dl))
         z = z + a * dz
         y = y + a * dy

@@ -35,6 +35,27 @@ def quadruped_fixture_config(g, **kw):
     return scenarios.quadruped_config(NB=int(g["meta_NB"]), N=int(g["meta_N"]), v0=float(g["meta_v0"]), **kw)
 
 
+def robust_fixture_config(g, **kw):
+    from _bmpc import abi
+    cfg = fixture_config(g, **kw)
+    cfg.controller = abi.CTRL_ROBUST
+    return cfg
+
+
+def check_robust_fixture(solve, g, tol=2e-5):
+    """robustMPC fixture: chain QP optimum of every recorded closed-loop step (no tree outputs)."""
+    for k in range(int(g["meta_steps"])):
+        pre = "s%d_" % k
+        r = solve(g[pre + "x0"], g[pre + "z0"], g[pre + "xref"])
+        assert r["status"][0] in (0, 1)
+        assert r["uPred"][0].shape == g[pre + "uPred"].shape and r["xPred"][0].shape == g[pre + "xPred"].shape
+        np.testing.assert_allclose(r["uPred"][0], g[pre + "uPred"], atol=tol)
+        np.testing.assert_allclose(r["xPred"][0], g[pre + "xPred"], atol=tol)
+        assert np.abs(r["u0"][0] - g[pre + "uPred"][0]).max() < TOL_U0
+        obj = float(g[pre + "objective"])
+        assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj)
+
+
 def check_fixture_closed_loop(solve, g, tol=1e-6):
     """`solve(x, z, xref) -> result dict` is called for every recorded step of a fixture; everything the reference
     produced for that step (tree data, linearisation trajectory, optimum) must be reproduced."""

@@ -58,12 +58,14 @@ class HostSim:
             raise RuntimeError("hostsim_sizes: %d %s" % (rc, lib().hostsim_last_error().decode()))
         self.nbranch, self.totalx, self.totalu = nb.value, tx.value, tu.value
         self.cap = capacity
-        self.uLin = np.zeros((capacity, self.totalu + 1, cfg.d))
+        internal_u = self.totalu + (1 if cfg.controller == abi.CTRL_ROBUST else 0)   # robust chains carry a dummy stage
+        self.uLin = np.zeros((capacity, internal_u + 1, cfg.d))
+        self.xprev = np.zeros((capacity, self.totalx, cfg.n))
         self.pbest = np.zeros((capacity, self.nbranch), dtype=np.int32)
         self.oldin = np.zeros((capacity, cfg.d))
         self.started = np.zeros(capacity, dtype=np.int32)
-        self.rho_cache = np.zeros((capacity, self.totalu, abi.MAX_ROWS + 1 + abi.MAX_D))
-        self.code_cache = np.zeros((capacity, self.totalu), dtype=np.int32)
+        self.rho_cache = np.zeros(capacity * internal_u * 16)          # flat: the kernel strides by its own row width
+        self.code_cache = np.zeros(capacity * internal_u, dtype=np.int64)
         self.cache_state = np.full((capacity, 2), -1, dtype=np.int32)
 
     def solve(self, x0, z0, xref, policy_params=None):
@@ -85,7 +87,7 @@ class HostSim:
         out = abi.Outputs(**{k: _ptr(v) for k, v in res.items()})
         rc = lib().hostsim_solve(C.byref(cfg), _ptr(x0), _ptr(z0), _ptr(xref), _ptr(pp), C.c_int64(B), _ptr(self.uLin),
                                  _ptr(self.pbest), _ptr(self.oldin), _ptr(self.started), _ptr(self.rho_cache),
-                                 _ptr(self.code_cache), _ptr(self.cache_state), C.byref(out))
+                                 _ptr(self.code_cache), _ptr(self.cache_state), _ptr(self.xprev), C.byref(out))
         if rc != 0:
             raise RuntimeError("hostsim_solve: %d %s" % (rc, lib().hostsim_last_error().decode()))
         return res

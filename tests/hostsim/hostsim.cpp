@@ -12,10 +12,10 @@
 
 namespace {
 bool g_split = false;
-template <class M, int NR, int MODE>
+template <class M, int NR, int MODE, int NC = 1>
 void run_layout(KParams& P) {
-  using S = Solver<M, NR, MODE>;
-  P.slab_reals = S::slab_reals(P.nup, P.nbranch);
+  using S = Solver<M, NR, MODE, NC>;
+  P.slab_reals = S::slab_reals(P.nup, P.nbx);
   std::vector<real> slab(P.slab_reals, 0.0), factor(S::factor_reals(P.nup) + 2, 0.0);
   S solver(P, slab.data(), factor.data(), 0);
   for (int i = 0; i < P.count; ++i) solver.solve(i);
@@ -36,20 +36,23 @@ int hostsim_sizes(const bmpc_config* cfg, int32_t* nbranch, int32_t* totalx, int
   const int rc = bmpc::make_params(*cfg, &P, &g_err);
   if (rc != BMPC_OK) return rc;
   *nbranch = P.nbranch;
-  *totalx = P.totalx;
-  *totalu = P.totalu;
+  *totalx = P.pub_totalx;
+  *totalu = P.pub_totalu;
   return BMPC_OK;
 }
 
 // All pointers are HOST pointers; uLin/pbest/oldin/started are the persistent state (caller-owned here).
 int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, const double* xref,
                   const double* policy_params, int64_t count, double* uLin, int32_t* pbest, double* oldin,
-                  int32_t* started, double* rho_cache, int32_t* code_cache, int32_t* cache_state,
-                  const bmpc_outputs* out) {
+                  int32_t* started, double* rho_cache, int64_t* code_cache, int32_t* cache_state,
+                  double* xprev, const bmpc_outputs* out) {
   KParams P;
   const int rc = bmpc::make_params(*cfg, &P, &g_err);
   if (rc != BMPC_OK) return rc;
-  if (!bmpc::supported_instance(cfg->model, cfg->n_rows)) { g_err = "unsupported (model, n_rows)"; return BMPC_E_UNSUPPORTED; }
+  if (!bmpc::supported_instance(cfg->model, cfg->n_rows, cfg->controller, P.zpw[P.zNB])) {
+    g_err = "unsupported (model, n_rows, controller)";
+    return BMPC_E_UNSUPPORTED;
+  }
   g_split = cfg->slab_mode == BMPC_SLAB_SPLIT;
   P.count = (int)count;
   P.x0 = x0;
@@ -61,10 +64,15 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   P.oldin = oldin;
   P.started = started;
   P.rho_cache = rho_cache;
-  P.code_cache = code_cache;
+  P.code_cache = reinterpret_cast<long long*>(code_cache);
   P.cache_state = cache_state;
+  P.xprev = (cfg->controller == BMPC_CTRL_ROBUST) ? xprev : nullptr;
   P.out = *out;
   const bool prox = cfg->controller == BMPC_CTRL_PROX;
+  if (cfg->controller == BMPC_CTRL_ROBUST) {
+    if (g_split) run_layout<HighwayModel, 11, BMPC_SLAB_SPLIT, 9>(P); else run_layout<HighwayModel, 11, BMPC_SLAB_SHARED, 9>(P);
+    return BMPC_OK;
+  }
   if (cfg->model == BMPC_MODEL_HIGHWAY) {
     switch (cfg->n_rows) {
       case 0: prox ? run<RateAug<HighwayModel>, 1>(P) : run<HighwayModel, 1>(P); break;

@@ -67,5 +67,9 @@ def test_error_codes_without_a_device():
     assert b"NB" in lib.bmpc_last_error(None)
     cfg = scenarios.highway_config()
     cfg.controller = abi.CTRL_ROBUST
+    cfg.dR[0] = 1.0          # robustMPC with input-rate costs is not built
     assert lib.bmpc_create(C.byref(cfg), C.byref(h)) == abi.E_UNSUPPORTED
+    cfg = scenarios.highway_config()
+    cfg.controller = 17
+    assert lib.bmpc_create(C.byref(cfg), C.byref(h)) == abi.E_INVALID
     assert lib.bmpc_create(None, C.byref(h)) == abi.E_INVALID

@@ -9,7 +9,7 @@ constraint violation <= 1e-5, bit-exact tree topology and branch indexing.
 import numpy as np
 import pytest
 
-from tests.helpers import (quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
+from tests.helpers import (check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
                            load_fixture, oracle_episode)
 from _bmpc import abi, scenarios
 from oracle.branch_mpc import TreeTopology
@@ -80,6 +80,33 @@ def test_quadruped_model_functions_match_reference(bmpc):
     for k in ("A", "B", "C", "xp", "zpred", "p", "dh"):
         np.testing.assert_allclose(r[k], g["qd_" + k], atol=1e-11, err_msg=k)
     np.testing.assert_allclose(r["hlin"], g["qd_hlin"], atol=1e-10)
+    mpc.close()
+
+
+def test_robust_chain_fixture_closed_loop(bmpc):
+    g = load_fixture("highway_robust_default")
+    mpc = bmpc.BatchedBranchMPC(robust_fixture_config(g))
+    assert (mpc.totalx, mpc.totalu) == (18, 17)
+    check_robust_fixture(lambda x, z, r: mpc.solve_host(x, z, r), g)
+    mpc.close()
+
+
+def test_robust_batch_4096(bmpc):
+    """BASELINE config 2: 4096-episode batch of the single-trajectory controller; sample checked against the oracle."""
+    from oracle import params
+    B = 4096
+    cfg = scenarios.highway_config(batch_capacity=B)
+    cfg.controller = abi.CTRL_ROBUST
+    mpc = bmpc.BatchedBranchMPC(cfg)
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=5)
+    r = mpc.solve_host(x0, z0, xref, pp, outputs=("u0", "uPred", "xPred", "objective", "status", "iters"))
+    assert (r["status"] <= abi.STATUS_MAXITER).all() and np.isfinite(r["objective"]).all()
+    assert (np.abs(r["uPred"][:, :, 0]) <= 6.0 + 1e-12).all() and (np.abs(r["uPred"][:, :, 1]) <= 0.3 + 1e-12).all()
+    for i in (0, 1000, 4095):
+        ora = params.highway_robust_mpc(lc_target=pp[i, 2])
+        u = ora.solve(x0[i], z0[i], xref[i])
+        assert np.abs(r["u0"][i] - u).max() < TOL_U0
+        assert abs(r["objective"][i] - ora.objective) <= TOL_OBJ * abs(ora.objective)
     mpc.close()
 
 

@@ -7,7 +7,7 @@ on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.
 import numpy as np
 import pytest
 
-from tests.helpers import (quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+from tests.helpers import (check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
                      oracle_episode)
 from _bmpc import scenarios
 from tests.hostsim.driver import HostSim
@@ -26,6 +26,14 @@ def test_quadruped_prox_fixture_closed_loop():
     hs = HostSim(quadruped_fixture_config(g), 1)
     assert [hs.totalx, hs.totalu] == list(g["s0_totals"])
     check_fixture_closed_loop(lambda x, z, r: hs.solve(x, z, r), g, tol=1e-5)
+
+
+def test_robust_chain_fixture_closed_loop():
+    """robustMPC: one ego chain against every obstacle node of the scenario tree (BASELINE config 2 semantics)."""
+    g = load_fixture("highway_robust_default")
+    hs = HostSim(robust_fixture_config(g), 1)
+    assert (hs.totalx, hs.totalu) == (18, 17)
+    check_robust_fixture(lambda x, z, r: hs.solve(x, z, r), g)
 
 
 def test_random_batch_against_oracle():

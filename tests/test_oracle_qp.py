@@ -103,3 +103,21 @@ def test_two_solvers_agree(golden_dir):
     if status == "Optimal":
         nxu = 28 * 4 + 25 * 2
         assert np.abs(zh[:nxu] - z[:nxu]).max() < 1e-4
+
+
+def test_robust_mpc_qp_matches_reference(golden_dir):
+    """robustMPC (MPC_branch.py:1275): assembled chain QP and optimum vs the unmodified reference, 3 closed-loop steps."""
+    g = _load(golden_dir, "highway_robust_default")
+    mpc = params.highway_robust_mpc(list(g["meta_policies"]), int(g["meta_NB"]), int(g["meta_N"]), g["meta_lc_target"])
+    for k in range(int(g["meta_steps"])):
+        pre = "s%d_" % k
+        mpc.solve(g[pre + "x0"], g[pre + "z0"], g[pre + "xref"])
+        P, q, A, l, u = mpc.qp
+        Pg = sp.coo_matrix((g[pre + "P_v"], (g[pre + "P_r"], g[pre + "P_c"])), shape=tuple(g[pre + "P_shape"])).tocsc()
+        Ag = sp.coo_matrix((g[pre + "A_v"], (g[pre + "A_r"], g[pre + "A_c"])), shape=tuple(g[pre + "A_shape"])).tocsc()
+        assert abs(sp.triu(P) - Pg).max() < 1e-11 and abs(A - Ag).max() < 1e-11
+        np.testing.assert_allclose(q, g[pre + "q"], atol=1e-11)
+        np.testing.assert_allclose(u, g[pre + "u"], atol=1e-11)
+        assert mpc.feasible == 1
+        np.testing.assert_allclose(mpc.uPred, g[pre + "uPred"], atol=1e-8)
+        np.testing.assert_allclose(mpc.xPred, g[pre + "xPred"], atol=1e-8)
