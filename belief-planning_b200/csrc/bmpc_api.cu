@@ -333,7 +333,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->oldin, cap * cfg->d * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->started, cap * sizeof(int)));
   if (cfg->controller == BMPC_CTRL_ROBUST) BMPC_CK(h, cudaMalloc(&h->xprev, cap * P.pub_totalx * cfg->n * sizeof(real)));
-  BMPC_CK(h, cudaMalloc(&h->rho_cache, cap * P.totalu * (BMPC_MAX_ROWS + 1 + BMPC_MAX_D) * sizeof(real)));
+  BMPC_CK(h, cudaMalloc(&h->rho_cache, cap * P.totalu * 16 * sizeof(real))  /* up to 11 rows + 3 inputs per node */);
   BMPC_CK(h, cudaMalloc(&h->code_cache, cap * P.totalu * sizeof(long long)));
   BMPC_CK(h, cudaMalloc(&h->cache_state, cap * 2 * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->cost, cap * sizeof(int)));
