@@ -89,3 +89,35 @@ def oracle_episode(x, z, xref, lc_target, steps):
         x = scenarios.euler_highway(x[None], u[None])[0]
         z = scenarios.euler_highway(z[None], np.array([[0.0, -0.1 * z[3]]]))[0]
     return out
+
+
+SWEEP = [(m, NB) for m in (2, 3, 4) for NB in (1, 2, 3)]          # BASELINE config 5: branching factor x depth
+POLICY_NAMES = ["maintain", "brake", "lc", "trackv"]
+
+
+def sweep_case(m, NB, count=2, seed=21):
+    """(config kwargs, oracle policy descriptors, x0, z0, xref, policy params) of one tree shape of the sweep."""
+    x0, z0, xref, pp3 = scenarios.highway_batch(count, seed=seed + 10 * m + NB)
+    pp = np.zeros((count, m, 4))
+    if m >= 3:
+        pp[:, 2, :] = pp3[:, 2, :]
+    if m >= 4:
+        pp[:, 3, 0] = 20.0
+    names = POLICY_NAMES[:m]
+    desc = [("trackv", 20.0) if p == "trackv" else p for p in names]
+    return dict(policies=names, NB=NB), desc, x0, z0, xref, pp
+
+
+def check_sweep_case(make_solver, m, NB):
+    kw, desc, x0, z0, xref, pp = sweep_case(m, NB)
+    solver = make_solver(scenarios.highway_config(batch_capacity=len(x0), **kw))
+    r = solver(x0, z0, xref, pp)
+    T = params.highway_branch_mpc(desc, NB=NB).topo
+    assert r["uPred"].shape[1:] == (T.totalu, 2) and r["xPred"].shape[1:] == (T.totalx, 4)
+    for i in range(len(x0)):
+        ora = params.highway_branch_mpc(desc, NB=NB, lc_target=pp[i, 2] if m >= 3 else (0.5, 1.8, 15.0, 0.0))
+        u = ora.solve(x0[i], z0[i], xref[i])
+        assert ora.feasible == 1
+        assert np.abs(r["u0"][i] - u).max() < TOL_U0, (m, NB, i)
+        assert abs(r["objective"][i] - ora.objective) <= TOL_OBJ * abs(ora.objective), (m, NB, i)
+        np.testing.assert_allclose(r["branch_w"][i], ora.w, atol=1e-9)

@@ -9,7 +9,7 @@ constraint violation <= 1e-5, bit-exact tree topology and branch indexing.
 import numpy as np
 import pytest
 
-from tests.helpers import (check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
+from tests.helpers import (SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
                            load_fixture, oracle_episode)
 from _bmpc import abi, scenarios
 from oracle.branch_mpc import TreeTopology
@@ -183,6 +183,15 @@ def test_full_batch_properties(bmpc):
     rc = mpc.solve_host(x0, z0, xref, pp)
     assert np.array_equal(rc["u0"][ids], r["u0"][ids])
     mpc.close()
+
+
+@pytest.mark.parametrize("m,NB", SWEEP)
+def test_tree_sweep_against_oracle(bmpc, m, NB):
+    """BASELINE config 5 shapes; (3,3) and (4,3) do not fit shared memory and run from the global/L2 slab."""
+    def make(cfg):
+        mpc = bmpc.BatchedBranchMPC(cfg)
+        return lambda *a: mpc.solve_host(*a)
+    check_sweep_case(make, m, NB)
 
 
 def test_plant_step_matches_reference_plant(bmpc):

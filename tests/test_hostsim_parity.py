@@ -7,7 +7,7 @@ on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.
 import numpy as np
 import pytest
 
-from tests.helpers import (check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+from tests.helpers import (SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
                      oracle_episode)
 from _bmpc import scenarios
 from tests.hostsim.driver import HostSim
@@ -68,3 +68,12 @@ def test_all_problems_of_a_batch_are_certified():
     assert np.array_equal(r["xPred"][:, 0], x0)
     # children of one parent start from the same state (buildEqConstr, MPC_branch.py:1007-1012)
     assert np.array_equal(r["xPred"][:, 1], r["xPred"][:, 9]) and np.array_equal(r["xPred"][:, 1], r["xPred"][:, 17])
+
+
+@pytest.mark.parametrize("m,NB", SWEEP)
+def test_tree_sweep_against_oracle(m, NB):
+    """Branching factor 2-4 x depth 1-3 (19 ... 737 state nodes): first control, objective and weights vs the oracle."""
+    def make(cfg):
+        hs = HostSim(cfg, cfg.batch_capacity)
+        return lambda *a: hs.solve(*a)
+    check_sweep_case(make, m, NB)
