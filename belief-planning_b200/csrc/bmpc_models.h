@@ -4,7 +4,7 @@
 #pragma once
 #include "bmpc_params.h"
 
-// softmin/softmax accumulators with a running shift: sum(exp(-g v) v)/sum(exp(-g v)) is invariant to
+// softmin/softmax accumulators with a running shift: sum(bmpc_exp(-g v) v)/sum(bmpc_exp(-g v)) is invariant to
 // subtracting a constant from the exponent, so the shifted form equals the reference's unshifted one
 // (highway_branch_dyn.py:151-162) without its overflow.
 struct SoftMinAcc {
@@ -12,12 +12,12 @@ struct SoftMinAcc {
   BMPC_D SoftMinAcc(real g) : vmin(1e300), num(0), den(0), gamma(g) {}
   BMPC_D void add(real v) {
     if (v < vmin) {
-      const real sc = (den > 0) ? exp(-gamma * (vmin - v)) : 0.0;
+      const real sc = (den > 0) ? bmpc_exp(-gamma * (vmin - v)) : 0.0;
       num *= sc;
       den *= sc;
       vmin = v;
     }
-    const real e = exp(-gamma * (v - vmin));
+    const real e = bmpc_exp(-gamma * (v - vmin));
     num += e * v;
     den += e;
   }
@@ -27,7 +27,7 @@ struct SoftMinAcc {
 // (dx e^dx + dy e^dy)/(e^dx + e^dy) and partials; veh_col core (highway_branch_dyn.py:231-234)
 BMPC_D void soft_box(real dx, real dy, real& h, real& gx, real& gy) {
   const real mx = fmax(dx, dy);
-  const real ex = exp(dx - mx), ey = exp(dy - mx);
+  const real ex = bmpc_exp(dx - mx), ey = bmpc_exp(dy - mx);
   const real wx = ex / (ex + ey), wy = 1.0 - wx;
   h = wx * dx + wy * dy;
   gx = wx * (1.0 + dx - h);
@@ -68,7 +68,7 @@ struct HighwayModel {
         // softmax([-7, -v], 5) = (a e^{5a} + b e^{5b})/(e^{5a} + e^{5b})
         const real a = -7.0, b = -x[2];
         const real mx = fmax(a, b);
-        const real ea = exp(5.0 * (a - mx)), eb = exp(5.0 * (b - mx));
+        const real ea = bmpc_exp(5.0 * (a - mx)), eb = bmpc_exp(5.0 * (b - mx));
         u[0] = (ea * a + eb * b) / (ea + eb);
         u[1] = -P.Kpsi * x[3];
         break;
@@ -182,16 +182,16 @@ struct HighwayModel {
       // lane_bdry_h (:195-206): softmin([y - lb, ub - y], 5)
       const real a = z[1] - P.lane_lo, b = P.lane_hi - z[1];
       const real mn = fmin(a, b);
-      const real ea = exp(-5.0 * (a - mn)), eb = exp(-5.0 * (b - mn));
+      const real ea = bmpc_exp(-5.0 * (a - mn)), eb = bmpc_exp(-5.0 * (b - mn));
       acc.add((ea * a + eb * b) / (ea + eb));
     }
     for (int i = 0; i < 4; ++i) zlast[i] = z[i];
     return acc.value();
   }
 
-  // un-normalised branch weight exp(s1 * softsat(hi, 1)) (:355-359); softsat(h,1) == sigmoid(h)
+  // un-normalised branch weight bmpc_exp(s1 * softsat(hi, 1)) (:355-359); softsat(h,1) == sigmoid(h)
   BMPC_D static real branch_weight(const KParams& P, real hi, real /*himax*/) {
-    return exp(P.s1 / (1.0 + exp(-hi)));
+    return bmpc_exp(P.s1 / (1.0 + bmpc_exp(-hi)));
   }
   static constexpr bool kWeightNeedsMax = false;
 };
@@ -301,8 +301,8 @@ struct QuadrupedModel {
     for (int i = 0; i < 3; ++i) zlast[i] = z[i];
     return acc.value();
   }
-  // exp(s1*hi), shifted by the group maximum (normalisation cancels the shift) (:211-216)
-  BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return exp(P.s1 * (hi - himax)); }
+  // bmpc_exp(s1*hi), shifted by the group maximum (normalisation cancels the shift) (:211-216)
+  BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return bmpc_exp(P.s1 * (hi - himax)); }
   static constexpr bool kWeightNeedsMax = true;
 };
 

@@ -18,7 +18,7 @@
 #else
 #define BMPC_HD
 #define BMPC_D inline
-#define BMPC_DN
+#define BMPC_DN inline
 #define BMPC_LANES 1
 #endif
 
@@ -62,7 +62,9 @@ BMPC_D int lanes_or_int(int v) {
 BMPC_D real bmpc_min(real a, real b) { return fmin(a, b); }
 BMPC_D real bmpc_max(real a, real b) { return fmax(a, b); }
 BMPC_D real bmpc_clamp(real v, real lo, real hi) { return fmin(fmax(v, lo), hi); }
-BMPC_D void bmpc_sincos(real a, real* s, real* c) {
+// Transcendentals are called through one out-of-line copy each: the inlined double-precision exp / sincos bodies
+// (~60-150 instructions per call site) otherwise dominate the code size of the tree-expansion phase.
+BMPC_DN void bmpc_sincos(real a, real* s, real* c) {
 #if defined(__CUDA_ARCH__)
   sincos(a, s, c);
 #else
@@ -70,3 +72,4 @@ BMPC_D void bmpc_sincos(real a, real* s, real* c) {
   *c = cos(a);
 #endif
 }
+BMPC_DN real bmpc_exp(real a) { return exp(a); }

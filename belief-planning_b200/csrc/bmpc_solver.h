@@ -271,6 +271,7 @@ struct Solver {
       }
       lanes_sync();
       // (a') probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         const int fc = bmpc_first_child(P, b, d);
         real himax = -1e300;
@@ -697,8 +698,13 @@ struct Solver {
     }
   }
 
+  // The root is "depth 0, one node": every sweep runs one loop nest over the levels, so that each node step is
+  // instantiated once (code size matters: the instruction cache is the first bottleneck of this kernel, profiles/).
   BMPC_DN void factorize(int mode) {
-    for (int d = P.NB; d >= 1; --d) {
+#pragma unroll 1
+    for (int d = P.NB; d >= 0; --d) {
+      const int nt = (d == 0) ? 1 : P.N;
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         const real w = Wbp()[b];
         real Pn[NX * NX];
@@ -712,19 +718,14 @@ struct Solver {
         } else {
           sum_children(b, d, Pn);
         }
-        for (int t = P.N - 1; t >= 0; --t)
-          node_factor(kp_of(b, t), w, Pn, mode, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0, false,
-                      P.ctrl == BMPC_CTRL_ROBUST && d == P.NB && t == P.N - 1);
+#pragma unroll 1
+        for (int t = nt - 1; t >= 0; --t)
+          node_factor(kp_of(b, t), w, Pn, mode, (d == 0) ? 0.0 : w, (d == P.NB && t == nt - 1) ? 0.0 : 1.0, d == 0,
+                      P.ctrl == BMPC_CTRL_ROBUST && d == P.NB && t == nt - 1);
         pack_sym(Pn, EXp() + NS * b);
       }
       lanes_sync();
     }
-    if (lane == 0) {
-      real Pn[NX * NX];
-      sum_children(0, 0, Pn);
-      node_factor(kp_of(0, 0), 1.0, Pn, mode, 0.0, 1.0, true);
-    }
-    lanes_sync();
   }
 
   // ========================================================================================
@@ -839,20 +840,21 @@ struct Solver {
   }
 
   BMPC_DN void choose_rho() {
-    if (lane == 0) {
-      real Sg[NX * NX];
-#pragma unroll
-      for (int i = 0; i < NX * NX; ++i) Sg[i] = 0.0;
-      node_cov(kp_of(0, 0), 1.0, Sg);
-      pack_sym(Sg, EXp());
-    }
-    lanes_sync();
-    for (int d = 1; d <= P.NB; ++d) {
+#pragma unroll 1
+    for (int d = 0; d <= P.NB; ++d) {
+      const int nt = (d == 0) ? 1 : P.N;
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real Sg[NX * NX];
-        unpack_sym(EXp() + NS * bmpc_parent(P, b, d), Sg);
+        if (d == 0) {
+#pragma unroll
+          for (int i = 0; i < NX * NX; ++i) Sg[i] = 0.0;
+        } else {
+          unpack_sym(EXp() + NS * bmpc_parent(P, b, d), Sg);
+        }
         const real w = Wbp()[b];
-        for (int t = 0; t < P.N; ++t) node_cov(kp_of(b, t), w, Sg);
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) node_cov(kp_of(b, t), w, Sg);
         pack_sym(Sg, EXp() + NS * b);
       }
       lanes_sync();
@@ -898,7 +900,10 @@ struct Solver {
   }
 
   BMPC_DN void backward() {
-    for (int d = P.NB; d >= 1; --d) {
+#pragma unroll 1
+    for (int d = P.NB; d >= 0; --d) {
+      const int nt = (d == 0) ? 1 : P.N;
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real pn[NX];
         if (d == P.NB) {
@@ -925,23 +930,13 @@ struct Solver {
             for (int i = 0; i < NX; ++i) pn[i] += EXp()[NS * (fc + c) + i];
         }
         const int kp0 = kp_of(b, 0);
-        for (int t = P.N - 1; t >= 0; --t) bw_step(kp0 + t, pn);
+#pragma unroll 1
+        for (int t = nt - 1; t >= 0; --t) bw_step(kp0 + t, pn);
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXp()[NS * b + i] = pn[i];
       }
       lanes_sync();
     }
-    if (lane == 0) {
-      real pn[NX];
-      const int fc = bmpc_first_child(P, 0, 0);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) pn[i] = EXp()[NS * fc + i];
-      for (int c = 1; c < P.m; ++c)
-#pragma unroll
-        for (int i = 0; i < NX; ++i) pn[i] += EXp()[NS * (fc + c) + i];
-      bw_step(kp_of(0, 0), pn);
-    }
-    lanes_sync();
   }
 
   BMPC_D void fw_step(int kp, real* x) {
@@ -969,23 +964,23 @@ struct Solver {
 
   BMPC_DN void forward() {
     ++nsolve;
-    if (lane == 0) {
-      real x[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
-      fw_step(kp_of(0, 0), x);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) EXXp()[i] = x[i];
-    }
-    lanes_sync();
-    for (int d = 1; d <= P.NB; ++d) {
+#pragma unroll 1
+    for (int d = 0; d <= P.NB; ++d) {
+      const int nt = (d == 0) ? 1 : P.N;
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
-        const int pa = bmpc_parent(P, b, d);
+        if (d == 0) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
+          for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
+        } else {
+          const int pa = bmpc_parent(P, b, d);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
+        }
         const int kp0 = kp_of(b, 0);
-        for (int t = 0; t < P.N; ++t) fw_step(kp0 + t, x);
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) fw_step(kp0 + t, x);
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXXp()[NX * b + i] = x[i];
       }
@@ -1023,6 +1018,7 @@ struct Solver {
   BMPC_D real admm_rows() {
     real res = 0.0;
     if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; set_changes = 0; }
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1109,6 +1105,7 @@ struct Solver {
   // values of the previous step (refreshed every P.rho_refresh solves) and skip the free factorisation + covariance sweep.
   BMPC_DN void store_rho() {
     real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1120,6 +1117,7 @@ struct Solver {
   }
   BMPC_DN void load_rho() {
     const real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1142,6 +1140,7 @@ struct Solver {
   // shifted codes of the previous optimum -> a consistent starting guess for the polish (multipliers start at their
   // natural values: 0 on kinks)
   BMPC_DN void guess_from_codes() {
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1167,6 +1166,7 @@ struct Solver {
   }
   BMPC_DN void store_codes() {
     code_t* codes = P.code_cache + (size_t)prob * P.totalu;
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1187,6 +1187,7 @@ struct Solver {
     if (fu > 0.5 && fu < 2.0) fu = 1.0;
     BMPC_TRACE("    rebalance: rows gap %.2e step %.2e -> x%.2f   inputs gap %.2e step %.2e -> x%.2f\n", gr, sr, fr, gu, su, fu);
     if (fr == 1.0 && fu == 1.0) return false;
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1224,6 +1225,7 @@ struct Solver {
   // imposed by a stiff penalty + augmented-Lagrangian refinement so that the same tree Riccati solves them)
   // ========================================================================================
   BMPC_DN void polish_guess() {
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1266,6 +1268,7 @@ struct Solver {
   }
 
   BMPC_DN void polish_assemble() {
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1318,6 +1321,7 @@ struct Solver {
   // multiplier (augmented-Lagrangian) update on the guessed-active rows; returns this lane's max residual
   BMPC_DN real polish_multipliers() {
     real res = 0.0;
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1347,6 +1351,7 @@ struct Solver {
 
   // pinned inputs take their bound value after the backward sweep (their gain rows and feed-forward are zero)
   BMPC_DN void polish_inject() {
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1420,18 +1425,22 @@ struct Solver {
 
   BMPC_DN real polish_adjoint() {
     real viol = 0.0;
-    for (int d = P.NB; d >= 1; --d) {
+#pragma unroll 1
+    for (int d = P.NB; d >= 0; --d) {
+      const int nt = (d == 0) ? 1 : P.N;
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         const real w = Wbp()[b];
         real lam[NX];
         if (d == P.NB) {
-          // terminal costate: 2 w Qf x_T (BranchMPCProx: - 2 w Qf' xRef as well); x_T was left in EXXp() by forward()
+          // terminal costate: 2 w Qf x_T (BranchMPCProx: - 2 w Qf' xRef as well; robustMPC: none, its terminal cost sits on
+          // the chain's last stage); x_T was left in EXX by forward()
           const real* xT = EXXp() + NX * b;
           const real* xref = P.xref + (size_t)prob * NXP;
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
             real v = 0.0;
-            if (i < NXP) {
+            if (i < NXP && P.ctrl != BMPC_CTRL_ROBUST) {
 #pragma unroll
               for (int j = 0; j < NXP; ++j) {
                 v += w * (P.Qf[(i < NXP ? i : 0) * NXP + j] + P.Qf[j * NXP + (i < NXP ? i : 0)]) * xT[j];
@@ -1450,23 +1459,13 @@ struct Solver {
         }
         const int kp0 = kp_of(b, 0);
         const int k0 = bmpc_ndu(P, b);
-        for (int t = P.N - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(k0 + t, b, t, kp0 + t, w, lam));
+#pragma unroll 1
+        for (int t = nt - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(k0 + t, b, t, kp0 + t, w, lam));
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXp()[NS * b + i] = lam[i];
       }
       lanes_sync();
     }
-    if (lane == 0) {
-      real lam[NX];
-      const int fc = bmpc_first_child(P, 0, 0);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) lam[i] = EXp()[NS * fc + i];
-      for (int c = 1; c < P.m; ++c)
-#pragma unroll
-        for (int i = 0; i < NX; ++i) lam[i] += EXp()[NS * (fc + c) + i];
-      viol = fmax(viol, adjoint_step(0, 0, 0, kp_of(0, 0), 1.0, lam));
-    }
-    lanes_sync();
     return viol;
   }
 
@@ -1479,6 +1478,7 @@ struct Solver {
     int changes = 0;
     real smax = 0.0;
     const real tol = 1e-7;
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
@@ -1718,32 +1718,24 @@ struct Solver {
     real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.pub_totalx * NXP : nullptr;
     real* xprev = P.xprev ? P.xprev + (size_t)prob * P.pub_totalx * NXP : nullptr;   // robustMPC's LTV shift source
     const bool robust = P.ctrl == BMPC_CTRL_ROBUST;
-    if (lane == 0) {
-      real x[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
-      if (xP) {
-#pragma unroll
-        for (int i = 0; i < NXP; ++i) xP[i] = x[i];
-      }
-      if (xprev) {
-#pragma unroll
-        for (int i = 0; i < NXP; ++i) xprev[i] = x[i];
-      }
-      J += emit_node(0, 0, kp_of(0, 0), 1.0, x, uLin, 0.0, 1.0);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) EXXp()[i] = x[i];
-    }
-    lanes_sync();
-    for (int d = 1; d <= P.NB; ++d) {
+#pragma unroll 1
+    for (int d = 0; d <= P.NB; ++d) {
+      const int nt = (d == 0) ? 1 : P.N;
+#pragma unroll 1
       for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
-        const int pa = bmpc_parent(P, b, d);
+        if (d == 0) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
+          for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
+        } else {
+          const int pa = bmpc_parent(P, b, d);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
+        }
         const real w = Wbp()[b];
         const int kx = bmpc_ndx(P, b);
-        for (int t = 0; t < P.N; ++t) {
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
           if (xP) {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + t) * NXP + i] = x[i];
@@ -1752,13 +1744,13 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xprev[(size_t)(kx + t) * NXP + i] = x[i];
           }
-          J += emit_node(b, t, kp_of(b, t), w, x, uLin, w, (d == P.NB && t == P.N - 1) ? 0.0 : 1.0,
-                         robust && d == P.NB && t == P.N - 1);
+          J += emit_node(b, t, kp_of(b, t), w, x, uLin, (d == 0) ? 0.0 : w, (d == P.NB && t == nt - 1) ? 0.0 : 1.0,
+                         robust && d == P.NB && t == nt - 1);
         }
         if (d == P.NB && !robust) {
           if (xP) {
 #pragma unroll
-            for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + P.N) * NXP + i] = x[i];
+            for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + nt) * NXP + i] = x[i];
           }
           const real* xref = P.xref + (size_t)prob * NXP;
 #pragma unroll
@@ -1784,6 +1776,7 @@ struct Solver {
   // any non-finite input left by the last forward sweep?
   BMPC_DN bool solution_is_finite() {
     int bad = 0;
+#pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
