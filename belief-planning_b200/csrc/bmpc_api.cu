@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ 
     slab = reinterpret_cast<real*>(smem_raw);
     if (SPLIT) factor = P.gws + (size_t)blockIdx.x * P.factor_reals;
   }
-  Solver<M, NR, MODE, NC> S(P, slab, factor, lane);
+  Solver<M, NR, MODE, NC> S(P, slab, factor, P.ipm + (size_t)blockIdx.x * P.ipm_reals, lane);
   for (;;) {
     int idx = 0;
     if (lane == 0) idx = atomicAdd(P.counter, 1);
@@ -187,6 +187,7 @@ struct bmpc_handle {
   int* order = nullptr;   // work order of the current launch
   int* counter = nullptr;
   real* gws = nullptr;
+  real* ipm_ws = nullptr;   // per-warp scratch of the interior-point fallback
   // staging for bmpc_solve_host
   real* stage_in = nullptr;   // x0 | z0 | xref | polpar
   void* stage_out = nullptr;
@@ -260,6 +261,7 @@ static int configure_instance(bmpc_handle* h) {
     h->gws_bytes_per_warp = (h->mode == BMPC_SLAB_GLOBAL) ? h->P.slab_reals * sizeof(real) : 0;
   }
   h->slab_bytes = (h->mode == BMPC_SLAB_GLOBAL) ? 0 : h->P.slab_reals * sizeof(real);
+  h->P.ipm_reals = Solver<M, NR, BMPC_SLAB_SHARED, NC>::ipm_reals(h->P.nup);
   return BMPC_OK;
 }
 
@@ -305,6 +307,7 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->order);
   cudaFree(h->counter);
   cudaFree(h->gws);
+  cudaFree(h->ipm_ws);
   cudaFree(h->stage_in);
   cudaFree(h->stage_out);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -340,6 +343,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->order, cap * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
   if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
+  BMPC_CK(h, cudaMalloc(&h->ipm_ws, (size_t)h->grid * h->P.ipm_reals * sizeof(real)));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
   BMPC_CK(h, cudaEventCreate(&h->ev1));
   return bmpc_reset(h, nullptr, 0);
@@ -439,7 +443,7 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.cache_state = h->cache_state;
   P.cost = h->cost;
   P.order = nullptr;
-  if (count > h->grid && h->cfg.reserved[4] == 0) {
+  if (count > h->grid && h->cfg.reserved[6] == 0) {
     bmpc_order_kernel<<<1, 1024, 0, s>>>(h->cost, (int)count, h->order);
     BMPC_CK(h, cudaGetLastError());
     P.order = h->order;
@@ -448,6 +452,7 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.out = *out;
   P.counter = h->counter;
   P.gws = h->gws;
+  P.ipm = h->ipm_ws;
   BMPC_CK(h, cudaMemsetAsync(h->counter, 0, sizeof(int), s));
   const int grid = (int)(count < h->grid ? count : h->grid);
   BMPC_CK(h, cudaEventRecord(h->ev0, s));

@@ -118,9 +118,9 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.max_iter = c.max_iter > 0 ? c.max_iter : 400;
   P.polish_first = c.polish_first > 0 ? c.polish_first : 10;
   P.polish_every = c.polish_every > 0 ? c.polish_every : 10;
-  P.polish_passes = c.polish_passes > 0 ? c.polish_passes : 8;
+  P.polish_passes = c.polish_passes > 0 ? c.polish_passes : 6;
   P.polish_al_iters = c.polish_al_iters > 0 ? c.polish_al_iters : 24;
-  P.polish_careful = c.polish_careful > 0 ? c.polish_careful : (c.polish_careful < 0 ? 0 : 12);
+  P.polish_careful = c.polish_careful > 0 ? c.polish_careful : 0;   // off: the interior-point fallback handles cycling sets
   P.warm_polish = c.warm_polish >= 0 ? 1 : 0;
   P.warm_passes = c.warm_polish > 0 ? c.warm_polish : 3;
   P.rho_refresh = c.rho_refresh > 0 ? c.rho_refresh : (c.rho_refresh < 0 ? 0 : 8);
@@ -132,8 +132,20 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e4;
   P.check_every = 5;
   P.polish_stable = c.reserved[2];
-  P.polish_force = c.reserved[3] > 0 ? c.reserved[3] : 80;
+  // measured on the B200 (profiles/r01_knob_matrix.md): the highway problems are cheapest when the ADMM runs until its
+  // implied active set is stable and the interior point only rescues repeated failures; the long, narrow quadruped trees
+  // (ADMM contracts slowly along 51 stages) when the polish is forced early and its first failure goes to the interior point
+  const bool quad = c.model == BMPC_MODEL_QUADRUPED;
+  P.polish_force = c.reserved[3] > 0 ? c.reserved[3] : (quad ? 20 : 80);
   P.rho_u_feedback = 1.0;
+  P.ipm_after = c.reserved[4] > 0 ? c.reserved[4] : (c.reserved[4] < 0 ? 0 : (quad ? 1 : 3));
+  P.ipm_max_iter = c.reserved[5] > 0 ? c.reserved[5] : 40;
+  P.cycles_ipm_only = c.reserved[7] == 1 ? 1 : 0;
+  P.ipm_mu_tol = 1.0e-10;
+  P.ipm_s0 = 1.0;
+  P.ipm_y0 = 0.5;
+  P.ipm = nullptr;
+  P.ipm_reals = 0;
   P.rebalance = c.reserved[0] == 1 ? 0 : 1;   // experimental switch
   *out = P;
   return BMPC_OK;

@@ -32,6 +32,9 @@ struct KParams {
   // ---- solver ----
   int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes, check_every, polish_stable, polish_force;
   real alpha, theta, theta_u, eps_abs, polish_big, polish_mult, rho_u_feedback;
+  int cycles_ipm_only;
+  int ipm_after, ipm_max_iter;  // interior-point fallback: after this many failed polish attempts (0 = never), iteration cap
+  real ipm_mu_tol, ipm_s0, ipm_y0;
   // ---- batch ----
   int count;
   const real* x0;
@@ -53,6 +56,8 @@ struct KParams {
   real* gws;                    // global workspace (only when the per-problem slab does not fit shared memory)
   size_t slab_reals;            // reals per problem slab
   size_t factor_reals;          // reals of the per-warp factor-field region (split placement)
+  real* ipm;                    // per-warp scratch of the interior-point fallback
+  size_t ipm_reals;
 };
 
 BMPC_HD inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }

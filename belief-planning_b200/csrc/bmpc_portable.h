@@ -59,6 +59,22 @@ BMPC_D int lanes_or_int(int v) {
 #endif
   return v;
 }
+// hides a constant from the optimiser: out-of-line phase functions that take a runtime selector must not be cloned per
+// call site (code size; nvcc 12.9 also emits unparsable '.specialized' clone names with -lineinfo)
+BMPC_D int bmpc_opaque(int v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+// num / den for a ratio test (den > 0): single precision on the device
+BMPC_D real bmpc_ratio(real num, real den) {
+#if defined(__CUDA_ARCH__)
+  return (real)__fdividef((float)num, (float)den);
+#else
+  return num / den;
+#endif
+}
 BMPC_D real bmpc_min(real a, real b) { return fmin(a, b); }
 BMPC_D real bmpc_max(real a, real b) { return fmax(a, b); }
 BMPC_D real bmpc_clamp(real v, real lo, real hi) { return fmin(fmax(v, lo), hi); }

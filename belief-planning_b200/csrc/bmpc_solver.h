@@ -17,7 +17,8 @@
 
 enum { ROW_INACTIVE = 0, ROW_UP_KINK = 1, ROW_UP_LIN = 2, ROW_LO_KINK = 3, ROW_LO_LIN = 4, ROW_IGNORED = 7 };
 enum { IN_FREE = 0, IN_AT_HI = 1, IN_AT_LO = 2 };
-enum { FACT_ADMM = 0, FACT_FREE = 1, FACT_POLISH = 2 };
+enum { FACT_ADMM = 0, FACT_FREE = 1, FACT_POLISH = 2, FACT_IPM = 3 };
+enum { IPM_PRED_ASM = 0, IPM_PRED_STEP = 1, IPM_CORR_ASM = 2, IPM_CORR_STEP = 3 };
 typedef long long code_t;   // per-node active-set code (see Solver::row_of / in_of)
 
 #define BMPC_NOLO (-1.0e300)
@@ -83,20 +84,32 @@ struct Solver {
     return (size_t)NFWP * nup + (size_t)nup + (size_t)BR * nbranch;
   }
   BMPC_HD static size_t factor_reals(int nup) { return SPLIT ? (size_t)NFAP * nup : 0; }
+  // interior-point fallback: per-node scratch in this warp's global region (rare path, see ipm_solve)
+  static constexpr int IP_X = 0;                    // current iterate x, u
+  static constexpr int IP_U = IP_X + NX;
+  static constexpr int IP_RS = IP_U + NU;           // per soft row: s+, y+, s-, y-
+  static constexpr int IP_IN = IP_RS + 4 * NR;      // per input: y+, y-
+  static constexpr int IP_KAP = IP_IN + 2 * NU;     // barrier curvature of the rows / inputs (penalties of FACT_IPM)
+  static constexpr int IP_COR = IP_KAP + NR + NU;   // per complementarity side: two carried values (see ipm_side)
+  static constexpr int NIP = IP_COR + 4 * NR + 4 * NU;
+  BMPC_HD static size_t ipm_reals(int nup) { return (size_t)NIP * nup; }
 
   const KParams& P;
   real* ws;     // slab base (shared memory is addressed through bmpc_smem on the device so that loads are LDS)
   real* fa;     // factor-field region (SPLIT only)
+  real* ip;     // interior-point scratch (global)
   int oSt, oWb, oEX, oEXL, oEXZ, oEXX;   // offsets (in reals) of the per-branch arrays inside the slab
   int lane, nup, prob;
   bool use_codes;   // this solve starts its polish from the cached active set of the previous step
   real gap_r, stp_r, gap_u, stp_u;   // last residual check: max primal gap |f'x - v| and max step |v+ - v| (rows / inputs)
   int set_changes;                   // last residual check: nodes whose implied active set differs from the previous check
   int nsolve;   // KKT solves (one backward + one forward sweep each) of the current problem
+  int ipm_iters;   // interior-point iterations of the current problem
+  real ipm_acc, ipm_ratio;   // per-lane results of the last ipm_pass
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
 
-  BMPC_D Solver(const KParams& P_, real* slab, real* factor, int lane_) : P(P_), ws(slab), fa(factor), lane(lane_), nup(P_.nup) {
+  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : P(P_), ws(slab), fa(factor), ip(ipm), lane(lane_), nup(P_.nup) {
     oSt = NFWP * nup;
     oWb = oSt + nup;
     oEX = oWb + P.nbx;
@@ -123,6 +136,7 @@ struct Solver {
     }
     return slab()[kp * NFWP + field];
   }
+  BMPC_D real& IPF(int field, int kp) { return ip[(size_t)field * nup + kp]; }   // field-major: the lanes of a node-parallel pass read consecutive addresses
   BMPC_D code_t* stp() { return reinterpret_cast<code_t*>(slab() + oSt); }
   BMPC_D real* Wbp() { return slab() + oWb; }
   BMPC_D real* EXp() { return slab() + oEX; }
@@ -514,6 +528,11 @@ struct Solver {
       for (int j = 0; j < NR; ++j) pr[j] = F(F_RHO + j, kp);
 #pragma unroll
       for (int a = 0; a < NU; ++a) pu[a] = F(F_RHO + NR + a, kp);
+    } else if (mode == FACT_IPM) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) pr[j] = IPF(IP_KAP + j, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) pu[a] = IPF(IP_KAP + NR + a, kp);
     } else if (mode == FACT_FREE) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) pr[j] = 0.0;
@@ -1635,6 +1654,296 @@ struct Solver {
   }
 
   // ========================================================================================
+  // Interior-point fallback (primal-dual, Mehrotra predictor-corrector) for problems whose active set the ADMM + polish
+  // combination does not settle (degenerate or conflicting sets: a fraction of a percent of the highway batches, a few
+  // percent of the quadruped ones).  Same exact-penalty QP, same tree Riccati: every soft row side gets a slack
+  //   upper:  a = hi + s - f'x > 0,  s >= 0,  multipliers y of the row and v = lam - y of s >= 0,  a y = s v = mu
+  //   lower:  a = f'x - lo + s > 0,  ...                                  inputs:  a = uhi - u | u - ulo,  a y = mu
+  // and the Newton step eliminates (a, s, y) per row: the row enters the stage Hessian with curvature
+  // kappa = y / (a + y s / v) (the penalties of FACT_IPM) and the linear term with sg (y + c) - kappa f'x, so that one
+  // factorisation + one backward/forward sweep return the full Newton target z+ (XQ/UQ); iterates move by
+  // z <- z + alpha (z+ - z), which keeps the dynamics residual shrinking by (1 - alpha) per iteration.
+  // The iteration state lives in this warp's global scratch (IPF): it is a rare path and must not cost shared memory.
+  // ========================================================================================
+  // One complementarity side.  soft: the side has a slack s (soft rows) or not (hard input bounds).
+  // c0/c1 carry, per phase: PRED_STEP -> (dy, ds) of the predictor; CORR_ASM -> (rc1, rc2) of the corrector;
+  // CORR_STEP -> (dy, ds) of the corrector, which the next PRED_ASM applies with step alpha before it assembles.
+  BMPC_DN void ipm_side(int phase, bool soft, real sg, real gap, real dt, real lam, real& s_io, real& y_io, real& c0,
+                        real& c1, real sigmu, real alpha, real& gsum, real& ksum) {
+    real ss = soft ? s_io : 0.0;
+    real y = y_io;
+    if (phase == IPM_PRED_ASM && alpha > 0.0) {
+      y += alpha * c0;
+      y_io = y;
+      if (soft) {
+        ss += alpha * c1;
+        s_io = ss;
+      }
+    }
+    const real a = gap + ss;
+    const real v = soft ? lam - y : 1.0;
+    const real rv = 1.0 / v;
+    const real rD = 1.0 / (a + y * ss * rv);
+    const real kap = y * rD;
+    real rc1, rc2;
+    if (phase == IPM_PRED_ASM || phase == IPM_PRED_STEP) {
+      rc1 = -a * y;
+      rc2 = -ss * v;
+    } else if (phase == IPM_CORR_ASM) {
+      const real dy = c0, ds = c1, da = -sg * dt + ds;
+      rc1 = sigmu - a * y - da * dy;
+      rc2 = soft ? sigmu - ss * v + ds * dy : 0.0;   // dv = -dy
+      c0 = rc1;
+      c1 = rc2;
+    } else {
+      rc1 = c0;
+      rc2 = c1;
+    }
+    const real c = (rc1 - y * rc2 * rv) * rD;
+    if (phase == IPM_PRED_ASM || phase == IPM_CORR_ASM) {
+      gsum += sg * (y + c);
+      ksum += kap;
+      if (phase == IPM_PRED_ASM) ipm_acc += a * y + ss * v;
+      return;
+    }
+    const real dy = sg * kap * dt + c;
+    const real ds = soft ? (rc2 + ss * dy) * rv : 0.0;
+    const real da = -sg * dt + ds;
+    // largest step keeping a, y (and s, v) positive: a ratio test, single precision is plenty (the step is damped by 0.995)
+    ipm_ratio = fmax(ipm_ratio, fmax(bmpc_ratio(-da, a), bmpc_ratio(-dy, y)));
+    if (soft) ipm_ratio = fmax(ipm_ratio, fmax(bmpc_ratio(-ds, ss), bmpc_ratio(dy, v)));
+    if (phase == IPM_PRED_STEP) ipm_acc += da * dy - (soft ? ds * dy : 0.0);   // second-order term of the predicted gap
+    c0 = dy;
+    c1 = ds;
+  }
+
+  // node-parallel pass of the interior-point iteration.  Leaves in ipm_acc the lane's complementarity sum (PRED_ASM) or
+  // the sum of the predictor's second-order products (PRED_STEP), in ipm_ratio the lane's largest step ratio
+  // max(-dq/q) over the positive quantities q (PRED_STEP, CORR_STEP).
+  // PRED_ASM with alpha > 0 first moves the iterate by the corrector step of the previous iteration.
+  BMPC_DN void ipm_pass(int phase, real sigmu, real alpha) {
+    ipm_acc = 0.0;
+    ipm_ratio = 0.0;
+    const bool assemble = (phase == IPM_PRED_ASM || phase == IPM_CORR_ASM);
+    const bool first = (phase == IPM_PRED_ASM && !(alpha > 0.0));
+#pragma unroll 1
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real lam = P.lam_lin * Wbp()[b];
+      real x[NX], u[NU], xp[NX], up[NU], qx[NX], qu[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        x[i] = IPF(IP_X + i, kp);
+        xp[i] = first ? x[i] : F(F_XQ + i, kp);
+        if (phase == IPM_PRED_ASM && !first) {
+          x[i] += alpha * (xp[i] - x[i]);
+          IPF(IP_X + i, kp) = x[i];
+        }
+        qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        u[a] = IPF(IP_U + a, kp);
+        up[a] = first ? u[a] : F(F_UQ + a, kp);
+        if (phase == IPM_PRED_ASM && !first) {
+          u[a] += alpha * (up[a] - u[a]);
+          IPF(IP_U + a, kp) = u[a];
+        }
+        qu[a] = (k == 0) ? rlin : 0.0;
+      }
+#pragma unroll 1
+      for (int j = 0; j < NR; ++j) {
+        real gs = 0.0, ks = 0.0;
+        if (F(F_RHO + j, kp) > 0.0) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real tv = row_value(kp, j, x);
+          const real dt = row_value(kp, j, xp) - tv;
+          ipm_side(phase, true, 1.0, hi - tv, dt, lam, IPF(IP_RS + 4 * j, kp), IPF(IP_RS + 4 * j + 1, kp),
+                   IPF(IP_COR + 4 * j, kp), IPF(IP_COR + 4 * j + 1, kp), sigmu, alpha, gs, ks);
+          if (lo > 0.5 * BMPC_NOLO)
+            ipm_side(phase, true, -1.0, tv - lo, dt, lam, IPF(IP_RS + 4 * j + 2, kp), IPF(IP_RS + 4 * j + 3, kp),
+                     IPF(IP_COR + 4 * j + 2, kp), IPF(IP_COR + 4 * j + 3, kp), sigmu, alpha, gs, ks);
+          if (assemble) add_row_grad(kp, j, gs - ks * tv, qx);
+        }
+        if (assemble) IPF(IP_KAP + j, kp) = ks;
+      }
+#pragma unroll 1
+      for (int a = 0; a < NU; ++a) {
+        real gs = 0.0, ks = 0.0, dummy = 0.0;
+        const real dt = (phase == IPM_PRED_ASM) ? 0.0 : up[a] - u[a];
+        ipm_side(phase, false, 1.0, P.uhi[a] - u[a], dt, 0.0, dummy, IPF(IP_IN + 2 * a, kp), IPF(IP_COR + 4 * NR + 4 * a, kp),
+                 IPF(IP_COR + 4 * NR + 4 * a + 1, kp), sigmu, alpha, gs, ks);
+        ipm_side(phase, false, -1.0, u[a] - P.ulo[a], dt, 0.0, dummy, IPF(IP_IN + 2 * a + 1, kp),
+                 IPF(IP_COR + 4 * NR + 4 * a + 2, kp), IPF(IP_COR + 4 * NR + 4 * a + 3, kp), sigmu, alpha, gs, ks);
+        if (assemble) {
+          IPF(IP_KAP + NR + a, kp) = ks;
+          qu[a] += gs - ks * u[a];
+        }
+      }
+      if (assemble) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = qx[i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
+      }
+    }
+    lanes_sync();
+  }
+
+  // start: (x, u) of the last KKT solve with the inputs pulled strictly inside their box, slacks that make every row
+  // side feasible with room, multipliers at the centre of their range; returns this lane's number of complementarity pairs
+  BMPC_DN int ipm_init() {
+    int pairs = 0;
+#pragma unroll 1
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wbp()[b];
+      const real lam = P.lam_lin * w;
+      real x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        x[i] = F(F_XQ + i, kp);
+        IPF(IP_X + i, kp) = x[i];
+      }
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        real lo = 0.0, hi = 0.0, tv = 0.0;
+        const bool on = F(F_RHO + j, kp) > 0.0;
+        if (on) {
+          row_bounds(kp, j, lo, hi);
+          tv = row_value(kp, j, x);
+          pairs += 2;
+          if (lo > 0.5 * BMPC_NOLO) pairs += 2;
+        }
+        IPF(IP_RS + 4 * j, kp) = fmax(tv - hi, 0.0) + P.ipm_s0;
+        IPF(IP_RS + 4 * j + 1, kp) = 0.5 * lam;
+        IPF(IP_RS + 4 * j + 2, kp) = fmax(lo - tv, 0.0) + P.ipm_s0;
+        IPF(IP_RS + 4 * j + 3, kp) = 0.5 * lam;
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real range = P.uhi[a] - P.ulo[a];
+        const real uc = bmpc_clamp(F(F_UQ + a, kp), P.ulo[a] + 0.1 * range, P.uhi[a] - 0.1 * range);
+        IPF(IP_U + a, kp) = uc;
+        IPF(IP_IN + 2 * a, kp) = P.ipm_y0 * lam * P.ipm_s0 / (P.uhi[a] - uc);
+        IPF(IP_IN + 2 * a + 1, kp) = P.ipm_y0 * lam * P.ipm_s0 / (uc - P.ulo[a]);
+        pairs += 2;
+      }
+    }
+    lanes_sync();
+    return pairs;
+  }
+
+  // active set + multipliers implied by the converged interior-point state -> starting guess of the polish
+  BMPC_DN void ipm_guess() {
+#pragma unroll 1
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real lam = P.lam_lin * Wbp()[b];
+      real x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = IPF(IP_X + i, kp);
+      code_t code = 0;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        int cj = ROW_IGNORED;
+        real ym = 0.0;
+        if (F(F_RHO + j, kp) > 0.0) {
+          real lo, hi;
+          row_bounds(kp, j, lo, hi);
+          const real tv = row_value(kp, j, x);
+          cj = ROW_INACTIVE;
+          {
+            const real s = IPF(IP_RS + 4 * j, kp), y = IPF(IP_RS + 4 * j + 1, kp);
+            const real a = hi - tv + s;
+            if (s * lam > (lam - y)) cj = ROW_UP_LIN;
+            else if (a * lam < y) { cj = ROW_UP_KINK; ym = y; }
+          }
+          if (lo > 0.5 * BMPC_NOLO) {
+            const real s = IPF(IP_RS + 4 * j + 2, kp), y = IPF(IP_RS + 4 * j + 3, kp);
+            const real a = tv - lo + s;
+            if (s * lam > (lam - y)) cj = ROW_LO_LIN;
+            else if (a * lam < y) { cj = ROW_LO_KINK; ym = -y; }
+          }
+        }
+        code |= row_bits(cj, j);
+        F(F_Y + j, kp) = ym;
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const real u = IPF(IP_U + a, kp);
+        const real range = P.uhi[a] - P.ulo[a];
+        const real yh = IPF(IP_IN + 2 * a, kp), yl = IPF(IP_IN + 2 * a + 1, kp);
+        int ca = IN_FREE;
+        real ym = 0.0;
+        if ((P.uhi[a] - u) * lam < yh * range) { ca = IN_AT_HI; ym = yh; }
+        else if ((u - P.ulo[a]) * lam < yl * range) { ca = IN_AT_LO; ym = -yl; }
+        code |= in_bits(ca, a);
+        F(F_Y + NR + a, kp) = ym;
+      }
+      stp()[kp] = code;
+    }
+    lanes_sync();
+  }
+
+  BMPC_DN void ipm_export() {   // interior-point iterate -> XQ/UQ (what finish() reads)
+#pragma unroll 1
+    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = IPF(IP_X + i, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = IPF(IP_U + a, kp);
+    }
+    lanes_sync();
+  }
+
+  // returns true when the complementarity gap and the carried residual factor reached their tolerances
+  BMPC_DN bool ipm_solve(int& nfact, int& iters) {
+    const int pairs = lanes_sum_int(ipm_init());
+    const real mu_tol = P.ipm_mu_tol * P.lam_lin;
+    real resfac = 1.0, alpha = 0.0;
+    for (int it = 0; it <= P.ipm_max_iter; ++it) {
+      ipm_pass(bmpc_opaque(IPM_PRED_ASM), 0.0, alpha);   // applies the previous step, then assembles the predictor
+      const real mu = lanes_sum(ipm_acc) / pairs;
+      BMPC_TRACE("    ipm %d: mu %.3e resfac %.2e\n", it, mu, resfac);
+      if (!(mu < 1e300)) return false;
+      if (mu < mu_tol && resfac < 1e-7) return true;
+      if (it == P.ipm_max_iter) break;
+      factorize(FACT_IPM);
+      ++nfact;
+      backward();
+      forward();
+      ipm_pass(bmpc_opaque(IPM_PRED_STEP), 0.0, 0.0);
+      const real a_aff = fmin(1.0, 1.0 / fmax(lanes_max(ipm_ratio), 1e-300));
+      // gap after the affine step: every product moves to (1 - a) q1 q2 + a^2 dq1 dq2
+      const real mu_aff = fmax((1.0 - a_aff) * mu + a_aff * a_aff * lanes_sum(ipm_acc) / pairs, 0.0);
+      real sigma = mu_aff / mu;
+      sigma = sigma * sigma * sigma;
+      ipm_pass(bmpc_opaque(IPM_CORR_ASM), sigma * mu, 0.0);
+      backward();
+      forward();
+      ipm_pass(bmpc_opaque(IPM_CORR_STEP), 0.0, 0.0);
+      alpha = fmin(1.0, 0.995 / fmax(lanes_max(ipm_ratio), 1e-300));
+      BMPC_TRACE("      a_aff %.3f sigma %.2e alpha %.4f\n", a_aff, sigma, alpha);
+      if (!(alpha > 0.0)) return false;
+      resfac *= (1.0 - alpha);
+      ++iters;
+      ++ipm_iters;
+    }
+    return false;
+  }
+
+  // ========================================================================================
   // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
   // ========================================================================================
   BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin, real rate, real sig, bool use_qf = false) {
@@ -1804,6 +2113,7 @@ struct Solver {
     if (P.ctrl == BMPC_CTRL_ROBUST) expand_chain();
     else expand_tree();
     nsolve = 0;
+    ipm_iters = 0;
     int nfact = 0, iters = 0, status = BMPC_STATUS_MAXITER;
     bool have_xu = false;
     if (reuse_rho) {
@@ -1823,6 +2133,10 @@ struct Solver {
       }
     }
     int next_polish = P.polish_first, polish_gap = P.polish_every, next_forced = P.polish_force;
+    int nfail = 0;
+    bool ipm_tried = false;
+    long long t_ipm = 0;
+    (void)t_ipm;
     if (!have_xu) {
       factorize(FACT_ADMM);
       ++nfact;
@@ -1849,12 +2163,36 @@ struct Solver {
         next_forced = iters + P.polish_force;
         next_polish = iters + polish_gap;
         polish_gap *= 2;   // back off: a problem whose active set is slow to settle should not pay for many attempts
-        if (polish(nfact, iters >= 4 * P.polish_first, true)) {
+        // ipm_after == 100 (tests): skip the polish attempt, the interior point runs at the first opportunity
+        if (P.ipm_after != 100 && polish(nfact, iters >= 4 * P.polish_first, true)) {
           status = BMPC_STATUS_POLISHED;
           have_xu = true;
           break;
         }
         if (conv) status = BMPC_STATUS_CONVERGED;
+        ++nfail;
+        if (!conv && P.ipm_after > 0 && (nfail >= P.ipm_after || P.ipm_after == 100) && !ipm_tried) {
+          // the active set does not settle: interior point on the same Riccati, then a polish from its (clean) active set
+          ipm_tried = true;
+#if defined(__CUDA_ARCH__)
+          const long long t_ipm0 = clock64();
+#endif
+          const bool ipm_ok = ipm_solve(nfact, iters);
+#if defined(__CUDA_ARCH__)
+          t_ipm += clock64() - t_ipm0;
+#endif
+          if (ipm_ok) {
+            ipm_guess();
+            if (polish(nfact, false, false)) {
+              status = BMPC_STATUS_POLISHED;
+            } else {
+              ipm_export();
+              status = BMPC_STATUS_CONVERGED;
+            }
+            have_xu = true;
+            break;
+          }
+        }
         if (!conv && P.rebalance) rebalance_rho();
         factorize(FACT_ADMM);
         ++nfact;
@@ -1886,10 +2224,10 @@ struct Solver {
       if (P.out.nfact) P.out.nfact[prob] = nfact;
       if (P.out.nsolve) P.out.nsolve[prob] = nsolve;
 #if defined(__CUDA_ARCH__)
-      if (P.out.cycles) P.out.cycles[prob] = (int64_t)(clock64() - t_start);
+      if (P.out.cycles) P.out.cycles[prob] = P.cycles_ipm_only ? (int64_t)t_ipm : (int64_t)(clock64() - t_start);
       if (P.cost) P.cost[prob] = (int)min((long long)0x7fffffff, (clock64() - t_start) >> 10);
 #else
-      if (P.out.cycles) P.out.cycles[prob] = 0;
+      if (P.out.cycles) P.out.cycles[prob] = ipm_iters;   // host build: no clock; reports the interior-point iterations instead
 #endif
     }
     lanes_sync();

@@ -108,9 +108,9 @@ typedef struct bmpc_config {
   int32_t max_iter;        /* ADMM iteration cap (default 400)                                   */
   int32_t polish_first;    /* first polish attempt after this many iterations (10)               */
   int32_t polish_every;    /* then this many later, doubling after each failed attempt (10)                          */
-  int32_t polish_passes;   /* active-set passes per polish attempt (8)                           */
+  int32_t polish_passes;   /* active-set passes per polish attempt (6)                           */
   int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (24)                     */
-  int32_t polish_careful;  /* extra one-change-at-a-time passes when the set iteration cycles (12; <0 = off) */
+  int32_t polish_careful;  /* extra one-change-at-a-time passes when the set iteration cycles (0 = off, the default) */
   int32_t warm_polish;     /* warm solves first try a polish from the previous optimum's shifted active set:
                               number of active-set passes for that attempt (3; <0 = off)        */
   int32_t rho_refresh;     /* warm solves reuse the cached rho for this many steps (8; <0 = recompute every solve)   */
@@ -123,7 +123,12 @@ typedef struct bmpc_config {
   int32_t slab_mode;      /* BMPC_SLAB_*: where a problem's working set lives (0 = library picks) */
   int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */
   int32_t device;         /* CUDA device ordinal                                      */
-  int32_t reserved[8];
+  int32_t reserved[8];    /* experiment switches, 0 = default: [0] 1 = no residual balancing of rho; [1] cap of resident
+                             warps per SM; [2] polish when at most this many nodes changed their implied set between
+                             checks; [3] polish at the latest every this many ADMM iterations (80; quadruped 20); [4] interior-point
+                             fallback after this many failed polish attempts (3; quadruped 1; <0 = never; 100 = always, without a polish attempt first); [5] its iteration cap (40);
+                             [6] 1 = natural work order instead of longest-first; [7] 1 = the cycles output counts the
+                             interior-point part only */
 } bmpc_config;
 
 /* Output device pointers; any may be NULL to skip that output. */

@@ -121,3 +121,42 @@ def check_sweep_case(make_solver, m, NB):
         assert np.abs(r["u0"][i] - u).max() < TOL_U0, (m, NB, i)
         assert abs(r["objective"][i] - ora.objective) <= TOL_OBJ * abs(ora.objective), (m, NB, i)
         np.testing.assert_allclose(r["branch_w"][i], ora.w, atol=1e-9)
+
+
+# ---- interior-point fallback -------------------------------------------------------------------------------------
+QUAD_HARD = [528, 545, 1006, 1225]   # quadruped_batch(2048, seed=1238): degenerate active sets, ADMM + polish alone end on MAXITER
+
+
+def force_interior_point(cfg):
+    """Knobs that send every problem through the interior-point fallback (no warm polish, no polish attempt before it)."""
+    cfg.warm_polish = -1
+    cfg.reserved[4] = 100
+    return cfg
+
+
+def check_quadruped_hard_cases(make_solver):
+    """Problems that defeat ADMM + active-set polish must come back from the interior-point fallback within the parity bars."""
+    x0, z0, xref = scenarios.quadruped_batch(2048, seed=1238)
+    idx = np.array(QUAD_HARD)
+    solver = make_solver(scenarios.quadruped_config(batch_capacity=len(idx)))
+    r = solver(x0[idx], z0[idx], xref[idx])
+    assert (r["status"] <= 1).all(), r["status"]
+    for n, i in enumerate(idx):
+        ora = params.quadruped_prox_mpc()
+        u = ora.solve(x0[i], z0[i], xref[i])
+        assert np.abs(r["u0"][n] - u).max() < TOL_U0, (i, r["status"][n])
+        assert abs(r["objective"][n] - ora.objective) <= TOL_OBJ * abs(ora.objective), (i, r["status"][n])
+
+
+def check_forced_interior_point(make_solver, count=6):
+    """Highway problems solved (almost) only by the interior point + its closing polish agree with the oracle."""
+    x0, z0, xref, pp = scenarios.highway_batch(count, seed=77)
+    solver = make_solver(force_interior_point(scenarios.highway_config(batch_capacity=count)))
+    r = solver(x0, z0, xref, pp)
+    assert (r["status"] <= 1).all(), r["status"]
+    for i in range(count):
+        ora = params.highway_branch_mpc(lc_target=pp[i, 2])
+        u = ora.solve(x0[i], z0[i], xref[i])
+        assert np.abs(r["u0"][i] - u).max() < TOL_U0, i
+        assert abs(r["objective"][i] - ora.objective) <= TOL_OBJ * abs(ora.objective), i
+    return r

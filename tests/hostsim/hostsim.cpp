@@ -16,8 +16,8 @@ template <class M, int NR, int MODE, int NC = 1>
 void run_layout(KParams& P) {
   using S = Solver<M, NR, MODE, NC>;
   P.slab_reals = S::slab_reals(P.nup, P.nbx);
-  std::vector<real> slab(P.slab_reals, 0.0), factor(S::factor_reals(P.nup) + 2, 0.0);
-  S solver(P, slab.data(), factor.data(), 0);
+  std::vector<real> slab(P.slab_reals, 0.0), factor(S::factor_reals(P.nup) + 2, 0.0), ipm(S::ipm_reals(P.nup), 0.0);
+  S solver(P, slab.data(), factor.data(), ipm.data(), 0);
   for (int i = 0; i < P.count; ++i) solver.solve(i);
 }
 template <class M, int NR>

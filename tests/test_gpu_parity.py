@@ -9,7 +9,7 @@ constraint violation <= 1e-5, bit-exact tree topology and branch indexing.
 import numpy as np
 import pytest
 
-from tests.helpers import (SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
+from tests.helpers import (check_quadruped_hard_cases, check_forced_interior_point, SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, TOL_VIOL, check_fixture_closed_loop, fixture_config,
                            load_fixture, oracle_episode)
 from _bmpc import abi, scenarios
 from oracle.branch_mpc import TreeTopology
@@ -192,6 +192,39 @@ def test_tree_sweep_against_oracle(bmpc, m, NB):
         mpc = bmpc.BatchedBranchMPC(cfg)
         return lambda *a: mpc.solve_host(*a)
     check_sweep_case(make, m, NB)
+
+
+def _gpu_solver(bmpc):
+    def make(cfg):
+        mpc = bmpc.BatchedBranchMPC(cfg)
+        return lambda *a: mpc.solve_host(*a)
+    return make
+
+
+def test_interior_point_rescues_degenerate_quadruped_problems(bmpc):
+    check_quadruped_hard_cases(_gpu_solver(bmpc))
+
+
+def test_forced_interior_point_matches_oracle(bmpc):
+    check_forced_interior_point(_gpu_solver(bmpc))
+
+
+def test_quadruped_batch_8192(bmpc):
+    """BASELINE config 4 at full size: every problem certified or converged by the interior point, sample vs the oracle."""
+    from oracle import params
+    B = 8192
+    mpc = bmpc.BatchedBranchMPC(scenarios.quadruped_config(batch_capacity=B))
+    x0, z0, xref = scenarios.quadruped_batch(B, seed=1238)
+    r = mpc.solve_host(x0, z0, xref)
+    assert (r["status"] <= abi.STATUS_CONVERGED).all() and (r["status"] == abi.STATUS_POLISHED).mean() > 0.98
+    assert np.isfinite(r["objective"]).all()
+    soft = np.where(r["status"] == abi.STATUS_CONVERGED)[0]
+    for i in list(soft[:3]) + [0, 4095, 8191]:
+        ora = params.quadruped_prox_mpc()
+        u = ora.solve(x0[i], z0[i], xref[i])
+        assert np.abs(r["u0"][i] - u).max() < TOL_U0, i
+        assert abs(r["objective"][i] - ora.objective) <= TOL_OBJ * abs(ora.objective), i
+    mpc.close()
 
 
 def test_plant_step_matches_reference_plant(bmpc):

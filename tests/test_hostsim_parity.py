@@ -7,7 +7,7 @@ on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.
 import numpy as np
 import pytest
 
-from tests.helpers import (SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+from tests.helpers import (check_quadruped_hard_cases, check_forced_interior_point, force_interior_point, SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
                      oracle_episode)
 from _bmpc import scenarios
 from tests.hostsim.driver import HostSim
@@ -77,3 +77,31 @@ def test_tree_sweep_against_oracle(m, NB):
         hs = HostSim(cfg, cfg.batch_capacity)
         return lambda *a: hs.solve(*a)
     check_sweep_case(make, m, NB)
+
+
+def _hostsim(cfg):
+    hs = HostSim(cfg, cfg.batch_capacity)
+    return lambda *a: hs.solve(*a)
+
+
+def test_interior_point_rescues_degenerate_quadruped_problems():
+    check_quadruped_hard_cases(_hostsim)
+
+
+def test_forced_interior_point_matches_oracle():
+    r = check_forced_interior_point(_hostsim)
+    assert (r["cycles"] > 0).sum() >= 4        # host build: `cycles` reports the interior-point iterations
+
+
+def test_forced_interior_point_fixture_closed_loop():
+    g = load_fixture("highway_branch_default")
+    hs = HostSim(force_interior_point(fixture_config(g)), 1)
+    check_fixture_closed_loop(lambda x, z, r: hs.solve(x, z, r), g)
+
+
+def test_no_problem_ends_on_the_iteration_cap():
+    B = 512
+    x0, z0, xref = scenarios.quadruped_batch(B, seed=1238)
+    hs = HostSim(scenarios.quadruped_config(), B)
+    r = hs.solve(x0, z0, xref)
+    assert (r["status"] <= 1).all() and (r["status"] == 0).mean() > 0.98

@@ -19,7 +19,19 @@ dev = torch.device("cuda", 0)
 OUTS = ("u0", "status", "iters", "nfact", "nsolve")
 
 
+def apply_env(cfg):
+    """experiment overrides: BMPC_R<k>=v sets cfg.reserved[k]; BMPC_<knob>=v sets a named solver knob"""
+    for k in range(8):
+        if os.environ.get("BMPC_R%d" % k):
+            cfg.reserved[k] = int(os.environ["BMPC_R%d" % k])
+    for knob in ("polish_careful", "polish_passes", "polish_first", "polish_every", "warm_polish", "rho_refresh", "max_iter"):
+        if os.environ.get("BMPC_" + knob):
+            setattr(cfg, knob, int(os.environ["BMPC_" + knob]))
+    return cfg
+
+
 def run(name, cfg, x0, z0, xref, pp, plant_policy, warm_steps=6):
+    cfg = apply_env(cfg)
     mpc = batch.BatchedBranchMPC(cfg)
     B = x0.shape[0]
     tx, tz, tr = [torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in (x0, z0, xref)]
@@ -49,6 +61,9 @@ def run(name, cfg, x0, z0, xref, pp, plant_policy, warm_steps=6):
 
 def main():
     which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5"]
+    sweep = [(m, NB) for m in (2, 3, 4) for NB in (1, 2, 3)]
+    if os.environ.get("BMPC_SWEEP"):      # e.g. BMPC_SWEEP=3x3,4x2
+        sweep = [tuple(int(v) for v in t.split("x")) for t in os.environ["BMPC_SWEEP"].split(",")]
     if "cfg3" in which:
         B = 16384
         x0, z0, xref, pp = scenarios.highway_batch(B, seed=1237)
@@ -67,8 +82,8 @@ def main():
     if "cfg5" in which:
         names = ["maintain", "brake", "lc", "trackv"]
         per = 65536 // 9
-        for m in (2, 3, 4):
-            for NB in (1, 2, 3):
+        for m, NB in sweep:
+            if True:
                 x0, z0, xref, pp3 = scenarios.highway_batch(per, seed=1239 + 10 * m + NB)
                 pp = np.zeros((per, m, 4))
                 if m >= 3:

@@ -17,6 +17,9 @@ for a in sys.argv[1:]:
 occ = knobs.pop("occ", 0)
 cfg = scenarios.highway_config(batch_capacity=B, **knobs)
 cfg.reserved[1] = occ
+for _k in range(8):
+    if os.environ.get('BMPC_R%d' % _k):
+        cfg.reserved[_k] = int(os.environ['BMPC_R%d' % _k])
 mpc = batch.BatchedBranchMPC(cfg)
 info = mpc.launch_info()
 print("launch:", info, flush=True)
@@ -44,5 +47,9 @@ for s in range(int(os.environ.get('STEPS', '4'))):
           % (s, ms, np.bincount(st, minlength=4).tolist(), cyc.sum() / warps / 1.965e6, cyc.max() / 1.965e6,
              np.percentile(cyc, 99) / 1.965e6, cyc.mean() / 1.965e6))
     print("   cycles ~ %.0f*nsolve + %.0f*nfact + %.0f ; mean nsolve %.1f nfact %.2f iters %.1f" % (coef[0], coef[1], coef[2], ns.mean(), nf.mean(), it.mean()))
+    if cfg.reserved[7] == 1:
+        used = cyc > 0
+        print("   interior point: used by %.3f of the problems, %.3f ms each, share of all problem time %.3f (x warps: %.2f ms of the kernel)"
+              % (used.mean(), cyc[used].mean() / 1.965e6 if used.any() else 0, 0, cyc.sum() / warps / 1.965e6))
     mpc.plant_step(tx, out["u0"], tz, 0, tp)
 mpc.close()
