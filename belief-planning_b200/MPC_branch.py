@@ -119,16 +119,8 @@ class _BatchedController:
         self._topo = topo
         return solver
 
-    def solve(self, x, z, xRef=None):
-        """Computes the control action(s).  x, z: (n,) or (B, n); xRef: (n,) or (B, n) or None (keep the previous)."""
-        if xRef is not None:
-            self.xRef = xRef
-        x = np.asarray(x, dtype=float)
-        single = x.ndim == 1
-        X = np.atleast_2d(x)
-        Z = np.atleast_2d(np.asarray(z, dtype=float))
-        B = X.shape[0]
-        R = np.broadcast_to(np.atleast_2d(np.asarray(self.xRef, dtype=float)), (B, self.n))
+    def _ensure_solver(self, B):
+        """The batched handle for (at least) B episodes with the model's current policy kinds."""
         model = self.predictiveModel
         if self._solver is not None and (B > self._capacity or [dd.kind for dd in model.descriptors] != self._kinds):
             self._solver.close()
@@ -136,10 +128,10 @@ class _BatchedController:
         if self._solver is None:
             self._solver = self._make_solver(B)
             self._capacity = B
-        pp = np.broadcast_to(model.policy_params(), (B, self.m, 4))        # update_backup() -> new per-episode parameters
-        t0 = datetime.datetime.now()
-        r = self._solver.solve_host(X, Z, R, pp)
-        self.solverTime = datetime.datetime.now() - t0
+        return self._solver
+
+    def _absorb(self, r, single):
+        """Result arrays of a batched solve -> the attributes the reference leaves behind (MPC_branch.py:1204-1229)."""
         ok = r["status"] <= abi.STATUS_MAXITER
         self.status = r["status"][0] if single else r["status"]
         self.feasible = int(ok[0]) if single else ok.astype(int)
@@ -159,6 +151,24 @@ class _BatchedController:
         self.timeStep += 1
         self.BT = True                              # "a tree exists": later solves are updatetree solves
         return self.OldInput
+
+    def solve(self, x, z, xRef=None):
+        """Computes the control action(s).  x, z: (n,) or (B, n); xRef: (n,) or (B, n) or None (keep the previous)."""
+        if xRef is not None:
+            self.xRef = xRef
+        x = np.asarray(x, dtype=float)
+        single = x.ndim == 1
+        X = np.atleast_2d(x)
+        Z = np.atleast_2d(np.asarray(z, dtype=float))
+        B = X.shape[0]
+        R = np.broadcast_to(np.atleast_2d(np.asarray(self.xRef, dtype=float)), (B, self.n))
+        model = self.predictiveModel
+        solver = self._ensure_solver(B)
+        pp = np.broadcast_to(model.policy_params(), (B, self.m, 4))        # update_backup() -> new per-episode parameters
+        t0 = datetime.datetime.now()
+        r = solver.solve_host(X, Z, R, pp)
+        self.solverTime = datetime.datetime.now() - t0
+        return self._absorb(r, single)
 
     def reset(self, episode_ids=None):
         """Forget the warm-start state of the given episodes (all by default): their next solve is an inittree solve."""

@@ -61,6 +61,13 @@ class Outputs(C.Structure):
 
 OUTPUT_NAMES = [f[0] for f in Outputs._fields_]
 
+class EnvState(C.Structure):
+    """bmpc_env_state (include/branchmpc.h)."""
+    _fields_ = [("x", C.c_void_p), ("z", C.c_void_p), ("lane", C.c_void_p), ("policy_params", C.c_void_p),
+                ("goal", C.c_void_p), ("obs_policy", C.c_void_p), ("collided", C.c_void_p), ("xref", C.c_void_p),
+                ("u_obs", C.c_void_p)]
+
+
 # every symbol include/branchmpc.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("bmpc_version", C.c_int, []),
@@ -88,6 +95,8 @@ SYMBOLS = [
                                          C.c_void_p]),
     ("bmpc_plant_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                   C.c_void_p]),
+    ("bmpc_env_step", C.c_int, [C.c_void_p, C.POINTER(EnvState), C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                C.POINTER(Outputs), C.c_void_p]),
     ("bmpc_get_launch_info", C.c_int, [C.c_void_p, _pi, _pi, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("bmpc_launch_count", C.c_int64, [C.c_void_p]),
     ("bmpc_measure_fp64_peak", C.c_double, [C.c_int, C.c_int]),

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "bmpc_env.cuh"
 #include "bmpc_hmm.cuh"
 #include "bmpc_host.h"
 #include "bmpc_solver.h"
@@ -584,6 +585,43 @@ int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32
     bmpc_plant_kernel<HighwayModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
   else
     bmpc_plant_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int32_t t, int32_t n_lane,
+                  const double* quad_sizes, const bmpc_outputs* out, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (!env || !out || count < 0 || t < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (!env->x || !env->z || !env->obs_policy || !env->collided || !env->xref || !env->u_obs || !out->u0) {
+    h->err = "bmpc_env_step needs x, z, obs_policy, collided, xref, u_obs and out->u0";
+    return BMPC_E_INVALID;
+  }
+  const bool highway = h->cfg.model == BMPC_MODEL_HIGHWAY;
+  if (highway && (!env->lane || !env->policy_params || n_lane < 1)) {
+    h->err = "highway environment needs lane, policy_params and n_lane";
+    return BMPC_E_INVALID;
+  }
+  if (!highway && (!env->goal || !quad_sizes)) { h->err = "quadruped environment needs goal and quad_sizes"; return BMPC_E_INVALID; }
+  if (h->cfg.controller == BMPC_CTRL_ROBUST) { h->err = "the environment drives the branch controllers"; return BMPC_E_UNSUPPORTED; }
+  if (count == 0) return BMPC_OK;
+  if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_INVALID; }
+  BMPC_CK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  EnvArgs a;
+  a.x = env->x; a.z = env->z; a.lane = env->lane; a.polpar = env->policy_params; a.goal = env->goal;
+  a.obs_policy = env->obs_policy; a.collided = env->collided; a.xref = env->xref; a.u_obs = env->u_obs;
+  a.count = (int)count; a.t = t; a.n_lane = n_lane;
+  const int threads = 128, blocks = (int)((count + threads - 1) / threads);
+  if (highway) bmpc_env_pre_highway<<<blocks, threads, 0, s>>>(h->P, a);
+  else bmpc_env_pre_quadruped<<<blocks, threads, 0, s>>>(h->P, a, quad_sizes[0], quad_sizes[1], quad_sizes[2]);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  const int rc = bmpc_solve(h, env->x, env->z, env->xref, env->policy_params, count, out, stream);
+  if (rc != BMPC_OK) return rc;
+  if (highway) bmpc_env_post<HighwayModel><<<blocks, threads, 0, s>>>(h->P, env->x, env->z, out->u0, env->u_obs, (int)count);
+  else bmpc_env_post<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, env->x, env->z, out->u0, env->u_obs, (int)count);
   BMPC_CK(h, cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

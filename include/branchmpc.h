@@ -235,6 +235,30 @@ int bmpc_hmm_belief_update(const double* ego, const double* xb, const double* b,
 int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32_t obstacle_policy,
                     const double* policy_params, int64_t count, void* stream);
 
+/* Closed-loop environment state of a batch of episodes (device pointers, caller-owned).  Replaces the per-episode
+ * Python objects of Highway_env_branch.py:28-81 (vehicle, Highway_env) and quadruped_env.py:24-65 (robot, Quad_env). */
+typedef struct bmpc_env_state {
+  double* x;             /* [count][n] ego state, advanced in place                                              */
+  double* z;             /* [count][n] obstacle state, advanced in place                                         */
+  int32_t* lane;         /* [count][2] highway: lane index of ego / obstacle (vehicle.laneidx); NULL for the quadruped */
+  double* policy_params; /* [count][m][4] per-episode policy parameters handed to the controller; the lane-change row is
+                            rewritten when the obstacle changes lane (update_backup, Highway_env_branch.py:117-118)   */
+  const double* goal;    /* [count][n] quadruped: desired final state x_des (quadruped_env.py:57); NULL on the highway */
+  int32_t* obs_policy;   /* [count] out: arg-max backup policy of the obstacle (veh_set[1].backupidx)             */
+  int32_t* collided;     /* [count] in/out: sticky collision flag of Highway_sim (Highway_env_branch.py:421-429)   */
+  double* xref;          /* [count][n] out: the reference this step handed to the controller                       */
+  double* u_obs;         /* [count][d] out: the input applied to the obstacle                                      */
+} bmpc_env_state;
+
+/* One closed-loop step of every episode, all on `stream`: Highway_env.step (Highway_env_branch.py:83-184) or
+ * Quad_env.step (quadruped_env.py:67-130) - obstacle arg-max policy from the numeric collision functions, lane
+ * bookkeeping and lane-change target, the xRef rule, the controller solve (as bmpc_solve with the state's x, z, xref and
+ * policy_params; `out` as there, out->u0 is required) and both Euler plants.  t is the step counter t_ of the reference
+ * (t == 0 initialises the lane indices), n_lane the environment's lane count (highway).  quad_sizes = {L1, L2, col_tol}
+ * for the quadruped (Quad_constants), NULL on the highway. */
+int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int32_t t, int32_t n_lane,
+                  const double* quad_sizes, const bmpc_outputs* out, void* stream);
+
 /* How the solve kernel is launched for this handle: resolved BMPC_SLAB_* placement, number of persistent warps
  * (= thread blocks of 32), dynamic shared memory per warp, bytes of the per-warp global region. */
 int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warps, int64_t* smem_bytes,

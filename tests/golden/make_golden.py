@@ -302,3 +302,61 @@ if __name__ == "__main__":
         run_quadruped("quadruped_prox_default", [0, 0, 0], [2, 0.3, np.pi], [5., 5., 0.], steps=3)
     if "hmm" in which:
         hmm_vectors()
+
+
+def run_highway_env(name, steps, x_ego=None, x_obs=None, N_lane=4):
+    """Closed loop of the reference's OWN environment (Highway_env_branch.Highway_env.step + the collision check of
+    Highway_sim, :83-184, :393-445) around the reference BranchMPC: lane bookkeeping, lane-change target updates, the
+    obstacle's arg-max policy (numeric veh_col / lane_bdry_h branches), the xRef rule and both Euler plants."""
+    print("highway env fixture", name)
+    with refenv.reference_imports():
+        import Highway_env_branch as henv
+    np.random.seed(11)           # the coin flips only touch desired_x, which nothing reads (Highway_env_branch.py:121-133)
+    cons = highway_cons()
+    lc_target = np.array([0.5, 1.8, 15., 0.])      # main_branch.py:35
+    model = hw.PredictiveModel(4, 2, 8, highway_policies(["maintain", "brake", "lc"], cons, lc_target), 0.1, cons)
+    par = Init_MPC.initBranchMPC(4, 2, 8, 2, lc_target, 6.0, 0.3, N_lane, cons.W)
+    mpc = MPC_branch.BranchMPC(par, model)
+    env = henv.Highway_env(2, mpc, N_lane)
+    if x_ego is not None:
+        env.veh_set[0].state = np.array(x_ego, dtype=float)
+    if x_obs is not None:
+        env.veh_set[1].state = np.array(x_obs, dtype=float)
+    store = {"meta_steps": np.array(steps), "meta_N_lane": np.array(N_lane), "x_init": env.veh_set[0].state.copy(),
+             "z_init": env.veh_set[1].state.copy()}
+    rec = {k: [] for k in ("x", "z", "lane", "backupidx", "xref", "u_ego", "u_obs", "lc_target", "collision")}
+    solve = mpc.solve
+    seen = {}
+
+    def spy(x, z, xRef=None):
+        seen["xref"] = np.array(xRef, dtype=float)
+        return solve(x, z, xRef)
+
+    mpc.solve = spy
+    collision = False
+    for t in range(steps):
+        a, b = env.veh_set
+        dis = max(abs(a.state[0] - b.state[0]) - 0.5 * (a.v_length + b.v_length),
+                  abs(a.state[1] - b.state[1]) - 0.5 * (a.v_width + b.v_width))     # Highway_sim :421-429
+        collision = collision or dis < 0
+        u_set, x_set, *_ = env.step(t)
+        # the lane-change target the MODEL's compiled graphs now use: first Euler step of the lc rollout from the zero
+        # state is dt*[0, 0, 0.8558 v_t, 0.3162 y_t] (psi_t = 0 in every target the env builds).  The lambda itself cannot
+        # be probed: it closes over the local `xRef` of step(), which is rebound to the MPC reference afterwards (:168).
+        first = np.array(model.zpred_eval(np.zeros(4)))[0, 8:12]
+        rec["lc_target"].append(np.array([0.0, first[3] / (0.1 * 0.3162), first[2] / (0.1 * 0.8558), 0.0]))
+        rec["x"].append(np.array(x_set[0])); rec["z"].append(np.array(x_set[1]))
+        rec["lane"].append([env.veh_set[0].laneidx, env.veh_set[1].laneidx])
+        rec["backupidx"].append(env.veh_set[1].backupidx)
+        rec["xref"].append(seen["xref"]); rec["u_ego"].append(np.array(u_set[0])); rec["u_obs"].append(np.array(u_set[1]))
+        rec["collision"].append(collision)
+        print("   t %d  x %s  z %s  obs policy %d  xref %s" % (t, np.round(x_set[0], 4), np.round(x_set[1], 4),
+                                                             env.veh_set[1].backupidx, np.round(seen["xref"], 3)))
+    for k, v in rec.items():
+        store[k] = np.array(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+
+
+if __name__ == "__main__" and ("env" in sys.argv[1:]):
+    run_highway_env("highway_env_default", steps=30)
+    run_highway_env("highway_env_overtake", steps=24, x_ego=[2.0, 5.5, 24.0, 0.0], x_obs=[14.0, 5.4, 17.0, 0.0])

@@ -75,3 +75,19 @@ def test_parameter_objects_keep_the_reference_quirks():
     q = Init_MPC.initquadBranchMPC(3, 3, 25, 2, np.array([5., 5., 0.]), 0.2, 0.1, 0.5)
     assert q.Fx.shape == (0, 3) and q.dR.tolist() == [0.9, 5, 1]
     assert isinstance(BranchMPCParams(n=2, d=1, Q=np.eye(2)).xRef, np.ndarray)
+
+
+def test_environment_modules_keep_the_reference_surface():
+    """Highway_env_branch / quadruped_env drop-ins: names and signatures of the reference (no GPU needed to import)."""
+    import inspect
+    import Highway_env_branch as henv
+    import quadruped_env as qenv
+    assert henv.v0 == 20 and henv.lane_width == 3.6
+    assert list(inspect.signature(henv.Highway_env.__init__).parameters)[:4] == ["self", "NV", "mpc", "N_lane"]
+    assert list(inspect.signature(henv.Highway_env.step).parameters) == ["self", "t_"]
+    assert list(inspect.signature(henv.Highway_sim).parameters) == ["env", "T"]
+    assert list(inspect.signature(henv.sim_overtake).parameters)[:2] == ["mpc", "N_lane"]
+    v = henv.vehicle([1, 2, 3, 0.1], dt=0.1)
+    assert v.v_length == 4 and v.v_width == 2.4 and v.laneidx == 0 and v.backupidx == 0
+    assert list(inspect.signature(qenv.Quad_env.__init__).parameters)[:4] == ["self", "NR", "mpc", "x_des"]
+    assert list(inspect.signature(qenv.Robot_sim).parameters) == ["env", "T"]

@@ -86,3 +86,54 @@ def test_batched_solve_through_the_same_interface():
         ui = one.solve(x0[i], z0[i], xref[i])
         assert np.array_equal(ui, u[i])
         one.reset()
+
+
+def test_highway_env_dropin_reproduces_reference_sim():
+    """main_branch.sim_overtake's loop (Highway_env_branch.Highway_sim) through the drop-in environment: the recorded
+    trace of the reference's own environment is reproduced state by state."""
+    import Highway_env_branch as henv
+    g = load_fixture("highway_env_default")
+    mpc, model, cons, _ = _main_branch_setup()
+    env = henv.Highway_env(NV=2, mpc=mpc, N_lane=4)
+    steps = 12
+    state_rec, input_rec, _, choice_rec, xPred_rec, zPred_rec, w_rec, collision = henv.Highway_sim(env, steps * env.dt)
+    assert state_rec.shape == (2, steps, 4) and input_rec.shape == (2, steps, 2)
+    np.testing.assert_allclose(state_rec[0], g["x"][:steps], atol=1e-5)
+    np.testing.assert_allclose(state_rec[1], g["z"][:steps], atol=1e-8)
+    np.testing.assert_allclose(input_rec[1], g["u_obs"][:steps], atol=1e-9)
+    assert [int(c) for c in choice_rec[1]] == [int(c) for c in g["backupidx"][:steps]]
+    assert collision == bool(g["collision"][steps - 1])
+    assert len(xPred_rec[0]) == 12 and xPred_rec[0][0].shape == (9, 4) and len(w_rec[0]) == 12
+    assert mpc.timeStep == steps and mpc.uPred.shape == (97, 2)
+
+
+def test_highway_env_dropin_batched():
+    import Highway_env_branch as henv
+    from _bmpc import scenarios
+    mpc, model, cons, _ = _main_branch_setup()
+    B = 256
+    x0, z0, _, _ = scenarios.highway_batch(B, seed=5)
+    env = henv.Highway_env(NV=2, mpc=mpc, N_lane=4, x0=np.stack([x0, z0], axis=1))
+    state_rec, input_rec, *_rest, collision = henv.Highway_sim(env, 0.5)
+    assert state_rec.shape == (B, 2, 5, 4) and collision.shape == (B,)
+    assert np.isfinite(state_rec).all() and (np.abs(input_rec[:, 0, :, 0]) <= 6 + 1e-9).all()
+    assert mpc.uPred.shape == (B, 97, 2) and (np.asarray(mpc.feasible) == 1).all()
+
+
+def test_quadruped_env_dropin_runs():
+    from Init_MPC import initquadBranchMPC
+    from MPC_branch import BranchMPCProx
+    from quadruped_branch_dyn import PredictiveModel, backup_forward, backup_stop
+    from utils import Quad_constants
+    import quadruped_env as qenv
+    cons = Quad_constants(s1=2, s2=3, c2=0.5, alpha=1, R=1.2, vxm=0.2, vym=0.1, rm=0.5, L1=0.5, W1=0.3, L2=1, W2=0.6,
+                          col_tol=0.2, col_alpha=5)
+    v0 = 0.2
+    model = PredictiveModel(3, 3, 25, [lambda x: backup_forward(x, v0), lambda x: backup_stop(x)], 0.2, cons)
+    x_des = np.array([5., -3., 0.])
+    mpc = BranchMPCProx(initquadBranchMPC(3, 3, 25, 2, x_des, 0.2, 0.1, 0.5), model)
+    env = qenv.Quad_env(2, mpc, x_des)
+    state_rec, input_rec, xPred_rec, zPred_rec = qenv.Robot_sim(env, 0.6)      # main_quadruped.py crashes here in the reference
+    assert state_rec.shape == (2, 3, 3) and np.isfinite(state_rec).all()
+    assert (input_rec[0, :, 0] <= 0.2 + 1e-9).all() and (input_rec[0, :, 0] >= -1e-9).all()
+    assert mpc.uPred.shape == (151, 3) and mpc.feasible == 1
