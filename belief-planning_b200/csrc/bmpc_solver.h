@@ -136,6 +136,21 @@ struct Solver {
     }
     return slab()[kp * NFWP + field];
   }
+  // phase accounting (development aid): with reserved[7] = k > 0 the `cycles` output reports the time spent in phase k
+  // (1 interior point, 2 tree expansion, 3 rho selection/cache, 4 factorisations, 5 backward+forward sweeps, 6 node-parallel
+  // polish passes, 7 adjoint sweep, 8 ADMM row phase, 9 final pass + caches)
+  long long t_phase;
+  BMPC_D long long prof_begin(int k) {
+#if defined(__CUDA_ARCH__)
+    if (P.cycles_mode == k) return clock64();
+#endif
+    return 0;
+  }
+  BMPC_D void prof_end(int k, long long t0) {
+#if defined(__CUDA_ARCH__)
+    if (P.cycles_mode == k) t_phase += clock64() - t0;
+#endif
+  }
   BMPC_D real& IPF(int field, int kp) { return ip[(size_t)field * nup + kp]; }   // field-major: the lanes of a node-parallel pass read consecutive addresses
   BMPC_D code_t* stp() { return reinterpret_cast<code_t*>(slab() + oSt); }
   BMPC_D real* Wbp() { return slab() + oWb; }
@@ -224,6 +239,7 @@ struct Solver {
   }
 
   BMPC_DN void expand_tree() {
+    const long long prof_t0 = prof_begin(2);
     const int started = P.started[prob];
     const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     int* pbest = P.pbest + (size_t)prob * P.nbranch;
@@ -347,6 +363,7 @@ struct Solver {
     rlin = 0.0;
 #pragma unroll
     for (int a = 0; a < NU; ++a) rlin += -2.0 * P.oldin[(size_t)prob * NU + a] * P.dR[a];
+    prof_end(2, prof_t0);
   }
 
   // ----------------------------------------------------------------------------------------
@@ -357,6 +374,7 @@ struct Solver {
   // t = (depth-1) N + i + 1 in BFS order (:1336-1383); slot t gives node t its collision rows.
   // ----------------------------------------------------------------------------------------
   BMPC_DN void expand_chain() {
+    const long long prof_t0 = prof_begin(2);
     const int started = P.started[prob];
     const int Nx = P.totalu, Nu = P.totalu - 1;   // states incl. the terminal one / real inputs
     const real* uPrev = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
@@ -459,6 +477,7 @@ struct Solver {
     }
     rlin = 0.0;
     lanes_sync();
+    prof_end(2, prof_t0);
   }
 
   // ========================================================================================
@@ -720,6 +739,7 @@ struct Solver {
   // The root is "depth 0, one node": every sweep runs one loop nest over the levels, so that each node step is
   // instantiated once (code size matters: the instruction cache is the first bottleneck of this kernel, profiles/).
   BMPC_DN void factorize(int mode) {
+    const long long prof_t0 = prof_begin(4);
 #pragma unroll 1
     for (int d = P.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : P.N;
@@ -745,6 +765,7 @@ struct Solver {
       }
       lanes_sync();
     }
+    prof_end(4, prof_t0);
   }
 
   // ========================================================================================
@@ -859,6 +880,7 @@ struct Solver {
   }
 
   BMPC_DN void choose_rho() {
+    const long long prof_t0 = prof_begin(3);
 #pragma unroll 1
     for (int d = 0; d <= P.NB; ++d) {
       const int nt = (d == 0) ? 1 : P.N;
@@ -878,6 +900,7 @@ struct Solver {
       }
       lanes_sync();
     }
+    prof_end(3, prof_t0);
   }
 
   // ========================================================================================
@@ -919,6 +942,7 @@ struct Solver {
   }
 
   BMPC_DN void backward() {
+    const long long prof_t0 = prof_begin(5);
 #pragma unroll 1
     for (int d = P.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : P.N;
@@ -956,6 +980,7 @@ struct Solver {
       }
       lanes_sync();
     }
+    prof_end(5, prof_t0);
   }
 
   BMPC_D void fw_step(int kp, real* x) {
@@ -982,6 +1007,7 @@ struct Solver {
   }
 
   BMPC_DN void forward() {
+    const long long prof_t0 = prof_begin(5);
     ++nsolve;
 #pragma unroll 1
     for (int d = 0; d <= P.NB; ++d) {
@@ -1005,6 +1031,7 @@ struct Solver {
       }
       lanes_sync();
     }
+    prof_end(5, prof_t0);
   }
 
   // ========================================================================================
@@ -1033,8 +1060,11 @@ struct Solver {
 
   // update=false: only assemble q~ from the current state (start / after a failed polish)
   // check=true : also return max(primal residual, scaled dual residual) over this lane's nodes
+  // (measured: one out-of-line copy with runtime switches shrinks the kernel's main body from 45 KB to 13 KB but is 8 %
+  // slower - the specialised no-check variant is the hot one and must stay compact)
   template <bool UPDATE, bool CHECK>
   BMPC_D real admm_rows() {
+    const long long prof_t0 = prof_begin(8);
     real res = 0.0;
     if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; set_changes = 0; }
 #pragma unroll 1
@@ -1117,12 +1147,13 @@ struct Solver {
       }
     }
     lanes_sync();
-    return res;
+    { const auto prof_rv = res; prof_end(8, prof_t0); return prof_rv; }
   }
 
   // rho cache: the curvature-matched rho changes slowly from one MPC step to the next, so warm solves reuse the
   // values of the previous step (refreshed every P.rho_refresh solves) and skip the free factorisation + covariance sweep.
   BMPC_DN void store_rho() {
+    const long long prof_t0 = prof_begin(3);
     real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
@@ -1133,8 +1164,10 @@ struct Solver {
       for (int j = 0; j < NR + NU; ++j) cache[(size_t)k * (NR + NU) + j] = F(F_RHO + j, kp);
     }
     lanes_sync();
+    prof_end(3, prof_t0);
   }
   BMPC_DN void load_rho() {
+    const long long prof_t0 = prof_begin(3);
     const real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
@@ -1155,10 +1188,12 @@ struct Solver {
       }
     }
     lanes_sync();
+    prof_end(3, prof_t0);
   }
   // shifted codes of the previous optimum -> a consistent starting guess for the polish (multipliers start at their
   // natural values: 0 on kinks)
   BMPC_DN void guess_from_codes() {
+    const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
@@ -1182,8 +1217,10 @@ struct Solver {
       stp()[kp] = ncode;
     }
     lanes_sync();
+    prof_end(6, prof_t0);
   }
   BMPC_DN void store_codes() {
+    const long long prof_t0 = prof_begin(9);
     code_t* codes = P.code_cache + (size_t)prob * P.totalu;
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
@@ -1192,6 +1229,7 @@ struct Solver {
       codes[k] = stp()[kp_of(b, t)];
     }
     lanes_sync();
+    prof_end(9, prof_t0);
   }
 
   // Residual balancing (Boyd et al. 2011, 3.4.1) on top of the curvature-matched rho: with rho in matched units the
@@ -1244,6 +1282,7 @@ struct Solver {
   // imposed by a stiff penalty + augmented-Lagrangian refinement so that the same tree Riccati solves them)
   // ========================================================================================
   BMPC_DN void polish_guess() {
+    const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
@@ -1284,9 +1323,11 @@ struct Solver {
       stp()[kp] = code;
     }
     lanes_sync();
+    prof_end(6, prof_t0);
   }
 
   BMPC_DN void polish_assemble() {
+    const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
@@ -1335,10 +1376,12 @@ struct Solver {
       for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = qu[a];
     }
     lanes_sync();
+    prof_end(6, prof_t0);
   }
 
   // multiplier (augmented-Lagrangian) update on the guessed-active rows; returns this lane's max residual
   BMPC_DN real polish_multipliers() {
+    const long long prof_t0 = prof_begin(6);
     real res = 0.0;
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
@@ -1365,11 +1408,12 @@ struct Solver {
       }
     }
     lanes_sync();
-    return res;
+    { const auto prof_rv = res; prof_end(6, prof_t0); return prof_rv; }
   }
 
   // pinned inputs take their bound value after the backward sweep (their gain rows and feed-forward are zero)
   BMPC_DN void polish_inject() {
+    const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
     for (int k = lane; k < P.totalu; k += BMPC_LANES) {
       int b, t;
@@ -1381,6 +1425,7 @@ struct Solver {
         if (pinned(code, a)) F(F_UQ + a, kp) = pinned_value(code, a);
     }
     lanes_sync();
+    prof_end(6, prof_t0);
   }
 
   // Adjoint (costate) sweep of the equality-constrained solution in XQ/UQ: lam_k = dstage/dxi + A~' lam_{k+1}.  The
@@ -1443,6 +1488,7 @@ struct Solver {
   }
 
   BMPC_DN real polish_adjoint() {
+    const long long prof_t0 = prof_begin(7);
     real viol = 0.0;
 #pragma unroll 1
     for (int d = P.NB; d >= 0; --d) {
@@ -1485,7 +1531,7 @@ struct Solver {
       }
       lanes_sync();
     }
-    return viol;
+    { const auto prof_rv = viol; prof_end(7, prof_t0); return prof_rv; }
   }
 
   // Primal-dual active-set update from the last equality-constrained solve.  Every candidate change carries a score in
@@ -1494,6 +1540,7 @@ struct Solver {
   // restricted=true (stalled refinement): only kink rows whose multiplier is out of range by more than the last
   // multiplier step are revised; everything else is left for a settled solve.
   BMPC_DN int polish_update_sets(bool restricted, real thresh, bool apply, real& score_max) {
+    const long long prof_t0 = prof_begin(6);
     int changes = 0;
     real smax = 0.0;
     const real tol = 1e-7;
@@ -1589,7 +1636,7 @@ struct Solver {
     }
     lanes_sync();
     score_max = smax;
-    return changes;
+    { const auto prof_rv = changes; prof_end(6, prof_t0); return prof_rv; }
   }
 
   // returns true when the guessed active set was verified (then XQ/UQ hold the optimal x,u).
@@ -2022,6 +2069,7 @@ struct Solver {
   }
 
   BMPC_DN real finish() {
+    const long long prof_t0 = prof_begin(9);
     real J = 0.0;
     real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
     real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.pub_totalx * NXP : nullptr;
@@ -2079,7 +2127,7 @@ struct Solver {
       }
       lanes_sync();
     }
-    return lanes_sum(J);
+    { const auto prof_rv = lanes_sum(J); prof_end(9, prof_t0); return prof_rv; }
   }
 
   // any non-finite input left by the last forward sweep?
@@ -2110,6 +2158,7 @@ struct Solver {
     int* cstate = P.cache_state + (size_t)prob * 2;   // [0] age of the cached rho (-1: none), [1] cached codes valid
     const bool reuse_rho = warm && P.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < P.rho_refresh;
     use_codes = warm && P.warm_polish && cstate[1] == 1 && reuse_rho;
+    t_phase = 0;
     if (P.ctrl == BMPC_CTRL_ROBUST) expand_chain();
     else expand_tree();
     nsolve = 0;
@@ -2135,8 +2184,6 @@ struct Solver {
     int next_polish = P.polish_first, polish_gap = P.polish_every, next_forced = P.polish_force;
     int nfail = 0;
     bool ipm_tried = false;
-    long long t_ipm = 0;
-    (void)t_ipm;
     if (!have_xu) {
       factorize(FACT_ADMM);
       ++nfact;
@@ -2174,13 +2221,9 @@ struct Solver {
         if (!conv && P.ipm_after > 0 && (nfail >= P.ipm_after || P.ipm_after == 100) && !ipm_tried) {
           // the active set does not settle: interior point on the same Riccati, then a polish from its (clean) active set
           ipm_tried = true;
-#if defined(__CUDA_ARCH__)
-          const long long t_ipm0 = clock64();
-#endif
+          const long long t_ipm0 = prof_begin(1);
           const bool ipm_ok = ipm_solve(nfact, iters);
-#if defined(__CUDA_ARCH__)
-          t_ipm += clock64() - t_ipm0;
-#endif
+          prof_end(1, t_ipm0);
           if (ipm_ok) {
             ipm_guess();
             if (polish(nfact, false, false)) {
@@ -2224,7 +2267,7 @@ struct Solver {
       if (P.out.nfact) P.out.nfact[prob] = nfact;
       if (P.out.nsolve) P.out.nsolve[prob] = nsolve;
 #if defined(__CUDA_ARCH__)
-      if (P.out.cycles) P.out.cycles[prob] = P.cycles_ipm_only ? (int64_t)t_ipm : (int64_t)(clock64() - t_start);
+      if (P.out.cycles) P.out.cycles[prob] = P.cycles_mode > 0 ? (int64_t)t_phase : (int64_t)(clock64() - t_start);
       if (P.cost) P.cost[prob] = (int)min((long long)0x7fffffff, (clock64() - t_start) >> 10);
 #else
       if (P.out.cycles) P.out.cycles[prob] = ipm_iters;   // host build: no clock; reports the interior-point iterations instead

@@ -166,9 +166,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": (1e3 * B / value) if value else None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "highway Branch MPC m=3 NB=2 N=8, closed-loop warm solves; CPU restatement of the "
-                                   "reference path (casadi/osqp are not installable here); each step = one warm solve on "
-                                   "every host core"},
+            "config": {"workload": WORKLOAD,
+                       "sample": "bounded sample of that workload: each step = one warm closed-loop solve of one episode on every "
+                                 "host core (CPU restatement of the reference path, oracle/; casadi/osqp are not "
+                                 "installable here)"},
             "cpu_baseline": dict(last, value=value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_all}
@@ -299,9 +300,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": solve_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "highway Branch MPC (BASELINE configs[2]): m=3 policies [maintain, brake, lane-change], "
-                                   "NB=2, N=8 -> 13 branches / 106 state nodes / 97 input nodes; closed-loop warm solves "
-                                   "(updatetree path), 16384 episodes per GPU" if B == 16384 else
+            "config": {"workload": WORKLOAD if B == 16384 else
                                    "highway Branch MPC m=3 NB=2 N=8, closed-loop warm solves, %d episodes per GPU" % B,
                        "batch_per_gpu": B, "parallelism": "episodes sharded over %d GPU(s), no collective on the solve path" % world,
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
@@ -309,7 +308,10 @@ def run_gpu(args):
                        "mean_admm_iters": float(it.mean()), "mean_factorizations": mean_nf, "mean_kkt_solves": mean_ns},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": hbm_achieved / peaks["hbm_gbs"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 16384 episodes from the ncu --set full
+                         # capture profiles/r01_solve_kernel_v6_ncu_raw.csv (108.5 MB + 14.6 MB); not re-measured per run
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_16384 if B == 16384 else None, "peak_source": peak_src,
                          "note": "latency/FP64-pipe bound, not HBM bound (arithmetic intensity >> ridge): see fp64",
                          "algorithmic_bytes_per_solve": algorithmic_bytes_per_solve(),
                          "fp64": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -325,6 +327,11 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+WORKLOAD = ("highway Branch MPC (BASELINE configs[2]): m=3 policies [maintain, brake, lane-change], NB=2, N=8 -> 13 branches / "
+            "106 state nodes / 97 input nodes; closed-loop warm solves (updatetree path), 16384 episodes per GPU")
+NCU_DRAM_BYTES_PER_LAUNCH_16384 = 108535040 + 14563840
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,7 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="episodes per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-problems", type=int, default=2, help="episodes per host core in the cpu_baseline leg")
+    ap.add_argument("--cpu-problems", type=int, default=4, help="episodes per host core in the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -127,8 +127,9 @@ typedef struct bmpc_config {
                              warps per SM; [2] polish when at most this many nodes changed their implied set between
                              checks; [3] polish at the latest every this many ADMM iterations (80; quadruped 20); [4] interior-point
                              fallback after this many failed polish attempts (3; quadruped 1; <0 = never; 100 = always, without a polish attempt first); [5] its iteration cap (40);
-                             [6] 1 = natural work order instead of longest-first; [7] 1 = the cycles output counts the
-                             interior-point part only */
+                             [6] 1 = natural work order instead of longest-first; [7] k > 0 = the cycles output counts phase k only
+                             (1 interior point, 2 expansion, 3 rho, 4 factorisations, 5 sweeps, 6 polish passes,
+                             7 adjoint, 8 ADMM rows, 9 final pass) */
 } bmpc_config;
 
 /* Output device pointers; any may be NULL to skip that output. */
