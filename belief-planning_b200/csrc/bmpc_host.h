@@ -122,7 +122,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.polish_al_iters = c.polish_al_iters > 0 ? c.polish_al_iters : 24;
   P.polish_careful = c.polish_careful > 0 ? c.polish_careful : 0;   // off: the interior-point fallback handles cycling sets
   P.warm_polish = c.warm_polish >= 0 ? 1 : 0;
-  P.warm_passes = c.warm_polish > 0 ? c.warm_polish : 3;
+  P.warm_passes = c.warm_polish > 0 ? c.warm_polish : (c.model == BMPC_MODEL_QUADRUPED ? 6 : 3);   // measured (profiles/r01_knob_matrix.md)
   P.rho_refresh = c.rho_refresh > 0 ? c.rho_refresh : (c.rho_refresh < 0 ? 0 : 8);
   P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
   P.theta = c.theta > 0.0 ? c.theta : 1.0;

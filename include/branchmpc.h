@@ -112,7 +112,7 @@ typedef struct bmpc_config {
   int32_t polish_al_iters; /* augmented-Lagrangian refinements per pass (24)                     */
   int32_t polish_careful;  /* extra one-change-at-a-time passes when the set iteration cycles (0 = off, the default) */
   int32_t warm_polish;     /* warm solves first try a polish from the previous optimum's shifted active set:
-                              number of active-set passes for that attempt (3; <0 = off)        */
+                              number of active-set passes for that attempt (3; quadruped 6; <0 = off)        */
   int32_t rho_refresh;     /* warm solves reuse the cached rho for this many steps (8; <0 = recompute every solve)   */
   double alpha;            /* over-relaxation (1.6)                                              */
   double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */

@@ -59,8 +59,35 @@ def run(name, cfg, x0, z0, xref, pp, plant_policy, warm_steps=6):
     return line
 
 
+def run_env(name, B=16384, steps=30):
+    """Closed loop entirely on the device (bmpc_env_step: obstacle policy + lanes + xRef + solve + plants per episode)."""
+    from _bmpc import env as benv
+    x0, z0, _, _ = scenarios.highway_batch(B, seed=1240)
+    mpc = batch.BatchedBranchMPC(apply_env(scenarios.highway_config(batch_capacity=B)))
+    e = benv.BatchedHighwayEnv(mpc, x0, z0, 4)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    stat = []
+    for t in range(steps):
+        out = e.step(outputs=("u0", "status", "iters"))
+        ev[t + 1].record()
+        stat.append(out["status"].clone())
+    torch.cuda.synchronize()
+    ms = [ev[t].elapsed_time(ev[t + 1]) for t in range(steps)]
+    warm = ms[5:]
+    h = e.host()
+    line = {"config": name, "episodes": B, "steps": steps, "cold_step_ms": round(ms[0], 3), "warm_step_ms_mean": round(float(np.mean(warm)), 3),
+            "episode_steps_per_s": round(B / float(np.mean(warm)) * 1e3), "status_all_steps": torch.bincount(torch.cat(stat), minlength=4).tolist(),
+            "collided": int(h["collided"].sum()), "obstacle_policy_hist_last": np.bincount(h["obs_policy"], minlength=3).tolist(),
+            "launches_per_step": 4}
+    print(json.dumps(line), flush=True)
+    mpc.close()
+
+
 def main():
-    which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5"]
+    which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5", "env"]
+    if "env" in which:
+        run_env("closed loop on the device: Highway_env.step x 16384 episodes (row f1)")
     sweep = [(m, NB) for m in (2, 3, 4) for NB in (1, 2, 3)]
     if os.environ.get("BMPC_SWEEP"):      # e.g. BMPC_SWEEP=3x3,4x2
         sweep = [tuple(int(v) for v in t.split("x")) for t in os.environ["BMPC_SWEEP"].split(",")]
