@@ -1738,8 +1738,10 @@ struct Solver {
       rc2 = -ss * v;
     } else if (phase == IPM_CORR_ASM) {
       const real dy = c0, ds = c1, da = -sg * dt + ds;
-      rc1 = sigmu - a * y - da * dy;
-      rc2 = soft ? sigmu - ss * v + ds * dy : 0.0;   // dv = -dy
+      // second-order (Mehrotra) term weighted by `alpha` = omega in [0,1]: a short affine step means the affine direction
+      // is a poor predictor and its products would throw the iterate off centre (weighted correctors, Colombo & Gondzio)
+      rc1 = sigmu - a * y - alpha * da * dy;
+      rc2 = soft ? sigmu - ss * v + alpha * ds * dy : 0.0;   // dv = -dy
       c0 = rc1;
       c1 = rc2;
     } else {
@@ -1976,7 +1978,7 @@ struct Solver {
       const real mu_aff = fmax((1.0 - a_aff) * mu + a_aff * a_aff * lanes_sum(ipm_acc) / pairs, 0.0);
       real sigma = mu_aff / mu;
       sigma = sigma * sigma * sigma;
-      ipm_pass(bmpc_opaque(IPM_CORR_ASM), sigma * mu, 0.0);
+      ipm_pass(bmpc_opaque(IPM_CORR_ASM), sigma * mu, a_aff);
       backward();
       forward();
       ipm_pass(bmpc_opaque(IPM_CORR_STEP), 0.0, 0.0);
