@@ -141,7 +141,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.ipm_after = c.reserved[4] > 0 ? c.reserved[4] : (c.reserved[4] < 0 ? 0 : (quad ? 1 : 3));
   P.ipm_max_iter = c.reserved[5] > 0 ? c.reserved[5] : 40;
   P.cycles_mode = c.reserved[7] > 0 ? c.reserved[7] : 0;
-  P.ipm_mu_tol = 1.0e-9;
+  P.ipm_mu_tol = 1.0e-10;
   P.ipm_s0 = 1.0;
   P.ipm_y0 = 0.5;
   P.ipm = nullptr;

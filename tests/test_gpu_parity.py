@@ -69,7 +69,7 @@ def test_quadruped_prox_fixture_closed_loop(bmpc):
     g = load_fixture("quadruped_prox_default")
     mpc = bmpc.BatchedBranchMPC(quadruped_fixture_config(g))
     assert (mpc.topology() == g["s0_tree"]).all() and [mpc.totalx, mpc.totalu] == list(g["s0_totals"])
-    check_fixture_closed_loop(lambda x, z, r: mpc.solve_host(x, z, r), g, tol=1e-5)
+    check_fixture_closed_loop(lambda x, z, r: mpc.solve_host(x, z, r), g, tol=5e-5)   # see tests/test_hostsim_parity.py
     mpc.close()
 
 
