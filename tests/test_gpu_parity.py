@@ -194,6 +194,42 @@ def test_tree_sweep_against_oracle(bmpc, m, NB):
     check_sweep_case(make, m, NB)
 
 
+@pytest.mark.parametrize("m,NB", SWEEP)
+def test_tree_sweep_full_size_properties(bmpc, m, NB):
+    """BASELINE config 5 at its per-shape share of the 65536 episodes (7281): every problem certified or converged, hard
+    constraints hold, siblings share their first state bit for bit, weights of every level sum to one, and a shuffled
+    batch gives the shuffled results bit for bit (episodes are independent: what makes the sharding over GPUs exact)."""
+    B = 65536 // 9
+    names = ["maintain", "brake", "lc", "trackv"][:m]
+    cfg = scenarios.highway_config(policies=names, NB=NB, batch_capacity=B)
+    mpc = bmpc.BatchedBranchMPC(cfg)
+    x0, z0, xref, pp3 = scenarios.highway_batch(B, seed=1239 + 10 * m + NB)
+    pp = np.zeros((B, m, 4))
+    if m >= 3:
+        pp[:, 2, :] = pp3[:, 2, :]
+    if m >= 4:
+        pp[:, 3, 0] = 20.0
+    outs = ("u0", "uPred", "xPred", "branch_w", "objective", "status")
+    r = mpc.solve_host(x0, z0, xref, pp, outputs=outs)
+    assert (r["status"] <= abi.STATUS_CONVERGED).all() and (r["status"] == abi.STATUS_POLISHED).mean() > 0.99
+    assert np.isfinite(r["objective"]).all() and np.isfinite(r["xPred"]).all()
+    assert _violations(r, x0, cfg) <= TOL_VIOL
+    topo = mpc.topology()
+    for b in range(mpc.nbranch):
+        kids = topo[topo[:, 4] == b]
+        for c in kids[1:]:
+            assert np.array_equal(r["xPred"][:, kids[0][2]], r["xPred"][:, c[2]])
+    for d in range(1, NB + 1):
+        level = topo[topo[:, 1] == d][:, 0]
+        assert np.abs(r["branch_w"][:, level].sum(axis=1) - 1.0).max() < 1e-12
+    perm = np.random.default_rng(m * 10 + NB).permutation(B)
+    mpc.reset()
+    r2 = mpc.solve_host(x0[perm], z0[perm], xref[perm], pp[perm], outputs=outs)
+    for k in ("u0", "objective", "status"):
+        assert np.array_equal(r2[k], r[k][perm]), k
+    mpc.close()
+
+
 def _gpu_solver(bmpc):
     def make(cfg):
         mpc = bmpc.BatchedBranchMPC(cfg)
