@@ -21,7 +21,8 @@
 // MODE = BMPC_SLAB_SHARED (whole slab in shared memory), BMPC_SLAB_SPLIT (iterate fields in shared memory, factor fields
 // in this warp's global region, which stays L2-resident), BMPC_SLAB_GLOBAL (everything in the global region).
 template <class M, int NR, int MODE, int NC = 1>
-__global__ void __launch_bounds__(32) bmpc_solve_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32) bmpc_solve_kernel() {
+  const KParams& P = bmpc_cP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   constexpr bool SPLIT = (MODE == BMPC_SLAB_SPLIT);
@@ -165,6 +166,7 @@ __global__ void bmpc_dfma_kernel(double* out, int iters) {
 // ------------------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------------------
+#define BMPC_PSTAGE 8
 struct bmpc_handle {
   bmpc_config cfg;
   KParams P;            // call-independent part
@@ -189,6 +191,9 @@ struct bmpc_handle {
   int* counter = nullptr;
   real* gws = nullptr;
   real* ipm_ws = nullptr;   // per-warp scratch of the interior-point fallback
+  KParams* pstage = nullptr;              // pinned staging ring of parameter blocks (source of the constant-memory upload)
+  cudaEvent_t pstage_evt[BMPC_PSTAGE] = {};
+  unsigned pstage_next = 0;
   // staging for bmpc_solve_host
   real* stage_in = nullptr;   // x0 | z0 | xref | polpar
   void* stage_out = nullptr;
@@ -200,6 +205,9 @@ struct bmpc_handle {
 };
 
 static std::string g_create_error;
+
+struct ConstSlot { cudaEvent_t done = nullptr; cudaStream_t stream = nullptr; bool used = false; };
+static ConstSlot g_const[16];   // per device: the last solve launch that reads bmpc_cP
 
 #define BMPC_CK(h, call)                                                                           \
   do {                                                                                             \
@@ -269,11 +277,11 @@ static int configure_instance(bmpc_handle* h) {
 template <class M, int NR, int NC = 1>
 static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStream_t s) {
   if (h->mode == BMPC_SLAB_SHARED) {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, 32, h->slab_bytes, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, 32, h->slab_bytes, s>>>();
   } else if (h->mode == BMPC_SLAB_SPLIT) {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, 32, h->slab_bytes, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, 32, h->slab_bytes, s>>>();
   } else {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, 32, 0, s>>>(P);
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, 32, 0, s>>>();
   }
   BMPC_CK(h, cudaGetLastError());
   return BMPC_OK;
@@ -309,6 +317,8 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->counter);
   cudaFree(h->gws);
   cudaFree(h->ipm_ws);
+  if (h->pstage) cudaFreeHost(h->pstage);
+  for (int i = 0; i < BMPC_PSTAGE; ++i) if (h->pstage_evt[i]) cudaEventDestroy(h->pstage_evt[i]);
   cudaFree(h->stage_in);
   cudaFree(h->stage_out);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -345,6 +355,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
   if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
   BMPC_CK(h, cudaMalloc(&h->ipm_ws, (size_t)h->grid * h->P.ipm_reals * sizeof(real)));
+  BMPC_CK(h, cudaMallocHost(&h->pstage, BMPC_PSTAGE * sizeof(KParams)));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
   BMPC_CK(h, cudaEventCreate(&h->ev1));
   return bmpc_reset(h, nullptr, 0);
@@ -456,10 +467,24 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.ipm = h->ipm_ws;
   BMPC_CK(h, cudaMemsetAsync(h->counter, 0, sizeof(int), s));
   const int grid = (int)(count < h->grid ? count : h->grid);
+  // the parameter block travels through constant memory: one symbol per device, so launches from other streams or handles
+  // are ordered behind the previous solve kernel of this device before the symbol is rewritten
+  ConstSlot& cs = g_const[h->device & 15];
+  if (!cs.done) BMPC_CK(h, cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
+  if (cs.used && cs.stream != s) BMPC_CK(h, cudaStreamWaitEvent(s, cs.done, 0));
+  KParams* stage = h->pstage + (h->pstage_next++ % BMPC_PSTAGE);
+  if (h->pstage_evt[stage - h->pstage]) BMPC_CK(h, cudaEventSynchronize(h->pstage_evt[stage - h->pstage]));
+  else BMPC_CK(h, cudaEventCreateWithFlags(&h->pstage_evt[stage - h->pstage], cudaEventDisableTiming));
+  *stage = P;
+  BMPC_CK(h, cudaMemcpyToSymbolAsync(bmpc_cP, stage, sizeof(KParams), 0, cudaMemcpyHostToDevice, s));
+  BMPC_CK(h, cudaEventRecord(h->pstage_evt[stage - h->pstage], s));
   BMPC_CK(h, cudaEventRecord(h->ev0, s));
   const int rc = BMPC_DISPATCH(h, launch_instance, h, P, grid, s);
   if (rc != BMPC_OK) return rc;
   BMPC_CK(h, cudaEventRecord(h->ev1, s));
+  BMPC_CK(h, cudaEventRecord(cs.done, s));
+  cs.used = true;
+  cs.stream = s;
   h->timed = true;
   h->launches += 1;
   return BMPC_OK;

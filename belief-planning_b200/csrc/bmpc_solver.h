@@ -46,6 +46,8 @@ BMPC_D real row_dual(real sh, real rlo, real rhi, real lam) {
 //   GLOBAL: everything in the per-warp global region (trees too large for shared memory).
 #if defined(__CUDACC__)
 extern __shared__ __align__(16) real bmpc_smem[];
+// parameter block of the solve kernel in flight on this device (written stream-ordered before every launch, bmpc_solve)
+__constant__ KParams bmpc_cP;
 #endif
 
 // NR = soft rows per node: NC collision rows (1 for the branch controllers; robustMPC has one per obstacle node of the
@@ -94,7 +96,14 @@ struct Solver {
   static constexpr int NIP = IP_COR + 4 * NR + 4 * NU;
   BMPC_HD static size_t ipm_reals(int nup) { return (size_t)NIP * nup; }
 
-  const KParams& P;
+#if defined(__CUDA_ARCH__)
+  // device: every phase function reads the parameter block straight from constant memory (LDC with immediate offsets)
+  // instead of through a reference member (a generic load per field in each out-of-line function)
+#define PP bmpc_cP
+#else
+  const KParams& P_host;
+#define PP P_host
+#endif
   real* ws;     // slab base (shared memory is addressed through bmpc_smem on the device so that loads are LDS)
   real* fa;     // factor-field region (SPLIT only)
   real* ip;     // interior-point scratch (global)
@@ -109,13 +118,17 @@ struct Solver {
   real rlin;  // linear cost on every component of the root input: -2 * OldInput . dR  (MPC_branch.py:1099)
   const real* polpar;
 
-  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : P(P_), ws(slab), fa(factor), ip(ipm), lane(lane_), nup(P_.nup) {
+#if defined(__CUDA_ARCH__)
+  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : ws(slab), fa(factor), ip(ipm), lane(lane_), nup(P_.nup) {
+#else
+  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : P_host(P_), ws(slab), fa(factor), ip(ipm), lane(lane_), nup(P_.nup) {
+#endif
     oSt = NFWP * nup;
     oWb = oSt + nup;
-    oEX = oWb + P.nbx;
-    oEXL = oEX + NS * P.nbx;
-    oEXZ = oEXL + NX * P.nbx;
-    oEXX = oEXZ + NX * P.nbx;
+    oEX = oWb + PP.nbx;
+    oEXL = oEX + NS * PP.nbx;
+    oEXZ = oEXL + NX * PP.nbx;
+    oEXX = oEXZ + NX * PP.nbx;
     prob = 0;
     use_codes = false;
     nsolve = 0;
@@ -142,13 +155,13 @@ struct Solver {
   long long t_phase;
   BMPC_D long long prof_begin(int k) {
 #if defined(__CUDA_ARCH__)
-    if (P.cycles_mode == k) return clock64();
+    if (PP.cycles_mode == k) return clock64();
 #endif
     return 0;
   }
   BMPC_D void prof_end(int k, long long t0) {
 #if defined(__CUDA_ARCH__)
-    if (P.cycles_mode == k) t_phase += clock64() - t0;
+    if (PP.cycles_mode == k) t_phase += clock64() - t0;
 #endif
   }
   BMPC_D real& IPF(int field, int kp) { return ip[(size_t)field * nup + kp]; }   // field-major: the lanes of a node-parallel pass read consecutive addresses
@@ -165,11 +178,11 @@ struct Solver {
   BMPC_D static code_t in_bits(int v, int a) { return (code_t)v << (3 * NR + 2 * a); }
   static_assert(3 * NR + 2 * NU <= 62, "active-set code does not fit 64 bits");
 
-  BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(P, b) + t + b; }
+  BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(PP, b) + t + b; }
   BMPC_D void node_of(int k, int& b, int& t) const {
-    if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / P.N; t = (k - 1) % P.N; }
+    if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / PP.N; t = (k - 1) % PP.N; }
   }
-  BMPC_D const real* pol_par(int i) const { return polpar ? polpar + 4 * i : P.pol_par[i]; }
+  BMPC_D const real* pol_par(int i) const { return polpar ? polpar + 4 * i : PP.pol_par[i]; }
 
   // ========================================================================================
   // Tree expansion: obstacle rollouts, branch probabilities/weights, ego linearisation rollouts,
@@ -184,7 +197,7 @@ struct Solver {
       if (j < ncol) {
         real zxy[2] = {F(F_FC + 2 * j, kp), F(F_FC + 2 * j + 1, kp)};
         real h, dhx, dhy;
-        M::collision(P, xbar, zxy, h, dhx, dhy);
+        M::collision(PP, xbar, zxy, h, dhx, dhy);
         const real fx = -dhx, fy = -dhy;
         const real hi0 = h - (dhx * xbar[0] + dhy * xbar[1]);
         F(F_FC + 2 * j, kp) = fx;
@@ -202,37 +215,37 @@ struct Solver {
     for (int j = NC; j < NR; ++j) {
       real v = 0.0;
 #pragma unroll
-      for (int i = 0; i < NXP; ++i) v += P.rf[j - NC][i] * xbar[i];
-      F(F_S + j, kp) = bmpc_clamp(v, P.rlo[j - NC], P.rhi[j - NC]);
+      for (int i = 0; i < NXP; ++i) v += PP.rf[j - NC][i] * xbar[i];
+      F(F_S + j, kp) = bmpc_clamp(v, PP.rlo[j - NC], PP.rhi[j - NC]);
     }
   }
 
   BMPC_D void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn, int ncol = 1) {
     const int kp = kp_of(b, t);
     real lin[M::NLIN], cc[M::NCC];
-    M::linearize(P, xbar, ubar, lin, cc, xn);
+    M::linearize(PP, xbar, ubar, lin, cc, xn);
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
 #pragma unroll
     for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
-    const real* xref = P.xref + (size_t)prob * NXP;
+    const real* xref = PP.xref + (size_t)prob * NXP;
     // linear state cost -2 w (xRef' Q° + xbar' dQ): Q° = Qf on the last node of a leaf branch of BranchMPC (:1095)
-    const real* Ql = (leaf_last && P.ctrl == BMPC_CTRL_BRANCH) ? P.Qf : P.Q;
+    const real* Ql = (leaf_last && PP.ctrl == BMPC_CTRL_BRANCH) ? PP.Qf : PP.Q;
 #pragma unroll
     for (int j = 0; j < NXP; ++j) {
       real a = 0.0, c = 0.0;
 #pragma unroll
       for (int i = 0; i < NXP; ++i) {
         a += xref[i] * Ql[i * NXP + j];
-        c += xbar[i] * P.Q[i * NXP + j];
+        c += xbar[i] * PP.Q[i * NXP + j];
       }
-      F(F_Q + j, kp) = -2.0 * w * (a + P.dq_scale * c);
+      F(F_Q + j, kp) = -2.0 * w * (a + PP.dq_scale * c);
     }
     rows_setup(kp, xbar, ncol);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ubar[a], P.ulo[a], P.uhi[a]);
-    if (P.out.xLin) {
-      real* o = P.out.xLin + ((size_t)prob * P.totalu + (bmpc_ndu(P, b) + t)) * NXP;
+    for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ubar[a], PP.ulo[a], PP.uhi[a]);
+    if (PP.out.xLin) {
+      real* o = PP.out.xLin + ((size_t)prob * PP.totalu + (bmpc_ndu(PP, b) + t)) * NXP;
 #pragma unroll
       for (int i = 0; i < NXP; ++i) o[i] = xbar[i];
     }
@@ -240,19 +253,19 @@ struct Solver {
 
   BMPC_DN void expand_tree() {
     const long long prof_t0 = prof_begin(2);
-    const int started = P.started[prob];
-    const real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
-    int* pbest = P.pbest + (size_t)prob * P.nbranch;
-    const code_t* codes = P.code_cache + (size_t)prob * P.totalu;
-    const real* x0 = P.x0 + (size_t)prob * NXP;
-    const real* z0 = P.z0 + (size_t)prob * NXP;
+    const int started = PP.started[prob];
+    const real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
+    int* pbest = PP.pbest + (size_t)prob * PP.nbranch;
+    const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    const real* x0 = PP.x0 + (size_t)prob * NXP;
+    const real* z0 = PP.z0 + (size_t)prob * NXP;
     if (lane == 0) {
       real ub[NU], xb[NXP], xn[NXP];
 #pragma unroll
       for (int i = 0; i < NXP; ++i) xb[i] = x0[i];
       // root input: previous first input of the most likely child (updatetree :1029-1031); zero on the first solve
       const int best = started ? pbest[0] : 0;
-      const int kbest = bmpc_ndu(P, bmpc_first_child(P, 0, 0) + best);
+      const int kbest = bmpc_ndu(PP, bmpc_first_child(PP, 0, 0) + best);
 #pragma unroll
       for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[kbest * NU + a] : 0.0;
       const int kp = kp_of(0, 0);
@@ -260,8 +273,8 @@ struct Solver {
       F(F_FC, kp) = z0[0];
       F(F_FC + 1, kp) = z0[1];
       Wbp()[0] = 1.0;
-      if (P.out.zPred) {
-        real* o = P.out.zPred + (size_t)prob * P.totalu * NXP;
+      if (PP.out.zPred) {
+        real* o = PP.out.zPred + (size_t)prob * PP.totalu * NXP;
 #pragma unroll
         for (int i = 0; i < NXP; ++i) o[i] = z0[i];
       }
@@ -274,20 +287,20 @@ struct Solver {
       }
     }
     lanes_sync();
-    const int m = P.m;
-    for (int d = 0; d < P.NB; ++d) {
+    const int m = PP.m;
+    for (int d = 0; d < PP.NB; ++d) {
       // (a) obstacle rollouts under each policy + safety value of each (zpred_eval, branch_eval); lanes = (branch, policy)
-      const int cnt = P.pw[d] * m;
+      const int cnt = PP.pw[d] * m;
       for (int idx = lane; idx < cnt; idx += BMPC_LANES) {
-        const int b = P.off[d] + idx / m;
+        const int b = PP.off[d] + idx / m;
         const int i = idx % m;
-        const int c = bmpc_first_child(P, b, d) + i;
+        const int c = bmpc_first_child(PP, b, d) + i;
         real zl[NXP];
-        const int kc = bmpc_ndu(P, c);
+        const int kc = bmpc_ndu(PP, c);
         const int kpc = kp_of(c, 0);
-        real* zout = P.out.zPred ? P.out.zPred + ((size_t)prob * P.totalu + kc) * NXP : nullptr;
-        const real hi = M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), EXLp() + NX * b,
-                                         EXZp() + NX * b, zl, P.N, [&](int t, const real* z) {
+        real* zout = PP.out.zPred ? PP.out.zPred + ((size_t)prob * PP.totalu + kc) * NXP : nullptr;
+        const real hi = M::policy_safety(PP, PP.pol_kind[i], pol_par(i), PP.pol_kind[0], pol_par(0), EXLp() + NX * b,
+                                         EXZp() + NX * b, zl, PP.N, [&](int t, const real* z) {
                                            F(F_FC, kpc + t) = z[0];
                                            F(F_FC + 1, kpc + t) = z[1];
                                            if (zout) {
@@ -302,18 +315,18 @@ struct Solver {
       lanes_sync();
       // (a') probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
-        const int fc = bmpc_first_child(P, b, d);
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+        const int fc = bmpc_first_child(PP, b, d);
         real himax = -1e300;
         for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
         real sum = 0.0;
-        for (int j = 0; j < m; ++j) sum += M::branch_weight(P, EXp()[NS * (fc + j)], himax);
+        for (int j = 0; j < m; ++j) sum += M::branch_weight(PP, EXp()[NS * (fc + j)], himax);
         int best = 0;
         real pb = -1.0;
         for (int j = 0; j < m; ++j) {
-          const real p = M::branch_weight(P, EXp()[NS * (fc + j)], himax) / sum;
+          const real p = M::branch_weight(PP, EXp()[NS * (fc + j)], himax) / sum;
           Wbp()[fc + j] = Wbp()[b] * p;
-          if (P.out.branch_p) P.out.branch_p[((size_t)prob * P.nbranch + b) * m + j] = p;
+          if (PP.out.branch_p) PP.out.branch_p[((size_t)prob * PP.nbranch + b) * m + j] = p;
           if (p > pb) { pb = p; best = j; }
         }
         // pbest[b] (old value) was consumed when b's own trajectory was shifted, one level up (or at the root above)
@@ -322,30 +335,30 @@ struct Solver {
       lanes_sync();
       // (b) ego linearisation trajectory of every child branch: time-shifted previous inputs
       //     (updatetree :1025-1033), nonlinear rollout + per-node linearisation (:1048-1059)
-      for (int c = P.off[d + 1] + lane; c < P.off[d + 2]; c += BMPC_LANES) {
-        const int b = bmpc_parent(P, c, d + 1);
-        const bool leaf = (d + 1 == P.NB);
+      for (int c = PP.off[d + 1] + lane; c < PP.off[d + 2]; c += BMPC_LANES) {
+        const int b = bmpc_parent(PP, c, d + 1);
+        const bool leaf = (d + 1 == PP.NB);
         const real w = Wbp()[c];
-        const int kc = bmpc_ndu(P, c);
+        const int kc = bmpc_ndu(PP, c);
         int klast;
         if (leaf) {
-          klast = kc + P.N - 1;   // repeat the shifted last input (:1033)
+          klast = kc + PP.N - 1;   // repeat the shifted last input (:1033)
         } else {
-          klast = bmpc_ndu(P, bmpc_first_child(P, c, d + 1) + (started ? pbest[c] : 0));
+          klast = bmpc_ndu(PP, bmpc_first_child(PP, c, d + 1) + (started ? pbest[c] : 0));
         }
         real xb[NXP], xn[NXP], ub[NU];
 #pragma unroll
         for (int i = 0; i < NXP; ++i) xb[i] = EXXp()[NX * b + i];
-        for (int t = 0; t < P.N; ++t) {
-          const int ksrc = (t < P.N - 1) ? kc + t + 1 : klast;
+        for (int t = 0; t < PP.N; ++t) {
+          const int ksrc = (t < PP.N - 1) ? kc + t + 1 : klast;
 #pragma unroll
           for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[ksrc * NU + a] : 0.0;
           if (use_codes) stp()[kp_of(c, t)] = codes[ksrc];   // the active set shifts in time like the inputs
-          if (t == P.N - 1) {
+          if (t == PP.N - 1) {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) EXLp()[NX * c + i] = xb[i];
           }
-          node_setup(c, t, xb, ub, w, leaf && t == P.N - 1, xn);
+          node_setup(c, t, xb, ub, w, leaf && t == PP.N - 1, xn);
 #pragma unroll
           for (int i = 0; i < NXP; ++i) xb[i] = xn[i];
         }
@@ -354,15 +367,15 @@ struct Solver {
       }
       lanes_sync();
       // commit the new arg-max children of this level (their old values are no longer needed)
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EXp()[NS * b + 1];
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EXp()[NS * b + 1];
       lanes_sync();
     }
-    if (P.out.branch_w) {
-      for (int b = lane; b < P.nbranch; b += BMPC_LANES) P.out.branch_w[(size_t)prob * P.nbranch + b] = Wbp()[b];
+    if (PP.out.branch_w) {
+      for (int b = lane; b < PP.nbranch; b += BMPC_LANES) PP.out.branch_w[(size_t)prob * PP.nbranch + b] = Wbp()[b];
     }
     rlin = 0.0;
 #pragma unroll
-    for (int a = 0; a < NU; ++a) rlin += -2.0 * P.oldin[(size_t)prob * NU + a] * P.dR[a];
+    for (int a = 0; a < NU; ++a) rlin += -2.0 * PP.oldin[(size_t)prob * NU + a] * PP.dR[a];
     prof_end(2, prof_t0);
   }
 
@@ -375,13 +388,13 @@ struct Solver {
   // ----------------------------------------------------------------------------------------
   BMPC_DN void expand_chain() {
     const long long prof_t0 = prof_begin(2);
-    const int started = P.started[prob];
-    const int Nx = P.totalu, Nu = P.totalu - 1;   // states incl. the terminal one / real inputs
-    const real* uPrev = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
-    const real* xPrev = P.xprev + (size_t)prob * P.pub_totalx * NXP;
-    const code_t* codes = P.code_cache + (size_t)prob * P.totalu;
-    const real* x0 = P.x0 + (size_t)prob * NXP;
-    const real* z0 = P.z0 + (size_t)prob * NXP;
+    const int started = PP.started[prob];
+    const int Nx = PP.totalu, Nu = PP.totalu - 1;   // states incl. the terminal one / real inputs
+    const real* uPrev = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
+    const real* xPrev = PP.xprev + (size_t)prob * PP.pub_totalx * NXP;
+    const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    const real* x0 = PP.x0 + (size_t)prob * NXP;
+    const real* z0 = PP.z0 + (size_t)prob * NXP;
     auto kp_chain = [&](int k) { return k == 0 ? kp_of(0, 0) : kp_of(1, k - 1); };
     // 1. linearisation trajectory, parked in the sweep vectors
     if (!started) {
@@ -397,7 +410,7 @@ struct Solver {
           for (int i = 0; i < NXP; ++i) F(F_XQ + i, kp) = x[i];
 #pragma unroll
           for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = 0.0;
-          M::step(P, x, u, xn);
+          M::step(PP, x, u, xn);
 #pragma unroll
           for (int i = 0; i < NXP; ++i) x[i] = xn[i];
         }
@@ -423,18 +436,18 @@ struct Solver {
       for (int i = 0; i < NXP; ++i) EXZp()[i] = z0[i];
     }
     lanes_sync();
-    const int m = P.zm;
-    for (int d = 0; d < P.zNB; ++d) {
-      const int cnt = P.zpw[d] * m;
+    const int m = PP.zm;
+    for (int d = 0; d < PP.zNB; ++d) {
+      const int cnt = PP.zpw[d] * m;
       for (int idx = lane; idx < cnt; idx += BMPC_LANES) {
-        const int b = P.zoff[d] + idx / m;
+        const int b = PP.zoff[d] + idx / m;
         const int i = idx % m;
-        const int c = P.zoff[d + 1] + (b - P.zoff[d]) * m + i;
-        const int j = c - P.zoff[d + 1];                 // position inside the slot (BFS order)
+        const int c = PP.zoff[d + 1] + (b - PP.zoff[d]) * m + i;
+        const int j = c - PP.zoff[d + 1];                 // position inside the slot (BFS order)
         real zl[NXP];
-        M::policy_safety(P, P.pol_kind[i], pol_par(i), P.pol_kind[0], pol_par(0), x0, EXZp() + NX * b, zl, P.zN,
+        M::policy_safety(PP, PP.pol_kind[i], pol_par(i), PP.pol_kind[0], pol_par(0), x0, EXZp() + NX * b, zl, PP.zN,
                          [&](int t, const real* z) {
-                           const int kp = kp_chain(d * P.zN + t + 1);
+                           const int kp = kp_chain(d * PP.zN + t + 1);
                            F(F_FC + 2 * (j < NC ? j : 0), kp) = z[0];
                            F(F_FC + 2 * (j < NC ? j : 0) + 1, kp) = z[1];
                          });
@@ -444,7 +457,7 @@ struct Solver {
       lanes_sync();
     }
     // 3. per-node data: every node is linearised about its own (x, u) of the shifted trajectory - no rollout dependence
-    const real* xref = P.xref + (size_t)prob * NXP;
+    const real* xref = PP.xref + (size_t)prob * NXP;
     for (int k = lane; k < Nx; k += BMPC_LANES) {
       const int kp = kp_chain(k);
       real xb[NXP], ub[NU], xn[NXP], lin[M::NLIN], cc[M::NCC];
@@ -452,12 +465,12 @@ struct Solver {
       for (int i = 0; i < NXP; ++i) xb[i] = F(F_XQ + i, kp);
 #pragma unroll
       for (int a = 0; a < NU; ++a) ub[a] = F(F_UQ + a, kp);
-      M::linearize(P, xb, ub, lin, cc, xn);
+      M::linearize(PP, xb, ub, lin, cc, xn);
 #pragma unroll
       for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
 #pragma unroll
       for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
-      const real* Ql = (k == Nx - 1) ? P.Qf : P.Q;       // buildCost :1541-1556: q = -2 xRef' blockdiag(Q.., Qf)
+      const real* Ql = (k == Nx - 1) ? PP.Qf : PP.Q;       // buildCost :1541-1556: q = -2 xRef' blockdiag(Q.., Qf)
 #pragma unroll
       for (int jj = 0; jj < NXP; ++jj) {
         real a = 0.0;
@@ -465,11 +478,11 @@ struct Solver {
         for (int i = 0; i < NXP; ++i) a += xref[i] * Ql[i * NXP + jj];
         F(F_Q + jj, kp) = -2.0 * a;
       }
-      const int depth = (k == 0) ? 0 : (k - 1) / P.zN + 1;
-      const int ncol = (k <= P.zN * P.zNB) ? P.zpw[depth] : 0;   // the terminal state has state rows only (:1470-1482)
+      const int depth = (k == 0) ? 0 : (k - 1) / PP.zN + 1;
+      const int ncol = (k <= PP.zN * PP.zNB) ? PP.zpw[depth] : 0;   // the terminal state has state rows only (:1470-1482)
       rows_setup(kp, xb, ncol);
 #pragma unroll
-      for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ub[a], P.ulo[a], P.uhi[a]);
+      for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ub[a], PP.ulo[a], PP.uhi[a]);
     }
     if (lane == 0) {
       Wbp()[0] = 1.0;     // slack weights are not branch-weighted in robustMPC (:1562)
@@ -531,14 +544,14 @@ struct Solver {
   // fixed-input helpers of the polish: value of input a when the active-set code pins it to a bound, else 0
   BMPC_D real pinned_value(code_t code, int a) {
     const int ca = in_of(code, a);
-    return ca == IN_AT_HI ? P.uhi[a] : (ca == IN_AT_LO ? P.ulo[a] : 0.0);
+    return ca == IN_AT_HI ? PP.uhi[a] : (ca == IN_AT_LO ? PP.ulo[a] : 0.0);
   }
   BMPC_D bool pinned(code_t code, int a) { return in_of(code, a) != IN_FREE; }
 
   // Stiff penalty of a guessed-active row in the polish: polish_mult times the row's curvature-matched stiffness
   // (rho/theta = 1/(f' Sigma f)), at least polish_big*w, so that every augmented-Lagrangian step contracts strongly.
   BMPC_D real big_row(int kp, int j, real w) {
-    return fmin(fmax(P.polish_big * w, P.polish_mult * F(F_RHO + j, kp) / P.theta), 1.0e12 * w);
+    return fmin(fmax(PP.polish_big * w, PP.polish_mult * F(F_RHO + j, kp) / PP.theta), 1.0e12 * w);
   }
   // penalties of the node's soft rows and inputs for the requested factorisation
   BMPC_D void penalties(int kp, real w, int mode, real* pr, real* pu) {
@@ -577,7 +590,7 @@ struct Solver {
   // rate = weight of the input-rate pair (previous input, this input), sig = 0 where the reference drops the pair's
   // own-input term (leaf last node, MPC_branch.py:303), root = the root-input quirks apply (:311-312)
   BMPC_D void node_factor(int kp, real w, real* Pn, int mode, real rate, real sig, bool root, bool use_qf = false) {
-    const real* Qs = use_qf ? P.Qf : P.Q;   // robustMPC: the dummy stage carries the terminal cost Qf
+    const real* Qs = use_qf ? PP.Qf : PP.Q;   // robustMPC: the dummy stage carries the terminal cost Qf
     real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -594,7 +607,7 @@ struct Solver {
         real up[NU];
 #pragma unroll
         for (int a = 0; a < NU; ++a) up[a] = pinned_value(pcode, a);
-        M::addBu(P, lin, up, C);
+        M::addBu(PP, lin, up, C);
       }
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
@@ -606,14 +619,14 @@ struct Solver {
     }
     real T[NX * NX];  // P+ A  (row i = A' applied to row i of P+)
 #pragma unroll
-    for (int i = 0; i < NX; ++i) M::mulAT(P, lin, Pn + i * NX, T + i * NX);
+    for (int i = 0; i < NX; ++i) M::mulAT(PP, lin, Pn + i * NX, T + i * NX);
     real G[NU * NX];  // B' P+ A
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
       real col[NX], g2[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) col[i] = T[i * NX + j];
-      M::mulBT(P, lin, col, g2);
+      M::mulBT(PP, lin, col, g2);
 #pragma unroll
       for (int a = 0; a < NU; ++a) G[a * NX + j] = g2[a];
     }
@@ -621,30 +634,30 @@ struct Solver {
     {
       real PB[NX * NU];  // P+ B (row i = B' applied to row i of P+)
 #pragma unroll
-      for (int i = 0; i < NX; ++i) M::mulBT(P, lin, Pn + i * NX, PB + i * NU);
+      for (int i = 0; i < NX; ++i) M::mulBT(PP, lin, Pn + i * NX, PB + i * NU);
 #pragma unroll
       for (int b2 = 0; b2 < NU; ++b2) {
         real col[NX], g2[NU];
 #pragma unroll
         for (int i = 0; i < NX; ++i) col[i] = PB[i * NU + b2];
-        M::mulBT(P, lin, col, g2);
+        M::mulBT(PP, lin, col, g2);
 #pragma unroll
-        for (int a = 0; a < NU; ++a) S[a * NU + b2] = g2[a] + w * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
+        for (int a = 0; a < NU; ++a) S[a * NU + b2] = g2[a] + w * (PP.R[a * NU + b2] + PP.R[b2 * NU + a]);
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) S[a * NU + a] += pu[a];
       if (RATE) {
 #pragma unroll
-        for (int a = 0; a < NU; ++a) S[a * NU + a] += 2.0 * rate * sig * P.dR[a];
+        for (int a = 0; a < NU; ++a) S[a * NU + a] += 2.0 * rate * sig * PP.dR[a];
         if (root) {
           // Hu[0:d,0:d] += dR broadcasts the vector over the rows (:312); OSQP keeps the upper triangle
 #pragma unroll
           for (int a = 0; a < NU; ++a)
 #pragma unroll
-            for (int b2 = 0; b2 < NU; ++b2) S[a * NU + b2] += 2.0 * P.dR[a > b2 ? a : b2];
+            for (int b2 = 0; b2 < NU; ++b2) S[a * NU + b2] += 2.0 * PP.dR[a > b2 ? a : b2];
         }
 #pragma unroll
-        for (int a = 0; a < NU; ++a) G[a * NX + NXP + a] += -2.0 * rate * P.dR[a];   // cross term previous input x input
+        for (int a = 0; a < NU; ++a) G[a * NX + NXP + a] += -2.0 * rate * PP.dR[a];   // cross term previous input x input
       }
     }
     real Si[NU * NU];
@@ -685,18 +698,18 @@ struct Solver {
       }
     // P = Q~ + A' T - G' K
     real Pnew[NX * NX];
-    const real qs = w * (1.0 + P.dq_scale);
+    const real qs = w * (1.0 + PP.dq_scale);
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
       real col[NX], o[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) col[i] = T[i * NX + j];
-      M::mulAT(P, lin, col, o);
+      M::mulAT(PP, lin, col, o);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         real v = o[i];
         if (i < NXP && j < NXP) v += qs * (Qs[i * NXP + j] + Qs[j * NXP + i]);
-        if (RATE && i == j && i >= NXP) v += 2.0 * rate * P.dR[i - NXP];
+        if (RATE && i == j && i >= NXP) v += 2.0 * rate * PP.dR[i - NXP];
 #pragma unroll
         for (int a = 0; a < NU; ++a) v -= G[a * NX + i] * K[a * NX + j];
         Pnew[i * NX + j] = v;
@@ -717,7 +730,7 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * P.rf[j - NC][i] * P.rf[j - NC][i2];
+          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * PP.rf[j - NC][i] * PP.rf[j - NC][i2];
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i)
@@ -726,9 +739,9 @@ struct Solver {
   }
 
   BMPC_D void sum_children(int b, int d, real* Pn) {
-    const int fc = bmpc_first_child(P, b, d);
+    const int fc = bmpc_first_child(PP, b, d);
     unpack_sym(EXp() + NS * fc, Pn);
-    for (int c = 1; c < P.m; ++c) {
+    for (int c = 1; c < PP.m; ++c) {
       real Pc[NX * NX];
       unpack_sym(EXp() + NS * (fc + c), Pc);
 #pragma unroll
@@ -741,26 +754,26 @@ struct Solver {
   BMPC_DN void factorize(int mode) {
     const long long prof_t0 = prof_begin(4);
 #pragma unroll 1
-    for (int d = P.NB; d >= 0; --d) {
-      const int nt = (d == 0) ? 1 : P.N;
+    for (int d = PP.NB; d >= 0; --d) {
+      const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
         const real w = Wbp()[b];
         real Pn[NX * NX];
-        if (d == P.NB) {
+        if (d == PP.NB) {
           // terminal node: x' (w Qf) x in the reference's H, doubled by H <- 2H (:1094, :1112)
 #pragma unroll
           for (int i = 0; i < NX; ++i)
 #pragma unroll
             for (int j = 0; j < NX; ++j)
-              Pn[i * NX + j] = (i < NXP && j < NXP && P.ctrl != BMPC_CTRL_ROBUST) ? w * (P.Qf[i * NXP + j] + P.Qf[j * NXP + i]) : 0.0;
+              Pn[i * NX + j] = (i < NXP && j < NXP && PP.ctrl != BMPC_CTRL_ROBUST) ? w * (PP.Qf[i * NXP + j] + PP.Qf[j * NXP + i]) : 0.0;
         } else {
           sum_children(b, d, Pn);
         }
 #pragma unroll 1
         for (int t = nt - 1; t >= 0; --t)
-          node_factor(kp_of(b, t), w, Pn, mode, (d == 0) ? 0.0 : w, (d == P.NB && t == nt - 1) ? 0.0 : 1.0, d == 0,
-                      P.ctrl == BMPC_CTRL_ROBUST && d == P.NB && t == nt - 1);
+          node_factor(kp_of(b, t), w, Pn, mode, (d == 0) ? 0.0 : w, (d == PP.NB && t == nt - 1) ? 0.0 : 1.0, d == 0,
+                      PP.ctrl == BMPC_CTRL_ROBUST && d == PP.NB && t == nt - 1);
         pack_sym(Pn, EXp() + NS * b);
       }
       lanes_sync();
@@ -797,7 +810,7 @@ struct Solver {
       for (int j = 0; j < NC; ++j) {
         const real fx = F(F_FC + 2 * j, kp), fy = F(F_FC + 2 * j + 1, kp);
         const real q0 = fx * fx * Sg[0] + 2.0 * fx * fy * Sg[1] + fy * fy * Sg[NX + 1];
-        const real r0 = (q0 > 1e-12) ? fmin(P.theta / q0, rho_max) : 0.0;
+        const real r0 = (q0 > 1e-12) ? fmin(PP.theta / q0, rho_max) : 0.0;
         F(F_RHO + j, kp) = r0;
         F(F_S + j, kp) *= r0;
       }
@@ -807,8 +820,8 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NXP; ++i2) q += P.rf[j - NC][i] * P.rf[j - NC][i2] * Sg[i * NX + i2];
-        const real rj = (q > 1e-12) ? fmin(P.theta / q, rho_max) : 0.0;
+          for (int i2 = 0; i2 < NXP; ++i2) q += PP.rf[j - NC][i] * PP.rf[j - NC][i2] * Sg[i * NX + i2];
+        const real rj = (q > 1e-12) ? fmin(PP.theta / q, rho_max) : 0.0;
         F(F_RHO + j, kp) = rj;
         F(F_S + j, kp) *= rj;
       }
@@ -821,9 +834,9 @@ struct Solver {
         real ks = 0.0;
 #pragma unroll
         for (int i2 = 0; i2 < NX; ++i2) ks += K[a * NX + i2] * Sg[i2 * NX + i];
-        var += P.rho_u_feedback * ks * K[a * NX + i];
+        var += PP.rho_u_feedback * ks * K[a * NX + i];
       }
-      const real ra = fmin(P.theta_u / var, rho_max);
+      const real ra = fmin(PP.theta_u / var, rho_max);
       F(F_RHO + NR + a, kp) = ra;
       F(F_SU + a, kp) *= ra;
     }
@@ -839,11 +852,11 @@ struct Solver {
         for (int j = 0; j < NX; ++j) v += K[a * NX + j] * Sg[i * NX + j];
         kv[a] = -v;
       }
-      M::mulA(P, lin, Sg + i * NX, T + i * NX);
-      M::addBu(P, lin, kv, T + i * NX);
+      M::mulA(PP, lin, Sg + i * NX, T + i * NX);
+      M::addBu(PP, lin, kv, T + i * NX);
     }
     real Bd[NX * NU];
-    M::denseB(P, lin, Bd);
+    M::denseB(PP, lin, Bd);
     real Sn[NX * NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
@@ -857,8 +870,8 @@ struct Solver {
         for (int i = 0; i < NX; ++i) v += K[a * NX + i] * col[i];
         kv[a] = -v;
       }
-      M::mulA(P, lin, col, o);
-      M::addBu(P, lin, kv, o);
+      M::mulA(PP, lin, col, o);
+      M::addBu(PP, lin, kv, o);
 #pragma unroll
       for (int i = 0; i < NX; ++i) Sn[i * NX + j] = o[i];
     }
@@ -882,16 +895,16 @@ struct Solver {
   BMPC_DN void choose_rho() {
     const long long prof_t0 = prof_begin(3);
 #pragma unroll 1
-    for (int d = 0; d <= P.NB; ++d) {
-      const int nt = (d == 0) ? 1 : P.N;
+    for (int d = 0; d <= PP.NB; ++d) {
+      const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
         real Sg[NX * NX];
         if (d == 0) {
 #pragma unroll
           for (int i = 0; i < NX * NX; ++i) Sg[i] = 0.0;
         } else {
-          unpack_sym(EXp() + NS * bmpc_parent(P, b, d), Sg);
+          unpack_sym(EXp() + NS * bmpc_parent(PP, b, d), Sg);
         }
         const real w = Wbp()[b];
 #pragma unroll 1
@@ -912,7 +925,7 @@ struct Solver {
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
 #pragma unroll
     for (int i = 0; i < NX; ++i) g[i] = pn[i] + F(F_H0 + i, kp);
-    M::mulBT(P, lin, g, r);
+    M::mulBT(PP, lin, g, r);
 #pragma unroll
     for (int a = 0; a < NU; ++a) r[a] += F(F_UQ + a, kp);
     {
@@ -931,7 +944,7 @@ struct Solver {
 #pragma unroll
     for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = kff[a];
     real p[NX];
-    M::mulAT(P, lin, g, p);
+    M::mulAT(PP, lin, g, p);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       real v = p[i] + F(F_XQ + i, kp);
@@ -944,31 +957,31 @@ struct Solver {
   BMPC_DN void backward() {
     const long long prof_t0 = prof_begin(5);
 #pragma unroll 1
-    for (int d = P.NB; d >= 0; --d) {
-      const int nt = (d == 0) ? 1 : P.N;
+    for (int d = PP.NB; d >= 0; --d) {
+      const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
         real pn[NX];
-        if (d == P.NB) {
+        if (d == PP.NB) {
 #pragma unroll
           for (int i = 0; i < NX; ++i) pn[i] = 0.0;   // BranchMPC terminal node: no linear term (MPC_branch.py:1094)
-          if (P.ctrl == BMPC_CTRL_PROX) {
+          if (PP.ctrl == BMPC_CTRL_PROX) {
             // BranchMPCProx: -2 w xRef' Qf (:308)
-            const real* xref = P.xref + (size_t)prob * NXP;
+            const real* xref = PP.xref + (size_t)prob * NXP;
             const real w = Wbp()[b];
 #pragma unroll
             for (int j = 0; j < NXP; ++j) {
               real a = 0.0;
 #pragma unroll
-              for (int i = 0; i < NXP; ++i) a += xref[i] * P.Qf[i * NXP + j];
+              for (int i = 0; i < NXP; ++i) a += xref[i] * PP.Qf[i * NXP + j];
               pn[j] = -2.0 * w * a;
             }
           }
         } else {
-          const int fc = bmpc_first_child(P, b, d);
+          const int fc = bmpc_first_child(PP, b, d);
 #pragma unroll
           for (int i = 0; i < NX; ++i) pn[i] = EXp()[NS * fc + i];
-          for (int c = 1; c < P.m; ++c)
+          for (int c = 1; c < PP.m; ++c)
 #pragma unroll
             for (int i = 0; i < NX; ++i) pn[i] += EXp()[NS * (fc + c) + i];
         }
@@ -999,8 +1012,8 @@ struct Solver {
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = x[i];
-    M::mulA(P, lin, x, xn);
-    M::addBu(P, lin, u, xn);
+    M::mulA(PP, lin, x, xn);
+    M::addBu(PP, lin, u, xn);
     M::addC(cc, xn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -1010,16 +1023,16 @@ struct Solver {
     const long long prof_t0 = prof_begin(5);
     ++nsolve;
 #pragma unroll 1
-    for (int d = 0; d <= P.NB; ++d) {
-      const int nt = (d == 0) ? 1 : P.N;
+    for (int d = 0; d <= PP.NB; ++d) {
+      const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
         if (d == 0) {
 #pragma unroll
-          for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
+          for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? PP.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
         } else {
-          const int pa = bmpc_parent(P, b, d);
+          const int pa = bmpc_parent(PP, b, d);
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
         }
@@ -1042,11 +1055,11 @@ struct Solver {
     if (j < NC) return F(F_FC + 2 * j, kp) * x[0] + F(F_FC + 2 * j + 1, kp) * x[1];
     real v = 0.0;
 #pragma unroll
-    for (int i = 0; i < NXP; ++i) v += P.rf[j - NC][i] * x[i];
+    for (int i = 0; i < NXP; ++i) v += PP.rf[j - NC][i] * x[i];
     return v;
   }
   BMPC_D void row_bounds(int kp, int j, real& lo, real& hi) {
-    if (j < NC) { lo = BMPC_NOLO; hi = F(F_HC + j, kp); } else { lo = P.rlo[j - NC]; hi = P.rhi[j - NC]; }
+    if (j < NC) { lo = BMPC_NOLO; hi = F(F_HC + j, kp); } else { lo = PP.rlo[j - NC]; hi = PP.rhi[j - NC]; }
   }
   BMPC_D void add_row_grad(int kp, int j, real gcoef, real* qx) {
     if (j < NC) {
@@ -1054,7 +1067,7 @@ struct Solver {
       qx[1] += F(F_FC + 2 * j + 1, kp) * gcoef;
     } else {
 #pragma unroll
-      for (int i = 0; i < NXP; ++i) qx[i] += P.rf[j - NC][i] * gcoef;
+      for (int i = 0; i < NXP; ++i) qx[i] += PP.rf[j - NC][i] * gcoef;
     }
   }
 
@@ -1068,12 +1081,12 @@ struct Solver {
     real res = 0.0;
     if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; set_changes = 0; }
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
-      const real lam = P.lam_lin * w;
+      const real lam = PP.lam_lin * w;
       code_t ncode = 0;   // CHECK: the active set the ADMM state currently implies (compared with the previous check)
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
@@ -1092,7 +1105,7 @@ struct Solver {
           if (UPDATE) {
             const real rfx = rho * row_value(kp, j, x);
             const real rv = sh - y;
-            const real shn = P.alpha * rfx + (1.0 - P.alpha) * rv + y;
+            const real shn = PP.alpha * rfx + (1.0 - PP.alpha) * rv + y;
             const real yn = row_dual(shn, rlo, rhi, lam);
             if (CHECK) {
               const real rvn = shn - yn;
@@ -1115,16 +1128,16 @@ struct Solver {
       for (int a = 0; a < NU; ++a) {
         const real rho = F(F_RHO + NR + a, kp);
         real sh = F(F_SU + a, kp);
-        real rv = bmpc_clamp(sh, rho * P.ulo[a], rho * P.uhi[a]);
+        real rv = bmpc_clamp(sh, rho * PP.ulo[a], rho * PP.uhi[a]);
         if (UPDATE) {
           const real ru = rho * u[a];
-          const real shn = P.alpha * ru + (1.0 - P.alpha) * rv + (sh - rv);
-          const real rvn = bmpc_clamp(shn, rho * P.ulo[a], rho * P.uhi[a]);
+          const real shn = PP.alpha * ru + (1.0 - PP.alpha) * rv + (sh - rv);
+          const real rvn = bmpc_clamp(shn, rho * PP.ulo[a], rho * PP.uhi[a]);
           if (CHECK) {
             res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
             gap_u = fmax(gap_u, fabs(ru - rvn) / rho);
             stp_u = fmax(stp_u, fabs(rvn - rv) / rho);
-            ncode |= in_bits((shn > rho * P.uhi[a]) ? IN_AT_HI : (shn < rho * P.ulo[a]) ? IN_AT_LO : IN_FREE, a);
+            ncode |= in_bits((shn > rho * PP.uhi[a]) ? IN_AT_HI : (shn < rho * PP.ulo[a]) ? IN_AT_LO : IN_FREE, a);
             if (fabs(ru - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [in] k %d a %d rho %.3e prim %.3e dual %.3e u %.4f w %.3e\n", k, a, rho, fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w), u[a], w);
           }
           F(F_SU + a, kp) = shn;
@@ -1154,9 +1167,9 @@ struct Solver {
   // values of the previous step (refreshed every P.rho_refresh solves) and skip the free factorisation + covariance sweep.
   BMPC_DN void store_rho() {
     const long long prof_t0 = prof_begin(3);
-    real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
+    real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1168,9 +1181,9 @@ struct Solver {
   }
   BMPC_DN void load_rho() {
     const long long prof_t0 = prof_begin(3);
-    const real* cache = P.rho_cache + (size_t)prob * P.totalu * (NR + NU);
+    const real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1195,7 +1208,7 @@ struct Solver {
   BMPC_DN void guess_from_codes() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1221,9 +1234,9 @@ struct Solver {
   }
   BMPC_DN void store_codes() {
     const long long prof_t0 = prof_begin(9);
-    code_t* codes = P.code_cache + (size_t)prob * P.totalu;
+    code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       codes[k] = stp()[kp_of(b, t)];
@@ -1245,11 +1258,11 @@ struct Solver {
     BMPC_TRACE("    rebalance: rows gap %.2e step %.2e -> x%.2f   inputs gap %.2e step %.2e -> x%.2f\n", gr, sr, fr, gu, su, fu);
     if (fr == 1.0 && fu == 1.0) return false;
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real lam = P.lam_lin * Wbp()[b];
+      const real lam = PP.lam_lin * Wbp()[b];
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const real rho = F(F_RHO + j, kp);
@@ -1267,7 +1280,7 @@ struct Solver {
         for (int a = 0; a < NU; ++a) {
           const real rho = F(F_RHO + NR + a, kp);
           const real sh = F(F_SU + a, kp);
-          const real rv = bmpc_clamp(sh, rho * P.ulo[a], rho * P.uhi[a]);
+          const real rv = bmpc_clamp(sh, rho * PP.ulo[a], rho * PP.uhi[a]);
           F(F_SU + a, kp) = fu * rv + (sh - rv);
           F(F_RHO + NR + a, kp) = fu * rho;
         }
@@ -1284,11 +1297,11 @@ struct Solver {
   BMPC_DN void polish_guess() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real lam = P.lam_lin * Wbp()[b];
+      const real lam = PP.lam_lin * Wbp()[b];
       code_t code = 0;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
@@ -1315,8 +1328,8 @@ struct Solver {
         const real sh = F(F_SU + a, kp);
         int ca = IN_FREE;
         real y = 0.0;
-        if (sh > rho * P.uhi[a]) { ca = IN_AT_HI; y = sh - rho * P.uhi[a]; }
-        else if (sh < rho * P.ulo[a]) { ca = IN_AT_LO; y = sh - rho * P.ulo[a]; }
+        if (sh > rho * PP.uhi[a]) { ca = IN_AT_HI; y = sh - rho * PP.uhi[a]; }
+        else if (sh < rho * PP.ulo[a]) { ca = IN_AT_LO; y = sh - rho * PP.ulo[a]; }
         code |= in_bits(ca, a);
         F(F_Y + NR + a, kp) = y;
       }
@@ -1329,12 +1342,12 @@ struct Solver {
   BMPC_DN void polish_assemble() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
-      const real lam = P.lam_lin * w;
+      const real lam = PP.lam_lin * w;
       const code_t code = stp()[kp];
       real qx[NX], qu[NU];
 #pragma unroll
@@ -1356,18 +1369,18 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) { up[a] = pinned_value(code, a); qu[a] = (k == 0) ? rlin : 0.0; }
       const real rate = (k == 0) ? 0.0 : w;
-      const real sig = (b >= P.off[P.NB] && t == P.N - 1) ? 0.0 : 1.0;
+      const real sig = (b >= PP.off[PP.NB] && t == PP.N - 1) ? 0.0 : 1.0;
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
 #pragma unroll
         for (int b2 = 0; b2 < NU; ++b2) {
-          real r2 = w * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
-          if (RATE && k == 0) r2 += 2.0 * P.dR[a > b2 ? a : b2];
+          real r2 = w * (PP.R[a * NU + b2] + PP.R[b2 * NU + a]);
+          if (RATE && k == 0) r2 += 2.0 * PP.dR[a > b2 ? a : b2];
           qu[a] += r2 * up[b2];
         }
         if (RATE) {
-          qu[a] += 2.0 * rate * sig * P.dR[a] * up[a];
-          qx[NXP + (RATE ? a : 0)] += -2.0 * rate * P.dR[a] * up[a];
+          qu[a] += 2.0 * rate * sig * PP.dR[a] * up[a];
+          qx[NXP + (RATE ? a : 0)] += -2.0 * rate * PP.dR[a] * up[a];
         }
       }
 #pragma unroll
@@ -1384,7 +1397,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(6);
     real res = 0.0;
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1400,7 +1413,7 @@ struct Solver {
           real lo, hi;
           row_bounds(kp, j, lo, hi);
           const real r = row_value(kp, j, x) - (cj == ROW_UP_KINK ? hi : lo);
-          if (fabs(r) > 1e-6) BMPC_TRACE("      k %d row %d code %d r %.2e y %.3e lam %.3e big %.2e f=(%.3f,%.3f)\n", k, j, cj, r, F(F_Y + j, kp), P.lam_lin * w, big_row(kp, j, w), F(F_FC, kp), F(F_FC + 1, kp));
+          if (fabs(r) > 1e-6) BMPC_TRACE("      k %d row %d code %d r %.2e y %.3e lam %.3e big %.2e f=(%.3f,%.3f)\n", k, j, cj, r, F(F_Y + j, kp), PP.lam_lin * w, big_row(kp, j, w), F(F_FC, kp), F(F_FC + 1, kp));
           const real yn = F(F_Y + j, kp) + big_row(kp, j, w) * r;
           F(F_Y + j, kp) = yn;
           res = fmax(res, fabs(r));
@@ -1415,7 +1428,7 @@ struct Solver {
   BMPC_DN void polish_inject() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1441,33 +1454,33 @@ struct Solver {
     for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
     const code_t code = stp()[kp];
     const real rate = (k == 0) ? 0.0 : w;
-    const real sig = (b >= P.off[P.NB] && t == P.N - 1) ? 0.0 : 1.0;
-    M::mulBT(P, lin, lam, gu);
+    const real sig = (b >= PP.off[PP.NB] && t == PP.N - 1) ? 0.0 : 1.0;
+    M::mulBT(PP, lin, lam, gu);
     real viol = 0.0;
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
       real g = gu[a] + ((k == 0) ? rlin : 0.0);
 #pragma unroll
       for (int b2 = 0; b2 < NU; ++b2) {
-        real r2 = w * (P.R[a * NU + b2] + P.R[b2 * NU + a]);
-        if (RATE && k == 0) r2 += 2.0 * P.dR[a > b2 ? a : b2];
+        real r2 = w * (PP.R[a * NU + b2] + PP.R[b2 * NU + a]);
+        if (RATE && k == 0) r2 += 2.0 * PP.dR[a > b2 ? a : b2];
         g += r2 * u[b2];
       }
-      if (RATE) g += 2.0 * rate * P.dR[a] * (sig * u[a] - x[NXP + (RATE ? a : 0)]);
+      if (RATE) g += 2.0 * rate * PP.dR[a] * (sig * u[a] - x[NXP + (RATE ? a : 0)]);
       if (pinned(code, a)) F(F_Y + NR + a, kp) = -g;
       else viol = fmax(viol, fabs(g));
     }
-    const real qs = w * (1.0 + P.dq_scale);
-    const real lamw = P.lam_lin * w;
+    const real qs = w * (1.0 + PP.dq_scale);
+    const real lamw = PP.lam_lin * w;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       real v = 0.0;
       if (i < NXP) {
         v = F(F_Q + (i < NXP ? i : 0), kp);
 #pragma unroll
-        for (int j = 0; j < NXP; ++j) v += qs * (P.Q[(i < NXP ? i : 0) * NXP + j] + P.Q[j * NXP + (i < NXP ? i : 0)]) * x[j];
+        for (int j = 0; j < NXP; ++j) v += qs * (PP.Q[(i < NXP ? i : 0) * NXP + j] + PP.Q[j * NXP + (i < NXP ? i : 0)]) * x[j];
       } else if (RATE) {
-        v = 2.0 * rate * P.dR[i - NXP] * (x[i] - u[i - NXP]);
+        v = 2.0 * rate * PP.dR[i - NXP] * (x[i] - u[i - NXP]);
       }
       st_x[i] = v;
     }
@@ -1481,7 +1494,7 @@ struct Solver {
       if (g != 0.0) add_row_grad(kp, j, g, st_x);
     }
     real al[NX];
-    M::mulAT(P, lin, lam, al);
+    M::mulAT(PP, lin, lam, al);
 #pragma unroll
     for (int i = 0; i < NX; ++i) lam[i] = st_x[i] + al[i];
     return viol;
@@ -1491,39 +1504,39 @@ struct Solver {
     const long long prof_t0 = prof_begin(7);
     real viol = 0.0;
 #pragma unroll 1
-    for (int d = P.NB; d >= 0; --d) {
-      const int nt = (d == 0) ? 1 : P.N;
+    for (int d = PP.NB; d >= 0; --d) {
+      const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
         const real w = Wbp()[b];
         real lam[NX];
-        if (d == P.NB) {
+        if (d == PP.NB) {
           // terminal costate: 2 w Qf x_T (BranchMPCProx: - 2 w Qf' xRef as well; robustMPC: none, its terminal cost sits on
           // the chain's last stage); x_T was left in EXX by forward()
           const real* xT = EXXp() + NX * b;
-          const real* xref = P.xref + (size_t)prob * NXP;
+          const real* xref = PP.xref + (size_t)prob * NXP;
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
             real v = 0.0;
-            if (i < NXP && P.ctrl != BMPC_CTRL_ROBUST) {
+            if (i < NXP && PP.ctrl != BMPC_CTRL_ROBUST) {
 #pragma unroll
               for (int j = 0; j < NXP; ++j) {
-                v += w * (P.Qf[(i < NXP ? i : 0) * NXP + j] + P.Qf[j * NXP + (i < NXP ? i : 0)]) * xT[j];
-                if (P.ctrl == BMPC_CTRL_PROX) v -= 2.0 * w * P.Qf[j * NXP + (i < NXP ? i : 0)] * xref[j];
+                v += w * (PP.Qf[(i < NXP ? i : 0) * NXP + j] + PP.Qf[j * NXP + (i < NXP ? i : 0)]) * xT[j];
+                if (PP.ctrl == BMPC_CTRL_PROX) v -= 2.0 * w * PP.Qf[j * NXP + (i < NXP ? i : 0)] * xref[j];
               }
             }
             lam[i] = v;
           }
         } else {
-          const int fc = bmpc_first_child(P, b, d);
+          const int fc = bmpc_first_child(PP, b, d);
 #pragma unroll
           for (int i = 0; i < NX; ++i) lam[i] = EXp()[NS * fc + i];
-          for (int c = 1; c < P.m; ++c)
+          for (int c = 1; c < PP.m; ++c)
 #pragma unroll
             for (int i = 0; i < NX; ++i) lam[i] += EXp()[NS * (fc + c) + i];
         }
         const int kp0 = kp_of(b, 0);
-        const int k0 = bmpc_ndu(P, b);
+        const int k0 = bmpc_ndu(PP, b);
 #pragma unroll 1
         for (int t = nt - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(k0 + t, b, t, kp0 + t, w, lam));
 #pragma unroll
@@ -1545,12 +1558,12 @@ struct Solver {
     real smax = 0.0;
     const real tol = 1e-7;
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
-      const real lam = P.lam_lin * w;
+      const real lam = PP.lam_lin * w;
       const real ytol = 1e-9 * lam;
       const code_t code = stp()[kp];
       code_t ncode = 0;
@@ -1567,7 +1580,7 @@ struct Solver {
           row_bounds(kp, j, lo, hi);
           const real fx = row_value(kp, j, x);
           const real y = F(F_Y + j, kp);
-          const real stiff = F(F_RHO + j, kp) / P.theta;
+          const real stiff = F(F_RHO + j, kp) / PP.theta;
           if (restricted) {
             if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) {
               const real m2 = 2.0 * big_row(kp, j, w) * fabs(fx - (cj == ROW_UP_KINK ? hi : lo));
@@ -1610,11 +1623,11 @@ struct Solver {
         const real u = F(F_UQ + a, kp);
         const real y = F(F_Y + NR + a, kp);
         const real utol = 1e-9 * w;
-        const real stiff = F(F_RHO + NR + a, kp) / P.theta_u;
+        const real stiff = F(F_RHO + NR + a, kp) / PP.theta_u;
         if (restricted) {
         } else if (ca == IN_FREE) {
-          if (u > P.uhi[a] + tol) { na = IN_AT_HI; score = stiff * (u - P.uhi[a]); }
-          else if (u < P.ulo[a] - tol) { na = IN_AT_LO; score = stiff * (P.ulo[a] - u); }
+          if (u > PP.uhi[a] + tol) { na = IN_AT_HI; score = stiff * (u - PP.uhi[a]); }
+          else if (u < PP.ulo[a] - tol) { na = IN_AT_LO; score = stiff * (PP.ulo[a] - u); }
         } else if (ca == IN_AT_HI) {
           if (y < -utol) { na = IN_FREE; score = -y; }
         } else {
@@ -1647,10 +1660,10 @@ struct Solver {
   // point) show up as multipliers running past their bounds and are revised without waiting for convergence.
   BMPC_DN bool polish(int& nfact, bool allow_careful, bool from_admm_state) {
     if (from_admm_state) polish_guess();
-    const int base_passes = from_admm_state ? P.polish_passes : P.warm_passes;
+    const int base_passes = from_admm_state ? PP.polish_passes : PP.warm_passes;
     int prev_changes = 1 << 30;
     bool careful = false;
-    const int max_passes = base_passes + P.polish_careful;
+    const int max_passes = base_passes + PP.polish_careful;
     for (int pass = 0; pass < max_passes; ++pass) {
       if (!careful && pass >= base_passes) return false;
       factorize(FACT_POLISH);
@@ -1658,7 +1671,7 @@ struct Solver {
       real res = 1.0, prev = 1e300;
       bool stalled = false;
       int al = 0;
-      for (; al < P.polish_al_iters; ++al) {
+      for (; al < PP.polish_al_iters; ++al) {
         polish_assemble();
         backward();
         polish_inject();
@@ -1691,7 +1704,7 @@ struct Solver {
       if (settled && !careful) {
         // the all-at-once primal-dual iteration is not contracting: fall back to one change per pass
         if (changes > prev_changes) {
-          if (!allow_careful || P.polish_careful <= 0) return false;
+          if (!allow_careful || PP.polish_careful <= 0) return false;
           careful = true;
         }
         prev_changes = changes;
@@ -1776,11 +1789,11 @@ struct Solver {
     const bool assemble = (phase == IPM_PRED_ASM || phase == IPM_CORR_ASM);
     const bool first = (phase == IPM_PRED_ASM && !(alpha > 0.0));
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real lam = P.lam_lin * Wbp()[b];
+      const real lam = PP.lam_lin * Wbp()[b];
       real x[NX], u[NU], xp[NX], up[NU], qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
@@ -1823,9 +1836,9 @@ struct Solver {
       for (int a = 0; a < NU; ++a) {
         real gs = 0.0, ks = 0.0, dummy = 0.0;
         const real dt = (phase == IPM_PRED_ASM) ? 0.0 : up[a] - u[a];
-        ipm_side(phase, false, 1.0, P.uhi[a] - u[a], dt, 0.0, dummy, IPF(IP_IN + 2 * a, kp), IPF(IP_COR + 4 * NR + 4 * a, kp),
+        ipm_side(phase, false, 1.0, PP.uhi[a] - u[a], dt, 0.0, dummy, IPF(IP_IN + 2 * a, kp), IPF(IP_COR + 4 * NR + 4 * a, kp),
                  IPF(IP_COR + 4 * NR + 4 * a + 1, kp), sigmu, alpha, gs, ks);
-        ipm_side(phase, false, -1.0, u[a] - P.ulo[a], dt, 0.0, dummy, IPF(IP_IN + 2 * a + 1, kp),
+        ipm_side(phase, false, -1.0, u[a] - PP.ulo[a], dt, 0.0, dummy, IPF(IP_IN + 2 * a + 1, kp),
                  IPF(IP_COR + 4 * NR + 4 * a + 2, kp), IPF(IP_COR + 4 * NR + 4 * a + 3, kp), sigmu, alpha, gs, ks);
         if (assemble) {
           IPF(IP_KAP + NR + a, kp) = ks;
@@ -1847,12 +1860,12 @@ struct Solver {
   BMPC_DN int ipm_init() {
     int pairs = 0;
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
       const real w = Wbp()[b];
-      const real lam = P.lam_lin * w;
+      const real lam = PP.lam_lin * w;
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
@@ -1869,18 +1882,18 @@ struct Solver {
           pairs += 2;
           if (lo > 0.5 * BMPC_NOLO) pairs += 2;
         }
-        IPF(IP_RS + 4 * j, kp) = fmax(tv - hi, 0.0) + P.ipm_s0;
+        IPF(IP_RS + 4 * j, kp) = fmax(tv - hi, 0.0) + PP.ipm_s0;
         IPF(IP_RS + 4 * j + 1, kp) = 0.5 * lam;
-        IPF(IP_RS + 4 * j + 2, kp) = fmax(lo - tv, 0.0) + P.ipm_s0;
+        IPF(IP_RS + 4 * j + 2, kp) = fmax(lo - tv, 0.0) + PP.ipm_s0;
         IPF(IP_RS + 4 * j + 3, kp) = 0.5 * lam;
       }
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        const real range = P.uhi[a] - P.ulo[a];
-        const real uc = bmpc_clamp(F(F_UQ + a, kp), P.ulo[a] + 0.1 * range, P.uhi[a] - 0.1 * range);
+        const real range = PP.uhi[a] - PP.ulo[a];
+        const real uc = bmpc_clamp(F(F_UQ + a, kp), PP.ulo[a] + 0.1 * range, PP.uhi[a] - 0.1 * range);
         IPF(IP_U + a, kp) = uc;
-        IPF(IP_IN + 2 * a, kp) = P.ipm_y0 * lam * P.ipm_s0 / (P.uhi[a] - uc);
-        IPF(IP_IN + 2 * a + 1, kp) = P.ipm_y0 * lam * P.ipm_s0 / (uc - P.ulo[a]);
+        IPF(IP_IN + 2 * a, kp) = PP.ipm_y0 * lam * PP.ipm_s0 / (PP.uhi[a] - uc);
+        IPF(IP_IN + 2 * a + 1, kp) = PP.ipm_y0 * lam * PP.ipm_s0 / (uc - PP.ulo[a]);
         pairs += 2;
       }
     }
@@ -1891,11 +1904,11 @@ struct Solver {
   // active set + multipliers implied by the converged interior-point state -> starting guess of the polish
   BMPC_DN void ipm_guess() {
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
-      const real lam = P.lam_lin * Wbp()[b];
+      const real lam = PP.lam_lin * Wbp()[b];
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = IPF(IP_X + i, kp);
@@ -1928,12 +1941,12 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         const real u = IPF(IP_U + a, kp);
-        const real range = P.uhi[a] - P.ulo[a];
+        const real range = PP.uhi[a] - PP.ulo[a];
         const real yh = IPF(IP_IN + 2 * a, kp), yl = IPF(IP_IN + 2 * a + 1, kp);
         int ca = IN_FREE;
         real ym = 0.0;
-        if ((P.uhi[a] - u) * lam < yh * range) { ca = IN_AT_HI; ym = yh; }
-        else if ((u - P.ulo[a]) * lam < yl * range) { ca = IN_AT_LO; ym = -yl; }
+        if ((PP.uhi[a] - u) * lam < yh * range) { ca = IN_AT_HI; ym = yh; }
+        else if ((u - PP.ulo[a]) * lam < yl * range) { ca = IN_AT_LO; ym = -yl; }
         code |= in_bits(ca, a);
         F(F_Y + NR + a, kp) = ym;
       }
@@ -1944,7 +1957,7 @@ struct Solver {
 
   BMPC_DN void ipm_export() {   // interior-point iterate -> XQ/UQ (what finish() reads)
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1959,9 +1972,9 @@ struct Solver {
   // returns true when the complementarity gap and the carried residual factor reached their tolerances
   BMPC_DN bool ipm_solve(int& nfact, int& iters) {
     const int pairs = lanes_sum_int(ipm_init());
-    const real mu_tol = P.ipm_mu_tol * P.lam_lin;
+    const real mu_tol = PP.ipm_mu_tol * PP.lam_lin;
     real resfac = 1.0, alpha = 0.0;
-    for (int it = 0; it <= P.ipm_max_iter; ++it) {
+    for (int it = 0; it <= PP.ipm_max_iter; ++it) {
       ipm_pass(bmpc_opaque(IPM_PRED_ASM), 0.0, alpha);   // applies the previous step, then assembles the predictor
       const real mu = lanes_sum(ipm_acc) / pairs;
       BMPC_TRACE("    ipm %d: mu %.3e resfac %.2e\n", it, mu, resfac);
@@ -1969,7 +1982,7 @@ struct Solver {
       // the end game is superlinear, so the tight tolerance usually costs one more iteration; degenerate problems (pairs with
       // both factors vanishing) stall near 1e-9 lam, which is still 1e-7 from the optimum, and are accepted there
       if (mu < (it < 20 ? mu_tol : 10.0 * mu_tol) && resfac < 1e-7) return true;
-      if (it == P.ipm_max_iter) break;
+      if (it == PP.ipm_max_iter) break;
       factorize(FACT_IPM);
       ++nfact;
       backward();
@@ -1998,18 +2011,18 @@ struct Solver {
   // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
   // ========================================================================================
   BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin, real rate, real sig, bool use_qf = false) {
-    const real* Qs = use_qf ? P.Qf : P.Q;
-    const int k = bmpc_ndu(P, b) + t;
+    const real* Qs = use_qf ? PP.Qf : PP.Q;
+    const int k = bmpc_ndu(PP, b) + t;
     real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
 #pragma unroll
     for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) u[a] = bmpc_clamp(F(F_UQ + a, kp), P.ulo[a], P.uhi[a]);
+    for (int a = 0; a < NU; ++a) u[a] = bmpc_clamp(F(F_UQ + a, kp), PP.ulo[a], PP.uhi[a]);
     // objective (slacks eliminated)
     real J = 0.0;
-    const real qs = w * (1.0 + P.dq_scale);
+    const real qs = w * (1.0 + PP.dq_scale);
 #pragma unroll
     for (int i = 0; i < NXP; ++i) {
       real a = 0.0;
@@ -2022,23 +2035,23 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         const real v = x[NXP + (RATE ? a : 0)];
-        J += rate * P.dR[a] * (v * v - 2.0 * v * u[a] + sig * u[a] * u[a]);
+        J += rate * PP.dR[a] * (v * v - 2.0 * v * u[a] + sig * u[a] * u[a]);
       }
       if (k == 0) {
 #pragma unroll
         for (int a = 0; a < NU; ++a)
 #pragma unroll
-          for (int b2 = 0; b2 < NU; ++b2) J += P.dR[a > b2 ? a : b2] * u[a] * u[b2];   // root quirk (:312)
+          for (int b2 = 0; b2 < NU; ++b2) J += PP.dR[a > b2 ? a : b2] * u[a] * u[b2];   // root quirk (:312)
       }
     }
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
       real v = 0.0;
 #pragma unroll
-      for (int b2 = 0; b2 < NU; ++b2) v += P.R[a * NU + b2] * u[b2];
+      for (int b2 = 0; b2 < NU; ++b2) v += PP.R[a * NU + b2] * u[b2];
       J += w * u[a] * v + ((k == 0) ? rlin * u[a] : 0.0);
     }
-    const real lam = P.lam_lin * w;
+    const real lam = PP.lam_lin * w;
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       real lo, hi;
@@ -2046,26 +2059,26 @@ struct Solver {
       const real fx = row_value(kp, j, x);
       J += lam * (fmax(fx - hi, 0.0) + fmax(lo - fx, 0.0));
     }
-    if (P.out.uPred && k < P.pub_totalu) {
-      real* o = P.out.uPred + ((size_t)prob * P.pub_totalu + k) * NU;
+    if (PP.out.uPred && k < PP.pub_totalu) {
+      real* o = PP.out.uPred + ((size_t)prob * PP.pub_totalu + k) * NU;
 #pragma unroll
       for (int a = 0; a < NU; ++a) o[a] = u[a];
     }
 #pragma unroll
     for (int a = 0; a < NU; ++a) uLin[(size_t)k * NU + a] = u[a];
-    if (k == P.totalu - 1) {
+    if (k == PP.totalu - 1) {
 #pragma unroll
       for (int a = 0; a < NU; ++a) uLin[(size_t)(k + 1) * NU + a] = u[a];   // uLin gets the last row twice (:1229)
     }
     if (k == 0) {
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        P.oldin[(size_t)prob * NU + a] = u[a];
-        if (P.out.u0) P.out.u0[(size_t)prob * NU + a] = u[a];
+        PP.oldin[(size_t)prob * NU + a] = u[a];
+        if (PP.out.u0) PP.out.u0[(size_t)prob * NU + a] = u[a];
       }
     }
-    M::mulA(P, lin, x, xn);
-    M::addBu(P, lin, u, xn);
+    M::mulA(PP, lin, x, xn);
+    M::addBu(PP, lin, u, xn);
     M::addC(cc, xn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -2075,26 +2088,26 @@ struct Solver {
   BMPC_DN real finish() {
     const long long prof_t0 = prof_begin(9);
     real J = 0.0;
-    real* uLin = P.uLin + (size_t)prob * (P.totalu + 1) * NU;
-    real* xP = P.out.xPred ? P.out.xPred + (size_t)prob * P.pub_totalx * NXP : nullptr;
-    real* xprev = P.xprev ? P.xprev + (size_t)prob * P.pub_totalx * NXP : nullptr;   // robustMPC's LTV shift source
-    const bool robust = P.ctrl == BMPC_CTRL_ROBUST;
+    real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
+    real* xP = PP.out.xPred ? PP.out.xPred + (size_t)prob * PP.pub_totalx * NXP : nullptr;
+    real* xprev = PP.xprev ? PP.xprev + (size_t)prob * PP.pub_totalx * NXP : nullptr;   // robustMPC's LTV shift source
+    const bool robust = PP.ctrl == BMPC_CTRL_ROBUST;
 #pragma unroll 1
-    for (int d = 0; d <= P.NB; ++d) {
-      const int nt = (d == 0) ? 1 : P.N;
+    for (int d = 0; d <= PP.NB; ++d) {
+      const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = P.off[d] + lane; b < P.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
         if (d == 0) {
 #pragma unroll
-          for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? P.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
+          for (int i = 0; i < NX; ++i) x[i] = (i < NXP) ? PP.x0[(size_t)prob * NXP + (i < NXP ? i : 0)] : 0.0;
         } else {
-          const int pa = bmpc_parent(P, b, d);
+          const int pa = bmpc_parent(PP, b, d);
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
         }
         const real w = Wbp()[b];
-        const int kx = bmpc_ndx(P, b);
+        const int kx = bmpc_ndx(PP, b);
 #pragma unroll 1
         for (int t = 0; t < nt; ++t) {
           if (xP) {
@@ -2105,25 +2118,25 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xprev[(size_t)(kx + t) * NXP + i] = x[i];
           }
-          J += emit_node(b, t, kp_of(b, t), w, x, uLin, (d == 0) ? 0.0 : w, (d == P.NB && t == nt - 1) ? 0.0 : 1.0,
-                         robust && d == P.NB && t == nt - 1);
+          J += emit_node(b, t, kp_of(b, t), w, x, uLin, (d == 0) ? 0.0 : w, (d == PP.NB && t == nt - 1) ? 0.0 : 1.0,
+                         robust && d == PP.NB && t == nt - 1);
         }
-        if (d == P.NB && !robust) {
+        if (d == PP.NB && !robust) {
           if (xP) {
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + nt) * NXP + i] = x[i];
           }
-          const real* xref = P.xref + (size_t)prob * NXP;
+          const real* xref = PP.xref + (size_t)prob * NXP;
 #pragma unroll
           for (int i = 0; i < NXP; ++i) {
             real a = 0.0, c = 0.0;
 #pragma unroll
             for (int j = 0; j < NXP; ++j) {
-              a += P.Qf[i * NXP + j] * x[j];
-              c += P.Qf[j * NXP + i] * xref[j];
+              a += PP.Qf[i * NXP + j] * x[j];
+              c += PP.Qf[j * NXP + i] * xref[j];
             }
             // terminal x' (w Qf) x; BranchMPC has no linear term there (:1094), BranchMPCProx has -2 w xRef' Qf (:308)
-            J += w * x[i] * a - ((P.ctrl == BMPC_CTRL_PROX) ? 2.0 * w * c * x[i] : 0.0);
+            J += w * x[i] * a - ((PP.ctrl == BMPC_CTRL_PROX) ? 2.0 * w * c * x[i] : 0.0);
           }
         }
 #pragma unroll
@@ -2138,7 +2151,7 @@ struct Solver {
   BMPC_DN bool solution_is_finite() {
     int bad = 0;
 #pragma unroll 1
-    for (int k = lane; k < P.totalu; k += BMPC_LANES) {
+    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -2157,13 +2170,13 @@ struct Solver {
     const long long t_start = clock64();
 #endif
     prob = prob_;
-    polpar = P.polpar ? P.polpar + (size_t)prob * P.zm * 4 : nullptr;
-    const int warm = P.started[prob];
-    int* cstate = P.cache_state + (size_t)prob * 2;   // [0] age of the cached rho (-1: none), [1] cached codes valid
-    const bool reuse_rho = warm && P.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < P.rho_refresh;
-    use_codes = warm && P.warm_polish && cstate[1] == 1 && reuse_rho;
+    polpar = PP.polpar ? PP.polpar + (size_t)prob * PP.zm * 4 : nullptr;
+    const int warm = PP.started[prob];
+    int* cstate = PP.cache_state + (size_t)prob * 2;   // [0] age of the cached rho (-1: none), [1] cached codes valid
+    const bool reuse_rho = warm && PP.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < PP.rho_refresh;
+    use_codes = warm && PP.warm_polish && cstate[1] == 1 && reuse_rho;
     t_phase = 0;
-    if (P.ctrl == BMPC_CTRL_ROBUST) expand_chain();
+    if (PP.ctrl == BMPC_CTRL_ROBUST) expand_chain();
     else expand_tree();
     nsolve = 0;
     ipm_iters = 0;
@@ -2185,7 +2198,7 @@ struct Solver {
         have_xu = true;
       }
     }
-    int next_polish = P.polish_first, polish_gap = P.polish_every, next_forced = P.polish_force;
+    int next_polish = PP.polish_first, polish_gap = PP.polish_every, next_forced = PP.polish_force;
     int nfail = 0;
     bool ipm_tried = false;
     if (!have_xu) {
@@ -2193,11 +2206,11 @@ struct Solver {
       ++nfact;
       admm_rows<false, false>();
     }
-    while (!have_xu && iters < P.max_iter) {
+    while (!have_xu && iters < PP.max_iter) {
       backward();
       forward();
       ++iters;
-      const bool check = (iters % P.check_every == 0);
+      const bool check = (iters % PP.check_every == 0);
       real res = 1e300;
       int moved = 1 << 20;
       if (check) {
@@ -2206,23 +2219,23 @@ struct Solver {
       } else {
         admm_rows<true, false>();
       }
-      const bool conv = res < P.eps_abs;
+      const bool conv = res < PP.eps_abs;
       if (check) BMPC_TRACE("  it %d res %.3e set changes %d\n", iters, res, moved);
       // polish when the active set implied by the ADMM state has stopped moving (or, at the latest, every force_every)
-      const bool due = check && iters >= next_polish && (moved <= P.polish_stable || iters >= next_forced);
+      const bool due = check && iters >= next_polish && (moved <= PP.polish_stable || iters >= next_forced);
       if (due || conv) {
-        next_forced = iters + P.polish_force;
+        next_forced = iters + PP.polish_force;
         next_polish = iters + polish_gap;
         polish_gap *= 2;   // back off: a problem whose active set is slow to settle should not pay for many attempts
         // ipm_after == 100 (tests): skip the polish attempt, the interior point runs at the first opportunity
-        if (P.ipm_after != 100 && polish(nfact, iters >= 4 * P.polish_first, true)) {
+        if (PP.ipm_after != 100 && polish(nfact, iters >= 4 * PP.polish_first, true)) {
           status = BMPC_STATUS_POLISHED;
           have_xu = true;
           break;
         }
         if (conv) status = BMPC_STATUS_CONVERGED;
         ++nfail;
-        if (!conv && P.ipm_after > 0 && (nfail >= P.ipm_after || P.ipm_after == 100) && !ipm_tried) {
+        if (!conv && PP.ipm_after > 0 && (nfail >= PP.ipm_after || PP.ipm_after == 100) && !ipm_tried) {
           // the active set does not settle: interior point on the same Riccati, then a polish from its (clean) active set
           ipm_tried = true;
           const long long t_ipm0 = prof_begin(1);
@@ -2240,7 +2253,7 @@ struct Solver {
             break;
           }
         }
-        if (!conv && P.rebalance) rebalance_rho();
+        if (!conv && PP.rebalance) rebalance_rho();
         factorize(FACT_ADMM);
         ++nfact;
         admm_rows<false, false>();
@@ -2256,25 +2269,25 @@ struct Solver {
       const real J = finish();
       if (status == BMPC_STATUS_POLISHED) store_codes();
       if (lane == 0) {
-        if (P.out.status) P.out.status[prob] = status;
-        if (P.out.objective) P.out.objective[prob] = J;
-        P.started[prob] = 1;
+        if (PP.out.status) PP.out.status[prob] = status;
+        if (PP.out.objective) PP.out.objective[prob] = J;
+        PP.started[prob] = 1;
         cstate[0] = reuse_rho ? cstate[0] + 1 : 0;
         cstate[1] = (status == BMPC_STATUS_POLISHED) ? 1 : 0;
       }
     } else if (lane == 0) {
       // the reference keeps its previous plan when the solver fails (MPC_branch.py:1224): outputs and warm start untouched
-      if (P.out.status) P.out.status[prob] = BMPC_STATUS_NUMERIC;
+      if (PP.out.status) PP.out.status[prob] = BMPC_STATUS_NUMERIC;
     }
     if (lane == 0) {
-      if (P.out.iters) P.out.iters[prob] = iters;
-      if (P.out.nfact) P.out.nfact[prob] = nfact;
-      if (P.out.nsolve) P.out.nsolve[prob] = nsolve;
+      if (PP.out.iters) PP.out.iters[prob] = iters;
+      if (PP.out.nfact) PP.out.nfact[prob] = nfact;
+      if (PP.out.nsolve) PP.out.nsolve[prob] = nsolve;
 #if defined(__CUDA_ARCH__)
-      if (P.out.cycles) P.out.cycles[prob] = P.cycles_mode > 0 ? (int64_t)t_phase : (int64_t)(clock64() - t_start);
-      if (P.cost) P.cost[prob] = (int)min((long long)0x7fffffff, (clock64() - t_start) >> 10);
+      if (PP.out.cycles) PP.out.cycles[prob] = PP.cycles_mode > 0 ? (int64_t)t_phase : (int64_t)(clock64() - t_start);
+      if (PP.cost) PP.cost[prob] = (int)min((long long)0x7fffffff, (clock64() - t_start) >> 10);
 #else
-      if (P.out.cycles) P.out.cycles[prob] = ipm_iters;   // host build: no clock; reports the interior-point iterations instead
+      if (PP.out.cycles) PP.out.cycles[prob] = ipm_iters;   // host build: no clock; reports the interior-point iterations instead
 #endif
     }
     lanes_sync();

@@ -263,6 +263,35 @@ def test_quadruped_batch_8192(bmpc):
     mpc.close()
 
 
+def test_two_handles_on_two_streams(bmpc):
+    """The solve kernel reads its parameter block from one constant-memory symbol per device: launches of different handles
+    on different streams must be ordered by the library so that neither sees the other's block."""
+    import torch
+    dev = torch.device("cuda", 0)
+    B = 2048
+    hx, hz, hr, hp = scenarios.highway_batch(B, seed=8)
+    qx, qz, qr = scenarios.quadruped_batch(B, seed=9)
+    a = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=B))
+    b = bmpc.BatchedBranchMPC(scenarios.quadruped_config(batch_capacity=B))
+    ref_a = a.solve_host(hx, hz, hr, hp, outputs=("u0", "objective", "status"))
+    ref_b = b.solve_host(qx, qz, qr, outputs=("u0", "objective", "status"))
+    a.reset()
+    b.reset()
+    ta = [torch.as_tensor(v, device=dev) for v in (hx, hz, hr, hp)]
+    tb = [torch.as_tensor(v, device=dev) for v in (qx, qz, qr)]
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        oa = a.solve(*ta, outputs=("u0", "objective", "status"), stream=s1.cuda_stream)
+    with torch.cuda.stream(s2):
+        ob = b.solve(*tb, outputs=("u0", "objective", "status"), stream=s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(oa["u0"].cpu().numpy(), ref_a["u0"]) and np.array_equal(oa["status"].cpu().numpy(), ref_a["status"])
+    assert np.array_equal(ob["u0"].cpu().numpy(), ref_b["u0"]) and np.array_equal(ob["status"].cpu().numpy(), ref_b["status"])
+    a.close()
+    b.close()
+
+
 def test_plant_step_matches_reference_plant(bmpc):
     import torch
     B = 1000
