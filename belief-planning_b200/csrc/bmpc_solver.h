@@ -107,8 +107,21 @@ struct Solver {
   real* ws;     // slab base (shared memory is addressed through bmpc_smem on the device so that loads are LDS)
   real* fa;     // factor-field region (SPLIT only)
   real* ip;     // interior-point scratch (global)
-  int oSt, oWb, oEX, oEXL, oEXZ, oEXX;   // offsets (in reals) of the per-branch arrays inside the slab
-  int lane, nup, prob;
+  // offsets (in reals) of the per-branch arrays inside the slab: recomputed from the constant-memory block where needed
+  // (a member would be a generic load through `this` in every out-of-line function)
+  BMPC_D int oSt() const { return NFWP * PP.nup; }
+  BMPC_D int oWb() const { return oSt() + PP.nup; }
+  BMPC_D int oEX() const { return oWb() + PP.nbx; }
+  BMPC_D int oEXL() const { return oEX() + NS * PP.nbx; }
+  BMPC_D int oEXZ() const { return oEXL() + NX * PP.nbx; }
+  BMPC_D int oEXX() const { return oEXZ() + NX * PP.nbx; }
+#if defined(__CUDA_ARCH__)
+#define BMPC_LANE_ID ((int)(threadIdx.x & 31))
+#else
+  int lane_host;
+#define BMPC_LANE_ID lane_host
+#endif
+  int prob;
   bool use_codes;   // this solve starts its polish from the cached active set of the previous step
   real gap_r, stp_r, gap_u, stp_u;   // last residual check: max primal gap |f'x - v| and max step |v+ - v| (rows / inputs)
   int set_changes;                   // last residual check: nodes whose implied active set differs from the previous check
@@ -119,16 +132,11 @@ struct Solver {
   const real* polpar;
 
 #if defined(__CUDA_ARCH__)
-  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : ws(slab), fa(factor), ip(ipm), lane(lane_), nup(P_.nup) {
+  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : ws(slab), fa(factor), ip(ipm) {
+    (void)lane_;
 #else
-  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : P_host(P_), ws(slab), fa(factor), ip(ipm), lane(lane_), nup(P_.nup) {
+  BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : P_host(P_), ws(slab), fa(factor), ip(ipm), lane_host(lane_) {
 #endif
-    oSt = NFWP * nup;
-    oWb = oSt + nup;
-    oEX = oWb + PP.nbx;
-    oEXL = oEX + NS * PP.nbx;
-    oEXZ = oEXL + NX * PP.nbx;
-    oEXX = oEXZ + NX * PP.nbx;
     prob = 0;
     use_codes = false;
     nsolve = 0;
@@ -164,13 +172,13 @@ struct Solver {
     if (PP.cycles_mode == k) t_phase += clock64() - t0;
 #endif
   }
-  BMPC_D real& IPF(int field, int kp) { return ip[(size_t)field * nup + kp]; }   // field-major: the lanes of a node-parallel pass read consecutive addresses
-  BMPC_D code_t* stp() { return reinterpret_cast<code_t*>(slab() + oSt); }
-  BMPC_D real* Wbp() { return slab() + oWb; }
-  BMPC_D real* EXp() { return slab() + oEX; }
-  BMPC_D real* EXLp() { return slab() + oEXL; }
-  BMPC_D real* EXZp() { return slab() + oEXZ; }
-  BMPC_D real* EXXp() { return slab() + oEXX; }
+  BMPC_D real& IPF(int field, int kp) { return ip[(size_t)field * PP.nup + kp]; }   // field-major: the lanes of a node-parallel pass read consecutive addresses
+  BMPC_D code_t* stp() { return reinterpret_cast<code_t*>(slab() + oSt()); }
+  BMPC_D real* Wbp() { return slab() + oWb(); }
+  BMPC_D real* EXp() { return slab() + oEX(); }
+  BMPC_D real* EXLp() { return slab() + oEXL(); }
+  BMPC_D real* EXZp() { return slab() + oEXZ(); }
+  BMPC_D real* EXXp() { return slab() + oEXX(); }
   // active-set code of a node: 3 bits per soft row, then 2 bits per input
   BMPC_D static int row_of(code_t c, int j) { return (int)((c >> (3 * j)) & 7); }
   BMPC_D static int in_of(code_t c, int a) { return (int)((c >> (3 * NR + 2 * a)) & 3); }
@@ -259,7 +267,7 @@ struct Solver {
     const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
     const real* x0 = PP.x0 + (size_t)prob * NXP;
     const real* z0 = PP.z0 + (size_t)prob * NXP;
-    if (lane == 0) {
+    if (BMPC_LANE_ID == 0) {
       real ub[NU], xb[NXP], xn[NXP];
 #pragma unroll
       for (int i = 0; i < NXP; ++i) xb[i] = x0[i];
@@ -291,7 +299,7 @@ struct Solver {
     for (int d = 0; d < PP.NB; ++d) {
       // (a) obstacle rollouts under each policy + safety value of each (zpred_eval, branch_eval); lanes = (branch, policy)
       const int cnt = PP.pw[d] * m;
-      for (int idx = lane; idx < cnt; idx += BMPC_LANES) {
+      for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_LANES) {
         const int b = PP.off[d] + idx / m;
         const int i = idx % m;
         const int c = bmpc_first_child(PP, b, d) + i;
@@ -315,7 +323,7 @@ struct Solver {
       lanes_sync();
       // (a') probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         const int fc = bmpc_first_child(PP, b, d);
         real himax = -1e300;
         for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
@@ -335,7 +343,7 @@ struct Solver {
       lanes_sync();
       // (b) ego linearisation trajectory of every child branch: time-shifted previous inputs
       //     (updatetree :1025-1033), nonlinear rollout + per-node linearisation (:1048-1059)
-      for (int c = PP.off[d + 1] + lane; c < PP.off[d + 2]; c += BMPC_LANES) {
+      for (int c = PP.off[d + 1] + BMPC_LANE_ID; c < PP.off[d + 2]; c += BMPC_LANES) {
         const int b = bmpc_parent(PP, c, d + 1);
         const bool leaf = (d + 1 == PP.NB);
         const real w = Wbp()[c];
@@ -367,11 +375,11 @@ struct Solver {
       }
       lanes_sync();
       // commit the new arg-max children of this level (their old values are no longer needed)
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EXp()[NS * b + 1];
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EXp()[NS * b + 1];
       lanes_sync();
     }
     if (PP.out.branch_w) {
-      for (int b = lane; b < PP.nbranch; b += BMPC_LANES) PP.out.branch_w[(size_t)prob * PP.nbranch + b] = Wbp()[b];
+      for (int b = BMPC_LANE_ID; b < PP.nbranch; b += BMPC_LANES) PP.out.branch_w[(size_t)prob * PP.nbranch + b] = Wbp()[b];
     }
     rlin = 0.0;
 #pragma unroll
@@ -398,7 +406,7 @@ struct Solver {
     auto kp_chain = [&](int k) { return k == 0 ? kp_of(0, 0) : kp_of(1, k - 1); };
     // 1. linearisation trajectory, parked in the sweep vectors
     if (!started) {
-      if (lane == 0) {
+      if (BMPC_LANE_ID == 0) {
         real x[NXP], xn[NXP], u[NU];
 #pragma unroll
         for (int i = 0; i < NXP; ++i) x[i] = x0[i];
@@ -416,7 +424,7 @@ struct Solver {
         }
       }
     } else {
-      for (int k = lane; k < Nx; k += BMPC_LANES) {
+      for (int k = BMPC_LANE_ID; k < Nx; k += BMPC_LANES) {
         const int kp = kp_chain(k);
         const int kx = (k + 1 < Nx) ? k + 1 : Nx - 1;
         const int ku = (k + 1 < Nu) ? k + 1 : Nu - 1;
@@ -428,7 +436,7 @@ struct Solver {
       }
     }
     // 2. obstacle scenario tree -> collision-row slots of the chain nodes
-    if (lane == 0) {
+    if (BMPC_LANE_ID == 0) {
       const int kp = kp_chain(0);
       F(F_FC, kp) = z0[0];
       F(F_FC + 1, kp) = z0[1];
@@ -439,7 +447,7 @@ struct Solver {
     const int m = PP.zm;
     for (int d = 0; d < PP.zNB; ++d) {
       const int cnt = PP.zpw[d] * m;
-      for (int idx = lane; idx < cnt; idx += BMPC_LANES) {
+      for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_LANES) {
         const int b = PP.zoff[d] + idx / m;
         const int i = idx % m;
         const int c = PP.zoff[d + 1] + (b - PP.zoff[d]) * m + i;
@@ -458,7 +466,7 @@ struct Solver {
     }
     // 3. per-node data: every node is linearised about its own (x, u) of the shifted trajectory - no rollout dependence
     const real* xref = PP.xref + (size_t)prob * NXP;
-    for (int k = lane; k < Nx; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < Nx; k += BMPC_LANES) {
       const int kp = kp_chain(k);
       real xb[NXP], ub[NU], xn[NXP], lin[M::NLIN], cc[M::NCC];
 #pragma unroll
@@ -484,7 +492,7 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ub[a], PP.ulo[a], PP.uhi[a]);
     }
-    if (lane == 0) {
+    if (BMPC_LANE_ID == 0) {
       Wbp()[0] = 1.0;     // slack weights are not branch-weighted in robustMPC (:1562)
       Wbp()[1] = 1.0;
     }
@@ -757,7 +765,7 @@ struct Solver {
     for (int d = PP.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         const real w = Wbp()[b];
         real Pn[NX * NX];
         if (d == PP.NB) {
@@ -898,7 +906,7 @@ struct Solver {
     for (int d = 0; d <= PP.NB; ++d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         real Sg[NX * NX];
         if (d == 0) {
 #pragma unroll
@@ -960,7 +968,7 @@ struct Solver {
     for (int d = PP.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         real pn[NX];
         if (d == PP.NB) {
 #pragma unroll
@@ -1026,7 +1034,7 @@ struct Solver {
     for (int d = 0; d <= PP.NB; ++d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
         if (d == 0) {
 #pragma unroll
@@ -1081,7 +1089,7 @@ struct Solver {
     real res = 0.0;
     if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; set_changes = 0; }
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1169,7 +1177,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(3);
     real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1183,7 +1191,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(3);
     const real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1208,7 +1216,7 @@ struct Solver {
   BMPC_DN void guess_from_codes() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1236,7 +1244,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(9);
     code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       codes[k] = stp()[kp_of(b, t)];
@@ -1258,7 +1266,7 @@ struct Solver {
     BMPC_TRACE("    rebalance: rows gap %.2e step %.2e -> x%.2f   inputs gap %.2e step %.2e -> x%.2f\n", gr, sr, fr, gu, su, fu);
     if (fr == 1.0 && fu == 1.0) return false;
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1297,7 +1305,7 @@ struct Solver {
   BMPC_DN void polish_guess() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1342,7 +1350,7 @@ struct Solver {
   BMPC_DN void polish_assemble() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1397,7 +1405,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(6);
     real res = 0.0;
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1428,7 +1436,7 @@ struct Solver {
   BMPC_DN void polish_inject() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1507,7 +1515,7 @@ struct Solver {
     for (int d = PP.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         const real w = Wbp()[b];
         real lam[NX];
         if (d == PP.NB) {
@@ -1558,7 +1566,7 @@ struct Solver {
     real smax = 0.0;
     const real tol = 1e-7;
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1789,7 +1797,7 @@ struct Solver {
     const bool assemble = (phase == IPM_PRED_ASM || phase == IPM_CORR_ASM);
     const bool first = (phase == IPM_PRED_ASM && !(alpha > 0.0));
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1860,7 +1868,7 @@ struct Solver {
   BMPC_DN int ipm_init() {
     int pairs = 0;
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1904,7 +1912,7 @@ struct Solver {
   // active set + multipliers implied by the converged interior-point state -> starting guess of the polish
   BMPC_DN void ipm_guess() {
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1957,7 +1965,7 @@ struct Solver {
 
   BMPC_DN void ipm_export() {   // interior-point iterate -> XQ/UQ (what finish() reads)
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -2096,7 +2104,7 @@ struct Solver {
     for (int d = 0; d <= PP.NB; ++d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + lane; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         real x[NX];
         if (d == 0) {
 #pragma unroll
@@ -2151,7 +2159,7 @@ struct Solver {
   BMPC_DN bool solution_is_finite() {
     int bad = 0;
 #pragma unroll 1
-    for (int k = lane; k < PP.totalu; k += BMPC_LANES) {
+    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -2268,18 +2276,18 @@ struct Solver {
     if (solution_is_finite()) {
       const real J = finish();
       if (status == BMPC_STATUS_POLISHED) store_codes();
-      if (lane == 0) {
+      if (BMPC_LANE_ID == 0) {
         if (PP.out.status) PP.out.status[prob] = status;
         if (PP.out.objective) PP.out.objective[prob] = J;
         PP.started[prob] = 1;
         cstate[0] = reuse_rho ? cstate[0] + 1 : 0;
         cstate[1] = (status == BMPC_STATUS_POLISHED) ? 1 : 0;
       }
-    } else if (lane == 0) {
+    } else if (BMPC_LANE_ID == 0) {
       // the reference keeps its previous plan when the solver fails (MPC_branch.py:1224): outputs and warm start untouched
       if (PP.out.status) PP.out.status[prob] = BMPC_STATUS_NUMERIC;
     }
-    if (lane == 0) {
+    if (BMPC_LANE_ID == 0) {
       if (PP.out.iters) PP.out.iters[prob] = iters;
       if (PP.out.nfact) PP.out.nfact[prob] = nfact;
       if (PP.out.nsolve) PP.out.nsolve[prob] = nsolve;
