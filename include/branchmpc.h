@@ -66,8 +66,9 @@ extern "C" {
 
 /* per-problem solver status (bmpc_outputs.status) */
 #define BMPC_STATUS_POLISHED 0  /* active set verified: exact optimum of the QP (to round-off)   */
-#define BMPC_STATUS_CONVERGED 1 /* ADMM residuals below tolerance, polish not verified           */
-#define BMPC_STATUS_MAXITER 2   /* iteration cap reached; best iterate returned                  */
+#define BMPC_STATUS_CONVERGED 1 /* ADMM residuals below eps_abs, or the interior-point fallback converged (complementarity
+                                   gap <= 1e-9 Qslack[1], ~1e-7 from the optimum); active set not verified by the polish */
+#define BMPC_STATUS_MAXITER 2   /* iteration caps of ADMM and of the interior point reached; best iterate returned */
 #define BMPC_STATUS_NUMERIC 3   /* non-finite data met; previous plan kept (reference: feasible=0) */
 
 typedef struct bmpc_config {
