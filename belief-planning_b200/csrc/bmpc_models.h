@@ -58,7 +58,7 @@ struct HighwayModel {
   }
 
   // symbolic branch of each backup policy (:54-148)
-  BMPC_D static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) {
+  BMPC_DN static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) {
     switch (kind) {
       case BMPC_POLICY_MAINTAIN:
         u[0] = 0.0;
@@ -167,6 +167,7 @@ struct HighwayModel {
     real xe[4] = {xe0[0], xe0[1], xe0[2], xe0[3]};
     real z[4] = {z0[0], z0[1], z0[2], z0[3]};
     SoftMinAcc acc(5.0);
+#pragma unroll 1
     for (int t = 0; t < nsteps; ++t) {
       real u[2], xn[4];
       policy(P, kind0, par0, xe, u);
@@ -287,6 +288,7 @@ struct QuadrupedModel {
     real xe[3] = {xe0[0], xe0[1], xe0[2]};
     real z[3] = {z0[0], z0[1], z0[2]};
     SoftMinAcc acc(5.0);
+#pragma unroll 1
     for (int t = 0; t < nsteps; ++t) {
       real u[3], xn[3];
       policy(P, kind0, par0, xe, u);

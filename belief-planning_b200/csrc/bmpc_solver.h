@@ -228,7 +228,7 @@ struct Solver {
     }
   }
 
-  BMPC_D void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn, int ncol = 1) {
+  BMPC_DN void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn, int ncol = 1) {
     const int kp = kp_of(b, t);
     real lin[M::NLIN], cc[M::NCC];
     M::linearize(PP, xbar, ubar, lin, cc, xn);
@@ -326,11 +326,14 @@ struct Solver {
       for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
         const int fc = bmpc_first_child(PP, b, d);
         real himax = -1e300;
+#pragma unroll 1
         for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
         real sum = 0.0;
+#pragma unroll 1
         for (int j = 0; j < m; ++j) sum += M::branch_weight(PP, EXp()[NS * (fc + j)], himax);
         int best = 0;
         real pb = -1.0;
+#pragma unroll 1
         for (int j = 0; j < m; ++j) {
           const real p = M::branch_weight(PP, EXp()[NS * (fc + j)], himax) / sum;
           Wbp()[fc + j] = Wbp()[b] * p;
@@ -357,6 +360,7 @@ struct Solver {
         real xb[NXP], xn[NXP], ub[NU];
 #pragma unroll
         for (int i = 0; i < NXP; ++i) xb[i] = EXXp()[NX * b + i];
+#pragma unroll 1
         for (int t = 0; t < PP.N; ++t) {
           const int ksrc = (t < PP.N - 1) ? kc + t + 1 : klast;
 #pragma unroll
@@ -749,6 +753,7 @@ struct Solver {
   BMPC_D void sum_children(int b, int d, real* Pn) {
     const int fc = bmpc_first_child(PP, b, d);
     unpack_sym(EXp() + NS * fc, Pn);
+#pragma unroll 1
     for (int c = 1; c < PP.m; ++c) {
       real Pc[NX * NX];
       unpack_sym(EXp() + NS * (fc + c), Pc);
@@ -989,6 +994,7 @@ struct Solver {
           const int fc = bmpc_first_child(PP, b, d);
 #pragma unroll
           for (int i = 0; i < NX; ++i) pn[i] = EXp()[NS * fc + i];
+#pragma unroll 1
           for (int c = 1; c < PP.m; ++c)
 #pragma unroll
             for (int i = 0; i < NX; ++i) pn[i] += EXp()[NS * (fc + c) + i];
@@ -1170,6 +1176,8 @@ struct Solver {
     lanes_sync();
     { const auto prof_rv = res; prof_end(8, prof_t0); return prof_rv; }
   }
+
+  BMPC_DN void admm_assemble() { admm_rows<false, false>(); }   // cold variant, two call sites: one out-of-line copy
 
   // rho cache: the curvature-matched rho changes slowly from one MPC step to the next, so warm solves reuse the
   // values of the previous step (refreshed every P.rho_refresh solves) and skip the free factorisation + covariance sweep.
@@ -1539,6 +1547,7 @@ struct Solver {
           const int fc = bmpc_first_child(PP, b, d);
 #pragma unroll
           for (int i = 0; i < NX; ++i) lam[i] = EXp()[NS * fc + i];
+#pragma unroll 1
           for (int c = 1; c < PP.m; ++c)
 #pragma unroll
             for (int i = 0; i < NX; ++i) lam[i] += EXp()[NS * (fc + c) + i];
@@ -2212,7 +2221,7 @@ struct Solver {
     if (!have_xu) {
       factorize(FACT_ADMM);
       ++nfact;
-      admm_rows<false, false>();
+      admm_assemble();
     }
     while (!have_xu && iters < PP.max_iter) {
       backward();
@@ -2264,7 +2273,7 @@ struct Solver {
         if (!conv && PP.rebalance) rebalance_rho();
         factorize(FACT_ADMM);
         ++nfact;
-        admm_rows<false, false>();
+        admm_assemble();
         if (conv) break;
       }
     }
