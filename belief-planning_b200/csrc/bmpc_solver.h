@@ -1230,7 +1230,7 @@ struct Solver {
       const int kp = kp_of(b, t);
       const code_t code = stp()[kp];
       code_t ncode = 0;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         int cj = row_of(code, j);
         if (!(F(F_RHO + j, kp) > 0.0)) cj = ROW_IGNORED;
@@ -1319,7 +1319,7 @@ struct Solver {
       const int kp = kp_of(b, t);
       const real lam = PP.lam_lin * Wbp()[b];
       code_t code = 0;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         const real rho = F(F_RHO + j, kp);
         int cj = ROW_IGNORED;
@@ -1368,7 +1368,7 @@ struct Solver {
       real qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         const int cj = row_of(code, j);
         real lo, hi;
@@ -1422,7 +1422,7 @@ struct Solver {
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         const int cj = row_of(code, j);
         if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) {
@@ -1500,7 +1500,7 @@ struct Solver {
       }
       st_x[i] = v;
     }
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NR; ++j) {
       const int cj = row_of(code, j);
       real g = 0.0;
@@ -1587,7 +1587,7 @@ struct Solver {
       real x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         const int cj = row_of(code, j);
         int nj = cj;
@@ -2069,7 +2069,7 @@ struct Solver {
       J += w * u[a] * v + ((k == 0) ? rlin * u[a] : 0.0);
     }
     const real lam = PP.lam_lin * w;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NR; ++j) {
       real lo, hi;
       row_bounds(kp, j, lo, hi);
