@@ -180,6 +180,10 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    # stdout carries exactly one JSON line: the image sets NCCL_DEBUG=VERSION, which makes NCCL printf a version banner to
+    # stdout (NCCL_DEBUG_FILE does not catch it); must be changed before the library is loaded
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "NONE"
     import torch
     import torch.distributed as dist
     from _bmpc import batch, scenarios, shard
@@ -192,8 +196,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: whatever NCCL logs (the image's default prints a version banner) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
