@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -206,7 +207,7 @@ struct bmpc_handle {
 
 static std::string g_create_error;
 
-struct ConstSlot { cudaEvent_t done = nullptr; cudaStream_t stream = nullptr; bool used = false; };
+struct ConstSlot { cudaEvent_t done = nullptr; cudaStream_t stream = nullptr; bool used = false; std::mutex mu; };
 static ConstSlot g_const[16];   // per device: the last solve launch that reads bmpc_cP
 
 #define BMPC_CK(h, call)                                                                           \
@@ -470,6 +471,7 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   // the parameter block travels through constant memory: one symbol per device, so launches from other streams or handles
   // are ordered behind the previous solve kernel of this device before the symbol is rewritten
   ConstSlot& cs = g_const[h->device & 15];
+  std::lock_guard<std::mutex> lock(cs.mu);   // distinct handles may be driven from distinct host threads
   if (!cs.done) BMPC_CK(h, cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
   if (cs.used && cs.stream != s) BMPC_CK(h, cudaStreamWaitEvent(s, cs.done, 0));
   KParams* stage = h->pstage + (h->pstage_next++ % BMPC_PSTAGE);

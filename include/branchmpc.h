@@ -176,7 +176,10 @@ int bmpc_ulin_rows(const bmpc_handle* h);
 /* One MPC step for episodes 0..count-1 (episode i uses persistent slot i).
  *   x0, z0, xref : [count][n] device float64   (solve(x, z, xRef), MPC_branch.py:1171)
  *   policy_params: [count][m][4] device float64 or NULL (per-episode lane-change target etc.;
- *                  the reference rebuilds its model for this, highway_branch_dyn.py:331)       */
+ *                  the reference rebuilds its model for this, highway_branch_dyn.py:331)
+ * The kernel's parameter block travels through one constant-memory symbol per device: the call uploads it stream-ordered
+ * and orders itself behind the previous solve launch on that device (other handles, other streams); it waits on a small
+ * ring of host events, so it cannot be recorded into a CUDA graph. */
 int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                const double* policy_params, int64_t count, const bmpc_outputs* out, void* stream);
 
