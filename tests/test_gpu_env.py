@@ -93,3 +93,29 @@ def test_quadruped_env_matches_oracle_env(mods):
             np.testing.assert_allclose(h["x"][i], oracles[k].x, atol=1e-4)
             np.testing.assert_allclose(h["z"][i], oracles[k].z, atol=1e-9)
     mpc.close()
+
+
+def test_default_scenario_full_length_against_oracle(mods):
+    """BASELINE config 1: the reference's own workload (main_branch.py sim_overtake: ego [0,1.8,20,0], obstacle [5,5.4,20,0],
+    100 closed-loop steps) on the device against the oracle environment + oracle controller, step by step.  The loop feeds on
+    its own outputs, so the comparison tolerance grows with the step count; discrete decisions must agree exactly."""
+    from oracle import params
+    from oracle.env import HighwayEnvOracle
+    batch, env = mods
+    steps = 100
+    mpc = batch.BatchedBranchMPC(scenarios.highway_config(batch_capacity=1))
+    e = env.BatchedHighwayEnv(mpc, [0., 1.8, 20., 0.], [5., 5.4, 20., 0.], 4)
+    ora = HighwayEnvOracle(params.highway_branch_mpc(N_lane=4), 4)
+    worst = 0.0
+    for t in range(steps):
+        out = e.step()
+        u, _ = ora.step(t)
+        h = e.host()
+        assert int(out["status"].cpu().numpy()[0]) <= 1, t
+        assert int(h["obs_policy"][0]) == ora.backupidx and list(h["lane"][0]) == ora.lane, t
+        worst = max(worst, float(np.abs(out["u0"].cpu().numpy()[0] - u).max()))
+        assert worst < TOL_U0, (t, worst)
+        np.testing.assert_allclose(h["x"][0], ora.x, atol=1e-4)
+        np.testing.assert_allclose(h["z"][0], ora.z, atol=1e-9)
+    assert bool(h["collided"][0]) == bool(ora.collision)
+    mpc.close()
