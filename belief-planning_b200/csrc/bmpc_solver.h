@@ -1107,7 +1107,7 @@ struct Solver {
       for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0; }
 #pragma unroll
       for (int a = 0; a < NU; ++a) { u[a] = F(F_UQ + a, kp); qu[a] = (k == 0) ? rlin : 0.0; }
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         const real rho = F(F_RHO + j, kp);
         if (rho > 0.0) {
