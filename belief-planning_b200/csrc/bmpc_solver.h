@@ -1238,7 +1238,7 @@ struct Solver {
         ncode |= row_bits(cj, j);
         F(F_Y + j, kp) = 0.0;
       }
-#pragma unroll
+#pragma unroll 1
       for (int a = 0; a < NU; ++a) {
         ncode |= in_bits(in_of(code, a), a);
         F(F_Y + NR + a, kp) = 0.0;
@@ -1338,7 +1338,7 @@ struct Solver {
         code |= row_bits(cj, j);
         F(F_Y + j, kp) = y;
       }
-#pragma unroll
+#pragma unroll 1
       for (int a = 0; a < NU; ++a) {
         const real rho = F(F_RHO + NR + a, kp);
         const real sh = F(F_SU + a, kp);
@@ -1632,7 +1632,7 @@ struct Solver {
         }
         ncode |= row_bits(nj, j);
       }
-#pragma unroll
+#pragma unroll 1
       for (int a = 0; a < NU; ++a) {
         const int ca = in_of(code, a);
         int na = ca;
