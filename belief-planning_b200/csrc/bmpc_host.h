@@ -127,6 +127,8 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
   P.theta = c.theta > 0.0 ? c.theta : 1.0;
   P.theta_u = c.theta_u > 0.0 ? c.theta_u : 1.0;
+  P.inv_theta = 1.0 / P.theta;
+  P.inv_theta_u = 1.0 / P.theta_u;
   P.eps_abs = c.eps_abs > 0.0 ? c.eps_abs : 1.0e-6;
   P.polish_big = c.polish_big > 0.0 ? c.polish_big : 1.0e4;
   P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e4;

@@ -32,6 +32,7 @@ struct KParams {
   // ---- solver ----
   int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes, check_every, polish_stable, polish_force;
   real alpha, theta, theta_u, eps_abs, polish_big, polish_mult, rho_u_feedback;
+  real inv_theta, inv_theta_u;  // reciprocals (the polish passes scale by them per row)
   int cycles_mode;              // 0: `cycles` = whole solve; k > 0: time spent in phase k (see Solver::prof_begin)
   int ipm_after, ipm_max_iter;  // interior-point fallback: after this many failed polish attempts (0 = never), iteration cap
   real ipm_mu_tol, ipm_s0, ipm_y0;

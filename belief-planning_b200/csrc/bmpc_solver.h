@@ -563,7 +563,7 @@ struct Solver {
   // Stiff penalty of a guessed-active row in the polish: polish_mult times the row's curvature-matched stiffness
   // (rho/theta = 1/(f' Sigma f)), at least polish_big*w, so that every augmented-Lagrangian step contracts strongly.
   BMPC_D real big_row(int kp, int j, real w) {
-    return fmin(fmax(PP.polish_big * w, PP.polish_mult * F(F_RHO + j, kp) / PP.theta), 1.0e12 * w);
+    return fmin(fmax(PP.polish_big * w, PP.polish_mult * F(F_RHO + j, kp) * PP.inv_theta), 1.0e12 * w);
   }
   // penalties of the node's soft rows and inputs for the requested factorisation
   BMPC_D void penalties(int kp, real w, int mode, real* pr, real* pu) {
@@ -1102,6 +1102,8 @@ struct Solver {
       const real w = Wbp()[b];
       const real lam = PP.lam_lin * w;
       code_t ncode = 0;   // CHECK: the active set the ADMM state currently implies (compared with the previous check)
+      const real iw100 = CHECK ? 0.01 / w : 0.0;
+      (void)iw100;
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) { x[i] = F(F_XQ + i, kp); qx[i] = (i < NXP) ? F(F_Q + (i < NXP ? i : 0), kp) : 0.0; }
@@ -1123,9 +1125,10 @@ struct Solver {
             const real yn = row_dual(shn, rlo, rhi, lam);
             if (CHECK) {
               const real rvn = shn - yn;
-              res = fmax(res, fmax(fabs(rfx - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
-              gap_r = fmax(gap_r, fabs(rfx - rvn) / rho);
-              stp_r = fmax(stp_r, fabs(rvn - rv) / rho);
+              const real irho = 1.0 / rho;                 // one division per row instead of four
+              res = fmax(res, fmax(fabs(rfx - rvn) * irho, fabs(rvn - rv) * iw100));
+              gap_r = fmax(gap_r, fabs(rfx - rvn) * irho);
+              stp_r = fmax(stp_r, fabs(rvn - rv) * irho);
               const int cj = (shn > rhi + lam) ? ROW_UP_LIN : (shn > rhi) ? ROW_UP_KINK : (shn >= rlo) ? ROW_INACTIVE
                              : (shn >= rlo - lam) ? ROW_LO_KINK : ROW_LO_LIN;
               ncode |= row_bits(cj, j);
@@ -1148,9 +1151,10 @@ struct Solver {
           const real shn = PP.alpha * ru + (1.0 - PP.alpha) * rv + (sh - rv);
           const real rvn = bmpc_clamp(shn, rho * PP.ulo[a], rho * PP.uhi[a]);
           if (CHECK) {
-            res = fmax(res, fmax(fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w)));
-            gap_u = fmax(gap_u, fabs(ru - rvn) / rho);
-            stp_u = fmax(stp_u, fabs(rvn - rv) / rho);
+            const real irho = 1.0 / rho;
+            res = fmax(res, fmax(fabs(ru - rvn) * irho, fabs(rvn - rv) * iw100));
+            gap_u = fmax(gap_u, fabs(ru - rvn) * irho);
+            stp_u = fmax(stp_u, fabs(rvn - rv) * irho);
             ncode |= in_bits((shn > rho * PP.uhi[a]) ? IN_AT_HI : (shn < rho * PP.ulo[a]) ? IN_AT_LO : IN_FREE, a);
             if (fabs(ru - rvn) / rho > 5e-2 || fabs(rvn - rv) / (100.0 * w) > 5e-2) BMPC_TRACE("      [in] k %d a %d rho %.3e prim %.3e dual %.3e u %.4f w %.3e\n", k, a, rho, fabs(ru - rvn) / rho, fabs(rvn - rv) / (100.0 * w), u[a], w);
           }
@@ -1597,7 +1601,7 @@ struct Solver {
           row_bounds(kp, j, lo, hi);
           const real fx = row_value(kp, j, x);
           const real y = F(F_Y + j, kp);
-          const real stiff = F(F_RHO + j, kp) / PP.theta;
+          const real stiff = F(F_RHO + j, kp) * PP.inv_theta;
           if (restricted) {
             if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) {
               const real m2 = 2.0 * big_row(kp, j, w) * fabs(fx - (cj == ROW_UP_KINK ? hi : lo));
@@ -1640,7 +1644,7 @@ struct Solver {
         const real u = F(F_UQ + a, kp);
         const real y = F(F_Y + NR + a, kp);
         const real utol = 1e-9 * w;
-        const real stiff = F(F_RHO + NR + a, kp) / PP.theta_u;
+        const real stiff = F(F_RHO + NR + a, kp) * PP.inv_theta_u;
         if (restricted) {
         } else if (ca == IN_FREE) {
           if (u > PP.uhi[a] + tol) { na = IN_AT_HI; score = stiff * (u - PP.uhi[a]); }
