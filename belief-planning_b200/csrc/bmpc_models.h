@@ -21,14 +21,14 @@ struct SoftMinAcc {
     num += e * v;
     den += e;
   }
-  BMPC_D real value() const { return num / den; }
+  BMPC_D real value() const { return bmpc_div(num, den); }
 };
 
 // (dx e^dx + dy e^dy)/(e^dx + e^dy) and partials; veh_col core (highway_branch_dyn.py:231-234)
 BMPC_D void soft_box(real dx, real dy, real& h, real& gx, real& gy) {
   const real mx = fmax(dx, dy);
   const real ex = bmpc_exp(dx - mx), ey = bmpc_exp(dy - mx);
-  const real wx = ex / (ex + ey), wy = 1.0 - wx;
+  const real wx = bmpc_div(ex, ex + ey), wy = 1.0 - wx;
   h = wx * dx + wy * dy;
   gx = wx * (1.0 + dx - h);
   gy = wy * (1.0 + dy - h);
@@ -69,7 +69,7 @@ struct HighwayModel {
         const real a = -7.0, b = -x[2];
         const real mx = fmax(a, b);
         const real ea = bmpc_exp(5.0 * (a - mx)), eb = bmpc_exp(5.0 * (b - mx));
-        u[0] = (ea * a + eb * b) / (ea + eb);
+        u[0] = bmpc_div(ea * a + eb * b, ea + eb);
         u[1] = -P.Kpsi * x[3];
         break;
       }
@@ -184,7 +184,7 @@ struct HighwayModel {
       const real a = z[1] - P.lane_lo, b = P.lane_hi - z[1];
       const real mn = fmin(a, b);
       const real ea = bmpc_exp(-5.0 * (a - mn)), eb = bmpc_exp(-5.0 * (b - mn));
-      acc.add((ea * a + eb * b) / (ea + eb));
+      acc.add(bmpc_div(ea * a + eb * b, ea + eb));
     }
     for (int i = 0; i < 4; ++i) zlast[i] = z[i];
     return acc.value();
@@ -192,7 +192,7 @@ struct HighwayModel {
 
   // un-normalised branch weight bmpc_exp(s1 * softsat(hi, 1)) (:355-359); softsat(h,1) == sigmoid(h)
   BMPC_D static real branch_weight(const KParams& P, real hi, real /*himax*/) {
-    return bmpc_exp(P.s1 / (1.0 + bmpc_exp(-hi)));
+    return bmpc_exp(bmpc_div(P.s1, 1.0 + bmpc_exp(-hi)));
   }
   static constexpr bool kWeightNeedsMax = false;
 };

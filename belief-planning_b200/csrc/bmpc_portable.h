@@ -75,6 +75,15 @@ BMPC_D real bmpc_ratio(real num, real den) {
   return num / den;
 #endif
 }
+// a / b through the hardware reciprocal (one ulp from the IEEE quotient): the full double division is a long sequence with
+// a slow path, and the expansion phase does ~200 of them per solve
+BMPC_D real bmpc_div(real a, real b) {
+#if defined(__CUDA_ARCH__)
+  return a * __drcp_rn(b);
+#else
+  return a / b;
+#endif
+}
 BMPC_D real bmpc_min(real a, real b) { return fmin(a, b); }
 BMPC_D real bmpc_max(real a, real b) { return fmax(a, b); }
 BMPC_D real bmpc_clamp(real v, real lo, real hi) { return fmin(fmax(v, lo), hi); }

@@ -335,7 +335,7 @@ struct Solver {
         real pb = -1.0;
 #pragma unroll 1
         for (int j = 0; j < m; ++j) {
-          const real p = M::branch_weight(PP, EXp()[NS * (fc + j)], himax) / sum;
+          const real p = bmpc_div(M::branch_weight(PP, EXp()[NS * (fc + j)], himax), sum);
           Wbp()[fc + j] = Wbp()[b] * p;
           if (PP.out.branch_p) PP.out.branch_p[((size_t)prob * PP.nbranch + b) * m + j] = p;
           if (p > pb) { pb = p; best = j; }
@@ -530,7 +530,7 @@ struct Solver {
   BMPC_D static void invert_spd(const real* S, real* Si) {
     if constexpr (NU == 2) {
       const real det = S[0] * S[3] - S[1] * S[2];
-      const real id = 1.0 / det;
+      const real id = bmpc_div(1.0, det);
       Si[0] = S[3] * id;
       Si[1] = -S[1] * id;
       Si[2] = -S[2] * id;
@@ -540,7 +540,7 @@ struct Solver {
       const real a = S[0], b = S[1], c = S[2], d = S[4], e = S[5], f = S[8];
       const real A = d * f - e * e, B = c * e - b * f, C = b * e - c * d;
       const real det = a * A + b * B + c * C;
-      const real id = 1.0 / det;
+      const real id = bmpc_div(1.0, det);
       Si[0] = A * id;
       Si[1] = B * id;
       Si[2] = C * id;
@@ -1102,7 +1102,7 @@ struct Solver {
       const real w = Wbp()[b];
       const real lam = PP.lam_lin * w;
       code_t ncode = 0;   // CHECK: the active set the ADMM state currently implies (compared with the previous check)
-      const real iw100 = CHECK ? 0.01 / w : 0.0;
+      const real iw100 = CHECK ? bmpc_div(0.01, w) : 0.0;
       (void)iw100;
       real x[NX], u[NU], qx[NX], qu[NU];
 #pragma unroll
@@ -1125,7 +1125,7 @@ struct Solver {
             const real yn = row_dual(shn, rlo, rhi, lam);
             if (CHECK) {
               const real rvn = shn - yn;
-              const real irho = 1.0 / rho;                 // one division per row instead of four
+              const real irho = bmpc_div(1.0, rho);        // one reciprocal per row instead of four divisions
               res = fmax(res, fmax(fabs(rfx - rvn) * irho, fabs(rvn - rv) * iw100));
               gap_r = fmax(gap_r, fabs(rfx - rvn) * irho);
               stp_r = fmax(stp_r, fabs(rvn - rv) * irho);
@@ -1151,7 +1151,7 @@ struct Solver {
           const real shn = PP.alpha * ru + (1.0 - PP.alpha) * rv + (sh - rv);
           const real rvn = bmpc_clamp(shn, rho * PP.ulo[a], rho * PP.uhi[a]);
           if (CHECK) {
-            const real irho = 1.0 / rho;
+            const real irho = bmpc_div(1.0, rho);
             res = fmax(res, fmax(fabs(ru - rvn) * irho, fabs(rvn - rv) * iw100));
             gap_u = fmax(gap_u, fabs(ru - rvn) * irho);
             stp_u = fmax(stp_u, fabs(rvn - rv) * irho);
