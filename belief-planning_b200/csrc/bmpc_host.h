@@ -127,6 +127,8 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
   P.theta = c.theta > 0.0 ? c.theta : 1.0;
   P.theta_u = c.theta_u > 0.0 ? c.theta_u : 1.0;
+  P.inv_N = nextafterf(1.0f / (float)P.N, 2.0f);
+  P.inv_m = nextafterf(1.0f / (float)P.m, 2.0f);
   P.inv_theta = 1.0 / P.theta;
   P.inv_theta_u = 1.0 / P.theta_u;
   P.eps_abs = c.eps_abs > 0.0 ? c.eps_abs : 1.0e-6;

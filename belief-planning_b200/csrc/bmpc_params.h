@@ -32,6 +32,7 @@ struct KParams {
   // ---- solver ----
   int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes, check_every, polish_stable, polish_force;
   real alpha, theta, theta_u, eps_abs, polish_big, polish_mult, rho_u_feedback;
+  float inv_N, inv_m;           // reciprocals, rounded up, for exact small-integer division (bmpc_idiv)
   real inv_theta, inv_theta_u;  // reciprocals (the polish passes scale by them per row)
   int cycles_mode;              // 0: `cycles` = whole solve; k > 0: time spent in phase k (see Solver::prof_begin)
   int ipm_after, ipm_max_iter;  // interior-point fallback: after this many failed polish attempts (0 = never), iteration cap
@@ -61,6 +62,10 @@ struct KParams {
   size_t ipm_reals;
 };
 
+// floor(q / d) for 0 <= q < 2^16 through a single-precision multiply with the rounded-up reciprocal `inv` of d (exact:
+// tests/test_host_logic.py checks every q < 65536 for every d the ABI admits); the integer division instruction sequence is
+// ~25 instructions and sat in every node-parallel loop
+BMPC_HD inline int bmpc_idiv(int q, float inv) { return (int)((float)q * inv); }
 BMPC_HD inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }
 BMPC_HD inline int bmpc_ndx(const KParams& P, int b) {
   const int ol = P.off[P.NB];   // first leaf branch
@@ -71,5 +76,5 @@ BMPC_HD inline int bmpc_depth(const KParams& P, int b) {
   while (b >= P.off[d + 1]) ++d;
   return d;
 }
-BMPC_HD inline int bmpc_parent(const KParams& P, int b, int d) { return P.off[d - 1] + (b - P.off[d]) / P.m; }
+BMPC_HD inline int bmpc_parent(const KParams& P, int b, int d) { return P.off[d - 1] + bmpc_idiv(b - P.off[d], P.inv_m); }
 BMPC_HD inline int bmpc_first_child(const KParams& P, int b, int d) { return P.off[d + 1] + (b - P.off[d]) * P.m; }

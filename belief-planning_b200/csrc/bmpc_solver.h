@@ -188,7 +188,7 @@ struct Solver {
 
   BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(PP, b) + t + b; }
   BMPC_D void node_of(int k, int& b, int& t) const {
-    if (k == 0) { b = 0; t = 0; } else { b = 1 + (k - 1) / PP.N; t = (k - 1) % PP.N; }
+    if (k == 0) { b = 0; t = 0; } else { const int q = bmpc_idiv(k - 1, PP.inv_N); b = 1 + q; t = (k - 1) - q * PP.N; }
   }
   BMPC_D const real* pol_par(int i) const { return polpar ? polpar + 4 * i : PP.pol_par[i]; }
 
@@ -300,8 +300,9 @@ struct Solver {
       // (a) obstacle rollouts under each policy + safety value of each (zpred_eval, branch_eval); lanes = (branch, policy)
       const int cnt = PP.pw[d] * m;
       for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_LANES) {
-        const int b = PP.off[d] + idx / m;
-        const int i = idx % m;
+        const int bq = bmpc_idiv(idx, PP.inv_m);
+        const int b = PP.off[d] + bq;
+        const int i = idx - bq * m;
         const int c = bmpc_first_child(PP, b, d) + i;
         real zl[NXP];
         const int kc = bmpc_ndu(PP, c);
@@ -452,8 +453,9 @@ struct Solver {
     for (int d = 0; d < PP.zNB; ++d) {
       const int cnt = PP.zpw[d] * m;
       for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_LANES) {
-        const int b = PP.zoff[d] + idx / m;
-        const int i = idx % m;
+        const int bq = bmpc_idiv(idx, nextafterf(1.0f / (float)m, 2.0f));   // obstacle tree of the robust chain: m = zm here
+        const int b = PP.zoff[d] + bq;
+        const int i = idx - bq * m;
         const int c = PP.zoff[d + 1] + (b - PP.zoff[d]) * m + i;
         const int j = c - PP.zoff[d + 1];                 // position inside the slot (BFS order)
         real zl[NXP];

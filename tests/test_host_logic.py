@@ -57,3 +57,13 @@ def test_scenario_batch_is_seeded_and_in_range():
     assert ((z0[:, 0] >= -15) & (z0[:, 0] <= 25)).all()
     lanes = (pp[:, 2, 1] - 1.8) / 3.6
     assert np.allclose(lanes, np.round(lanes)) and lanes.min() >= 0 and lanes.max() <= 3
+
+
+def test_reciprocal_integer_division_is_exact():
+    """bmpc_idiv (csrc/bmpc_params.h): floor(q / d) as int(float32(q) * nextafter(float32(1/d), 2)) for every q < 65536 and
+    every divisor the tree numbering can meet (N, m <= 64)."""
+    q = np.arange(65536)
+    for d in range(1, 65):
+        inv = np.nextafter(np.float32(1.0) / np.float32(d), np.float32(2.0))
+        got = (q.astype(np.float32) * inv).astype(np.int64)
+        assert np.array_equal(got, q // d), d
