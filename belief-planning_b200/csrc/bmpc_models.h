@@ -11,13 +11,15 @@ struct SoftMinAcc {
   real vmin, num, den, gamma;
   BMPC_D SoftMinAcc(real g) : vmin(1e300), num(0), den(0), gamma(g) {}
   BMPC_D void add(real v) {
+    real e = 1.0;   // exp(0) when v is the new minimum
     if (v < vmin) {
       const real sc = (den > 0) ? bmpc_exp(-gamma * (vmin - v)) : 0.0;
       num *= sc;
       den *= sc;
       vmin = v;
+    } else {
+      e = bmpc_exp(-gamma * (v - vmin));
     }
-    const real e = bmpc_exp(-gamma * (v - vmin));
     num += e * v;
     den += e;
   }
@@ -26,8 +28,9 @@ struct SoftMinAcc {
 
 // (dx e^dx + dy e^dy)/(e^dx + e^dy) and partials; veh_col core (highway_branch_dyn.py:231-234)
 BMPC_D void soft_box(real dx, real dy, real& h, real& gx, real& gy) {
-  const real mx = fmax(dx, dy);
-  const real ex = bmpc_exp(dx - mx), ey = bmpc_exp(dy - mx);
+  // one of the two shifted exponentials is exp(0) = 1: a single call
+  const real e = bmpc_exp(-fabs(dx - dy));
+  const real ex = (dx >= dy) ? 1.0 : e, ey = (dx >= dy) ? e : 1.0;
   const real wx = bmpc_div(ex, ex + ey), wy = 1.0 - wx;
   h = wx * dx + wy * dy;
   gx = wx * (1.0 + dx - h);
@@ -67,8 +70,8 @@ struct HighwayModel {
       case BMPC_POLICY_BRAKE: {
         // softmax([-7, -v], 5) = (a e^{5a} + b e^{5b})/(e^{5a} + e^{5b})
         const real a = -7.0, b = -x[2];
-        const real mx = fmax(a, b);
-        const real ea = bmpc_exp(5.0 * (a - mx)), eb = bmpc_exp(5.0 * (b - mx));
+        const real e = bmpc_exp(-5.0 * fabs(a - b));
+        const real ea = (a >= b) ? 1.0 : e, eb = (a >= b) ? e : 1.0;
         u[0] = bmpc_div(ea * a + eb * b, ea + eb);
         u[1] = -P.Kpsi * x[3];
         break;
@@ -182,8 +185,8 @@ struct HighwayModel {
       acc.add(h);
       // lane_bdry_h (:195-206): softmin([y - lb, ub - y], 5)
       const real a = z[1] - P.lane_lo, b = P.lane_hi - z[1];
-      const real mn = fmin(a, b);
-      const real ea = bmpc_exp(-5.0 * (a - mn)), eb = bmpc_exp(-5.0 * (b - mn));
+      const real e = bmpc_exp(-5.0 * fabs(a - b));
+      const real ea = (a <= b) ? 1.0 : e, eb = (a <= b) ? e : 1.0;
       acc.add(bmpc_div(ea * a + eb * b, ea + eb));
     }
     for (int i = 0; i < 4; ++i) zlast[i] = z[i];
