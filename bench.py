@@ -314,7 +314,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": hbm_achieved / peaks["hbm_gbs"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 16384 episodes from the ncu --set full
-                         # capture profiles/r01_solve_kernel_v11_ncu_raw.csv (110.2 MB + 15.5 MB); not re-measured per run
+                         # capture profiles/r01_solve_kernel_v12_ncu_raw.csv (110.0 MB + 14.2 MB); not re-measured per run
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH_16384 if B == 16384 else None, "peak_source": peak_src,
                          "note": "latency/FP64-pipe bound, not HBM bound (arithmetic intensity >> ridge): see fp64",
                          "algorithmic_bytes_per_solve": algorithmic_bytes_per_solve(),
@@ -333,7 +333,7 @@ def run_gpu(args):
 
 WORKLOAD = ("highway Branch MPC (BASELINE configs[2]): m=3 policies [maintain, brake, lane-change], NB=2, N=8 -> 13 branches / "
             "106 state nodes / 97 input nodes; closed-loop warm solves (updatetree path), 16384 episodes per GPU")
-NCU_DRAM_BYTES_PER_LAUNCH_16384 = 110210048 + 15525376
+NCU_DRAM_BYTES_PER_LAUNCH_16384 = 109988864 + 14200832
 
 
 def main():
