@@ -357,6 +357,6 @@ def run_highway_env(name, steps, x_ego=None, x_obs=None, N_lane=4):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
 
 
-if __name__ == "__main__" and ("env" in sys.argv[1:]):
+if __name__ == "__main__" and ("env" in sys.argv[1:] or len(sys.argv) == 1):
     run_highway_env("highway_env_default", steps=30)
     run_highway_env("highway_env_overtake", steps=24, x_ego=[2.0, 5.5, 24.0, 0.0], x_obs=[14.0, 5.4, 17.0, 0.0])
