@@ -131,22 +131,31 @@ class _BatchedController:
         return self._solver
 
     def _absorb(self, r, single):
-        """Result arrays of a batched solve -> the attributes the reference leaves behind (MPC_branch.py:1204-1229)."""
-        ok = r["status"] <= abi.STATUS_MAXITER
-        self.status = r["status"][0] if single else r["status"]
+        """Result arrays of a batched solve -> the attributes the reference leaves behind (MPC_branch.py:1204-1229).
+        Only solved problems are adopted (feasible = 1 for the solver's 'solved' alone, :1269-1272); an episode whose
+        solve failed keeps its previous plan (:1224), per episode in a batch."""
+        ok = r["status"] <= abi.STATUS_CONVERGED
+        self.status = r["status"][0] if single else r["status"].copy()
         self.feasible = int(ok[0]) if single else ok.astype(int)
-        self.iterations = r["iters"][0] if single else r["iters"]
-        pick = (lambda a: a[0]) if single else (lambda a: a)
-        if single and not ok[0] and self.uPred is not None:
-            pass                                   # the reference keeps its previous plan (MPC_branch.py:1224)
+        self.iterations = r["iters"][0] if single else r["iters"].copy()
+        B = len(ok)
+        fresh = self.uPred is None or (np.ndim(self.uPred) == 3) == single or (not single and self.uPred.shape[0] != B)
+        names = ("xPred", "uPred", "xLin", "zPred", "branch_w", "branch_p", "objective")
+        if fresh:
+            if not ok.all() and self.uPred is None and single:
+                raise RuntimeError("the first solve failed (status %d): there is no previous plan to keep" % r["status"][0])
+            self._res = {k: np.array(r[k]) for k in names}          # copies out of the library's pinned result block
         else:
-            self.xPred, self.uPred = pick(r["xPred"]), pick(r["uPred"])
-            self.xLin = self.xPred
-            self.uLin = np.concatenate([r["uPred"], r["uPred"][:, -1:]], axis=1)
-            self.uLin = pick(self.uLin)
-            self._xbar, self.zPred = pick(r["xLin"]), pick(r["zPred"])
-            self.branch_w, self.branch_p = pick(r["branch_w"]), pick(r["branch_p"])
-            self.objective = pick(r["objective"])
+            for k in names:
+                self._res[k][ok] = r[k][ok]
+        res = self._res
+        pick = (lambda a: a[0]) if single else (lambda a: a)
+        self.xPred, self.uPred = pick(res["xPred"]), pick(res["uPred"])
+        self.xLin = self.xPred
+        self.uLin = pick(np.concatenate([res["uPred"], res["uPred"][:, -1:]], axis=1))
+        self._xbar, self.zPred = pick(res["xLin"]), pick(res["zPred"])
+        self.branch_w, self.branch_p = pick(res["branch_w"]), pick(res["branch_p"])
+        self.objective = pick(res["objective"])
         self.OldInput = self.uPred[0, :] if single else self.uPred[:, 0, :]
         self.timeStep += 1
         self.BT = True                              # "a tree exists": later solves are updatetree solves
@@ -166,7 +175,7 @@ class _BatchedController:
         solver = self._ensure_solver(B)
         pp = np.broadcast_to(model.policy_params(), (B, self.m, 4))        # update_backup() -> new per-episode parameters
         t0 = datetime.datetime.now()
-        r = solver.solve_host(X, Z, R, pp)
+        r = solver.solve_host_views(X, Z, R, pp)
         self.solverTime = datetime.datetime.now() - t0
         return self._absorb(r, single)
 

@@ -83,8 +83,10 @@ SYMBOLS = [
                              C.POINTER(Outputs), C.c_void_p]),
     ("bmpc_solve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.POINTER(Outputs)]),
-    ("bmpc_get_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
-    ("bmpc_set_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    ("bmpc_solve_host_views", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.POINTER(Outputs), C.POINTER(Outputs)]),
+    ("bmpc_get_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    ("bmpc_set_state", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     ("bmpc_eval_model", C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 8 + [C.c_void_p]),
     ("bmpc_hmm_backup_rollout", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _pi, C.c_int32, _dbl, _dbl, C.c_void_p,
                                           C.c_int32, C.c_void_p]),

@@ -81,7 +81,7 @@ class BatchedBranchMPC:
             bufs = {}
             for k in names:
                 dt = torch.int64 if k == "cycles" else (torch.int32 if k in _INT_OUTPUTS else torch.float64)
-                bufs[k] = torch.empty((count,) + _OUT_SHAPES[k](self), dtype=dt, device=dev)
+                bufs[k] = torch.zeros((count,) + _OUT_SHAPES[k](self), dtype=dt, device=dev)
             self._dev_out = {key: bufs}          # keep only the latest shape
         return self._dev_out[key]
 
@@ -100,8 +100,6 @@ class BatchedBranchMPC:
                 raise ValueError("policy_params must be a contiguous CUDA float64 tensor of (count, m, 4)")
             pp = policy_params.data_ptr()
         bufs = self.device_outputs(count, outputs)
-        if "branch_p" in bufs:
-            bufs["branch_p"].fill_(float("nan"))
         out = abi.Outputs(**{k: bufs[k].data_ptr() for k in bufs})
         if stream is None:
             stream = torch.cuda.current_stream(x0.device).cuda_stream
@@ -140,13 +138,43 @@ class BatchedBranchMPC:
                     "bmpc_solve_host")
         return res
 
+    def solve_host_views(self, x0, z0, xref, policy_params=None, outputs=tuple(abi.OUTPUT_NAMES)):
+        """As solve_host, without the copy out of the library's pinned result block: the returned arrays are views that
+        stay valid until this handle's next host solve (the drop-in controllers copy what they keep)."""
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=np.float64)
+        xref = np.ascontiguousarray(np.atleast_2d(xref), dtype=np.float64)
+        count = x0.shape[0]
+        if x0.shape != (count, self.cfg.n) or z0.shape != x0.shape or xref.shape != x0.shape:
+            raise ValueError("x0, z0, xref must have shape (count, n)")
+        pp = None
+        if policy_params is not None:
+            pp = np.ascontiguousarray(policy_params, dtype=np.float64).reshape(count, self.cfg.m, 4)
+        want = abi.Outputs(**{k: 1 for k in outputs})
+        views = abi.Outputs()
+        self._check(self.lib.bmpc_solve_host_views(self.h, x0.ctypes.data, z0.ctypes.data, xref.ctypes.data,
+                                                   None if pp is None else pp.ctypes.data, count, C.byref(want),
+                                                   C.byref(views)), "bmpc_solve_host_views")
+        res = {}
+        for k in outputs:
+            dt = np.int64 if k == "cycles" else (np.int32 if k in _INT_OUTPUTS else np.float64)
+            shape = (count,) + _OUT_SHAPES[k](self)
+            nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+            buf = (C.c_char * nbytes).from_address(getattr(views, k))
+            res[k] = np.frombuffer(buf, dtype=dt).reshape(shape)
+        return res
+
     # -- persistent state ---------------------------------------------------------------------------------------
     def get_state(self, count=None):
         count = self.capacity if count is None else count
         st = {"uLin": np.empty((count, self.ulin_rows, self.cfg.d)), "pbest": np.empty((count, self.nbranch), np.int32),
               "old_input": np.empty((count, self.cfg.d)), "started": np.empty(count, np.int32)}
+        xprev = None
+        if self.cfg.controller == abi.CTRL_ROBUST:
+            st["xprev"] = np.empty((count, self.totalx, self.cfg.n))
+            xprev = st["xprev"].ctypes.data
         self._check(self.lib.bmpc_get_state(self.h, st["uLin"].ctypes.data, st["pbest"].ctypes.data,
-                                            st["old_input"].ctypes.data, st["started"].ctypes.data, count, 1),
+                                            st["old_input"].ctypes.data, st["started"].ctypes.data, xprev, count, 1),
                     "bmpc_get_state")
         return st
 
@@ -154,7 +182,9 @@ class BatchedBranchMPC:
         count = st["uLin"].shape[0]
         arrs = [np.ascontiguousarray(st["uLin"], np.float64), np.ascontiguousarray(st["pbest"], np.int32),
                 np.ascontiguousarray(st["old_input"], np.float64), np.ascontiguousarray(st["started"], np.int32)]
-        self._check(self.lib.bmpc_set_state(self.h, *[a.ctypes.data for a in arrs], count, 1), "bmpc_set_state")
+        xprev = np.ascontiguousarray(st["xprev"], np.float64) if "xprev" in st else None
+        self._check(self.lib.bmpc_set_state(self.h, *[a.ctypes.data for a in arrs],
+                                            None if xprev is None else xprev.ctypes.data, count, 1), "bmpc_set_state")
 
     # -- model functions (parity of rows M1-M5) -------------------------------------------------------------------
     def eval_model(self, x, z, u, policy_params=None):

@@ -2,6 +2,7 @@
 // ABI; every failure is an integer code plus a message in bmpc_last_error().
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <new>
@@ -22,10 +23,10 @@
 // MODE = BMPC_SLAB_SHARED (whole slab in shared memory), BMPC_SLAB_SPLIT (iterate fields in shared memory, factor fields
 // in this warp's global region, which stays L2-resident), BMPC_SLAB_GLOBAL (everything in the global region).
 template <class M, int NR, int MODE, int NC = 1>
-__global__ void __launch_bounds__(32) bmpc_solve_kernel() {
+__global__ void __launch_bounds__(BMPC_LANES, 4) bmpc_solve_kernel() {
   const KParams& P = bmpc_cP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x;
   constexpr bool SPLIT = (MODE == BMPC_SLAB_SPLIT);
   (void)smem_raw;
   real* slab;
@@ -40,7 +41,14 @@ __global__ void __launch_bounds__(32) bmpc_solve_kernel() {
   for (;;) {
     int idx = 0;
     if (lane == 0) idx = atomicAdd(P.counter, 1);
+#if BMPC_TEAM_WARPS > 1
+    __shared__ int next_problem;
+    if (lane == 0) next_problem = idx;
+    __syncthreads();
+    idx = next_problem;   // rewritten only after the barriers inside solve()
+#else
     idx = __shfl_sync(BMPC_FULL_MASK, idx, 0);
+#endif
     if (idx >= P.count) break;
     S.solve(P.order ? P.order[idx] : idx);
   }
@@ -69,6 +77,28 @@ __global__ void __launch_bounds__(1024) bmpc_order_kernel(const int* __restrict_
     const int c = cost[i];
     const int bkt = c <= 0 ? 0 : min(63, 2 * (31 - __clz(c)) + ((c >> max(0, 30 - __clz(c))) & 1));
     order[atomicAdd(&start[bkt], 1)] = i;
+  }
+}
+
+// Forget the persistent state of a list of episode slots: one block per listed episode (bmpc_reset with ids).
+struct ResetArgs {
+  real* uLin; int* pbest; real* oldin; real* xprev; int* started; int* cache_state; int* cost;
+  int ulin_reals, nbranch, d, xprev_reals;
+};
+__global__ void bmpc_reset_kernel(const ResetArgs a, const long long* __restrict__ ids, int count) {
+  const int i = blockIdx.x;
+  if (i >= count) return;
+  const size_t e = (size_t)ids[i];
+  for (int q = threadIdx.x; q < a.ulin_reals; q += blockDim.x) a.uLin[e * a.ulin_reals + q] = 0.0;
+  for (int q = threadIdx.x; q < a.nbranch; q += blockDim.x) a.pbest[e * a.nbranch + q] = 0;
+  for (int q = threadIdx.x; q < a.d; q += blockDim.x) a.oldin[e * a.d + q] = 0.0;
+  if (a.xprev)
+    for (int q = threadIdx.x; q < a.xprev_reals; q += blockDim.x) a.xprev[e * a.xprev_reals + q] = 0.0;
+  if (threadIdx.x == 0) {
+    a.started[e] = 0;
+    a.cache_state[2 * e] = -1;
+    a.cache_state[2 * e + 1] = -1;
+    a.cost[e] = 0;
   }
 }
 
@@ -195,10 +225,15 @@ struct bmpc_handle {
   KParams* pstage = nullptr;              // pinned staging ring of parameter blocks (source of the constant-memory upload)
   cudaEvent_t pstage_evt[BMPC_PSTAGE] = {};
   unsigned pstage_next = 0;
-  // staging for bmpc_solve_host
+  // staging for bmpc_solve_host: device and pinned host mirrors, one DMA each way per call
   real* stage_in = nullptr;   // x0 | z0 | xref | polpar
+  real* stage_in_host = nullptr;
   void* stage_out = nullptr;
+  void* stage_out_host = nullptr;
   size_t stage_out_bytes = 0;
+  long long* reset_ids = nullptr;   // device copy of the ids of the last bmpc_reset
+  size_t reset_ids_cap = 0;
+  cudaStream_t last_stream = nullptr;   // stream of the last solve (persistent-state accessors order themselves behind it)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   int64_t launches = 0;
@@ -228,7 +263,7 @@ static int try_mode(bmpc_handle* h, int max_optin, int* per_sm) {
   if (smem > (size_t)max_optin) return BMPC_OK;   // does not fit: caller falls through to the next mode
   if (smem > 0)
     BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, MODE, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE, NC>, 32, smem));
+  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE, NC>, BMPC_LANES, smem));
   return BMPC_OK;
 }
 
@@ -278,11 +313,11 @@ static int configure_instance(bmpc_handle* h) {
 template <class M, int NR, int NC = 1>
 static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStream_t s) {
   if (h->mode == BMPC_SLAB_SHARED) {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, 32, h->slab_bytes, s>>>();
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, BMPC_LANES, h->slab_bytes, s>>>();
   } else if (h->mode == BMPC_SLAB_SPLIT) {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, 32, h->slab_bytes, s>>>();
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, BMPC_LANES, h->slab_bytes, s>>>();
   } else {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, 32, 0, s>>>();
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, BMPC_LANES, 0, s>>>();
   }
   BMPC_CK(h, cudaGetLastError());
   return BMPC_OK;
@@ -322,6 +357,9 @@ static void free_handle(bmpc_handle* h) {
   for (int i = 0; i < BMPC_PSTAGE; ++i) if (h->pstage_evt[i]) cudaEventDestroy(h->pstage_evt[i]);
   cudaFree(h->stage_in);
   cudaFree(h->stage_out);
+  cudaFree(h->reset_ids);
+  if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
+  if (h->stage_out_host) cudaFreeHost(h->stage_out_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -386,30 +424,45 @@ int bmpc_destroy(bmpc_handle* h) {
   return BMPC_OK;
 }
 
+// The accessors of the persistent state (reset / get_state / set_state) are ordered behind the handle's last solve:
+// they run on that solve's stream (the legacy default stream before the first solve).
 int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count) {
   if (!h) return BMPC_E_INVALID;
   BMPC_CK(h, cudaSetDevice(h->device));
   const KParams& P = h->P;
   const size_t cap = (size_t)h->cfg.batch_capacity;
   const size_t ulin_row = (size_t)(P.totalu + 1) * h->cfg.d * sizeof(real);
+  const size_t xprev_row = (size_t)P.pub_totalx * h->cfg.n * sizeof(real);
+  cudaStream_t s = h->last_stream;
   if (!episode_ids) {
-    BMPC_CK(h, cudaMemset(h->uLin, 0, cap * ulin_row));
-    BMPC_CK(h, cudaMemset(h->pbest, 0, cap * P.nbranch * sizeof(int)));
-    BMPC_CK(h, cudaMemset(h->oldin, 0, cap * h->cfg.d * sizeof(real)));
-    BMPC_CK(h, cudaMemset(h->started, 0, cap * sizeof(int)));
-    BMPC_CK(h, cudaMemset(h->cache_state, 0xff, cap * 2 * sizeof(int)));
-    BMPC_CK(h, cudaMemset(h->cost, 0, cap * sizeof(int)));
+    BMPC_CK(h, cudaMemsetAsync(h->uLin, 0, cap * ulin_row, s));
+    BMPC_CK(h, cudaMemsetAsync(h->pbest, 0, cap * P.nbranch * sizeof(int), s));
+    BMPC_CK(h, cudaMemsetAsync(h->oldin, 0, cap * h->cfg.d * sizeof(real), s));
+    BMPC_CK(h, cudaMemsetAsync(h->started, 0, cap * sizeof(int), s));
+    BMPC_CK(h, cudaMemsetAsync(h->cache_state, 0xff, cap * 2 * sizeof(int), s));
+    BMPC_CK(h, cudaMemsetAsync(h->cost, 0, cap * sizeof(int), s));
+    if (h->xprev) BMPC_CK(h, cudaMemsetAsync(h->xprev, 0, cap * xprev_row, s));
     return BMPC_OK;
   }
-  for (int64_t i = 0; i < count; ++i) {
-    const int64_t e = episode_ids[i];
-    if (e < 0 || (size_t)e >= cap) { h->err = "episode id out of range"; return BMPC_E_INVALID; }
-    BMPC_CK(h, cudaMemset((char*)h->uLin + e * ulin_row, 0, ulin_row));
-    BMPC_CK(h, cudaMemset(h->pbest + e * P.nbranch, 0, P.nbranch * sizeof(int)));
-    BMPC_CK(h, cudaMemset(h->oldin + e * h->cfg.d, 0, h->cfg.d * sizeof(real)));
-    BMPC_CK(h, cudaMemset(h->started + e, 0, sizeof(int)));
-    BMPC_CK(h, cudaMemset(h->cache_state + 2 * e, 0xff, 2 * sizeof(int)));
+  if (count <= 0) return BMPC_OK;
+  for (int64_t i = 0; i < count; ++i)
+    if (episode_ids[i] < 0 || (size_t)episode_ids[i] >= cap) { h->err = "episode id out of range"; return BMPC_E_INVALID; }
+  if ((size_t)count > h->reset_ids_cap) {
+    BMPC_CK(h, cudaStreamSynchronize(s));
+    cudaFree(h->reset_ids);
+    h->reset_ids = nullptr;
+    h->reset_ids_cap = 0;
+    const size_t want = (size_t)count > cap ? (size_t)count : cap;
+    BMPC_CK(h, cudaMalloc(&h->reset_ids, want * sizeof(long long)));
+    h->reset_ids_cap = want;
   }
+  // pageable source: the copy has returned from the host buffer when the call returns
+  BMPC_CK(h, cudaMemcpyAsync(h->reset_ids, episode_ids, count * sizeof(long long), cudaMemcpyHostToDevice, s));
+  ResetArgs a{h->uLin, h->pbest, h->oldin, h->xprev, h->started, h->cache_state, h->cost,
+              (int)(ulin_row / sizeof(real)), P.nbranch, h->cfg.d, (int)(xprev_row / sizeof(real))};
+  bmpc_reset_kernel<<<(int)count, 64, 0, s>>>(a, h->reset_ids, (int)count);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
   return BMPC_OK;
 }
 
@@ -467,6 +520,9 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.gws = h->gws;
   P.ipm = h->ipm_ws;
   BMPC_CK(h, cudaMemsetAsync(h->counter, 0, sizeof(int), s));
+  // rows of branch_p that belong to leaf branches carry no probabilities: NaN pattern, on the solve's own stream
+  if (out->branch_p) BMPC_CK(h, cudaMemsetAsync(out->branch_p, 0xff, (size_t)count * h->P.nbranch * h->cfg.m * sizeof(real), s));
+  h->last_stream = s;
   const int grid = (int)(count < h->grid ? count : h->grid);
   // the parameter block travels through constant memory: one symbol per device, so launches from other streams or handles
   // are ordered behind the previous solve kernel of this device before the symbol is rewritten
@@ -492,94 +548,162 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   return BMPC_OK;
 }
 
-int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
-                    const double* policy_params, int64_t count, const bmpc_outputs* out) {
+// Host-buffer step.  Inputs are gathered into one pinned block and travel in one DMA; the requested outputs are packed
+// back to back on the device ([count] rows each), come back in one DMA into a pinned mirror and are handed out either as
+// views into that mirror (bmpc_solve_host_views: zero copy, valid until the handle's next host call) or copied into
+// the caller's arrays (bmpc_solve_host).
+static const int kNumOut = 13;
+static void out_sizes(const bmpc_handle* h, size_t* sz) {
+  const KParams& P = h->P;
+  const size_t n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
+  const size_t v[kNumOut] = {d * 8, (size_t)P.pub_totalu * d * 8, (size_t)P.pub_totalx * n * 8, (size_t)P.pub_totalu * n * 8,
+                             (size_t)P.pub_totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8};
+  for (int i = 0; i < kNumOut; ++i) sz[i] = v[i];
+}
+static void** out_slots(bmpc_outputs* o, void*** slots) {
+  void** v[kNumOut] = {(void**)&o->u0, (void**)&o->uPred, (void**)&o->xPred, (void**)&o->xLin, (void**)&o->zPred,
+                       (void**)&o->branch_w, (void**)&o->branch_p, (void**)&o->objective, (void**)&o->status,
+                       (void**)&o->iters, (void**)&o->nfact, (void**)&o->nsolve, (void**)&o->cycles};
+  for (int i = 0; i < kNumOut; ++i) slots[i] = v[i];
+  return nullptr;
+}
+
+// want: which outputs to produce (non-NULL members); views: receives host pointers into the pinned mirror
+static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                           const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views) {
   if (!h) return BMPC_E_INVALID;
-  if (!x0 || !z0 || !xref || !out || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (!x0 || !z0 || !xref || !want || !views || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
   if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
+  bmpc_outputs w = *want;
+  void** wslot[kNumOut];
+  void** vslot[kNumOut];
+  out_slots(&w, wslot);
+  out_slots(views, vslot);
+  for (int i = 0; i < kNumOut; ++i) *vslot[i] = nullptr;
   if (count == 0) return BMPC_OK;
   BMPC_CK(h, cudaSetDevice(h->device));
-  const KParams& P = h->P;
-  const size_t cap = (size_t)h->cfg.batch_capacity, n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
-  if (!h->stage_in) BMPC_CK(h, cudaMalloc(&h->stage_in, cap * (3 * n + 4 * m) * sizeof(real)));
-  // device staging of every output, laid out back to back
-  const size_t sz[13] = {d * 8, (size_t)P.pub_totalu * d * 8, (size_t)P.pub_totalx * n * 8, (size_t)P.pub_totalu * n * 8,
-                         (size_t)P.pub_totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8};
-  void* const host[13] = {out->u0, out->uPred, out->xPred, out->xLin, out->zPred, out->branch_w,
-                          out->branch_p, out->objective, out->status, out->iters, out->nfact, out->nsolve, out->cycles};
-  size_t per = 0;
-  for (int i = 0; i < 13; ++i) per += sz[i];
+  const size_t cap = (size_t)h->cfg.batch_capacity, n = h->cfg.n, m = h->cfg.m;
+  size_t sz[kNumOut], per = 0;
+  out_sizes(h, sz);
+  for (int i = 0; i < kNumOut; ++i) per += sz[i];
+  const size_t in_reals = cap * (3 * n + 4 * m);
+  if (!h->stage_in) {
+    BMPC_CK(h, cudaMalloc(&h->stage_in, in_reals * sizeof(real)));
+    BMPC_CK(h, cudaMallocHost(&h->stage_in_host, in_reals * sizeof(real)));
+  }
   if (!h->stage_out) {
     h->stage_out_bytes = cap * per;
     BMPC_CK(h, cudaMalloc(&h->stage_out, h->stage_out_bytes));
+    BMPC_CK(h, cudaMemset(h->stage_out, 0, h->stage_out_bytes));
+    BMPC_CK(h, cudaMallocHost(&h->stage_out_host, h->stage_out_bytes));
   }
+  cudaStream_t s = h->last_stream;
+  BMPC_CK(h, cudaStreamSynchronize(s));   // the previous call's views are dead from here on
+  // inputs: x0 | z0 | xref | polpar, [count] rows each, contiguous
+  real* hin = h->stage_in_host;
+  const size_t rows = (size_t)count;
+  memcpy(hin, x0, rows * n * 8);
+  memcpy(hin + rows * n, z0, rows * n * 8);
+  memcpy(hin + 2 * rows * n, xref, rows * n * 8);
+  size_t in_used = 3 * rows * n;
+  if (policy_params) {
+    memcpy(hin + in_used, policy_params, rows * m * 4 * 8);
+    in_used += rows * m * 4;
+  }
+  BMPC_CK(h, cudaMemcpyAsync(h->stage_in, hin, in_used * sizeof(real), cudaMemcpyHostToDevice, s));
   real* dx0 = h->stage_in;
-  real* dz0 = dx0 + cap * n;
-  real* dxr = dz0 + cap * n;
-  real* dpp = dxr + cap * n;
-  cudaStream_t s = 0;
-  BMPC_CK(h, cudaMemcpyAsync(dx0, x0, count * n * 8, cudaMemcpyHostToDevice, s));
-  BMPC_CK(h, cudaMemcpyAsync(dz0, z0, count * n * 8, cudaMemcpyHostToDevice, s));
-  BMPC_CK(h, cudaMemcpyAsync(dxr, xref, count * n * 8, cudaMemcpyHostToDevice, s));
-  if (policy_params) BMPC_CK(h, cudaMemcpyAsync(dpp, policy_params, count * m * 4 * 8, cudaMemcpyHostToDevice, s));
-  void* dev[13];
-  {
-    char* p = (char*)h->stage_out;
-    for (int i = 0; i < 13; ++i) {
-      dev[i] = host[i] ? p : nullptr;
-      p += cap * sz[i];
-    }
-  }
+  real* dz0 = dx0 + rows * n;
+  real* dxr = dz0 + rows * n;
+  real* dpp = dxr + rows * n;
+  // outputs: only the requested ones, packed; 8-byte outputs first keeps every block aligned
   bmpc_outputs dout;
-  dout.u0 = (double*)dev[0];
-  dout.uPred = (double*)dev[1];
-  dout.xPred = (double*)dev[2];
-  dout.xLin = (double*)dev[3];
-  dout.zPred = (double*)dev[4];
-  dout.branch_w = (double*)dev[5];
-  dout.branch_p = (double*)dev[6];
-  dout.objective = (double*)dev[7];
-  dout.status = (int32_t*)dev[8];
-  dout.iters = (int32_t*)dev[9];
-  dout.nfact = (int32_t*)dev[10];
-  dout.nsolve = (int32_t*)dev[11];
-  dout.cycles = (int64_t*)dev[12];
-  if (dev[6]) BMPC_CK(h, cudaMemsetAsync(dev[6], 0xff, count * sz[6], s));   // NaN pattern for leaf rows of branch_p
+  void** dslot[kNumOut];
+  out_slots(&dout, dslot);
+  size_t off = 0;
+  size_t offs[kNumOut];
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < kNumOut; ++i) {
+      const bool wide = (sz[i] % 8) == 0;
+      if (wide != (pass == 0)) continue;
+      if (*wslot[i]) {
+        *dslot[i] = (char*)h->stage_out + off;
+        offs[i] = off;
+        off += rows * sz[i];
+      } else {
+        *dslot[i] = nullptr;
+      }
+    }
   const int rc = bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
   if (rc != BMPC_OK) return rc;
-  for (int i = 0; i < 13; ++i)
-    if (host[i]) BMPC_CK(h, cudaMemcpyAsync(host[i], dev[i], count * sz[i], cudaMemcpyDeviceToHost, s));
+  BMPC_CK(h, cudaMemcpyAsync(h->stage_out_host, h->stage_out, off, cudaMemcpyDeviceToHost, s));
+  BMPC_CK(h, cudaStreamSynchronize(s));
+  for (int i = 0; i < kNumOut; ++i)
+    if (*wslot[i]) *vslot[i] = (char*)h->stage_out_host + offs[i];
+  return BMPC_OK;
+}
+
+int bmpc_solve_host_views(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                          const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views) {
+  return solve_host_impl(h, x0, z0, xref, policy_params, count, want, views);
+}
+
+int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                    const double* policy_params, int64_t count, const bmpc_outputs* out) {
+  if (!out) { if (h) h->err = "null argument"; return BMPC_E_INVALID; }
+  bmpc_outputs views;
+  const int rc = solve_host_impl(h, x0, z0, xref, policy_params, count, out, &views);
+  if (rc != BMPC_OK || count == 0) return rc;
+  bmpc_outputs o = *out;
+  void** oslot[kNumOut];
+  void** vslot[kNumOut];
+  out_slots(&o, oslot);
+  out_slots(&views, vslot);
+  size_t sz[kNumOut];
+  out_sizes(h, sz);
+  for (int i = 0; i < kNumOut; ++i)
+    if (*oslot[i]) memcpy(*oslot[i], *vslot[i], (size_t)count * sz[i]);
+  return BMPC_OK;
+}
+
+int bmpc_get_state(bmpc_handle* h, double* uLin, int32_t* pbest, double* old_input, int32_t* started, double* xprev,
+                   int64_t count, int on_host) {
+  if (!h) return BMPC_E_INVALID;
+  if (count < 0 || count > h->cfg.batch_capacity) { h->err = "count out of range"; return BMPC_E_CAPACITY; }
+  if (xprev && !h->xprev) { h->err = "xprev is robustMPC state"; return BMPC_E_INVALID; }
+  BMPC_CK(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind k = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  const KParams& P = h->P;
+  cudaStream_t s = h->last_stream;
+  if (uLin) BMPC_CK(h, cudaMemcpyAsync(uLin, h->uLin, count * (P.totalu + 1) * h->cfg.d * sizeof(real), k, s));
+  if (pbest) BMPC_CK(h, cudaMemcpyAsync(pbest, h->pbest, count * P.nbranch * sizeof(int), k, s));
+  if (old_input) BMPC_CK(h, cudaMemcpyAsync(old_input, h->oldin, count * h->cfg.d * sizeof(real), k, s));
+  if (started) BMPC_CK(h, cudaMemcpyAsync(started, h->started, count * sizeof(int), k, s));
+  if (xprev) BMPC_CK(h, cudaMemcpyAsync(xprev, h->xprev, count * P.pub_totalx * h->cfg.n * sizeof(real), k, s));
   BMPC_CK(h, cudaStreamSynchronize(s));
   return BMPC_OK;
 }
 
-int bmpc_get_state(bmpc_handle* h, double* uLin, int32_t* pbest, double* old_input, int32_t* started, int64_t count,
-                   int on_host) {
-  if (!h) return BMPC_E_INVALID;
-  if (count < 0 || count > h->cfg.batch_capacity) { h->err = "count out of range"; return BMPC_E_CAPACITY; }
-  BMPC_CK(h, cudaSetDevice(h->device));
-  const cudaMemcpyKind k = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  const KParams& P = h->P;
-  if (uLin) BMPC_CK(h, cudaMemcpy(uLin, h->uLin, count * (P.totalu + 1) * h->cfg.d * sizeof(real), k));
-  if (pbest) BMPC_CK(h, cudaMemcpy(pbest, h->pbest, count * P.nbranch * sizeof(int), k));
-  if (old_input) BMPC_CK(h, cudaMemcpy(old_input, h->oldin, count * h->cfg.d * sizeof(real), k));
-  if (started) BMPC_CK(h, cudaMemcpy(started, h->started, count * sizeof(int), k));
-  return BMPC_OK;
-}
-
 int bmpc_set_state(bmpc_handle* h, const double* uLin, const int32_t* pbest, const double* old_input,
-                   const int32_t* started, int64_t count, int on_host) {
+                   const int32_t* started, const double* xprev, int64_t count, int on_host) {
   if (!h) return BMPC_E_INVALID;
   if (count < 0 || count > h->cfg.batch_capacity) { h->err = "count out of range"; return BMPC_E_CAPACITY; }
+  if (xprev && !h->xprev) { h->err = "xprev is robustMPC state"; return BMPC_E_INVALID; }
+  if (h->xprev && started && !xprev) {
+    h->err = "robustMPC linearises about the previous predicted states: restoring `started` needs xprev as well";
+    return BMPC_E_INVALID;
+  }
   BMPC_CK(h, cudaSetDevice(h->device));
   const cudaMemcpyKind k = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const KParams& P = h->P;
-  if (uLin) BMPC_CK(h, cudaMemcpy(h->uLin, uLin, count * (P.totalu + 1) * h->cfg.d * sizeof(real), k));
-  if (pbest) BMPC_CK(h, cudaMemcpy(h->pbest, pbest, count * P.nbranch * sizeof(int), k));
-  if (old_input) BMPC_CK(h, cudaMemcpy(h->oldin, old_input, count * h->cfg.d * sizeof(real), k));
-  if (started) BMPC_CK(h, cudaMemcpy(h->started, started, count * sizeof(int), k));
+  cudaStream_t s = h->last_stream;
+  if (uLin) BMPC_CK(h, cudaMemcpyAsync(h->uLin, uLin, count * (P.totalu + 1) * h->cfg.d * sizeof(real), k, s));
+  if (pbest) BMPC_CK(h, cudaMemcpyAsync(h->pbest, pbest, count * P.nbranch * sizeof(int), k, s));
+  if (old_input) BMPC_CK(h, cudaMemcpyAsync(h->oldin, old_input, count * h->cfg.d * sizeof(real), k, s));
+  if (started) BMPC_CK(h, cudaMemcpyAsync(h->started, started, count * sizeof(int), k, s));
+  if (xprev) BMPC_CK(h, cudaMemcpyAsync(h->xprev, xprev, count * P.pub_totalx * h->cfg.n * sizeof(real), k, s));
   // a caller-supplied warm start invalidates the solver's own caches for those episodes
-  BMPC_CK(h, cudaMemset(h->cache_state, 0xff, count * 2 * sizeof(int)));
+  BMPC_CK(h, cudaMemsetAsync(h->cache_state, 0xff, count * 2 * sizeof(int), s));
+  BMPC_CK(h, cudaStreamSynchronize(s));
   return BMPC_OK;
 }
 
@@ -633,7 +757,7 @@ int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int3
   if (!highway && (!env->goal || !quad_sizes)) { h->err = "quadruped environment needs goal and quad_sizes"; return BMPC_E_INVALID; }
   if (h->cfg.controller == BMPC_CTRL_ROBUST) { h->err = "the environment drives the branch controllers"; return BMPC_E_UNSUPPORTED; }
   if (count == 0) return BMPC_OK;
-  if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_INVALID; }
+  if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
   BMPC_CK(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   EnvArgs a;
@@ -664,29 +788,28 @@ int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warp
   return BMPC_OK;
 }
 
-static int hmm_kinds_to_device(const int32_t* kinds, int m, int** dev) {
+static int hmm_kinds(const int32_t* kinds, int m, hmm::Kinds* out) {
   if (!kinds || m < 1 || m > BMPC_MAX_POLICIES) return BMPC_E_INVALID;
-  for (int j = 0; j < m; ++j)
+  for (int j = 0; j < BMPC_MAX_POLICIES; ++j) out->v[j] = 0;
+  for (int j = 0; j < m; ++j) {
     if (kinds[j] != BMPC_HMM_MAINTAIN && kinds[j] != BMPC_HMM_BRAKE) return BMPC_E_INVALID;
-  if (cudaMalloc(dev, m * sizeof(int)) != cudaSuccess) return BMPC_E_CUDA;
-  if (cudaMemcpy(*dev, kinds, m * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(*dev); return BMPC_E_CUDA; }
+    out->v[j] = kinds[j];
+  }
   return BMPC_OK;
 }
 
+// The three belief-state entry points only enqueue on the caller's stream: no allocation, no synchronisation.
 int bmpc_hmm_backup_rollout(const double* x0, int64_t count, int32_t M, int32_t m, const int32_t* policy_kind, int32_t N,
                             double dt, double Kpsi, double* xbackup, int32_t device, void* stream) {
   if (!x0 || !xbackup || count < 0 || M < 1 || N < 1) { g_create_error = "bad argument"; return BMPC_E_INVALID; }
   if (count == 0) return BMPC_OK;
   if (cudaSetDevice(device) != cudaSuccess) return BMPC_E_CUDA;
-  int* dk = nullptr;
-  const int rc = hmm_kinds_to_device(policy_kind, m, &dk);
+  hmm::Kinds dk;
+  const int rc = hmm_kinds(policy_kind, m, &dk);
   if (rc != BMPC_OK) return rc;
   const int64_t n = count * M * m;
   hmm::rollout_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x0, (int)count, M, m, dk, N, dt, Kpsi, xbackup);
-  const cudaError_t e = cudaGetLastError();
-  cudaStreamSynchronize((cudaStream_t)stream);
-  cudaFree(dk);
-  return e == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
 }
 
 int bmpc_hmm_rollout_sensitivity(const double* x0, int64_t count, int32_t m, const int32_t* policy_kind, int32_t steps,
@@ -695,16 +818,13 @@ int bmpc_hmm_rollout_sensitivity(const double* x0, int64_t count, int32_t m, con
   if (!x0 || !f0 || !xx || !QQ || !Qt || count < 0 || steps < 1) { g_create_error = "bad argument"; return BMPC_E_INVALID; }
   if (count == 0) return BMPC_OK;
   if (cudaSetDevice(device) != cudaSuccess) return BMPC_E_CUDA;
-  int* dk = nullptr;
-  const int rc = hmm_kinds_to_device(policy_kind, m, &dk);
+  hmm::Kinds dk;
+  const int rc = hmm_kinds(policy_kind, m, &dk);
   if (rc != BMPC_OK) return rc;
   const int64_t n = count * m;
   hmm::sensitivity_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x0, (int)count, m, dk, steps, ts, Kpsi, f0,
                                                                                      xx, QQ, Qt);
-  const cudaError_t e = cudaGetLastError();
-  cudaStreamSynchronize((cudaStream_t)stream);
-  cudaFree(dk);
-  return e == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? BMPC_OK : BMPC_E_CUDA;
 }
 
 int bmpc_hmm_belief_update(const double* ego, const double* xb, const double* b, const double* cbf, int64_t count,

@@ -34,7 +34,8 @@ __device__ __forceinline__ void xdot(const double* x, const double* u, double* f
 }
 
 // one thread per (episode, agent, policy): row (m*i + j) of xbackup, flattened component-major (casadi.reshape)
-__global__ void rollout_kernel(const double* __restrict__ x0, int count, int M, int m, const int* __restrict__ kinds, int N,
+struct Kinds { int v[BMPC_MAX_POLICIES]; };   // policy table by value: no device allocation per call
+__global__ void rollout_kernel(const double* __restrict__ x0, int count, int M, int m, const Kinds kinds, int N,
                                double dt, double Kpsi, double* __restrict__ xbackup) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= count * M * m) return;
@@ -42,7 +43,7 @@ __global__ void rollout_kernel(const double* __restrict__ x0, int count, int M, 
   double x[4], u[2], f[4];
   for (int q = 0; q < 4; ++q) x[q] = x0[((size_t)e * M + i) * 4 + q];
   double* row = xbackup + ((size_t)e * M * m + (size_t)m * i + j) * N * 4;
-  const int kind = kinds[j];
+  const int kind = kinds.v[j];
   for (int t = 0; t < N; ++t) {
     policy(kind, x, Kpsi, u);
     xdot(x, u, f);
@@ -54,13 +55,13 @@ __global__ void rollout_kernel(const double* __restrict__ x0, int count, int M, 
 }
 
 // one thread per (point, policy): states, sensitivity matrices dx_t/dx_0 and xdot - f0 BEFORE each of `steps` steps
-__global__ void sensitivity_kernel(const double* __restrict__ x0, int count, int m, const int* __restrict__ kinds, int steps,
+__global__ void sensitivity_kernel(const double* __restrict__ x0, int count, int m, const Kinds kinds, int steps,
                                    double ts, double Kpsi, const double* __restrict__ f0, double* __restrict__ xx,
                                    double* __restrict__ QQ, double* __restrict__ Qt) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= count * m) return;
   const int j = id % m, e = id / m;
-  const int kind = kinds[j];
+  const int kind = kinds.v[j];
   double x[4], Q[16];
   for (int q = 0; q < 4; ++q) x[q] = x0[(size_t)e * 4 + q];
   for (int q = 0; q < 16; ++q) Q[q] = (q % 5 == 0) ? 1.0 : 0.0;

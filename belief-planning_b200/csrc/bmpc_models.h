@@ -193,6 +193,18 @@ struct HighwayModel {
     return acc.value();
   }
 
+  // the two safety terms of one step of BF_traj (:337-349): vehicle distance veh_col(z, x1, [L+2, W+0.2]) and lane
+  // boundary softmin([y - lb, ub - y], 5) (:195-206); their soft-min over the N steps is the safety value of the policy
+  static constexpr int NSAFE = 2;
+  BMPC_D static void safety_terms(const KParams& P, const real* z, real xe0, real xe1, real* v) {
+    real gx, gy;
+    soft_box(fabs(z[0] - xe0) - (P.veh_L + 2.0), fabs(z[1] - xe1) - (P.veh_W + 0.2), v[0], gx, gy);
+    const real a = z[1] - P.lane_lo, b = P.lane_hi - z[1];
+    const real e = bmpc_exp(-5.0 * fabs(a - b));
+    const real ea = (a <= b) ? 1.0 : e, eb = (a <= b) ? e : 1.0;
+    v[1] = bmpc_div(ea * a + eb * b, ea + eb);
+  }
+
   // un-normalised branch weight bmpc_exp(s1 * softsat(hi, 1)) (:355-359); softsat(h,1) == sigmoid(h)
   BMPC_D static real branch_weight(const KParams& P, real hi, real /*himax*/) {
     return bmpc_exp(bmpc_div(P.s1, 1.0 + bmpc_exp(-hi)));
@@ -306,6 +318,11 @@ struct QuadrupedModel {
     for (int i = 0; i < 3; ++i) zlast[i] = z[i];
     return acc.value();
   }
+  static constexpr int NSAFE = 1;   // robot_col of the step (:204-210)
+  BMPC_D static void safety_terms(const KParams& P, const real* z, real xe0, real xe1, real* v) {
+    v[0] = fabs(z[0] - xe0) + fabs(z[1] - xe1) - P.quad_margin;
+    v[1] = 0.0;
+  }
   // bmpc_exp(s1*hi), shifted by the group maximum (normalisation cancels the shift) (:211-216)
   BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return bmpc_exp(P.s1 * (hi - himax)); }
   static constexpr bool kWeightNeedsMax = true;
@@ -377,5 +394,7 @@ struct RateAug {
     return M::policy_safety(P, kind, par, kind0, par0, xe0, z0, zlast, nsteps, emit);
   }
   BMPC_D static real branch_weight(const KParams& P, real hi, real himax) { return M::branch_weight(P, hi, himax); }
+  static constexpr int NSAFE = M::NSAFE;
+  BMPC_D static void safety_terms(const KParams& P, const real* z, real xe0, real xe1, real* v) { M::safety_terms(P, z, xe0, xe1, v); }
   static constexpr bool kWeightNeedsMax = M::kWeightNeedsMax;
 };

@@ -1,6 +1,8 @@
 // Portability layer of libbranchmpc: the solver text in bmpc_models.h / bmpc_solver.h is written once
-// against these few primitives.  nvcc builds it as the sm_100a kernel (one warp = one problem,
-// BMPC_LANES = 32); tests/hostsim builds the SAME text with g++ as a single-lane program
+// against these few primitives.  nvcc builds it as the sm_100a kernel: one TEAM of BMPC_TEAM_WARPS warps (one thread
+// block) owns one problem, BMPC_LANES = 32 * BMPC_TEAM_WARPS lanes; the node-parallel passes spread the tree's nodes
+// over all lanes of the team (97 highway nodes = one round of 96 lanes + the root), the tree sweeps use one lane per
+// branch of a level.  tests/hostsim builds the SAME text with g++ as a single-lane program
 // (BMPC_LANES = 1, barriers and reductions degenerate) so that the algorithm can be checked against
 // the oracle without a GPU.  The host-sim build is test infrastructure: the product library never
 // contains or calls it.
@@ -14,27 +16,72 @@
 #define BMPC_HD __host__ __device__
 #define BMPC_D __device__ __forceinline__
 #define BMPC_DN __device__ __noinline__
-#define BMPC_LANES 32
+#ifndef BMPC_TEAM_WARPS
+#define BMPC_TEAM_WARPS 3
+#endif
+#define BMPC_LANES (32 * BMPC_TEAM_WARPS)
+#define BMPC_BLANES 32
 #else
 #define BMPC_HD
 #define BMPC_D inline
 #define BMPC_DN inline
+#define BMPC_TEAM_WARPS 1
 #define BMPC_LANES 1
+#define BMPC_BLANES 1
 #endif
 
 typedef double real;
 
 #define BMPC_FULL_MASK 0xffffffffu
 
-BMPC_D void lanes_sync() {
+// team_sync(): every lane of the team (block).  The tree sweeps (lanes = branches of a level) are run by the team's first
+// warp alone (team_leader(), lane stride BMPC_BLANES, bsync() between levels) while the other warps wait at the next
+// team_sync(): followers that walked through the sweep code as well cost 30 % of the sweep time (measured).
+BMPC_D void team_sync() {
+#if defined(__CUDA_ARCH__)
+#if BMPC_TEAM_WARPS > 1
+  __syncthreads();
+#else
+  __syncwarp();
+#endif
+#endif
+}
+BMPC_D void lanes_sync() { team_sync(); }
+BMPC_D void bsync() {
 #if defined(__CUDA_ARCH__)
   __syncwarp();
 #endif
 }
+BMPC_D bool team_leader() {
+#if defined(__CUDA_ARCH__)
+  return threadIdx.x < 32;
+#else
+  return true;
+#endif
+}
+// Team-wide reductions: shuffles inside a warp, then one shared-memory slot per warp.  Every lane of the team gets the
+// same value (the solver branches on these results, so they must be uniform over the block).
+#if defined(__CUDA_ARCH__) && BMPC_TEAM_WARPS > 1
+#define BMPC_TEAM_COMBINE(T, v, OP)                                  \
+  {                                                                  \
+    __shared__ T red_[BMPC_TEAM_WARPS];                              \
+    __syncthreads();                                                 \
+    if ((threadIdx.x & 31) == 0) red_[threadIdx.x >> 5] = v;         \
+    __syncthreads();                                                 \
+    v = red_[0];                                                     \
+    _Pragma("unroll") for (int w_ = 1; w_ < BMPC_TEAM_WARPS; ++w_) { \
+      const T o_ = red_[w_];                                         \
+      v = OP;                                                        \
+    }                                                                \
+  }
+#else
+#define BMPC_TEAM_COMBINE(T, v, OP)
+#endif
 BMPC_D real lanes_max(real v) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(BMPC_FULL_MASK, v, o));
+  BMPC_TEAM_COMBINE(real, v, fmax(v, o_))
 #endif
   return v;
 }
@@ -42,6 +89,7 @@ BMPC_D real lanes_sum(real v) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BMPC_FULL_MASK, v, o);
+  BMPC_TEAM_COMBINE(real, v, v + o_)
 #endif
   return v;
 }
@@ -49,6 +97,7 @@ BMPC_D int lanes_sum_int(int v) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BMPC_FULL_MASK, v, o);
+  BMPC_TEAM_COMBINE(int, v, v + o_)
 #endif
   return v;
 }
@@ -56,6 +105,7 @@ BMPC_D int lanes_or_int(int v) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(BMPC_FULL_MASK, v, o);
+  BMPC_TEAM_COMBINE(int, v, v | o_)
 #endif
   return v;
 }
@@ -84,6 +134,7 @@ BMPC_D real bmpc_div(real a, real b) {
   return a / b;
 #endif
 }
+BMPC_D real bmpc_nan() { return nan(""); }
 BMPC_D real bmpc_min(real a, real b) { return fmin(a, b); }
 BMPC_D real bmpc_max(real a, real b) { return fmax(a, b); }
 BMPC_D real bmpc_clamp(real v, real lo, real hi) { return fmin(fmax(v, lo), hi); }

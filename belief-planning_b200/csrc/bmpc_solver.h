@@ -116,7 +116,7 @@ struct Solver {
   BMPC_D int oEXZ() const { return oEXL() + NX * PP.nbx; }
   BMPC_D int oEXX() const { return oEXZ() + NX * PP.nbx; }
 #if defined(__CUDA_ARCH__)
-#define BMPC_LANE_ID ((int)(threadIdx.x & 31))
+#define BMPC_LANE_ID ((int)threadIdx.x)
 #else
   int lane_host;
 #define BMPC_LANE_ID lane_host
@@ -187,6 +187,12 @@ struct Solver {
   static_assert(3 * NR + 2 * NU <= 62, "active-set code does not fit 64 bits");
 
   BMPC_D int kp_of(int b, int t) const { return bmpc_ndu(PP, b) + t + b; }
+  // Node-parallel passes: slot i of the team's lanes works on input node i + 1, the last slot on the root, so that the
+  // non-root nodes (a multiple of N, e.g. 96) fill whole rounds of the team and the root (whose soft rows are inert:
+  // its state is fixed) is one short extra round of lane 0.
+  BMPC_D int node_at(int i) const { return (i + 1 < PP.totalu) ? i + 1 : 0; }
+#define BMPC_FOR_NODES(k) \
+  for (int k##_i = BMPC_LANE_ID, k = node_at(k##_i); k##_i < PP.totalu; k##_i += BMPC_LANES, k = node_at(k##_i))
   BMPC_D void node_of(int k, int& b, int& t) const {
     if (k == 0) { b = 0; t = 0; } else { const int q = bmpc_idiv(k - 1, PP.inv_N); b = 1 + q; t = (k - 1) - q * PP.N; }
   }
@@ -228,34 +234,161 @@ struct Solver {
     }
   }
 
-  BMPC_DN void node_setup(int b, int t, const real* xbar, const real* ubar, real w, bool leaf_last, real* xn, int ncol = 1) {
-    const int kp = kp_of(b, t);
-    real lin[M::NLIN], cc[M::NCC];
-    M::linearize(PP, xbar, ubar, lin, cc, xn);
-#pragma unroll
-    for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
-#pragma unroll
-    for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
+  // Expansion scratch, parked in the gain fields (dead until the first factorisation): the obstacle state of the node's
+  // time step, the position of the ego "maintain" rollout, and the node's safety terms.
+  static constexpr int F_ZS = F_K;
+  static constexpr int F_ZE = F_ZS + NXP;
+  static constexpr int F_ZV = F_ZE + 2;
+  static_assert(NXP + 4 <= NU * NX, "expansion scratch does not fit the gain fields");
+
+  // per-node data that does not depend on the rollout order: linear cost, collision row, ADMM start, xLin output
+  // (the linearisation itself was stored by the rollout sweep, which needs the successor state anyway)
+  BMPC_DN void node_setup_all() {
     const real* xref = PP.xref + (size_t)prob * NXP;
-    // linear state cost -2 w (xRef' Q° + xbar' dQ): Q° = Qf on the last node of a leaf branch of BranchMPC (:1095)
-    const real* Ql = (leaf_last && PP.ctrl == BMPC_CTRL_BRANCH) ? PP.Qf : PP.Q;
+#pragma unroll 1
+    BMPC_FOR_NODES(k) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wbp()[b];
+      const bool leaf_last = (b >= PP.off[PP.NB] && t == PP.N - 1);
+      real xbar[NXP];
 #pragma unroll
-    for (int j = 0; j < NXP; ++j) {
-      real a = 0.0, c = 0.0;
+      for (int i = 0; i < NXP; ++i) xbar[i] = F(F_XQ + i, kp);
+      // linear state cost -2 w (xRef' Q° + xbar' dQ): Q° = Qf on the last node of a leaf branch of BranchMPC (:1095)
+      const real* Ql = (leaf_last && PP.ctrl == BMPC_CTRL_BRANCH) ? PP.Qf : PP.Q;
+#pragma unroll
+      for (int j = 0; j < NXP; ++j) {
+        real a = 0.0, c = 0.0;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) {
+          a += xref[i] * Ql[i * NXP + j];
+          c += xbar[i] * PP.Q[i * NXP + j];
+        }
+        F(F_Q + j, kp) = -2.0 * w * (a + PP.dq_scale * c);
+      }
+      rows_setup(kp, xbar, 1);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(F(F_UQ + a, kp), PP.ulo[a], PP.uhi[a]);
+      if (PP.out.xLin) {
+        real* o = PP.out.xLin + ((size_t)prob * PP.totalu + k) * NXP;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) o[i] = xbar[i];
+      }
+    }
+    lanes_sync();
+  }
+
+  // Order of the expansion (everything that is not a recursion in time runs node-parallel over the whole team):
+  //   1. node-parallel: time-shifted previous inputs and active-set codes of every node (updatetree :1025-1033)
+  //   2. per tree level, lanes = child branches: the three rollouts of a branch in one loop - obstacle under its policy
+  //      (zpred_eval), ego under policy 0 (BF_traj) and the ego linearisation trajectory with its per-node A, B, C
+  //      (:1048-1059); they do not depend on the branch probabilities
+  //   3. node-parallel: safety terms of every (branch, step); soft-min per branch in two passes (minimum, then the
+  //      shifted exponentials - identical to the reference's unshifted form, highway_branch_dyn.py:151-162)
+  //   4. lanes = parents: probabilities, weights, arg-max children (branch_eval)
+  //   5. node-parallel: cost vectors, collision rows (col_eval), ADMM start
+  // lanes = child branches of a tree level (first warp of the team only): obstacle rollout under the child's policy,
+  // ego rollout under policy 0, ego linearisation rollout with its per-node A, B, C
+  BMPC_DN void rollouts() {
+    const real* x0 = PP.x0 + (size_t)prob * NXP;
+    const real* z0 = PP.z0 + (size_t)prob * NXP;
+    const int m = PP.m;
+    if (BMPC_LANE_ID == 0) {
+      const int kp = kp_of(0, 0);
+      real xb[NXP], ub[NU], xn[NXP], lin[M::NLIN], cc[M::NCC];
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) xb[i] = x0[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) ub[a] = F(F_UQ + a, kp);
+      M::linearize(PP, xb, ub, lin, cc, xn);
+#pragma unroll
+      for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
+#pragma unroll
+      for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
+      F(F_FC, kp) = z0[0];
+      F(F_FC + 1, kp) = z0[1];
+      Wbp()[0] = 1.0;
+      if (PP.out.zPred) {
+        real* o = PP.out.zPred + (size_t)prob * PP.totalu * NXP;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) o[i] = z0[i];
+      }
 #pragma unroll
       for (int i = 0; i < NXP; ++i) {
-        a += xref[i] * Ql[i * NXP + j];
-        c += xbar[i] * PP.Q[i * NXP + j];
+        F(F_XQ + i, kp) = xb[i];
+        EXLp()[i] = xb[i];
+        EXZp()[i] = z0[i];
+        EXXp()[i] = xn[i];
       }
-      F(F_Q + j, kp) = -2.0 * w * (a + PP.dq_scale * c);
     }
-    rows_setup(kp, xbar, ncol);
+    bsync();
+#pragma unroll 1
+    for (int d = 0; d < PP.NB; ++d) {
+      const int cnt = PP.pw[d] * m;
+#pragma unroll 1
+      for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_BLANES) {
+        const int bq = bmpc_idiv(idx, PP.inv_m);
+        const int b = PP.off[d] + bq;
+        const int i = idx - bq * m;
+        const int c = bmpc_first_child(PP, b, d) + i;
+        const int kc = bmpc_ndu(PP, c);
+        const int kpc = kp_of(c, 0);
+        const real* par = pol_par(i);
+        const real* par0 = pol_par(0);
+        const int kind = PP.pol_kind[i], kind0 = PP.pol_kind[0];
+        real* zout = PP.out.zPred ? PP.out.zPred + ((size_t)prob * PP.totalu + kc) * NXP : nullptr;
+        real z[NXP], xe[NXP], xb[NXP];
 #pragma unroll
-    for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(ubar[a], PP.ulo[a], PP.uhi[a]);
-    if (PP.out.xLin) {
-      real* o = PP.out.xLin + ((size_t)prob * PP.totalu + (bmpc_ndu(PP, b) + t)) * NXP;
+        for (int q = 0; q < NXP; ++q) {
+          z[q] = EXZp()[NX * b + q];
+          xe[q] = EXLp()[NX * b + q];
+          xb[q] = EXXp()[NX * b + q];
+        }
+#pragma unroll 1
+        for (int t = 0; t < PP.N; ++t) {
+          const int kp = kpc + t;
+          real u[NU], xn[NXP];
+          M::policy(PP, kind0, par0, xe, u);
+          M::step(PP, xe, u, xn);
 #pragma unroll
-      for (int i = 0; i < NXP; ++i) o[i] = xbar[i];
+          for (int q = 0; q < NXP; ++q) xe[q] = xn[q];
+          M::policy(PP, kind, par, z, u);
+          M::step(PP, z, u, xn);
+#pragma unroll
+          for (int q = 0; q < NXP; ++q) {
+            z[q] = xn[q];
+            F(F_ZS + q, kp) = xn[q];
+            if (zout) zout[t * NXP + q] = xn[q];
+          }
+          F(F_FC, kp) = z[0];
+          F(F_FC + 1, kp) = z[1];
+          F(F_ZE, kp) = xe[0];
+          F(F_ZE + 1, kp) = xe[1];
+          real lin[M::NLIN], cc[M::NCC];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
+          M::linearize(PP, xb, u, lin, cc, xn);
+#pragma unroll
+          for (int q = 0; q < M::NLIN; ++q) F(F_LIN + q, kp) = lin[q];
+#pragma unroll
+          for (int q = 0; q < M::NCC; ++q) F(F_CC + q, kp) = cc[q];
+#pragma unroll
+          for (int q = 0; q < NXP; ++q) F(F_XQ + q, kp) = xb[q];
+          if (t == PP.N - 1) {
+#pragma unroll
+            for (int q = 0; q < NXP; ++q) EXLp()[NX * c + q] = xb[q];
+          }
+#pragma unroll
+          for (int q = 0; q < NXP; ++q) xb[q] = xn[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NXP; ++q) {
+          EXXp()[NX * c + q] = xb[q];
+          EXZp()[NX * c + q] = z[q];
+        }
+      }
+      bsync();
     }
   }
 
@@ -265,66 +398,94 @@ struct Solver {
     const real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
     int* pbest = PP.pbest + (size_t)prob * PP.nbranch;
     const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
-    const real* x0 = PP.x0 + (size_t)prob * NXP;
-    const real* z0 = PP.z0 + (size_t)prob * NXP;
-    if (BMPC_LANE_ID == 0) {
-      real ub[NU], xb[NXP], xn[NXP];
-#pragma unroll
-      for (int i = 0; i < NXP; ++i) xb[i] = x0[i];
-      // root input: previous first input of the most likely child (updatetree :1029-1031); zero on the first solve
-      const int best = started ? pbest[0] : 0;
-      const int kbest = bmpc_ndu(PP, bmpc_first_child(PP, 0, 0) + best);
-#pragma unroll
-      for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[kbest * NU + a] : 0.0;
-      const int kp = kp_of(0, 0);
-      if (use_codes) stp()[kp] = codes[kbest];
-      F(F_FC, kp) = z0[0];
-      F(F_FC + 1, kp) = z0[1];
-      Wbp()[0] = 1.0;
-      if (PP.out.zPred) {
-        real* o = PP.out.zPred + (size_t)prob * PP.totalu * NXP;
-#pragma unroll
-        for (int i = 0; i < NXP; ++i) o[i] = z0[i];
-      }
-      node_setup(0, 0, xb, ub, 1.0, false, xn);
-#pragma unroll
-      for (int i = 0; i < NXP; ++i) {
-        EXLp()[i] = xb[i];
-        EXZp()[i] = z0[i];
-        EXXp()[i] = xn[i];
-      }
-    }
-    lanes_sync();
     const int m = PP.m;
-    for (int d = 0; d < PP.NB; ++d) {
-      // (a) obstacle rollouts under each policy + safety value of each (zpred_eval, branch_eval); lanes = (branch, policy)
-      const int cnt = PP.pw[d] * m;
-      for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_LANES) {
-        const int bq = bmpc_idiv(idx, PP.inv_m);
-        const int b = PP.off[d] + bq;
-        const int i = idx - bq * m;
-        const int c = bmpc_first_child(PP, b, d) + i;
-        real zl[NXP];
-        const int kc = bmpc_ndu(PP, c);
-        const int kpc = kp_of(c, 0);
-        real* zout = PP.out.zPred ? PP.out.zPred + ((size_t)prob * PP.totalu + kc) * NXP : nullptr;
-        const real hi = M::policy_safety(PP, PP.pol_kind[i], pol_par(i), PP.pol_kind[0], pol_par(0), EXLp() + NX * b,
-                                         EXZp() + NX * b, zl, PP.N, [&](int t, const real* z) {
-                                           F(F_FC, kpc + t) = z[0];
-                                           F(F_FC + 1, kpc + t) = z[1];
-                                           if (zout) {
-#pragma unroll
-                                             for (int q = 0; q < NXP; ++q) zout[t * NXP + q] = z[q];
-                                           }
-                                         });
-#pragma unroll
-        for (int q = 0; q < NXP; ++q) EXZp()[NX * c + q] = zl[q];
-        EXp()[NS * c] = hi;   // exchange slot: safety value of child c
-      }
-      lanes_sync();
-      // (a') probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      int ksrc;
+      if (k == 0) {
+        // root input: previous first input of the most likely child (updatetree :1029-1031)
+        ksrc = bmpc_ndu(PP, bmpc_first_child(PP, 0, 0) + (started ? pbest[0] : 0));
+      } else if (t < PP.N - 1) {
+        ksrc = k + 1;
+      } else if (b >= PP.off[PP.NB]) {
+        ksrc = k;   // leaf: repeat the shifted last input (:1033)
+      } else {
+        ksrc = bmpc_ndu(PP, bmpc_first_child(PP, b, bmpc_depth(PP, b)) + (started ? pbest[b] : 0));
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_UQ + a, kp) = started ? uLin[ksrc * NU + a] : 0.0;   // zero on the first solve
+      if (use_codes) stp()[kp] = codes[ksrc];   // the active set shifts in time like the inputs
+    }
+    team_sync();
+    if (team_leader()) rollouts();
+    team_sync();
+    // safety value of every child branch: soft-min (gamma = 5) over the safety terms of its N steps
+#pragma unroll 1
+    BMPC_FOR_NODES(k) {
+      if (k == 0) continue;
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      real z[NXP], v[2];
+#pragma unroll
+      for (int q = 0; q < NXP; ++q) z[q] = F(F_ZS + q, kp);
+      M::safety_terms(PP, z, F(F_ZE, kp), F(F_ZE + 1, kp), v);
+      F(F_ZV, kp) = v[0];
+      if (M::NSAFE > 1) F(F_ZV + 1, kp) = v[1];
+    }
+    team_sync();
+    if (team_leader()) {
+#pragma unroll 1
+    for (int c = 1 + BMPC_LANE_ID; c < PP.nbranch; c += BMPC_BLANES) {
+      const int kpc = kp_of(c, 0);
+      real vmin = 1e300;
+#pragma unroll 1
+      for (int t = 0; t < PP.N; ++t) {
+        vmin = fmin(vmin, F(F_ZV, kpc + t));
+        if (M::NSAFE > 1) vmin = fmin(vmin, F(F_ZV + 1, kpc + t));
+      }
+      EXp()[NS * c + 2] = vmin;
+    }
+    }
+    team_sync();
+#pragma unroll 1
+    BMPC_FOR_NODES(k) {
+      if (k == 0) continue;
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real vmin = EXp()[NS * b + 2];
+      F(F_ZS, kp) = bmpc_exp(-5.0 * (F(F_ZV, kp) - vmin));
+      if (M::NSAFE > 1) F(F_ZS + 1, kp) = bmpc_exp(-5.0 * (F(F_ZV + 1, kp) - vmin));
+    }
+    team_sync();
+    if (team_leader()) {
+#pragma unroll 1
+    for (int c = 1 + BMPC_LANE_ID; c < PP.nbranch; c += BMPC_BLANES) {
+      const int kpc = kp_of(c, 0);
+      real num = 0.0, den = 0.0;
+#pragma unroll 1
+      for (int t = 0; t < PP.N; ++t) {
+        const real e0 = F(F_ZS, kpc + t);
+        num += e0 * F(F_ZV, kpc + t);
+        den += e0;
+        if (M::NSAFE > 1) {
+          const real e1 = F(F_ZS + 1, kpc + t);
+          num += e1 * F(F_ZV + 1, kpc + t);
+          den += e1;
+        }
+      }
+      EXp()[NS * c] = bmpc_div(num, den);   // exchange slot: safety value of child c
+    }
+    bsync();
+#pragma unroll 1
+    for (int d = 0; d < PP.NB; ++d) {
+      // probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
+#pragma unroll 1
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         const int fc = bmpc_first_child(PP, b, d);
         real himax = -1e300;
 #pragma unroll 1
@@ -341,48 +502,13 @@ struct Solver {
           if (PP.out.branch_p) PP.out.branch_p[((size_t)prob * PP.nbranch + b) * m + j] = p;
           if (p > pb) { pb = p; best = j; }
         }
-        // pbest[b] (old value) was consumed when b's own trajectory was shifted, one level up (or at the root above)
-        EXp()[NS * b + 1] = (real)best;
+        pbest[b] = best;   // the old value was consumed by the input shift above
       }
-      lanes_sync();
-      // (b) ego linearisation trajectory of every child branch: time-shifted previous inputs
-      //     (updatetree :1025-1033), nonlinear rollout + per-node linearisation (:1048-1059)
-      for (int c = PP.off[d + 1] + BMPC_LANE_ID; c < PP.off[d + 2]; c += BMPC_LANES) {
-        const int b = bmpc_parent(PP, c, d + 1);
-        const bool leaf = (d + 1 == PP.NB);
-        const real w = Wbp()[c];
-        const int kc = bmpc_ndu(PP, c);
-        int klast;
-        if (leaf) {
-          klast = kc + PP.N - 1;   // repeat the shifted last input (:1033)
-        } else {
-          klast = bmpc_ndu(PP, bmpc_first_child(PP, c, d + 1) + (started ? pbest[c] : 0));
-        }
-        real xb[NXP], xn[NXP], ub[NU];
-#pragma unroll
-        for (int i = 0; i < NXP; ++i) xb[i] = EXXp()[NX * b + i];
-#pragma unroll 1
-        for (int t = 0; t < PP.N; ++t) {
-          const int ksrc = (t < PP.N - 1) ? kc + t + 1 : klast;
-#pragma unroll
-          for (int a = 0; a < NU; ++a) ub[a] = started ? uLin[ksrc * NU + a] : 0.0;
-          if (use_codes) stp()[kp_of(c, t)] = codes[ksrc];   // the active set shifts in time like the inputs
-          if (t == PP.N - 1) {
-#pragma unroll
-            for (int i = 0; i < NXP; ++i) EXLp()[NX * c + i] = xb[i];
-          }
-          node_setup(c, t, xb, ub, w, leaf && t == PP.N - 1, xn);
-#pragma unroll
-          for (int i = 0; i < NXP; ++i) xb[i] = xn[i];
-        }
-#pragma unroll
-        for (int i = 0; i < NXP; ++i) EXXp()[NX * c + i] = xb[i];
-      }
-      lanes_sync();
-      // commit the new arg-max children of this level (their old values are no longer needed)
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) pbest[b] = (int)EXp()[NS * b + 1];
-      lanes_sync();
+      bsync();
     }
+    }
+    team_sync();
+    node_setup_all();
     if (PP.out.branch_w) {
       for (int b = BMPC_LANE_ID; b < PP.nbranch; b += BMPC_LANES) PP.out.branch_w[(size_t)prob * PP.nbranch + b] = Wbp()[b];
     }
@@ -766,13 +892,13 @@ struct Solver {
 
   // The root is "depth 0, one node": every sweep runs one loop nest over the levels, so that each node step is
   // instantiated once (code size matters: the instruction cache is the first bottleneck of this kernel, profiles/).
-  BMPC_DN void factorize(int mode) {
+  BMPC_DN void factorize_sweep(int mode) {
     const long long prof_t0 = prof_begin(4);
 #pragma unroll 1
     for (int d = PP.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         const real w = Wbp()[b];
         real Pn[NX * NX];
         if (d == PP.NB) {
@@ -791,9 +917,13 @@ struct Solver {
                       PP.ctrl == BMPC_CTRL_ROBUST && d == PP.NB && t == nt - 1);
         pack_sym(Pn, EXp() + NS * b);
       }
-      lanes_sync();
+      bsync();
     }
     prof_end(4, prof_t0);
+  }
+  BMPC_D void factorize(int mode) {
+    if (team_leader()) factorize_sweep(mode);
+    team_sync();
   }
 
   // ========================================================================================
@@ -907,13 +1037,13 @@ struct Solver {
       for (int j = 0; j < NX; ++j) Sg[i * NX + j] = 0.5 * (Sn[i * NX + j] + Sn[j * NX + i]);
   }
 
-  BMPC_DN void choose_rho() {
+  BMPC_DN void choose_rho_sweep() {
     const long long prof_t0 = prof_begin(3);
 #pragma unroll 1
     for (int d = 0; d <= PP.NB; ++d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         real Sg[NX * NX];
         if (d == 0) {
 #pragma unroll
@@ -926,9 +1056,13 @@ struct Solver {
         for (int t = 0; t < nt; ++t) node_cov(kp_of(b, t), w, Sg);
         pack_sym(Sg, EXp() + NS * b);
       }
-      lanes_sync();
+      bsync();
     }
     prof_end(3, prof_t0);
+  }
+  BMPC_D void choose_rho() {
+    if (team_leader()) choose_rho_sweep();
+    team_sync();
   }
 
   // ========================================================================================
@@ -969,13 +1103,13 @@ struct Solver {
     }
   }
 
-  BMPC_DN void backward() {
+  BMPC_DN void backward_sweep() {
     const long long prof_t0 = prof_begin(5);
 #pragma unroll 1
     for (int d = PP.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         real pn[NX];
         if (d == PP.NB) {
 #pragma unroll
@@ -1007,9 +1141,13 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXp()[NS * b + i] = pn[i];
       }
-      lanes_sync();
+      bsync();
     }
     prof_end(5, prof_t0);
+  }
+  BMPC_D void backward() {
+    if (team_leader()) backward_sweep();
+    team_sync();
   }
 
   BMPC_D void fw_step(int kp, real* x) {
@@ -1035,14 +1173,13 @@ struct Solver {
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
   }
 
-  BMPC_DN void forward() {
+  BMPC_DN void forward_sweep() {
     const long long prof_t0 = prof_begin(5);
-    ++nsolve;
 #pragma unroll 1
     for (int d = 0; d <= PP.NB; ++d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         real x[NX];
         if (d == 0) {
 #pragma unroll
@@ -1058,9 +1195,23 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXXp()[NX * b + i] = x[i];
       }
-      lanes_sync();
+      bsync();
     }
     prof_end(5, prof_t0);
+  }
+  BMPC_D void forward() {
+    ++nsolve;
+    if (team_leader()) forward_sweep();
+    team_sync();
+  }
+  // one KKT solve without anything between the two sweeps (ADMM, interior point): the team meets once
+  BMPC_D void kkt_solve() {
+    ++nsolve;
+    if (team_leader()) {
+      backward_sweep();
+      forward_sweep();
+    }
+    team_sync();
   }
 
   // ========================================================================================
@@ -1097,7 +1248,7 @@ struct Solver {
     real res = 0.0;
     if (CHECK) { gap_r = 0.0; stp_r = 0.0; gap_u = 0.0; stp_u = 0.0; set_changes = 0; }
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1191,7 +1342,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(3);
     real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1205,7 +1356,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(3);
     const real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1230,7 +1381,7 @@ struct Solver {
   BMPC_DN void guess_from_codes() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1258,7 +1409,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(9);
     code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       codes[k] = stp()[kp_of(b, t)];
@@ -1280,7 +1431,7 @@ struct Solver {
     BMPC_TRACE("    rebalance: rows gap %.2e step %.2e -> x%.2f   inputs gap %.2e step %.2e -> x%.2f\n", gr, sr, fr, gu, su, fu);
     if (fr == 1.0 && fu == 1.0) return false;
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1319,7 +1470,7 @@ struct Solver {
   BMPC_DN void polish_guess() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1364,7 +1515,7 @@ struct Solver {
   BMPC_DN void polish_assemble() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1419,7 +1570,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(6);
     real res = 0.0;
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1450,7 +1601,7 @@ struct Solver {
   BMPC_DN void polish_inject() {
     const long long prof_t0 = prof_begin(6);
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1466,70 +1617,97 @@ struct Solver {
   // Adjoint (costate) sweep of the equality-constrained solution in XQ/UQ: lam_k = dstage/dxi + A~' lam_{k+1}.  The
   // multiplier of a pinned input is minus the Lagrangian gradient with respect to it; for the free inputs that
   // gradient is zero (stationarity), whose largest violation is returned as a certificate.
-  BMPC_D real adjoint_step(int k, int b, int t, int kp, real w, real* lam) {
-    real lin[M::NLIN], x[NX], u[NU], gu[NU], st_x[NX];
+  // Only lam itself is a recursion: the stage gradients (state cost, soft-row terms, input cost) are computed for all
+  // nodes at once by adjoint_stage (node-parallel) and parked in the gain fields F_K, which are dead between the last
+  // KKT solve of a polish pass and the next factorisation; the sweep then adds A~' lam and B~' lam per node.
+  static constexpr int F_AX = F_K;        // stage gradient with respect to the (augmented) state
+  static constexpr int F_AU = F_K + NX;   // stage gradient with respect to the input, without B~' lam
+  static_assert(NX + NU <= NU * NX, "adjoint scratch does not fit the gain fields");
+  BMPC_DN void adjoint_stage() {
+#pragma unroll 1
+    BMPC_FOR_NODES(k) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wbp()[b];
+      real x[NX], u[NU], st_x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
+      const code_t code = stp()[kp];
+      const real rate = (k == 0) ? 0.0 : w;
+      const real sig = (b >= PP.off[PP.NB] && t == PP.N - 1) ? 0.0 : 1.0;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        real g = (k == 0) ? rlin : 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < NU; ++b2) {
+          real r2 = w * (PP.R[a * NU + b2] + PP.R[b2 * NU + a]);
+          if (RATE && k == 0) r2 += 2.0 * PP.dR[a > b2 ? a : b2];
+          g += r2 * u[b2];
+        }
+        if (RATE) g += 2.0 * rate * PP.dR[a] * (sig * u[a] - x[NXP + (RATE ? a : 0)]);
+        F(F_AU + a, kp) = g;
+      }
+      const real qs = w * (1.0 + PP.dq_scale);
+      const real lamw = PP.lam_lin * w;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        real v = 0.0;
+        if (i < NXP) {
+          v = F(F_Q + (i < NXP ? i : 0), kp);
+#pragma unroll
+          for (int j = 0; j < NXP; ++j) v += qs * (PP.Q[(i < NXP ? i : 0) * NXP + j] + PP.Q[j * NXP + (i < NXP ? i : 0)]) * x[j];
+        } else if (RATE) {
+          v = 2.0 * rate * PP.dR[i - NXP] * (x[i] - u[i - NXP]);
+        }
+        st_x[i] = v;
+      }
+#pragma unroll 1
+      for (int j = 0; j < NR; ++j) {
+        const int cj = row_of(code, j);
+        real g = 0.0;
+        if (cj == ROW_UP_LIN) g = lamw;
+        else if (cj == ROW_LO_LIN) g = -lamw;
+        else if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) g = F(F_Y + j, kp);
+        if (g != 0.0) add_row_grad(kp, j, g, st_x);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) F(F_AX + i, kp) = st_x[i];
+    }
+    lanes_sync();
+  }
+  BMPC_D real adjoint_step(int kp, real* lam) {
+    real lin[M::NLIN], gu[NU];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
-#pragma unroll
-    for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
     const code_t code = stp()[kp];
-    const real rate = (k == 0) ? 0.0 : w;
-    const real sig = (b >= PP.off[PP.NB] && t == PP.N - 1) ? 0.0 : 1.0;
     M::mulBT(PP, lin, lam, gu);
     real viol = 0.0;
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
-      real g = gu[a] + ((k == 0) ? rlin : 0.0);
-#pragma unroll
-      for (int b2 = 0; b2 < NU; ++b2) {
-        real r2 = w * (PP.R[a * NU + b2] + PP.R[b2 * NU + a]);
-        if (RATE && k == 0) r2 += 2.0 * PP.dR[a > b2 ? a : b2];
-        g += r2 * u[b2];
-      }
-      if (RATE) g += 2.0 * rate * PP.dR[a] * (sig * u[a] - x[NXP + (RATE ? a : 0)]);
+      const real g = gu[a] + F(F_AU + a, kp);
       if (pinned(code, a)) F(F_Y + NR + a, kp) = -g;
       else viol = fmax(viol, fabs(g));
-    }
-    const real qs = w * (1.0 + PP.dq_scale);
-    const real lamw = PP.lam_lin * w;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      real v = 0.0;
-      if (i < NXP) {
-        v = F(F_Q + (i < NXP ? i : 0), kp);
-#pragma unroll
-        for (int j = 0; j < NXP; ++j) v += qs * (PP.Q[(i < NXP ? i : 0) * NXP + j] + PP.Q[j * NXP + (i < NXP ? i : 0)]) * x[j];
-      } else if (RATE) {
-        v = 2.0 * rate * PP.dR[i - NXP] * (x[i] - u[i - NXP]);
-      }
-      st_x[i] = v;
-    }
-#pragma unroll 1
-    for (int j = 0; j < NR; ++j) {
-      const int cj = row_of(code, j);
-      real g = 0.0;
-      if (cj == ROW_UP_LIN) g = lamw;
-      else if (cj == ROW_LO_LIN) g = -lamw;
-      else if (cj == ROW_UP_KINK || cj == ROW_LO_KINK) g = F(F_Y + j, kp);
-      if (g != 0.0) add_row_grad(kp, j, g, st_x);
     }
     real al[NX];
     M::mulAT(PP, lin, lam, al);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) lam[i] = st_x[i] + al[i];
+    for (int i = 0; i < NX; ++i) lam[i] = F(F_AX + i, kp) + al[i];
     return viol;
   }
 
   BMPC_DN real polish_adjoint() {
     const long long prof_t0 = prof_begin(7);
+    adjoint_stage();
     real viol = 0.0;
+    if (team_leader()) {
 #pragma unroll 1
     for (int d = PP.NB; d >= 0; --d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         const real w = Wbp()[b];
         real lam[NX];
         if (d == PP.NB) {
@@ -1559,14 +1737,15 @@ struct Solver {
             for (int i = 0; i < NX; ++i) lam[i] += EXp()[NS * (fc + c) + i];
         }
         const int kp0 = kp_of(b, 0);
-        const int k0 = bmpc_ndu(PP, b);
 #pragma unroll 1
-        for (int t = nt - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(k0 + t, b, t, kp0 + t, w, lam));
+        for (int t = nt - 1; t >= 0; --t) viol = fmax(viol, adjoint_step(kp0 + t, lam));
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXp()[NS * b + i] = lam[i];
       }
-      lanes_sync();
+      bsync();
     }
+    }
+    team_sync();
     { const auto prof_rv = viol; prof_end(7, prof_t0); return prof_rv; }
   }
 
@@ -1581,7 +1760,7 @@ struct Solver {
     real smax = 0.0;
     const real tol = 1e-7;
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1812,7 +1991,7 @@ struct Solver {
     const bool assemble = (phase == IPM_PRED_ASM || phase == IPM_CORR_ASM);
     const bool first = (phase == IPM_PRED_ASM && !(alpha > 0.0));
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1883,7 +2062,7 @@ struct Solver {
   BMPC_DN int ipm_init() {
     int pairs = 0;
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1927,7 +2106,7 @@ struct Solver {
   // active set + multipliers implied by the converged interior-point state -> starting guess of the polish
   BMPC_DN void ipm_guess() {
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -1980,7 +2159,7 @@ struct Solver {
 
   BMPC_DN void ipm_export() {   // interior-point iterate -> XQ/UQ (what finish() reads)
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -2008,8 +2187,7 @@ struct Solver {
       if (it == PP.ipm_max_iter) break;
       factorize(FACT_IPM);
       ++nfact;
-      backward();
-      forward();
+      kkt_solve();
       ipm_pass(bmpc_opaque(IPM_PRED_STEP), 0.0, 0.0);
       const real a_aff = fmin(1.0, 1.0 / fmax(lanes_max(ipm_ratio), 1e-300));
       // gap after the affine step: every product moves to (1 - a) q1 q2 + a^2 dq1 dq2
@@ -2017,8 +2195,7 @@ struct Solver {
       real sigma = mu_aff / mu;
       sigma = sigma * sigma * sigma;
       ipm_pass(bmpc_opaque(IPM_CORR_ASM), sigma * mu, a_aff);
-      backward();
-      forward();
+      kkt_solve();
       ipm_pass(bmpc_opaque(IPM_CORR_STEP), 0.0, 0.0);
       alpha = fmin(1.0, 0.995 / fmax(lanes_max(ipm_ratio), 1e-300));
       BMPC_TRACE("      a_aff %.3f sigma %.2e alpha %.4f\n", a_aff, sigma, alpha);
@@ -2033,93 +2210,129 @@ struct Solver {
   // ========================================================================================
   // Final pass: clamp inputs, roll the linear dynamics out, write outputs and persistent state
   // ========================================================================================
-  BMPC_D real emit_node(int b, int t, int kp, real w, real* x, real* uLin, real rate, real sig, bool use_qf = false) {
-    const real* Qs = use_qf ? PP.Qf : PP.Q;
-    const int k = bmpc_ndu(PP, b) + t;
+  // The only recursion of the final pass is the rollout of the linear dynamics under the clamped inputs (finish_step,
+  // lanes = branches); objective terms and every output are written by the node-parallel emit_nodes afterwards.
+  BMPC_D void finish_step(int kp, real* x) {
     real lin[M::NLIN], cc[M::NCC], u[NU], xn[NX];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
 #pragma unroll
     for (int i = 0; i < M::NCC; ++i) cc[i] = F(F_CC + i, kp);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) u[a] = bmpc_clamp(F(F_UQ + a, kp), PP.ulo[a], PP.uhi[a]);
-    // objective (slacks eliminated)
-    real J = 0.0;
-    const real qs = w * (1.0 + PP.dq_scale);
-#pragma unroll
-    for (int i = 0; i < NXP; ++i) {
-      real a = 0.0;
-#pragma unroll
-      for (int j = 0; j < NXP; ++j) a += Qs[i * NXP + j] * x[j];
-      J += qs * x[i] * a + F(F_Q + i, kp) * x[i];
-    }
-    if (RATE) {
-      // input-rate pair (previous input v = x[NXP..], this input u): rate [v'dR v - 2 v'dR u + sig u'dR u]
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        const real v = x[NXP + (RATE ? a : 0)];
-        J += rate * PP.dR[a] * (v * v - 2.0 * v * u[a] + sig * u[a] * u[a]);
-      }
-      if (k == 0) {
-#pragma unroll
-        for (int a = 0; a < NU; ++a)
-#pragma unroll
-          for (int b2 = 0; b2 < NU; ++b2) J += PP.dR[a > b2 ? a : b2] * u[a] * u[b2];   // root quirk (:312)
-      }
-    }
-#pragma unroll
     for (int a = 0; a < NU; ++a) {
-      real v = 0.0;
-#pragma unroll
-      for (int b2 = 0; b2 < NU; ++b2) v += PP.R[a * NU + b2] * u[b2];
-      J += w * u[a] * v + ((k == 0) ? rlin * u[a] : 0.0);
-    }
-    const real lam = PP.lam_lin * w;
-#pragma unroll 1
-    for (int j = 0; j < NR; ++j) {
-      real lo, hi;
-      row_bounds(kp, j, lo, hi);
-      const real fx = row_value(kp, j, x);
-      J += lam * (fmax(fx - hi, 0.0) + fmax(lo - fx, 0.0));
-    }
-    if (PP.out.uPred && k < PP.pub_totalu) {
-      real* o = PP.out.uPred + ((size_t)prob * PP.pub_totalu + k) * NU;
-#pragma unroll
-      for (int a = 0; a < NU; ++a) o[a] = u[a];
+      u[a] = bmpc_clamp(F(F_UQ + a, kp), PP.ulo[a], PP.uhi[a]);
+      F(F_UQ + a, kp) = u[a];
     }
 #pragma unroll
-    for (int a = 0; a < NU; ++a) uLin[(size_t)k * NU + a] = u[a];
-    if (k == PP.totalu - 1) {
-#pragma unroll
-      for (int a = 0; a < NU; ++a) uLin[(size_t)(k + 1) * NU + a] = u[a];   // uLin gets the last row twice (:1229)
-    }
-    if (k == 0) {
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        PP.oldin[(size_t)prob * NU + a] = u[a];
-        if (PP.out.u0) PP.out.u0[(size_t)prob * NU + a] = u[a];
-      }
-    }
+    for (int i = 0; i < NX; ++i) F(F_XQ + i, kp) = x[i];
     M::mulA(PP, lin, x, xn);
     M::addBu(PP, lin, u, xn);
     M::addC(cc, xn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
-    return J;
   }
 
-  BMPC_DN real finish() {
-    const long long prof_t0 = prof_begin(9);
+  // objective of one node (slacks eliminated) + its rows of uPred / xPred / uLin / OldInput / xprev
+  BMPC_DN real emit_nodes() {
     real J = 0.0;
     real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
     real* xP = PP.out.xPred ? PP.out.xPred + (size_t)prob * PP.pub_totalx * NXP : nullptr;
     real* xprev = PP.xprev ? PP.xprev + (size_t)prob * PP.pub_totalx * NXP : nullptr;   // robustMPC's LTV shift source
     const bool robust = PP.ctrl == BMPC_CTRL_ROBUST;
 #pragma unroll 1
+    BMPC_FOR_NODES(k) {
+      int b, t;
+      node_of(k, b, t);
+      const int kp = kp_of(b, t);
+      const real w = Wbp()[b];
+      const bool leaf_last = (b >= PP.off[PP.NB] && t == PP.N - 1);
+      const real rate = (k == 0) ? 0.0 : w;
+      const real sig = leaf_last ? 0.0 : 1.0;
+      const real* Qs = (robust && leaf_last) ? PP.Qf : PP.Q;   // robustMPC: the dummy stage carries the terminal cost Qf
+      real x[NX], u[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
+      const real qs = w * (1.0 + PP.dq_scale);
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) {
+        real a = 0.0;
+#pragma unroll
+        for (int j = 0; j < NXP; ++j) a += Qs[i * NXP + j] * x[j];
+        J += qs * x[i] * a + F(F_Q + i, kp) * x[i];
+      }
+      if (RATE) {
+        // input-rate pair (previous input v = x[NXP..], this input u): rate [v'dR v - 2 v'dR u + sig u'dR u]
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          const real v = x[NXP + (RATE ? a : 0)];
+          J += rate * PP.dR[a] * (v * v - 2.0 * v * u[a] + sig * u[a] * u[a]);
+        }
+        if (k == 0) {
+#pragma unroll
+          for (int a = 0; a < NU; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < NU; ++b2) J += PP.dR[a > b2 ? a : b2] * u[a] * u[b2];   // root quirk (:312)
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        real v = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < NU; ++b2) v += PP.R[a * NU + b2] * u[b2];
+        J += w * u[a] * v + ((k == 0) ? rlin * u[a] : 0.0);
+      }
+      const real lam = PP.lam_lin * w;
+#pragma unroll 1
+      for (int j = 0; j < NR; ++j) {
+        real lo, hi;
+        row_bounds(kp, j, lo, hi);
+        const real fx = row_value(kp, j, x);
+        J += lam * (fmax(fx - hi, 0.0) + fmax(lo - fx, 0.0));
+      }
+      const int kx = bmpc_ndx(PP, b) + t;
+      if (xP) {
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) xP[(size_t)kx * NXP + i] = x[i];
+      }
+      if (xprev) {
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) xprev[(size_t)kx * NXP + i] = x[i];
+      }
+      if (PP.out.uPred && k < PP.pub_totalu) {
+        real* o = PP.out.uPred + ((size_t)prob * PP.pub_totalu + k) * NU;
+#pragma unroll
+        for (int a = 0; a < NU; ++a) o[a] = u[a];
+      }
+#pragma unroll
+      for (int a = 0; a < NU; ++a) uLin[(size_t)k * NU + a] = u[a];
+      if (k == PP.totalu - 1) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a) uLin[(size_t)(k + 1) * NU + a] = u[a];   // uLin gets the last row twice (:1229)
+      }
+      if (k == 0) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          PP.oldin[(size_t)prob * NU + a] = u[a];
+          if (PP.out.u0) PP.out.u0[(size_t)prob * NU + a] = u[a];
+        }
+      }
+    }
+    return J;
+  }
+
+  BMPC_DN real finish() {
+    const long long prof_t0 = prof_begin(9);
+    real J = 0.0;
+    real* xP = PP.out.xPred ? PP.out.xPred + (size_t)prob * PP.pub_totalx * NXP : nullptr;
+    const bool robust = PP.ctrl == BMPC_CTRL_ROBUST;
+    if (team_leader()) {
+#pragma unroll 1
     for (int d = 0; d <= PP.NB; ++d) {
       const int nt = (d == 0) ? 1 : PP.N;
 #pragma unroll 1
-      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_LANES) {
+      for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         real x[NX];
         if (d == 0) {
 #pragma unroll
@@ -2129,23 +2342,13 @@ struct Solver {
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = EXXp()[NX * pa + i];
         }
-        const real w = Wbp()[b];
-        const int kx = bmpc_ndx(PP, b);
+        const int kp0 = kp_of(b, 0);
 #pragma unroll 1
-        for (int t = 0; t < nt; ++t) {
-          if (xP) {
-#pragma unroll
-            for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + t) * NXP + i] = x[i];
-          }
-          if (xprev) {
-#pragma unroll
-            for (int i = 0; i < NXP; ++i) xprev[(size_t)(kx + t) * NXP + i] = x[i];
-          }
-          J += emit_node(b, t, kp_of(b, t), w, x, uLin, (d == 0) ? 0.0 : w, (d == PP.NB && t == nt - 1) ? 0.0 : 1.0,
-                         robust && d == PP.NB && t == nt - 1);
-        }
+        for (int t = 0; t < nt; ++t) finish_step(kp0 + t, x);
         if (d == PP.NB && !robust) {
+          const real w = Wbp()[b];
           if (xP) {
+            const int kx = bmpc_ndx(PP, b);
 #pragma unroll
             for (int i = 0; i < NXP; ++i) xP[(size_t)(kx + nt) * NXP + i] = x[i];
           }
@@ -2165,16 +2368,43 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NX; ++i) EXXp()[NX * b + i] = x[i];
       }
-      lanes_sync();
+      bsync();
     }
+    }
+    team_sync();
+    J += emit_nodes();
     { const auto prof_rv = lanes_sum(J); prof_end(9, prof_t0); return prof_rv; }
+  }
+
+  // A failed solve returns the plan the episode already had: previous inputs (uLin rows, OldInput; zeros before the first
+  // success) and, where the library keeps them (robustMPC), the previous predicted states; other states read NaN.
+  BMPC_DN void keep_plan() {
+    const real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
+    const real* xprev = PP.xprev ? PP.xprev + (size_t)prob * PP.pub_totalx * NXP : nullptr;
+#pragma unroll 1
+    BMPC_FOR_NODES(k) {
+      if (PP.out.uPred && k < PP.pub_totalu) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a) PP.out.uPred[((size_t)prob * PP.pub_totalu + k) * NU + a] = uLin[(size_t)k * NU + a];
+      }
+      if (k == 0 && PP.out.u0) {
+#pragma unroll
+        for (int a = 0; a < NU; ++a) PP.out.u0[(size_t)prob * NU + a] = PP.oldin[(size_t)prob * NU + a];
+      }
+    }
+    if (PP.out.xPred) {
+#pragma unroll 1
+      for (int q = BMPC_LANE_ID; q < PP.pub_totalx * NXP; q += BMPC_LANES)
+        PP.out.xPred[(size_t)prob * PP.pub_totalx * NXP + q] = xprev ? xprev[q] : bmpc_nan();
+    }
+    lanes_sync();
   }
 
   // any non-finite input left by the last forward sweep?
   BMPC_DN bool solution_is_finite() {
     int bad = 0;
 #pragma unroll 1
-    for (int k = BMPC_LANE_ID; k < PP.totalu; k += BMPC_LANES) {
+    BMPC_FOR_NODES(k) {
       int b, t;
       node_of(k, b, t);
       const int kp = kp_of(b, t);
@@ -2230,8 +2460,7 @@ struct Solver {
       admm_assemble();
     }
     while (!have_xu && iters < PP.max_iter) {
-      backward();
-      forward();
+      kkt_solve();
       ++iters;
       const bool check = (iters % PP.check_every == 0);
       real res = 1e300;
@@ -2285,10 +2514,13 @@ struct Solver {
     }
     if (!have_xu) {
       // XQ/UQ hold q~: one more KKT solve gives the (x,u) of the final ADMM state
-      backward();
-      forward();
+      kkt_solve();
     }
-    if (solution_is_finite()) {
+    // Only a solved problem is adopted (the reference sets feasible = 1 for OSQP's 'solved' alone and otherwise keeps its
+    // previous plan and linearisation inputs, MPC_branch.py:1224, :1269-1272): an iterate that ended on the iteration caps
+    // or on non-finite data is neither returned nor used as the next warm start.
+    const bool finite = solution_is_finite();
+    if (finite && status <= BMPC_STATUS_CONVERGED) {
       const real J = finish();
       if (status == BMPC_STATUS_POLISHED) store_codes();
       if (BMPC_LANE_ID == 0) {
@@ -2298,9 +2530,13 @@ struct Solver {
         cstate[0] = reuse_rho ? cstate[0] + 1 : 0;
         cstate[1] = (status == BMPC_STATUS_POLISHED) ? 1 : 0;
       }
-    } else if (BMPC_LANE_ID == 0) {
-      // the reference keeps its previous plan when the solver fails (MPC_branch.py:1224): outputs and warm start untouched
-      if (PP.out.status) PP.out.status[prob] = BMPC_STATUS_NUMERIC;
+    } else {
+      keep_plan();
+      if (BMPC_LANE_ID == 0) {
+        if (PP.out.status) PP.out.status[prob] = finite ? status : BMPC_STATUS_NUMERIC;
+        if (PP.out.objective) PP.out.objective[prob] = bmpc_nan();
+        cstate[1] = 0;
+      }
     }
     if (BMPC_LANE_ID == 0) {
       if (PP.out.iters) PP.out.iters[prob] = iters;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BMPC_VERSION 100
+#define BMPC_VERSION 200
 
 #define BMPC_MAX_N 4          /* state dimension supported by this build            */
 #define BMPC_MAX_D 3          /* input dimension                                    */
@@ -160,7 +160,8 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out);
 int bmpc_destroy(bmpc_handle* h);
 
 /* Forget the persistent state of the given episode slots (NULL = all): their next solve is a
- * first solve (inittree: zero inputs, MPC_branch.py:932-957). */
+ * first solve (inittree: zero inputs, MPC_branch.py:932-957).  One kernel (one block per listed slot) on the stream of
+ * the handle's last solve; episode_ids is a HOST array. */
 int bmpc_reset(bmpc_handle* h, const int64_t* episode_ids, int64_t count);
 
 /* Tree numbering tables (BFS order, MPC_branch.py:928-981).  Each array has bmpc_num_branches()
@@ -184,16 +185,25 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
                const double* policy_params, int64_t count, const bmpc_outputs* out, void* stream);
 
 /* Same step on HOST buffers: copies inputs to the device, solves, copies every non-NULL output
- * back and synchronises.  `out` holds HOST pointers here. */
+ * back and synchronises.  `out` holds HOST pointers here.  Inputs and outputs each travel in ONE transfer through
+ * pinned staging owned by the handle (runs on the stream of the handle's last solve). */
 int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                     const double* policy_params, int64_t count, const bmpc_outputs* out);
+/* Zero-copy variant (the call the drop-in BranchMPC.solve makes): `want` marks the requested outputs with non-NULL
+ * members (values ignored); `views` receives HOST pointers into the handle's pinned result block, [count] rows each,
+ * valid until the next bmpc_solve_host* call on this handle. */
+int bmpc_solve_host_views(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                          const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views);
 
 /* Persistent state access for tests / checkpointing (device or host pointers, see `on_host`).
- *   uLin [count][totalu+1][d], pbest [count][nbranch] (int32), old_input [count][d], started [count] (int32) */
-int bmpc_get_state(bmpc_handle* h, double* uLin, int32_t* pbest, double* old_input, int32_t* started,
+ *   uLin [count][bmpc_ulin_rows][d], pbest [count][nbranch] (int32), old_input [count][d], started [count] (int32),
+ *   xprev [count][totalx][n]: robustMPC only (its linearisation is the previous predicted trajectory shifted,
+ *   MPC_branch.py:1429-1431), NULL otherwise; restoring `started` into a robustMPC handle requires xprev.
+ * Like bmpc_reset they are ordered behind the handle's last solve (they run on its stream and synchronise it). */
+int bmpc_get_state(bmpc_handle* h, double* uLin, int32_t* pbest, double* old_input, int32_t* started, double* xprev,
                    int64_t count, int on_host);
 int bmpc_set_state(bmpc_handle* h, const double* uLin, const int32_t* pbest, const double* old_input,
-                   const int32_t* started, int64_t count, int on_host);
+                   const int32_t* started, const double* xprev, int64_t count, int on_host);
 
 /* Model functions evaluated on the device for a batch of points (parity tests of rows M1-M5):
  *   dyn_linearization: A [count][n][n], B [count][n][d], C [count][n], xp [count][n]
