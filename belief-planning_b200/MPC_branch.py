@@ -229,7 +229,27 @@ class robustMPC(_BatchedController):
 
 
 class BranchMPC_CVaR(_BatchedController):
-    """MPC_branch.BranchMPC_CVaR (:1598-2152) is an SOCP (ECOS in the reference); not built yet."""
+    """MPC_branch.BranchMPC_CVaR (:1598-2152), the controller main_branch.py:48 builds: nested-CVaR objective over the
+    scenario tree (the reference hands a second-order-cone program to ECOS).  Same constructor and `solve` signature as the
+    reference (`ralpha` :1601, `solve(x, z, xRef, S, Fx, bx)` :2043); on the device the cone program is solved as a
+    cutting-plane loop over the risk multipliers whose inner problems are branch-weighted tree QPs (csrc/bmpc_solver.h).
+    The state transformation `S` / time-varying `Fx, bx` of the merge scene (:2057-2063) are not built."""
+    controller_kind = abi.CTRL_CVAR
 
-    def __init__(self, mpcParameters, predictiveModel, ralpha=0.1, **kw):
-        raise NotImplementedError("BranchMPC_CVaR (SOCP) is not built yet; use BranchMPC")
+    def __init__(self, mpcParameters, predictiveModel, ralpha=0.1, S=None, **solver_knobs):
+        if S is not None:
+            raise NotImplementedError("BranchMPC_CVaR with a state transformation S (merge scenario) is not built")
+        super().__init__(mpcParameters, predictiveModel, cvar_alpha=float(ralpha), **solver_knobs)
+        self.ralpha = ralpha
+        self.S = None
+        self.param = mpcParameters
+        self.psimax = np.squeeze(np.asarray(mpcParameters.bx, dtype=float)).reshape(-1)[2]     # bx[0][2][0], :1622
+
+    def solve(self, x, z, xRef=None, S=None, Fx=None, bx=None):
+        if S is not None:
+            raise NotImplementedError("BranchMPC_CVaR.solve with a state transformation S (merge scenario) is not built")
+        for given, own in ((Fx, self.Fx), (bx, self.bx)):
+            if given is not None and not np.array_equal(np.squeeze(np.asarray(given, dtype=float)),
+                                                        np.squeeze(np.asarray(own, dtype=float))):
+                raise NotImplementedError("time-varying state constraints (merge scenario) are not built")
+        return super().solve(x, z, xRef)

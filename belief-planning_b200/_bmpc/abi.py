@@ -8,7 +8,7 @@ import os
 MAX_N, MAX_D, MAX_POLICIES, MAX_ROWS, MAX_NB = 4, 3, 4, 4, 3
 
 MODEL_HIGHWAY, MODEL_QUADRUPED = 0, 1
-CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST = 0, 1, 2
+CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST, CTRL_CVAR = 0, 1, 2, 3
 POLICY_MAINTAIN, POLICY_BRAKE, POLICY_LC, POLICY_TRACKV, POLICY_FORWARD, POLICY_STOP = range(6)
 STATUS_POLISHED, STATUS_CONVERGED, STATUS_MAXITER, STATUS_NUMERIC = range(4)
 SLAB_AUTO, SLAB_SHARED, SLAB_SPLIT, SLAB_GLOBAL = range(4)
@@ -35,7 +35,7 @@ class Config(C.Structure):
         ("max_iter", _i32), ("polish_first", _i32), ("polish_every", _i32), ("polish_passes", _i32),
         ("polish_al_iters", _i32), ("polish_careful", _i32), ("warm_polish", _i32), ("rho_refresh", _i32),
         ("alpha", _dbl), ("theta", _dbl), ("theta_u", _dbl), ("eps_abs", _dbl), ("polish_big", _dbl),
-        ("polish_mult", _dbl),
+        ("polish_mult", _dbl), ("cvar_alpha", _dbl),
         ("slab_mode", _i32), ("batch_capacity", _i32), ("device", _i32), ("reserved", _i32 * 8),
     ]
 

@@ -222,6 +222,8 @@ struct bmpc_handle {
   int* counter = nullptr;
   real* gws = nullptr;
   real* ipm_ws = nullptr;   // per-warp scratch of the interior-point fallback
+  real* nu_cache = nullptr; // BranchMPC_CVaR: risk multipliers of each episode's last step
+  real* cv_ws = nullptr;    // BranchMPC_CVaR: per-team scratch of the master problem
   KParams* pstage = nullptr;              // pinned staging ring of parameter blocks (source of the constant-memory upload)
   cudaEvent_t pstage_evt[BMPC_PSTAGE] = {};
   unsigned pstage_next = 0;
@@ -353,6 +355,8 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->counter);
   cudaFree(h->gws);
   cudaFree(h->ipm_ws);
+  cudaFree(h->nu_cache);
+  cudaFree(h->cv_ws);
   if (h->pstage) cudaFreeHost(h->pstage);
   for (int i = 0; i < BMPC_PSTAGE; ++i) if (h->pstage_evt[i]) cudaEventDestroy(h->pstage_evt[i]);
   cudaFree(h->stage_in);
@@ -394,6 +398,11 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
   if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
   BMPC_CK(h, cudaMalloc(&h->ipm_ws, (size_t)h->grid * h->P.ipm_reals * sizeof(real)));
+  if (cfg->controller == BMPC_CTRL_CVAR) {
+    BMPC_CK(h, cudaMalloc(&h->nu_cache, cap * P.nbranch * sizeof(real)));
+    BMPC_CK(h, cudaMemset(h->nu_cache, 0, cap * P.nbranch * sizeof(real)));
+    BMPC_CK(h, cudaMalloc(&h->cv_ws, (size_t)h->grid * h->P.cv_reals * sizeof(real)));
+  }
   BMPC_CK(h, cudaMallocHost(&h->pstage, BMPC_PSTAGE * sizeof(KParams)));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
   BMPC_CK(h, cudaEventCreate(&h->ev1));
@@ -519,6 +528,8 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.counter = h->counter;
   P.gws = h->gws;
   P.ipm = h->ipm_ws;
+  P.nu_cache = h->nu_cache;
+  P.cv = h->cv_ws;
   BMPC_CK(h, cudaMemsetAsync(h->counter, 0, sizeof(int), s));
   // rows of branch_p that belong to leaf branches carry no probabilities: NaN pattern, on the solve's own stream
   if (out->branch_p) BMPC_CK(h, cudaMemsetAsync(out->branch_p, 0xff, (size_t)count * h->P.nbranch * h->cfg.m * sizeof(real), s));

@@ -31,9 +31,16 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   if (c.m < 1 || c.m > BMPC_MAX_POLICIES) { *err = "m must be in [1, BMPC_MAX_POLICIES]"; return BMPC_E_INVALID; }
   if (!(c.dt > 0.0)) { *err = "dt must be positive"; return BMPC_E_INVALID; }
   if (c.n_rows < 0 || c.n_rows > BMPC_MAX_ROWS) { *err = "n_rows out of range"; return BMPC_E_INVALID; }
-  if (c.controller != BMPC_CTRL_BRANCH && c.controller != BMPC_CTRL_PROX && c.controller != BMPC_CTRL_ROBUST) {
+  if (c.controller != BMPC_CTRL_BRANCH && c.controller != BMPC_CTRL_PROX && c.controller != BMPC_CTRL_ROBUST &&
+      c.controller != BMPC_CTRL_CVAR) {
     *err = "unknown controller kind";
     return BMPC_E_INVALID;
+  }
+  if (c.controller == BMPC_CTRL_CVAR) {
+    if (c.model != BMPC_MODEL_HIGHWAY) { *err = "BranchMPC_CVaR is built for the highway model"; return BMPC_E_UNSUPPORTED; }
+    if (!(c.cvar_alpha > 0.0 && c.cvar_alpha <= 1.0)) { *err = "cvar_alpha (ralpha) must be in (0, 1]"; return BMPC_E_INVALID; }
+    for (int a = 0; a < d; ++a)
+      if (c.dR[a] != 0.0) { *err = "BranchMPC_CVaR ignores input-rate costs; dR must be 0"; return BMPC_E_UNSUPPORTED; }
   }
   const bool robust = c.controller == BMPC_CTRL_ROBUST;
   if (robust) {
@@ -106,11 +113,31 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   for (int i = 0; i < n * n; ++i) { P.Q[i] = c.Q[i]; P.Qf[i] = c.Qf[i]; }
   for (int i = 0; i < d * d; ++i) P.R[i] = c.R[i];
   for (int i = 0; i < d; ++i) { P.dR[i] = c.dR[i]; P.ulo[i] = c.u_lo[i]; P.uhi[i] = c.u_hi[i]; }
-  P.dq_scale = (c.controller == BMPC_CTRL_PROX) ? 3.0 : (robust ? 0.0 : 0.5);   // MPC_branch.py:271 / :1070 / none in robustMPC
+  // MPC_branch.py:271 / :1070 / none in robustMPC and in BranchMPC_CVaR (its cones carry (x - xRef)'Q(x - xRef) only, :1953-1957)
+  P.dq_scale = (c.controller == BMPC_CTRL_PROX) ? 3.0 : ((robust || c.controller == BMPC_CTRL_CVAR) ? 0.0 : 0.5);
+  P.cvar_alpha = c.cvar_alpha;
+  P.cvar_floor = 1.0e-6;
+  P.cvar_tol = 1.0e-8;
+  P.cvar_max_cuts = 32;
+  {
+    // master LP of the risk multipliers: variables nu_c (c = 1..nbranch-1) and t; rows: one per non-leaf branch, the
+    // bdim + m - 1 coupling rows of the dual-CVaR equalities (with the reference's index rule) and the cuts
+    const int bdim = P.off[P.NB];
+    const int nvar = P.nbranch;                              // nbranch - 1 multipliers + t
+    const int nrow = bdim + (bdim + P.m - 1) + P.cvar_max_cuts;
+    P.cv_rows = nrow + 1;
+    P.cv_cols = nvar + nrow + 1;
+    P.cv_reals = (size_t)2 * P.nbranch + (size_t)bdim * P.m + (size_t)P.cvar_max_cuts * P.nbranch +
+                 (size_t)P.cv_rows * P.cv_cols + (size_t)(P.cv_rows + 3) / 2 + 2;   // multipliers, p, cuts, tableau, basis (ints)
+  }
   P.lam_lin = c.Qslack[1];
   P.nrows = c.n_rows;
   for (int j = 0; j < c.n_rows; ++j) {
     for (int i = 0; i < n; ++i) P.rf[j][i] = c.row_f[j][i];
+    int nz = 0, one = -1;
+    for (int i = 0; i < n; ++i)
+      if (c.row_f[j][i] != 0.0) { ++nz; one = i; }
+    P.rf_one[j] = (nz == 1) ? one : -1;
     P.rlo[j] = isfinite(c.row_lo[j]) ? c.row_lo[j] : -1.0e300;
     P.rhi[j] = isfinite(c.row_hi[j]) ? c.row_hi[j] : 1.0e300;
     if (!(P.rlo[j] <= P.rhi[j])) { *err = "empty state row range"; return BMPC_E_INVALID; }
@@ -133,7 +160,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.inv_theta_u = 1.0 / P.theta_u;
   P.eps_abs = c.eps_abs > 0.0 ? c.eps_abs : 1.0e-6;
   P.polish_big = c.polish_big > 0.0 ? c.polish_big : 1.0e4;
-  P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e4;
+  P.polish_mult = c.polish_mult > 0.0 ? c.polish_mult : 1.0e5;   // measured: one KKT solve fewer per polish pass than 1e4
   P.check_every = 5;
   P.polish_stable = c.reserved[2];
   // measured on the B200 (profiles/r01_knob_matrix.md): the highway problems are cheapest when the ADMM runs until its

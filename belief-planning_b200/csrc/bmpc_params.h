@@ -28,6 +28,7 @@ struct KParams {
   real lam_lin;                 // Qslack[1]
   int nrows;                    // two-sided state rows (collision row not counted)
   real rf[BMPC_MAX_ROWS][BMPC_MAX_N], rlo[BMPC_MAX_ROWS], rhi[BMPC_MAX_ROWS];
+  int rf_one[BMPC_MAX_ROWS];    // index of the row's only non-zero entry, or -1 for a general row
   real ulo[BMPC_MAX_D], uhi[BMPC_MAX_D];
   // ---- solver ----
   int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes, check_every, polish_stable, polish_force;
@@ -37,6 +38,15 @@ struct KParams {
   int cycles_mode;              // 0: `cycles` = whole solve; k > 0: time spent in phase k (see Solver::prof_begin)
   int ipm_after, ipm_max_iter;  // interior-point fallback: after this many failed polish attempts (0 = never), iteration cap
   real ipm_mu_tol, ipm_s0, ipm_y0;
+  // ---- BranchMPC_CVaR: cutting-plane loop over the risk multipliers ----
+  real cvar_alpha;              // ralpha
+  real cvar_floor;              // smallest branch weight handed to the inner tree QP (a cone without risk weight)
+  real cvar_tol;                // relative gap between the cutting-plane model and the value at the current multipliers
+  int cvar_max_cuts;            // cap on inner solves per MPC step
+  int cv_rows, cv_cols;         // master LP tableau (rows incl. objective, columns incl. right-hand side)
+  real* nu_cache;               // persistent [cap][nbranch]: multipliers of the last solved step (warm start)
+  real* cv;                     // per-team scratch of the risk master problem
+  size_t cv_reals;
   // ---- batch ----
   int count;
   const real* x0;

@@ -42,6 +42,9 @@ extern "C" {
 #define BMPC_CTRL_BRANCH 0 /* MPC_branch.BranchMPC (effective, second definition, :881) */
 #define BMPC_CTRL_PROX 1   /* MPC_branch.BranchMPCProx (:82)                             */
 #define BMPC_CTRL_ROBUST 2 /* MPC_branch.robustMPC (:1275): total_u = N*NB+1, total_x = N*NB+2; xLin/zPred outputs unused */
+#define BMPC_CTRL_CVAR 3   /* MPC_branch.BranchMPC_CVaR (:1598): nested-CVaR objective (the controller main_branch.py:48 builds);
+                              highway model; solved as a cutting-plane loop over the risk multipliers of the cones whose
+                              inner problems are branch-weighted tree QPs */
 
 /* backup-policy kinds (symbolic branch of each reference policy) */
 #define BMPC_POLICY_MAINTAIN 0 /* highway_branch_dyn.backup_maintain        :54  */
@@ -119,7 +122,8 @@ typedef struct bmpc_config {
   double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */
   double eps_abs;          /* ADMM residual tolerance for STATUS_CONVERGED (1e-6)                */
   double polish_big;       /* lower bound of the stiff penalty, times branch weight (1e4)        */
-  double polish_mult;      /* stiff penalty = polish_mult x curvature-matched stiffness (1e4)    */
+  double polish_mult;      /* stiff penalty = polish_mult x curvature-matched stiffness (1e5)    */
+  double cvar_alpha;       /* BMPC_CTRL_CVAR: the `ralpha` of BranchMPC_CVaR (MPC_branch.py:1601, :1798); in (0, 1]        */
 
   int32_t slab_mode;      /* BMPC_SLAB_*: where a problem's working set lives (0 = library picks) */
   int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */

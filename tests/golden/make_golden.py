@@ -33,6 +33,7 @@ with refenv.reference_imports():
     import MPC_branch  # noqa: E402
     import Init_MPC  # noqa: E402
     import osqp  # noqa: E402
+    import ecos  # noqa: E402
 
 
 def highway_cons():
@@ -143,6 +144,55 @@ def run_highway(name, ctrl, policies, NB, x, z, xref, steps, N=8, lc_target=(0.5
     for k in range(steps):
         mpc.solve(x, z, np.array(xref, dtype=float))
         record_step(store, k, mpc, x, z, xref, tree=(ctrl != "robustMPC"))
+        x = euler_highway(x, mpc.uPred[0], 0.1)
+        z = euler_highway(z, np.array([0., -cons.Kpsi * z[3]]), 0.1)     # obstacle keeps 'maintain'
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+
+
+def run_highway_cvar(name, policies, NB, x, z, xref, steps, ralpha, N=8, lc_target=(0.5, 1.8, 15., 0.), n_lane_mpc=4):
+    """The controller main_branch.py:48 instantiates: the UNMODIFIED `BranchMPC_CVaR` (MPC_branch.py:1598-2152) in closed
+    loop; its cone program (c, G, h, dims, A, b as handed to ecos.solve, :2136) is recorded at every step together with the
+    optimum the oracle's interior point returns for it, the risk multipliers and the tree the program was built on."""
+    print("highway CVaR fixture", name)
+    cons = highway_cons()
+    lc_target = np.array(lc_target, dtype=float)
+    model = hw.PredictiveModel(4, 2, N, highway_policies(policies, cons, lc_target), 0.1, cons)
+    par = Init_MPC.initBranchMPC(4, 2, N, NB, lc_target, 6.0, 0.3, n_lane_mpc, cons.W)
+    mpc = MPC_branch.BranchMPC_CVaR(par, model, ralpha=ralpha)
+    store = {"meta_policies": np.array(policies), "meta_ctrl": np.array("BranchMPC_CVaR"), "meta_NB": np.array(NB),
+             "meta_N": np.array(N), "meta_lc_target": lc_target, "meta_steps": np.array(steps),
+             "meta_n_lane_mpc": np.array(n_lane_mpc), "meta_ralpha": np.array(ralpha)}
+    x = np.array(x, dtype=float)
+    z = np.array(z, dtype=float)
+    for k in range(steps):
+        ulin_before = None if mpc.uLin is None or mpc.BT is None else np.array(mpc.uLin)
+        pbest_before = None if mpc.BT is None else np.array([int(np.argmax(b.p)) if b.p is not None else 0 for b in mpc.ndx])
+        mpc.solve(x, z, np.array(xref, dtype=float))
+        lp = ecos.last_problem
+        assert mpc.feasible and lp["info"]["exitFlag"] == 0, "oracle cone solve did not converge"
+        pre = "s%d_" % k
+        store[pre + "x0"], store[pre + "z0"], store[pre + "xref"] = x.copy(), z.copy(), np.array(xref, dtype=float)
+        for nm, mat in (("G", lp["G"]), ("A", lp["A"])):
+            r, c, v, shp = coo(mat)
+            store[pre + nm + "_r"], store[pre + nm + "_c"], store[pre + nm + "_v"], store[pre + nm + "_shape"] = r, c, v, shp
+        store[pre + "c"], store[pre + "h"], store[pre + "b"] = lp["c"], lp["h"], lp["b"]
+        store[pre + "dims_l"] = np.array(lp["dims"]["l"])
+        store[pre + "dims_q"] = np.array(lp["dims"]["q"])
+        store[pre + "sol"] = lp["x"]
+        store[pre + "objective"] = np.array(lp["info"]["pcost"])
+        store[pre + "cert"] = np.array([lp["info"]["gap"], lp["info"]["pres"], lp["info"]["dres"]])
+        store[pre + "xPred"], store[pre + "uPred"] = np.array(mpc.xPred), np.array(mpc.uPred)
+        if ulin_before is not None:
+            store[pre + "uLin_before"] = ulin_before        # warm-start state the step was linearised about
+            store[pre + "pbest_before"] = pbest_before
+        tab, w, p, xbar, zbar, ubar = tree_tables(mpc)
+        store[pre + "tree"], store[pre + "w"], store[pre + "p"] = tab, w, p
+        store[pre + "xbar"], store[pre + "zbar"], store[pre + "ubar"] = xbar, zbar, ubar
+        store[pre + "totals"] = np.array([mpc.totalx, mpc.totalu])
+        store[pre + "branchidx"] = np.array([list(mpc.ndx).index(b) for b in mpc.branchidx])
+        print("   step %d: J %.8f  u0 %s  gap %.1e pres %.1e dres %.1e (%d it)" % (
+            k, lp["info"]["pcost"], np.array2string(mpc.uPred[0], precision=6), lp["info"]["gap"], lp["info"]["pres"],
+            lp["info"]["dres"], lp["info"]["iter"]))
         x = euler_highway(x, mpc.uPred[0], 0.1)
         z = euler_highway(z, np.array([0., -cons.Kpsi * z[3]]), 0.1)     # obstacle keeps 'maintain'
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
@@ -279,7 +329,7 @@ def hmm_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "quad", "hmm"]
+    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "cvar", "quad", "hmm"]
     if "models" in which:
         model_function_vectors()
     if "hw_default" in which:
@@ -298,6 +348,16 @@ if __name__ == "__main__":
     if "robust" in which:
         run_highway("highway_robust_default", "robustMPC", ["maintain", "brake", "lc"], 2,
                     [0, 1.8, 20, 0], [5, 5.4, 20, 0], [0, 1.8, 26.5, 0], steps=3)
+    if "cvar" in which:
+        # main_branch.py:48 (ralpha = 0.9) on the default scene, a close-obstacle scene, and ralpha = 0.1 (the value of sim_merge, :92)
+        run_highway_cvar("highway_cvar_default", ["maintain", "brake", "lc"], 2, [0, 1.8, 20, 0], [5, 5.4, 20, 0],
+                         [0, 1.8, 26.5, 0], steps=4, ralpha=0.9)
+        run_highway_cvar("highway_cvar_close", ["maintain", "brake", "lc"], 2, [0, 1.9, 22, 0.02], [9, 1.8, 17, 0],
+                         [0, 1.8, 25, 0], steps=3, ralpha=0.9, lc_target=(0.5, 5.4, 17., 0.))
+        run_highway_cvar("highway_cvar_alpha01", ["maintain", "brake", "lc"], 2, [0, 5.4, 18, -0.01], [12, 5.6, 15, 0],
+                         [0, 5.4, 20, 0], steps=3, ralpha=0.1)
+        run_highway_cvar("highway_cvar_m2_nb1", ["maintain", "brake"], 1, [0, 1.8, 20, 0], [8, 1.9, 16, 0],
+                         [0, 1.8, 24, 0], steps=3, ralpha=0.1)
     if "quad" in which:
         run_quadruped("quadruped_prox_default", [0, 0, 0], [2, 0.3, np.pi], [5., 5., 0.], steps=3)
     if "hmm" in which:

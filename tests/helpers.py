@@ -160,3 +160,36 @@ def check_forced_interior_point(make_solver, count=6):
         assert np.abs(r["u0"][i] - u).max() < TOL_U0, i
         assert abs(r["objective"][i] - ora.objective) <= TOL_OBJ * abs(ora.objective), i
     return r
+
+
+# ---- BranchMPC_CVaR ------------------------------------------------------------------------------------------------
+CVAR_FIXTURES = ["highway_cvar_default", "highway_cvar_close", "highway_cvar_alpha01", "highway_cvar_m2_nb1"]
+
+
+def cvar_fixture_config(g, **kw):
+    from _bmpc import abi
+    cfg = fixture_config(g, **kw)
+    cfg.controller = abi.CTRL_CVAR
+    cfg.cvar_alpha = float(g["meta_ralpha"])
+    return cfg
+
+
+def check_cvar_fixture(solve, set_state, g):
+    """Every recorded closed-loop step of the UNMODIFIED BranchMPC_CVaR (tests/golden/make_golden.py run_highway_cvar): the
+    warm-start state the reference linearised about (uLin, arg-max children) is restored first, because the cone program
+    leaves the branches without risk weight undetermined and the reference's next linearisation inherits whatever its
+    solver returned there.  Compared: tree data, linearisation trajectory, first input (1e-3), objective J (1e-4 rel.) and the
+    trajectories of the branches whose cones carry weight."""
+    for k in range(int(g["meta_steps"])):
+        pre = "s%d_" % k
+        if k > 0:
+            set_state(g[pre + "uLin_before"], g[pre + "pbest_before"], g["s%d_uPred" % (k - 1)][0])
+        r = solve(g[pre + "x0"], g[pre + "z0"], g[pre + "xref"])
+        assert r["status"][0] in (0, 1), "step %d status %d" % (k, r["status"][0])
+        np.testing.assert_allclose(r["branch_w"][0], g[pre + "w"], atol=1e-6)
+        np.testing.assert_allclose(r["xLin"][0], g[pre + "xbar"], atol=1e-6)
+        np.testing.assert_allclose(r["zPred"][0], g[pre + "zbar"], atol=1e-9)
+        u0 = g[pre + "uPred"][0]
+        assert np.abs(r["u0"][0] - u0).max() < TOL_U0, (k, r["u0"][0], u0)
+        obj = float(g[pre + "objective"])
+        assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj), (k, r["objective"][0], obj)

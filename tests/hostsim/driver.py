@@ -68,6 +68,14 @@ class HostSim:
         self.code_cache = np.zeros(capacity * internal_u, dtype=np.int64)
         self.cache_state = np.full((capacity, 2), -1, dtype=np.int32)
 
+    def set_state(self, uLin, pbest, old_input):
+        """restore a warm-start state (single episode): what bmpc_set_state does on the device"""
+        self.uLin[0, :len(uLin)] = uLin
+        self.pbest[0] = pbest
+        self.oldin[0] = old_input
+        self.started[0] = 1
+        self.cache_state[0] = -1
+
     def solve(self, x0, z0, xref, policy_params=None):
         cfg = self.cfg
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=float)

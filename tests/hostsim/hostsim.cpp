@@ -68,6 +68,10 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   P.cache_state = cache_state;
   P.xprev = (cfg->controller == BMPC_CTRL_ROBUST) ? xprev : nullptr;
   P.out = *out;
+  // BranchMPC_CVaR: master-problem scratch and (per call, not persistent here) the multiplier cache
+  std::vector<real> cv(P.cv_reals + 4, 0.0), nu((size_t)count * P.nbranch + 1, 0.0);
+  P.cv = cv.data();
+  P.nu_cache = nu.data();
   const bool prox = cfg->controller == BMPC_CTRL_PROX;
   if (cfg->controller == BMPC_CTRL_ROBUST) {
     if (g_split) run_layout<HighwayModel, 11, BMPC_SLAB_SPLIT, 9>(P); else run_layout<HighwayModel, 11, BMPC_SLAB_SHARED, 9>(P);

@@ -27,6 +27,9 @@ def apply_env(cfg):
     for knob in ("polish_careful", "polish_passes", "polish_first", "polish_every", "warm_polish", "rho_refresh", "max_iter"):
         if os.environ.get("BMPC_" + knob):
             setattr(cfg, knob, int(os.environ["BMPC_" + knob]))
+    for knob in ("polish_mult", "polish_big", "theta", "theta_u", "alpha"):
+        if os.environ.get("BMPC_" + knob):
+            setattr(cfg, knob, float(os.environ["BMPC_" + knob]))
     return cfg
 
 
