@@ -92,7 +92,7 @@ class _BatchedController:
         self._solver = None
         self._capacity = 0
         self.BT = None
-        self.xPred = self.uPred = self.xLin = self.uLin = None
+        self.xPred = self.uPred = self.xLin = None
         self.zPred = self.branch_w = self.branch_p = None
         self.OldInput = np.zeros(self.d)
         self.feasible = 0
@@ -133,26 +133,30 @@ class _BatchedController:
     def _absorb(self, r, single):
         """Result arrays of a batched solve -> the attributes the reference leaves behind (MPC_branch.py:1204-1229).
         Only solved problems are adopted (feasible = 1 for the solver's 'solved' alone, :1269-1272); an episode whose
-        solve failed keeps its previous plan (:1224), per episode in a batch."""
+        solve failed keeps its previous plan (:1224), per episode in a batch.
+        The arrays are views into the library's pinned result blocks (no copy: a 16384-episode step returns 190 MB): like
+        the reference's attributes they describe the LAST solve; they stay intact during the next call to solve() and are
+        recycled by the one after it - copy what has to live longer."""
         ok = r["status"] <= abi.STATUS_CONVERGED
-        self.status = r["status"][0] if single else r["status"].copy()
+        self.status = r["status"][0] if single else r["status"]
         self.feasible = int(ok[0]) if single else ok.astype(int)
-        self.iterations = r["iters"][0] if single else r["iters"].copy()
+        self.iterations = r["iters"][0] if single else r["iters"]
         B = len(ok)
-        fresh = self.uPred is None or (np.ndim(self.uPred) == 3) == single or (not single and self.uPred.shape[0] != B)
         names = ("xPred", "uPred", "xLin", "zPred", "branch_w", "branch_p", "objective")
-        if fresh:
-            if not ok.all() and self.uPred is None and single:
+        prev = getattr(self, "_res", None)
+        if ok.all() or prev is None or prev["uPred"].shape[0] != B:
+            if not ok.all() and single:
                 raise RuntimeError("the first solve failed (status %d): there is no previous plan to keep" % r["status"][0])
-            self._res = {k: np.array(r[k]) for k in names}          # copies out of the library's pinned result block
+            self._res = {k: r[k] for k in names}
         else:
+            merged = {k: np.array(prev[k]) for k in names}       # failed episodes keep their previous rows
             for k in names:
-                self._res[k][ok] = r[k][ok]
+                merged[k][ok] = r[k][ok]
+            self._res = merged
         res = self._res
         pick = (lambda a: a[0]) if single else (lambda a: a)
         self.xPred, self.uPred = pick(res["xPred"]), pick(res["uPred"])
         self.xLin = self.xPred
-        self.uLin = pick(np.concatenate([res["uPred"], res["uPred"][:, -1:]], axis=1))
         self._xbar, self.zPred = pick(res["xLin"]), pick(res["zPred"])
         self.branch_w, self.branch_p = pick(res["branch_w"]), pick(res["branch_p"])
         self.objective = pick(res["objective"])
@@ -160,6 +164,17 @@ class _BatchedController:
         self.timeStep += 1
         self.BT = True                              # "a tree exists": later solves are updatetree solves
         return self.OldInput
+
+    @property
+    def uLin(self):
+        """uPred with its last row repeated (unpackSolution, MPC_branch.py:1228-1229); built on access."""
+        if self.uPred is None:
+            return None
+        return np.concatenate([self.uPred, self.uPred[..., -1:, :]], axis=-2)
+
+    @uLin.setter
+    def uLin(self, value):
+        pass                                          # the warm start lives on the device (bmpc_set_state)
 
     def solve(self, x, z, xRef=None):
         """Computes the control action(s).  x, z: (n,) or (B, n); xRef: (n,) or (B, n) or None (keep the previous)."""

@@ -198,6 +198,7 @@ __global__ void bmpc_dfma_kernel(double* out, int iters) {
 // handle
 // ------------------------------------------------------------------------------------------------------------
 #define BMPC_PSTAGE 8
+#define BMPC_MAX_CAPTURED 32   // launches of one handle that may be recorded into CUDA graphs
 struct bmpc_handle {
   bmpc_config cfg;
   KParams P;            // call-independent part
@@ -224,6 +225,8 @@ struct bmpc_handle {
   real* ipm_ws = nullptr;   // per-warp scratch of the interior-point fallback
   real* nu_cache = nullptr; // BranchMPC_CVaR: risk multipliers of each episode's last step
   real* cv_ws = nullptr;    // BranchMPC_CVaR: per-team scratch of the master problem
+  KParams* captured = nullptr;            // pinned parameter blocks for launches recorded into CUDA graphs (BMPC_MAX_CAPTURED,
+  int captured_used = 0;                  // allocated at create: nothing may be allocated while a stream is capturing)
   KParams* pstage = nullptr;              // pinned staging ring of parameter blocks (source of the constant-memory upload)
   cudaEvent_t pstage_evt[BMPC_PSTAGE] = {};
   unsigned pstage_next = 0;
@@ -231,7 +234,8 @@ struct bmpc_handle {
   real* stage_in = nullptr;   // x0 | z0 | xref | polpar
   real* stage_in_host = nullptr;
   void* stage_out = nullptr;
-  void* stage_out_host = nullptr;
+  void* stage_out_host[2] = {nullptr, nullptr};   // alternating: the views of one call survive the next call
+  unsigned stage_out_turn = 0;
   size_t stage_out_bytes = 0;
   long long* reset_ids = nullptr;   // device copy of the ids of the last bmpc_reset
   size_t reset_ids_cap = 0;
@@ -314,9 +318,13 @@ static int configure_instance(bmpc_handle* h) {
 
 template <class M, int NR, int NC = 1>
 static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStream_t s) {
+  // the dynamic shared-memory limit is a property of the kernel instance, not of the handle: another handle of the same
+  // instance with a smaller tree may have lowered it since this one was created
   if (h->mode == BMPC_SLAB_SHARED) {
+    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->slab_bytes));
     bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, BMPC_LANES, h->slab_bytes, s>>>();
   } else if (h->mode == BMPC_SLAB_SPLIT) {
+    BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->slab_bytes));
     bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, BMPC_LANES, h->slab_bytes, s>>>();
   } else {
     bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, BMPC_LANES, 0, s>>>();
@@ -358,12 +366,14 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->nu_cache);
   cudaFree(h->cv_ws);
   if (h->pstage) cudaFreeHost(h->pstage);
+  if (h->captured) cudaFreeHost(h->captured);
   for (int i = 0; i < BMPC_PSTAGE; ++i) if (h->pstage_evt[i]) cudaEventDestroy(h->pstage_evt[i]);
   cudaFree(h->stage_in);
   cudaFree(h->stage_out);
   cudaFree(h->reset_ids);
   if (h->stage_in_host) cudaFreeHost(h->stage_in_host);
-  if (h->stage_out_host) cudaFreeHost(h->stage_out_host);
+  for (int i = 0; i < 2; ++i)
+    if (h->stage_out_host[i]) cudaFreeHost(h->stage_out_host[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -404,6 +414,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
     BMPC_CK(h, cudaMalloc(&h->cv_ws, (size_t)h->grid * h->P.cv_reals * sizeof(real)));
   }
   BMPC_CK(h, cudaMallocHost(&h->pstage, BMPC_PSTAGE * sizeof(KParams)));
+  BMPC_CK(h, cudaMallocHost(&h->captured, BMPC_MAX_CAPTURED * sizeof(KParams)));
   BMPC_CK(h, cudaEventCreate(&h->ev0));
   BMPC_CK(h, cudaEventCreate(&h->ev1));
   return bmpc_reset(h, nullptr, 0);
@@ -539,6 +550,21 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   // are ordered behind the previous solve kernel of this device before the symbol is rewritten
   ConstSlot& cs = g_const[h->device & 15];
   std::lock_guard<std::mutex> lock(cs.mu);   // distinct handles may be driven from distinct host threads
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (s) BMPC_CK(h, cudaStreamIsCapturing(s, &capturing));
+  if (capturing == cudaStreamCaptureStatusActive) {
+    // Recorded into a CUDA graph: the upload node reads its pinned source at every replay, so the block gets a buffer of its
+    // own that is never reused; nothing here may wait on the host, and the timing / ordering events stay out of the graph.
+    // The captured graph must not run concurrently with other solves of this device (they share the constant symbol).
+    if (h->captured_used >= BMPC_MAX_CAPTURED) { h->err = "too many captured launches for this handle"; return BMPC_E_CAPACITY; }
+    KParams* own = h->captured + h->captured_used++;
+    *own = P;
+    BMPC_CK(h, cudaMemcpyToSymbolAsync(bmpc_cP, own, sizeof(KParams), 0, cudaMemcpyHostToDevice, s));
+    const int rc = BMPC_DISPATCH(h, launch_instance, h, P, grid, s);
+    if (rc != BMPC_OK) return rc;
+    h->launches += 1;
+    return BMPC_OK;
+  }
   if (!cs.done) BMPC_CK(h, cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
   if (cs.used && cs.stream != s) BMPC_CK(h, cudaStreamWaitEvent(s, cs.done, 0));
   KParams* stage = h->pstage + (h->pstage_next++ % BMPC_PSTAGE);
@@ -606,10 +632,12 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
     h->stage_out_bytes = cap * per;
     BMPC_CK(h, cudaMalloc(&h->stage_out, h->stage_out_bytes));
     BMPC_CK(h, cudaMemset(h->stage_out, 0, h->stage_out_bytes));
-    BMPC_CK(h, cudaMallocHost(&h->stage_out_host, h->stage_out_bytes));
+    BMPC_CK(h, cudaMallocHost(&h->stage_out_host[0], h->stage_out_bytes));
+    BMPC_CK(h, cudaMallocHost(&h->stage_out_host[1], h->stage_out_bytes));
   }
   cudaStream_t s = h->last_stream;
-  BMPC_CK(h, cudaStreamSynchronize(s));   // the previous call's views are dead from here on
+  BMPC_CK(h, cudaStreamSynchronize(s));
+  char* host_out = (char*)h->stage_out_host[h->stage_out_turn++ & 1];   // the views handed out two calls ago die here
   // inputs: x0 | z0 | xref | polpar, [count] rows each, contiguous
   real* hin = h->stage_in_host;
   const size_t rows = (size_t)count;
@@ -646,10 +674,10 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
     }
   const int rc = bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
   if (rc != BMPC_OK) return rc;
-  BMPC_CK(h, cudaMemcpyAsync(h->stage_out_host, h->stage_out, off, cudaMemcpyDeviceToHost, s));
+  BMPC_CK(h, cudaMemcpyAsync(host_out, h->stage_out, off, cudaMemcpyDeviceToHost, s));
   BMPC_CK(h, cudaStreamSynchronize(s));
   for (int i = 0; i < kNumOut; ++i)
-    if (*wslot[i]) *vslot[i] = (char*)h->stage_out_host + offs[i];
+    if (*wslot[i]) *vslot[i] = host_out + offs[i];
   return BMPC_OK;
 }
 

@@ -1922,7 +1922,9 @@ struct Solver {
   // point) show up as multipliers running past their bounds and are revised without waiting for convergence.
   BMPC_DN bool polish(int& nfact, bool allow_careful, bool from_admm_state) {
     if (from_admm_state) polish_guess();
-    const int base_passes = from_admm_state ? PP.polish_passes : PP.warm_passes;
+    // between the cutting-plane iterations of BranchMPC_CVaR the branch weights jump from one vertex of the multiplier set to
+    // another: the verified active set of the last inner problem is several changes away, still far cheaper than ADMM
+    const int base_passes = from_admm_state ? PP.polish_passes : PP.warm_passes * (PP.ctrl == BMPC_CTRL_CVAR ? 3 : 1);
     int prev_changes = 1 << 30;
     bool careful = false;
     const int max_passes = base_passes + PP.polish_careful;

@@ -6,9 +6,13 @@ import numpy as np
 
 from _bmpc import abi, batch, config, policies
 from _bmpc.policies import PolicyProbe, PolicyDescriptor
+from numpy import arctan2   # quadruped_env.py:104 gets casadi's arctan2 through `from quadruped_branch_dyn import *`
+from utils import Quad_constants
 
+# the reference module has no __all__: `from quadruped_branch_dyn import *` (main_quadruped.py:4) also hands out the names it
+# imported itself - main_quadruped.py:31 relies on Quad_constants arriving that way
 __all__ = ["quad_kinetics", "softsat", "backup_forward", "backup_stop", "softmin", "softmax", "propagate_backup",
-           "robot_col", "PredictiveModel"]
+           "robot_col", "PredictiveModel", "Quad_constants", "np", "arctan2"]
 
 
 def quad_kinetics(x, u):

@@ -183,8 +183,11 @@ int bmpc_ulin_rows(const bmpc_handle* h);
  *   policy_params: [count][m][4] device float64 or NULL (per-episode lane-change target etc.;
  *                  the reference rebuilds its model for this, highway_branch_dyn.py:331)
  * The kernel's parameter block travels through one constant-memory symbol per device: the call uploads it stream-ordered
- * and orders itself behind the previous solve launch on that device (other handles, other streams); it waits on a small
- * ring of host events, so it cannot be recorded into a CUDA graph. */
+ * and orders itself behind the previous solve launch on that device (other handles, other streams), so solves of
+ * different handles on one device do not overlap.
+ * The call may be recorded into a CUDA graph (stream capture): the recorded launch keeps a private pinned copy of its
+ * parameter block, and every pointer argument must stay valid and in place for the replays; a replayed graph must not run
+ * concurrently with other solves on the same device.  bmpc_last_kernel_ms() does not see replayed launches. */
 int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                const double* policy_params, int64_t count, const bmpc_outputs* out, void* stream);
 
@@ -194,8 +197,9 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
 int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                     const double* policy_params, int64_t count, const bmpc_outputs* out);
 /* Zero-copy variant (the call the drop-in BranchMPC.solve makes): `want` marks the requested outputs with non-NULL
- * members (values ignored); `views` receives HOST pointers into the handle's pinned result block, [count] rows each,
- * valid until the next bmpc_solve_host* call on this handle. */
+ * members (values ignored); `views` receives HOST pointers into one of the handle's two pinned result blocks, [count] rows
+ * each; the blocks alternate, so the views of a call stay intact during the NEXT bmpc_solve_host* call on this handle and
+ * are overwritten by the one after it. */
 int bmpc_solve_host_views(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                           const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views);
 

@@ -47,9 +47,9 @@ def check_robust_fixture(solve, g, tol=2e-5):
     for k in range(int(g["meta_steps"])):
         pre = "s%d_" % k
         r = solve(g[pre + "x0"], g[pre + "z0"], g[pre + "xref"])
-        # the slots hold near-duplicate collision rows (policies that barely differ early on), so the active set can stay
-        # degenerate and the solve may end on the iteration cap; what is checked is the distance to the reference optimum
-        assert r["status"][0] in (0, 1, 2)
+        # the slots hold near-duplicate collision rows (policies that barely differ early on); the interior-point fallback
+        # settles such degenerate active sets, so the solve must end solved (polished or converged), never on the cap
+        assert r["status"][0] in (0, 1)
         assert r["uPred"][0].shape == g[pre + "uPred"].shape and r["xPred"][0].shape == g[pre + "xPred"].shape
         np.testing.assert_allclose(r["uPred"][0], g[pre + "uPred"], atol=tol)
         np.testing.assert_allclose(r["xPred"][0], g[pre + "xPred"], atol=tol)

@@ -88,4 +88,72 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   }
   return BMPC_OK;
 }
+
+int hostsim_topology(const bmpc_config* cfg, int32_t* ndx, int32_t* ndu, int32_t* depth, int32_t* parent) {
+  KParams P;
+  const int rc = bmpc::make_params(*cfg, &P, &g_err);
+  if (rc != BMPC_OK) return rc;
+  for (int b = 0; b < P.nbranch; ++b) {
+    const int d = bmpc_depth(P, b);
+    ndx[b] = bmpc_ndx(P, b);
+    ndu[b] = bmpc_ndu(P, b);
+    depth[b] = d;
+    parent[b] = d == 0 ? -1 : bmpc_parent(P, b, d);
+  }
+  return BMPC_OK;
+}
+}  // extern "C"
+
+namespace {
+// point-wise model functions with the same model text the kernels use (what bmpc_eval_model does on the device)
+template <class M>
+void eval_points(const KParams& P, const double* x, const double* z, const double* u, const double* polpar, int64_t count,
+                 double* A, double* B, double* C, double* xp, double* zpred, double* p, double* hlin, double* dh) {
+  constexpr int NX = M::NX, NU = M::NU;
+  for (int64_t i = 0; i < count; ++i) {
+    const real* xi = x + i * NX;
+    {
+      real lin[M::NLIN], cc[M::NCC], xn[NX];
+      M::linearize(P, xi, u + i * NU, lin, cc, xn);
+      M::denseA(P, lin, A + i * NX * NX);
+      M::denseB(P, lin, B + i * NX * NU);
+      M::expandC(cc, C + i * NX);
+      for (int q = 0; q < NX; ++q) xp[i * NX + q] = xn[q];
+    }
+    const real* zi = z + i * NX;
+    real h, dhx, dhy;
+    M::collision(P, xi, zi, h, dhx, dhy);
+    hlin[i] = h - (dhx * xi[0] + dhy * xi[1]);
+    for (int q = 0; q < NX; ++q) dh[i * NX + q] = 0.0;
+    dh[i * NX] = dhx;
+    dh[i * NX + 1] = dhy;
+    real hi[BMPC_MAX_POLICIES], himax = -1e300;
+    for (int k = 0; k < P.zm; ++k) {
+      const real* par = polpar ? polpar + (i * P.zm + k) * 4 : P.pol_par[k];
+      const real* par0 = polpar ? polpar + (i * P.zm) * 4 : P.pol_par[0];
+      real zl[NX];
+      real* zo = zpred + i * P.zN * P.zm * NX;
+      hi[k] = M::policy_safety(P, P.pol_kind[k], par, P.pol_kind[0], par0, xi, zi, zl, P.zN, [&](int t, const real* zz) {
+        for (int q = 0; q < NX; ++q) zo[((size_t)t * P.zm + k) * NX + q] = zz[q];
+      });
+      himax = fmax(himax, hi[k]);
+    }
+    real sum = 0.0;
+    for (int k = 0; k < P.zm; ++k) sum += M::branch_weight(P, hi[k], himax);
+    for (int k = 0; k < P.zm; ++k) p[i * P.zm + k] = M::branch_weight(P, hi[k], himax) / sum;
+  }
+}
+}  // namespace
+
+extern "C" {
+int hostsim_eval_model(const bmpc_config* cfg, const double* x, const double* z, const double* u, const double* polpar,
+                       int64_t count, double* A, double* B, double* C, double* xp, double* zpred, double* p, double* hlin,
+                       double* dh) {
+  KParams P;
+  const int rc = bmpc::make_params(*cfg, &P, &g_err);
+  if (rc != BMPC_OK) return rc;
+  if (cfg->model == BMPC_MODEL_HIGHWAY) eval_points<HighwayModel>(P, x, z, u, polpar, count, A, B, C, xp, zpred, p, hlin, dh);
+  else eval_points<QuadrupedModel>(P, x, z, u, polpar, count, A, B, C, xp, zpred, p, hlin, dh);
+  return BMPC_OK;
+}
 }

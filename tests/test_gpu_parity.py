@@ -100,7 +100,7 @@ def test_robust_batch_4096(bmpc):
     mpc = bmpc.BatchedBranchMPC(cfg)
     x0, z0, xref, pp = scenarios.highway_batch(B, seed=5)
     r = mpc.solve_host(x0, z0, xref, pp, outputs=("u0", "uPred", "xPred", "objective", "status", "iters"))
-    assert (r["status"] <= abi.STATUS_MAXITER).all() and np.isfinite(r["objective"]).all()
+    assert (r["status"] <= abi.STATUS_CONVERGED).all() and np.isfinite(r["objective"]).all()
     assert (np.abs(r["uPred"][:, :, 0]) <= 6.0 + 1e-12).all() and (np.abs(r["uPred"][:, :, 1]) <= 0.3 + 1e-12).all()
     for i in (0, 1000, 4095):
         ora = params.highway_robust_mpc(lc_target=pp[i, 2])
@@ -329,3 +329,86 @@ def test_errors_are_codes_not_crashes(bmpc):
 def test_smoke_entry(bmpc):
     import __graft_entry__ as entry
     entry.smoke()
+
+
+def test_solve_is_graph_capturable(bmpc):
+    """bmpc_solve + bmpc_plant_step recorded into a CUDA graph and replayed: the closed loop advances exactly like the
+    eagerly launched one (inputs, outputs and the persistent warm-start state all live at fixed device addresses)."""
+    import torch
+    B, steps = 512, 4
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=77)
+    dev = torch.device("cuda", 0)
+
+    def run(graphed):
+        mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=B))
+        tx, tz, tr, tp = [torch.as_tensor(a, device=dev).clone() for a in (x0, z0, xref, pp)]
+        outs = ("u0", "objective", "status")
+        hist = []
+        if graphed:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                out = mpc.solve(tx, tz, tr, tp, outputs=outs, stream=s.cuda_stream)     # allocate outputs, warm the caches
+                mpc.plant_step(tx, out["u0"], tz, 0, tp, stream=s.cuda_stream)
+                s.synchronize()
+                hist.append((out["u0"].cpu().numpy().copy(), out["status"].cpu().numpy().copy()))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    out = mpc.solve(tx, tz, tr, tp, outputs=outs, stream=torch.cuda.current_stream().cuda_stream)
+                    mpc.plant_step(tx, out["u0"], tz, 0, tp, stream=torch.cuda.current_stream().cuda_stream)
+                for _ in range(steps - 1):
+                    g.replay()
+                    torch.cuda.synchronize()
+                    hist.append((out["u0"].cpu().numpy().copy(), out["status"].cpu().numpy().copy()))
+        else:
+            for _ in range(steps):
+                out = mpc.solve(tx, tz, tr, tp, outputs=outs)
+                mpc.plant_step(tx, out["u0"], tz, 0, tp)
+                torch.cuda.synchronize()
+                hist.append((out["u0"].cpu().numpy().copy(), out["status"].cpu().numpy().copy()))
+        mpc.close()
+        return hist
+
+    eager, graph = run(False), run(True)
+    for (u_e, s_e), (u_g, s_g) in zip(eager, graph):
+        assert np.array_equal(s_e, s_g) and (s_e <= abi.STATUS_CONVERGED).all()
+        assert np.array_equal(u_e, u_g)
+
+
+def test_reset_of_many_episodes_is_one_kernel(bmpc):
+    """bmpc_reset(ids) is one launch (one block per listed slot), not five driver calls per id: 8192 ids in well under a
+    millisecond of device time, and the reset episodes solve cold again while the others stay warm."""
+    import time
+    import torch
+    B = 16384
+    mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=B))
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=3)
+    r0 = mpc.solve_host(x0, z0, xref, pp, outputs=("u0", "status"))
+    ids = np.arange(0, B, 2)
+    n0 = mpc.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mpc.reset(ids)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert mpc.launch_count() - n0 == 1
+    assert dt < 5e-3, dt            # host-side wall time incl. the 64 KB id upload; the kernel itself is ~10 us
+    st = mpc.get_state(B)
+    assert (st["started"][ids] == 0).all() and (st["started"][1::2] == 1).all()
+    assert (st["uLin"][ids] == 0).all() and np.abs(st["uLin"][1::2]).max() > 0
+    r1 = mpc.solve_host(x0, z0, xref, pp, outputs=("u0", "status"))
+    assert np.array_equal(r1["u0"][ids], r0["u0"][ids])          # cold again: same answer as the first cold solve
+    mpc.close()
+
+
+def test_handles_with_different_trees_share_a_kernel_instance(bmpc):
+    """Two handles of the same kernel instance (highway, two state rows) with a small and a large tree: the launch of the
+    large one must not inherit the dynamic shared-memory limit the small one set (regression: round 2)."""
+    small = bmpc.BatchedBranchMPC(scenarios.highway_config(NB=1, batch_capacity=4))
+    large = bmpc.BatchedBranchMPC(scenarios.highway_config(NB=3, batch_capacity=4))
+    tiny = bmpc.BatchedBranchMPC(scenarios.highway_config(NB=1, batch_capacity=4))      # created last: lowers the limit
+    x0, z0, xref, pp = scenarios.highway_batch(4, seed=9)
+    for h in (large, small, tiny, large):
+        r = h.solve_host(x0, z0, xref, pp, outputs=("u0", "status"))
+        assert (r["status"] <= abi.STATUS_CONVERGED).all()
+    for h in (small, large, tiny):
+        h.close()
