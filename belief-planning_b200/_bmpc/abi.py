@@ -8,7 +8,7 @@ import os
 MAX_N, MAX_D, MAX_POLICIES, MAX_ROWS, MAX_NB = 4, 3, 4, 4, 3
 
 MODEL_HIGHWAY, MODEL_QUADRUPED = 0, 1
-CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST, CTRL_CVAR = 0, 1, 2, 3
+CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST, CTRL_CVAR, CTRL_BELIEF = 0, 1, 2, 3, 4
 POLICY_MAINTAIN, POLICY_BRAKE, POLICY_LC, POLICY_TRACKV, POLICY_FORWARD, POLICY_STOP = range(6)
 STATUS_POLISHED, STATUS_CONVERGED, STATUS_MAXITER, STATUS_NUMERIC = range(4)
 SLAB_AUTO, SLAB_SHARED, SLAB_SPLIT, SLAB_GLOBAL = range(4)
@@ -36,6 +36,7 @@ class Config(C.Structure):
         ("polish_al_iters", _i32), ("polish_careful", _i32), ("warm_polish", _i32), ("rho_refresh", _i32),
         ("alpha", _dbl), ("theta", _dbl), ("theta_u", _dbl), ("eps_abs", _dbl), ("polish_big", _dbl),
         ("polish_mult", _dbl), ("cvar_alpha", _dbl),
+        ("hmm_M", _i32), ("hmm_col_alpha", _dbl), ("hmm_tran_diag", _dbl), ("hmm_thres", _dbl),
         ("slab_mode", _i32), ("batch_capacity", _i32), ("device", _i32), ("reserved", _i32 * 8),
     ]
 
@@ -56,7 +57,8 @@ class Outputs(C.Structure):
     """struct bmpc_outputs (device pointers for bmpc_solve, host pointers for bmpc_solve_host)"""
     _fields_ = [("u0", C.c_void_p), ("uPred", C.c_void_p), ("xPred", C.c_void_p), ("xLin", C.c_void_p),
                 ("zPred", C.c_void_p), ("branch_w", C.c_void_p), ("branch_p", C.c_void_p), ("objective", C.c_void_p),
-                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p), ("nsolve", C.c_void_p), ("cycles", C.c_void_p)]
+                ("status", C.c_void_p), ("iters", C.c_void_p), ("nfact", C.c_void_p), ("nsolve", C.c_void_p), ("cycles", C.c_void_p),
+                ("bPred", C.c_void_p)]
 
 
 OUTPUT_NAMES = [f[0] for f in Outputs._fields_]
@@ -81,6 +83,9 @@ SYMBOLS = [
     ("bmpc_ulin_rows", C.c_int, [C.c_void_p]),
     ("bmpc_solve", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                              C.POINTER(Outputs), C.c_void_p]),
+    ("bmpc_solve_belief", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                    C.POINTER(Outputs), C.c_void_p]),
+    ("bmpc_eval_belief", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_void_p]),
     ("bmpc_solve_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.POINTER(Outputs)]),
     ("bmpc_solve_host_views", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

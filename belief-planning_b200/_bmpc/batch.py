@@ -14,7 +14,10 @@ _OUT_SHAPES = {
     "xLin": lambda s: (s.totalu, s.cfg.n), "zPred": lambda s: (s.totalu, s.cfg.n), "branch_w": lambda s: (s.nbranch,),
     "branch_p": lambda s: (s.nbranch, s.cfg.m), "objective": lambda s: (), "status": lambda s: (),
     "iters": lambda s: (), "nfact": lambda s: (), "nsolve": lambda s: (), "cycles": lambda s: (),
+    "bPred": lambda s: (s.totalx, s.cfg.hmm_M * s.cfg.m),
 }
+# everything the tree controllers produce (bPred belongs to the belief-state MPC, bmpc_solve_belief)
+ALL_OUTPUTS = tuple(k for k in abi.OUTPUT_NAMES if k != "bPred")
 _INT_OUTPUTS = ("status", "iters", "nfact", "nsolve")
 LIGHT_OUTPUTS = ("u0", "objective", "status", "iters", "nfact", "nsolve")
 
@@ -118,7 +121,7 @@ class BatchedBranchMPC:
                                              int(obstacle_policy), pp, count, C.c_void_p(stream)), "bmpc_plant_step")
 
     # -- host path (the call the drop-in classes make) ---------------------------------------------------------
-    def solve_host(self, x0, z0, xref, policy_params=None, outputs=tuple(abi.OUTPUT_NAMES)):
+    def solve_host(self, x0, z0, xref, policy_params=None, outputs=ALL_OUTPUTS):
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=np.float64)
         xref = np.ascontiguousarray(np.atleast_2d(xref), dtype=np.float64)
@@ -138,7 +141,7 @@ class BatchedBranchMPC:
                     "bmpc_solve_host")
         return res
 
-    def solve_host_views(self, x0, z0, xref, policy_params=None, outputs=tuple(abi.OUTPUT_NAMES)):
+    def solve_host_views(self, x0, z0, xref, policy_params=None, outputs=ALL_OUTPUTS):
         """As solve_host, without the copy out of the library's pinned result block: the returned arrays are views that
         stay valid until this handle's next host solve (the drop-in controllers copy what they keep)."""
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
@@ -162,6 +165,55 @@ class BatchedBranchMPC:
             nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
             buf = (C.c_char * nbytes).from_address(getattr(views, k))
             res[k] = np.frombuffer(buf, dtype=dt).reshape(shape)
+        return res
+
+    # -- belief-state MPC -----------------------------------------------------------------------------------------
+    def solve_belief_host(self, x0, b0, xbackup, xref, outputs=("u0", "uPred", "xPred", "bPred", "objective", "status", "iters")):
+        """PredictiveControllers.MPC.solve(x0, b0, xbackup, xRef) for a batch: x0 (B,4), b0 (B,M,m), xbackup (B, M*m, cols),
+        xref (B,4) host arrays -> dict of host arrays (bmpc_solve_belief on device tensors, then copied back)."""
+        import torch
+        dev = torch.device("cuda", self.cfg.device)
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), np.float64)
+        B = x0.shape[0]
+        nb = self.cfg.hmm_M * self.cfg.m
+        b0 = np.ascontiguousarray(b0, np.float64).reshape(B, nb)
+        xbackup = np.ascontiguousarray(xbackup, np.float64).reshape(B, nb, -1)
+        xref = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(xref), (B, 4)), np.float64)
+        t = [torch.as_tensor(a, device=dev) for a in (x0, b0, xbackup, xref)]
+        shapes = dict(_OUT_SHAPES)
+        bufs = {}
+        for k in outputs:
+            dt = torch.int64 if k == "cycles" else (torch.int32 if k in _INT_OUTPUTS else torch.float64)
+            shp = (self.totalx, nb) if k == "bPred" else shapes[k](self)
+            bufs[k] = torch.zeros((B,) + shp, dtype=dt, device=dev)
+        out = abi.Outputs(**{k: v.data_ptr() for k, v in bufs.items()})
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self.lib.bmpc_solve_belief(self.h, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), xbackup.shape[-1],
+                                               t[3].data_ptr(), B, C.byref(out), C.c_void_p(stream)), "bmpc_solve_belief")
+        torch.cuda.synchronize(dev)
+        return {k: v.cpu().numpy() for k, v in bufs.items()}
+
+    def eval_belief(self, xb, xbackup, u):
+        """regressionAndLinearization for a batch of points: returns A, B, C, h0 (K, M, m), Jh (K, M, m, n), xbp."""
+        import torch
+        dev = torch.device("cuda", self.cfg.device)
+        M, m = self.cfg.hmm_M, self.cfg.m
+        nb, n = M * m, 4 + M * m
+        xb = np.ascontiguousarray(np.atleast_2d(xb), np.float64)
+        K = xb.shape[0]
+        t = [torch.as_tensor(np.ascontiguousarray(a, np.float64).reshape(K, -1), device=dev) for a in (xb, xbackup, u)]
+        o = {"A": (K, n, n), "B": (K, n, 2), "C": (K, n), "h0": (K, nb), "Jh": (K, nb, 2), "xbp": (K, n)}
+        r = {k: torch.zeros(s, dtype=torch.float64, device=dev) for k, s in o.items()}
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self.lib.bmpc_eval_belief(self.h, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), K, r["A"].data_ptr(),
+                                              r["B"].data_ptr(), r["C"].data_ptr(), r["h0"].data_ptr(), r["Jh"].data_ptr(),
+                                              r["xbp"].data_ptr(), C.c_void_p(stream)), "bmpc_eval_belief")
+        torch.cuda.synchronize(dev)
+        res = {k: v.cpu().numpy() for k, v in r.items()}
+        Jh = np.zeros((K, M, m, n))
+        Jh[..., 0:2] = res["Jh"].reshape(K, M, m, 2)
+        res["Jh"] = Jh
+        res["h0"] = res["h0"].reshape(K, M, m)
         return res
 
     # -- persistent state ---------------------------------------------------------------------------------------

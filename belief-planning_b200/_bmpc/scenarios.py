@@ -89,3 +89,20 @@ def euler_quadruped(x, u, dt=0.2):
     out[:, 1] += dt * (u[:, 0] * s + u[:, 1] * c)
     out[:, 2] += dt * u[:, 2]
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# belief-state MPC (Init_MPC.initMPCParams :7-34 + the HMM_constants the belief model reads)
+# ------------------------------------------------------------------------------------------------------------
+def belief_config(N=10, M=2, m=2, am=6.0, rm=0.3, N_lane=2, W=2.5, L=4.0, ylb=0.0, yub=7.2, col_alpha=5.0, s1=2.0,
+                  tran_diag=0.3, thres=0.1, dt=0.1, Kpsi=0.1, batch_capacity=1, device=0, **knobs):
+    pol = [(abi.POLICY_MAINTAIN, [0, 0, 0, 0]), (abi.POLICY_BRAKE, [0, 0, 0, 0])][:m]
+    spec = config.ModelSpec(abi.MODEL_HIGHWAY, 4, 2, N, dt, pol, veh_L=L, veh_W=W, Kpsi=Kpsi, s1=s1, lane_lo=ylb, lane_hi=yub)
+    Fx = np.array([[0., 1., 0., 0.], [0., -1., 0., 0.], [0., 0., 0., 1.], [0., 0., 0., -1.]])
+    bx = np.array([N_lane * LANE_W - W / 2, -W / 2, 0.25, 0.25])
+    Fu = np.kron(np.eye(2), np.array([1., -1.])).T
+    bu = np.array([am, 0.5 * am, rm, rm])
+    return config.make_config(spec, 4, 2, N, 1, np.diag([0., 0.5, 0.2, 5.]), np.diag([30., 100.]), Fx, bx, Fu, bu,
+                              np.array([0., 1000.]), controller=abi.CTRL_BELIEF, Qf=np.zeros((4, 4)), hmm_M=M,
+                              hmm_col_alpha=col_alpha, hmm_tran_diag=tran_diag, hmm_thres=thres,
+                              batch_capacity=batch_capacity, device=device, **knobs)

@@ -159,6 +159,58 @@ __global__ void bmpc_eval_kernel(const __grid_constant__ KParams P, const EvalAr
   }
 }
 
+// Point-wise belief-state model: HMM_backup_dyn.PredictiveModel.regressionAndLinearization (:216-229) for a batch of points.
+struct BeliefEvalArgs {
+  const real *xb, *xbackup, *u;
+  real *A, *B, *C, *h0, *Jh, *xbp;
+  int count;
+};
+__global__ void bmpc_belief_eval_kernel(const __grid_constant__ KParams P, const BeliefEvalArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.count) return;
+  const int M = P.hmm_M, m = P.zm, nb = M * m, n = 4 + nb;
+  const real* xb = a.xb + (size_t)e * n;
+  const real* xbk = a.xbackup + (size_t)e * nb * 4;
+  const real* u = a.u + (size_t)e * 2;
+  real lin[HighwayModel::NLIN], cc[HighwayModel::NCC], xn[4], bp[9], dbx[18], Hm[36];
+  HighwayModel::linearize(P, xb, u, lin, cc, xn);
+  BeliefModel::transition(P, xb, xbk, 4, 0, xb + 4, bp, dbx, Hm);
+  real* A = a.A + (size_t)e * n * n;
+  for (int q = 0; q < n * n; ++q) A[q] = 0.0;
+  real A4[16];
+  HighwayModel::denseA(P, lin, A4);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) A[i * n + j] = A4[i * 4 + j];
+  for (int q = 0; q < nb; ++q) {
+    const int ag = q % M, k = q / M;
+    A[(4 + q) * n] = dbx[2 * q];
+    A[(4 + q) * n + 1] = dbx[2 * q + 1];
+    for (int r = 0; r < m; ++r) A[(4 + q) * n + 4 + r * M + ag] = Hm[(ag * m + r) * m + k];
+  }
+  real* B = a.B + (size_t)e * n * 2;
+  for (int q = 0; q < n * 2; ++q) B[q] = 0.0;
+  B[2 * 2] = P.dt;
+  B[3 * 2 + 1] = P.dt;
+  real* xbp = a.xbp + (size_t)e * n;
+  for (int i = 0; i < 4; ++i) xbp[i] = xn[i];
+  for (int q = 0; q < nb; ++q) xbp[4 + q] = bp[q];
+  real* C = a.C + (size_t)e * n;
+  for (int i = 0; i < n; ++i) {
+    real v = xbp[i];
+    for (int j = 0; j < n; ++j) v -= A[i * n + j] * xb[j];
+    v -= B[i * 2] * u[0] + B[i * 2 + 1] * u[1];
+    C[i] = v;
+  }
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < m; ++j) {
+      real gx, gy;
+      const real h = BeliefModel::safety(P, xb, xbk + (size_t)(m * i + j) * 4, gx, gy);
+      a.h0[(size_t)e * nb + i * m + j] = h - (gx * xb[0] + gy * xb[1]);
+      a.Jh[((size_t)e * nb + i * m + j) * 2] = gx;
+      a.Jh[((size_t)e * nb + i * m + j) * 2 + 1] = gy;
+    }
+}
+
 // Euler plant step of ego (applied input) and obstacle (one of the backup policies), one thread per episode.
 template <class M>
 __global__ void bmpc_plant_kernel(const __grid_constant__ KParams P, real* x, const real* u, real* z, int pol,
@@ -225,6 +277,7 @@ struct bmpc_handle {
   real* ipm_ws = nullptr;   // per-warp scratch of the interior-point fallback
   real* nu_cache = nullptr; // BranchMPC_CVaR: risk multipliers of each episode's last step
   real* cv_ws = nullptr;    // BranchMPC_CVaR: per-team scratch of the master problem
+  real* bel_ws = nullptr;   // belief-state MPC: per-team linearisation trajectory of the augmented state
   KParams* captured = nullptr;            // pinned parameter blocks for launches recorded into CUDA graphs (BMPC_MAX_CAPTURED,
   int captured_used = 0;                  // allocated at create: nothing may be allocated while a stream is capturing)
   KParams* pstage = nullptr;              // pinned staging ring of parameter blocks (source of the constant-memory upload)
@@ -342,7 +395,7 @@ static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStrea
 // BranchMPCProx carries the previous input through the Riccati state (RateAug); BranchMPC does not need to.
 // robustMPC: highway model, 2 state rows + up to 9 obstacle nodes per time slot
 #define BMPC_DISPATCH(h, fn, ...)                                                                       \
-  ((h)->cfg.controller == BMPC_CTRL_ROBUST ? fn<HighwayModel, 11, 9>(__VA_ARGS__) :                     \
+  (bmpc_is_chain((h)->cfg.controller) ? fn<HighwayModel, 11, 9>(__VA_ARGS__) :                     \
    (h)->cfg.controller == BMPC_CTRL_PROX                                                                \
        ? BMPC_DISPATCH_M(h, fn, RateAug<HighwayModel>, RateAug<QuadrupedModel>, __VA_ARGS__)            \
        : BMPC_DISPATCH_M(h, fn, HighwayModel, QuadrupedModel, __VA_ARGS__))
@@ -365,6 +418,7 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->ipm_ws);
   cudaFree(h->nu_cache);
   cudaFree(h->cv_ws);
+  cudaFree(h->bel_ws);
   if (h->pstage) cudaFreeHost(h->pstage);
   if (h->captured) cudaFreeHost(h->captured);
   for (int i = 0; i < BMPC_PSTAGE; ++i) if (h->pstage_evt[i]) cudaEventDestroy(h->pstage_evt[i]);
@@ -408,6 +462,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->counter, sizeof(int)));
   if (h->gws_bytes_per_warp) BMPC_CK(h, cudaMalloc(&h->gws, (size_t)h->grid * h->gws_bytes_per_warp));
   BMPC_CK(h, cudaMalloc(&h->ipm_ws, (size_t)h->grid * h->P.ipm_reals * sizeof(real)));
+  if (cfg->controller == BMPC_CTRL_BELIEF) BMPC_CK(h, cudaMalloc(&h->bel_ws, (size_t)h->grid * h->P.bel_reals * sizeof(real)));
   if (cfg->controller == BMPC_CTRL_CVAR) {
     BMPC_CK(h, cudaMalloc(&h->nu_cache, cap * P.nbranch * sizeof(real)));
     BMPC_CK(h, cudaMemset(h->nu_cache, 0, cap * P.nbranch * sizeof(real)));
@@ -505,8 +560,29 @@ int bmpc_get_topology(const bmpc_handle* h, int32_t* ndx, int32_t* ndu, int32_t*
   return BMPC_OK;
 }
 
+struct BeliefArgs { const double* b0; const double* xbackup; int cols; };
+static int solve_impl(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
+                      int64_t count, const bmpc_outputs* out, void* stream, const BeliefArgs* bel);
+
 int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
                int64_t count, const bmpc_outputs* out, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (h->cfg.controller == BMPC_CTRL_BELIEF) { h->err = "the belief-state MPC is solved through bmpc_solve_belief"; return BMPC_E_INVALID; }
+  if (!z0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  return solve_impl(h, x0, z0, xref, policy_params, count, out, stream, nullptr);
+}
+
+int bmpc_solve_belief(bmpc_handle* h, const double* x0, const double* b0, const double* xbackup, int32_t xbackup_cols,
+                      const double* xref, int64_t count, const bmpc_outputs* out, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (h->cfg.controller != BMPC_CTRL_BELIEF) { h->err = "not a belief-state MPC handle"; return BMPC_E_INVALID; }
+  if (!b0 || !xbackup || xbackup_cols < 4 * h->cfg.N) { h->err = "b0, xbackup with at least 4 N columns per row are required"; return BMPC_E_INVALID; }
+  const BeliefArgs bel{b0, xbackup, xbackup_cols};
+  return solve_impl(h, x0, x0, xref, nullptr, count, out, stream, &bel);
+}
+
+static int solve_impl(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
+                      int64_t count, const bmpc_outputs* out, void* stream, const BeliefArgs* bel) {
   if (!h) return BMPC_E_INVALID;
   if (!x0 || !z0 || !xref || !out || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
   if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
@@ -541,6 +617,8 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
   P.ipm = h->ipm_ws;
   P.nu_cache = h->nu_cache;
   P.cv = h->cv_ws;
+  P.bel = h->bel_ws;
+  if (bel) { P.b0 = bel->b0; P.xbackup = bel->xbackup; P.xb_cols = bel->cols; }
   BMPC_CK(h, cudaMemsetAsync(h->counter, 0, sizeof(int), s));
   // rows of branch_p that belong to leaf branches carry no probabilities: NaN pattern, on the solve's own stream
   if (out->branch_p) BMPC_CK(h, cudaMemsetAsync(out->branch_p, 0xff, (size_t)count * h->P.nbranch * h->cfg.m * sizeof(real), s));
@@ -589,18 +667,20 @@ int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double*
 // back to back on the device ([count] rows each), come back in one DMA into a pinned mirror and are handed out either as
 // views into that mirror (bmpc_solve_host_views: zero copy, valid until the handle's next host call) or copied into
 // the caller's arrays (bmpc_solve_host).
-static const int kNumOut = 13;
+static const int kNumOut = 14;
 static void out_sizes(const bmpc_handle* h, size_t* sz) {
   const KParams& P = h->P;
   const size_t n = h->cfg.n, d = h->cfg.d, m = h->cfg.m;
+  const size_t nbel = (h->cfg.controller == BMPC_CTRL_BELIEF) ? (size_t)h->cfg.hmm_M * m : 0;
   const size_t v[kNumOut] = {d * 8, (size_t)P.pub_totalu * d * 8, (size_t)P.pub_totalx * n * 8, (size_t)P.pub_totalu * n * 8,
-                             (size_t)P.pub_totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8};
+                             (size_t)P.pub_totalu * n * 8, (size_t)P.nbranch * 8, (size_t)P.nbranch * m * 8, 8, 4, 4, 4, 4, 8,
+                             (size_t)P.pub_totalx * nbel * 8};
   for (int i = 0; i < kNumOut; ++i) sz[i] = v[i];
 }
 static void** out_slots(bmpc_outputs* o, void*** slots) {
   void** v[kNumOut] = {(void**)&o->u0, (void**)&o->uPred, (void**)&o->xPred, (void**)&o->xLin, (void**)&o->zPred,
                        (void**)&o->branch_w, (void**)&o->branch_p, (void**)&o->objective, (void**)&o->status,
-                       (void**)&o->iters, (void**)&o->nfact, (void**)&o->nsolve, (void**)&o->cycles};
+                       (void**)&o->iters, (void**)&o->nfact, (void**)&o->nsolve, (void**)&o->cycles, (void**)&o->bPred};
   for (int i = 0; i < kNumOut; ++i) slots[i] = v[i];
   return nullptr;
 }
@@ -763,6 +843,20 @@ int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const doub
   return BMPC_OK;
 }
 
+int bmpc_eval_belief(bmpc_handle* h, const double* xb, const double* xbackup, const double* u, int64_t count, double* A,
+                     double* B, double* C, double* h0, double* Jh, double* xbp, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (h->cfg.controller != BMPC_CTRL_BELIEF) { h->err = "not a belief-state MPC handle"; return BMPC_E_INVALID; }
+  if (!xb || !xbackup || !u || !A || !B || !C || !h0 || !Jh || !xbp || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (count == 0) return BMPC_OK;
+  BMPC_CK(h, cudaSetDevice(h->device));
+  BeliefEvalArgs a{xb, xbackup, u, A, B, C, h0, Jh, xbp, (int)count};
+  bmpc_belief_eval_kernel<<<(int)((count + 63) / 64), 64, 0, (cudaStream_t)stream>>>(h->P, a);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
 int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32_t obstacle_policy,
                     const double* policy_params, int64_t count, void* stream) {
   if (!h) return BMPC_E_INVALID;
@@ -794,7 +888,7 @@ int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int3
     return BMPC_E_INVALID;
   }
   if (!highway && (!env->goal || !quad_sizes)) { h->err = "quadruped environment needs goal and quad_sizes"; return BMPC_E_INVALID; }
-  if (h->cfg.controller == BMPC_CTRL_ROBUST) { h->err = "the environment drives the branch controllers"; return BMPC_E_UNSUPPORTED; }
+  if (bmpc_is_chain(h->cfg.controller)) { h->err = "the environment drives the branch controllers"; return BMPC_E_UNSUPPORTED; }
   if (count == 0) return BMPC_OK;
   if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
   BMPC_CK(h, cudaSetDevice(h->device));

@@ -32,7 +32,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   if (!(c.dt > 0.0)) { *err = "dt must be positive"; return BMPC_E_INVALID; }
   if (c.n_rows < 0 || c.n_rows > BMPC_MAX_ROWS) { *err = "n_rows out of range"; return BMPC_E_INVALID; }
   if (c.controller != BMPC_CTRL_BRANCH && c.controller != BMPC_CTRL_PROX && c.controller != BMPC_CTRL_ROBUST &&
-      c.controller != BMPC_CTRL_CVAR) {
+      c.controller != BMPC_CTRL_CVAR && c.controller != BMPC_CTRL_BELIEF) {
     *err = "unknown controller kind";
     return BMPC_E_INVALID;
   }
@@ -42,8 +42,17 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
     for (int a = 0; a < d; ++a)
       if (c.dR[a] != 0.0) { *err = "BranchMPC_CVaR ignores input-rate costs; dR must be 0"; return BMPC_E_UNSUPPORTED; }
   }
-  const bool robust = c.controller == BMPC_CTRL_ROBUST;
-  if (robust) {
+  const bool belief = c.controller == BMPC_CTRL_BELIEF;
+  if (belief) {
+    if (c.model != BMPC_MODEL_HIGHWAY) { *err = "the belief-state MPC is built for the highway model"; return BMPC_E_UNSUPPORTED; }
+    if (c.hmm_M < 1 || c.hmm_M * c.m > 9) { *err = "hmm_M * m must be in [1, 9]"; return BMPC_E_INVALID; }
+    if (c.NB != 1) { *err = "the belief-state MPC plans one chain: NB must be 1"; return BMPC_E_INVALID; }
+    if (!(c.hmm_tran_diag >= 0.0 && c.hmm_tran_diag <= 1.0) || !(c.hmm_col_alpha > 0.0)) { *err = "bad belief-model constants"; return BMPC_E_INVALID; }
+    for (int a = 0; a < d; ++a)
+      if (c.dR[a] != 0.0) { *err = "belief-state MPC with input-rate costs (dR != 0) is not built"; return BMPC_E_UNSUPPORTED; }
+  }
+  const bool robust = c.controller == BMPC_CTRL_ROBUST || belief;   // one ego chain with a dummy stage for the terminal state
+  if (c.controller == BMPC_CTRL_ROBUST) {
     for (int a = 0; a < d; ++a)
       if (c.dR[a] != 0.0) { *err = "robustMPC with input-rate costs (dR != 0) is not built"; return BMPC_E_UNSUPPORTED; }
   }
@@ -81,7 +90,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   // internal dummy stage that carries the terminal state's cost and soft rows
   P.m = robust ? 1 : c.m;
   P.NB = robust ? 1 : c.NB;
-  P.N = robust ? c.N * c.NB + 1 : c.N;
+  P.N = belief ? c.N : (robust ? c.N * c.NB + 1 : c.N);   // belief chain: root + N nodes = N + 1 states (PredictiveControllers.py:199)
   int pw = 1, off = 0;
   for (int k = 0; k <= P.NB; ++k) {
     P.pw[k] = pw;
@@ -115,6 +124,11 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   for (int i = 0; i < d; ++i) { P.dR[i] = c.dR[i]; P.ulo[i] = c.u_lo[i]; P.uhi[i] = c.u_hi[i]; }
   // MPC_branch.py:271 / :1070 / none in robustMPC and in BranchMPC_CVaR (its cones carry (x - xRef)'Q(x - xRef) only, :1953-1957)
   P.dq_scale = (c.controller == BMPC_CTRL_PROX) ? 3.0 : ((robust || c.controller == BMPC_CTRL_CVAR) ? 0.0 : 0.5);
+  P.hmm_M = c.hmm_M;
+  P.hmm_col_alpha = c.hmm_col_alpha;
+  P.hmm_tran_diag = c.hmm_tran_diag;
+  P.hmm_thres = c.hmm_thres;
+  P.bel_reals = belief ? (size_t)(P.totalu + 2) * 16 : 0;
   P.cvar_alpha = c.cvar_alpha;
   P.cvar_floor = 1.0e-6;
   P.cvar_tol = 1.0e-8;
@@ -185,7 +199,8 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
 // (model, number of soft rows incl. the collision row) -> which Solver instantiation runs
 inline bool supported_instance(int model, int n_rows, int controller = BMPC_CTRL_BRANCH, int obstacle_leaves = 1) {
   // robustMPC is instantiated for the highway model with the reference's two state rows and up to 9 obstacle nodes per slot
-  if (controller == BMPC_CTRL_ROBUST) return model == BMPC_MODEL_HIGHWAY && n_rows == 2 && obstacle_leaves <= 9;
+  if (controller == BMPC_CTRL_ROBUST || controller == BMPC_CTRL_BELIEF)
+    return model == BMPC_MODEL_HIGHWAY && n_rows == 2 && obstacle_leaves <= 9;
   if (model == BMPC_MODEL_HIGHWAY) return n_rows >= 0 && n_rows <= 2;
   if (model == BMPC_MODEL_QUADRUPED) return n_rows == 0;
   return false;

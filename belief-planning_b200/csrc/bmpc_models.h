@@ -329,6 +329,73 @@ struct QuadrupedModel {
 };
 
 // ------------------------------------------------------------------------------------------
+// Belief-state model (HMM_backup_dyn.PredictiveModel.calc_xp_expr, :238-267): the other agents follow one of m backup
+// policies; the belief b[i][:] over agent i's policies moves with the transition matrix H_i(x) (backup_trans :96-101) built
+// from the safety values h_ij = softmin(veh_col(x, xb_ij), lane_bdry_h(xb_ij), col_alpha) (:255).  Closed forms of the
+// CasADi graphs; the symbolic veh_col branch is normalised by the box size and not clipped (:136-143).
+// ------------------------------------------------------------------------------------------
+struct BeliefModel {
+  // h and its gradient with respect to the ego position (x, y)
+  BMPC_D static real safety(const KParams& P, const real* x, const real* xb, real& gx, real& gy) {
+    const real s0 = P.veh_L + 1.0, s1 = P.veh_W + 0.2;
+    const real ex = x[0] - xb[0], ey = x[1] - xb[1];
+    const real dx = bmpc_div(fabs(ex) - s0, s0), dy = bmpc_div(fabs(ey) - s1, s1);
+    real v, wgx, wgy;
+    soft_box(dx, dy, v, wgx, wgy);                          // alpha = 1: (dx e^dx + dy e^dy)/(e^dx + e^dy) and its partials
+    const real gvx = bmpc_div(wgx * sgn(ex), s0), gvy = bmpc_div(wgy * sgn(ey), s1);
+    // lane_bdry_h: softmin(y - ylb, yub - y, 5)
+    const real a = xb[1] - P.lane_lo, b = P.lane_hi - xb[1];
+    const real e = bmpc_exp(-5.0 * fabs(a - b));
+    const real ea = (a <= b) ? 1.0 : e, eb = (a <= b) ? e : 1.0;
+    const real lane = bmpc_div(ea * a + eb * b, ea + eb);
+    // softmin(v, lane, col_alpha)
+    const real g = P.hmm_col_alpha;
+    const real e2 = bmpc_exp(-g * fabs(v - lane));
+    const real ev = (v <= lane) ? 1.0 : e2, el = (v <= lane) ? e2 : 1.0;
+    const real wv = bmpc_div(ev, ev + el);
+    const real h = wv * v + (1.0 - wv) * lane;
+    const real dh = wv * (1.0 - g * (v - h));
+    gx = dh * gvx;
+    gy = dh * gvy;
+    return h;
+  }
+  // b+ (column-major flat belief, entry k M + i = agent i, policy k) from b and the ego position; optionally the
+  // Jacobian blocks: dbx[q][2] = d b+_q / d(x, y), and Hm[i][r][k] = H_i[r][k] (d b+_(i,k) / d b_(i,r))
+  BMPC_D static void transition(const KParams& P, const real* x, const real* xbackup, int xb_stride, int slice, const real* b,
+                                real* bp, real* dbx, real* Hm) {
+    const int M = P.hmm_M, m = P.zm;
+    for (int i = 0; i < M; ++i) {
+      real mh[BMPC_MAX_POLICIES], gh[BMPC_MAX_POLICIES][2], msum = 0.0, bsum = 0.0;
+      for (int j = 0; j < m; ++j) {
+        const real* xb = xbackup + (size_t)(m * i + j) * xb_stride + 4 * slice;
+        const real h = safety(P, x, xb, gh[j][0], gh[j][1]);
+        mh[j] = bmpc_div(1.0, 1.0 + bmpc_exp(-P.s1 * h));   // softsat(h, s1) == sigmoid(s1 h)
+        msum += mh[j];
+        bsum += b[j * M + i];
+      }
+      const real tau = P.hmm_tran_diag;
+      for (int k = 0; k < m; ++k) {
+        const real pik = bmpc_div(mh[k], msum);
+        bp[k * M + i] = (1.0 - tau) * bsum * pik + tau * b[k * M + i];
+        if (Hm)
+          for (int r = 0; r < m; ++r) Hm[(i * m + r) * m + k] = (1.0 - tau) * pik + (r == k ? tau : 0.0);
+        if (dbx) {
+          real ax = 0.0, ay = 0.0;
+          for (int l = 0; l < m; ++l) {
+            const real dpi = bmpc_div(((l == k) ? 1.0 : 0.0) - pik, msum);
+            const real c = (1.0 - tau) * bsum * dpi * P.s1 * mh[l] * (1.0 - mh[l]);
+            ax += c * gh[l][0];
+            ay += c * gh[l][1];
+          }
+          dbx[(k * M + i) * 2] = ax;
+          dbx[(k * M + i) * 2 + 1] = ay;
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // Input-rate costs (BranchMPCProx, MPC_branch.py:280-297) couple consecutive inputs.  The Riccati recursion carries the
 // previous input as extra state: xi = (x, v), v_{k+1} = u_k, i.e. A~ = [A 0; 0 0], B~ = [B; I], C~ = [C; 0].  This
 // wrapper presents a physical model M in that augmented form; everything that concerns the physical state (rollouts,

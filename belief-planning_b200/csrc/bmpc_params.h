@@ -44,6 +44,13 @@ struct KParams {
   real cvar_tol;                // relative gap between the cutting-plane model and the value at the current multipliers
   int cvar_max_cuts;            // cap on inner solves per MPC step
   int cv_rows, cv_cols;         // master LP tableau (rows incl. objective, columns incl. right-hand side)
+  // ---- belief-state MPC (PredictiveControllers.MPC): chain of N stages, state augmented with M x m beliefs ----
+  int hmm_M, xb_cols;           // agents; columns of one xbackup row
+  real hmm_col_alpha, hmm_tran_diag, hmm_thres;
+  const real* b0;               // [count][M][m]
+  const real* xbackup;          // [count][M*m][xb_cols]
+  real* bel;                    // per-team scratch: linearisation trajectory of the augmented state
+  size_t bel_reals;
   real* nu_cache;               // persistent [cap][nbranch]: multipliers of the last solved step (warm start)
   real* cv;                     // per-team scratch of the risk master problem
   size_t cv_reals;
@@ -75,6 +82,8 @@ struct KParams {
 // floor(q / d) for 0 <= q < 2^16 through a single-precision multiply with the rounded-up reciprocal `inv` of d (exact:
 // tests/test_host_logic.py checks every q < 65536 for every d the ABI admits); the integer division instruction sequence is
 // ~25 instructions and sat in every node-parallel loop
+// one ego chain instead of a tree: robustMPC and the belief-state MPC
+BMPC_HD inline bool bmpc_is_chain(int ctrl) { return ctrl == BMPC_CTRL_ROBUST || ctrl == BMPC_CTRL_BELIEF; }
 BMPC_HD inline int bmpc_idiv(int q, float inv) { return (int)((float)q * inv); }
 BMPC_HD inline int bmpc_ndu(const KParams& P, int b) { return b == 0 ? 0 : 1 + P.N * (b - 1); }
 BMPC_HD inline int bmpc_ndx(const KParams& P, int b) {

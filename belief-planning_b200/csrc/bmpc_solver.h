@@ -637,6 +637,154 @@ struct Solver {
     prof_end(2, prof_t0);
   }
 
+  // ----------------------------------------------------------------------------------------
+  // Belief-state MPC (PredictiveControllers.MPC, :56-340): ONE ego chain of N stages; the state of the reference's QP is
+  // [x; b] with b the beliefs over the other agents' policies (HMM_backup_dyn.PredictiveModel).  The beliefs carry no cost
+  // and no constraint, so they do not influence the optimal (x, u): the chain QP is solved in the physical state, and the
+  // belief part of xPred is propagated afterwards through the same linearised dynamics the reference's equality rows
+  // hold (belief_outputs).  What the beliefs DO decide is which rows exist: the row of (agent j, policy k) on node i+1 is
+  // imposed only if the belief entry of the linearisation trajectory exceeds hmm_thres (:211-216).
+  //   get_xLin (:115-127)            nonlinear rollout of [x; b] under the shifted previous inputs
+  //   computeLTVdynamics (:162-166)  stage i linearised about xLin[i+1] with the backup states of step i
+  //   buildIneqConstr (:195-242)     state rows on nodes 0..N-1, gated rows on nodes 1..N-1 from linearisation i+1
+  // ----------------------------------------------------------------------------------------
+  BMPC_D real* belX(int k) { return PP.bel + (size_t)cv_team() * PP.bel_reals + (size_t)k * 16; }   // xLin[k]: x (4), b (<= 9)
+  BMPC_DN void expand_belief() {
+    const long long prof_t0 = prof_begin(2);
+    const int started = PP.started[prob];
+    const int Nst = PP.totalu - 1;                          // stages N; chain states 0..N
+    const int nb = PP.hmm_M * PP.zm;
+    const real* uPrev = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
+    const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    const real* x0 = PP.x0 + (size_t)prob * NXP;
+    const real* b0 = PP.b0 + (size_t)prob * nb;
+    const real* xbk = PP.xbackup + (size_t)prob * nb * PP.xb_cols;
+    auto kp_chain = [&](int k) { return k == 0 ? kp_of(0, 0) : kp_of(1, k - 1); };
+    // uLin[i] of this call = previous uPred[min(i + 1, N - 1)] (:156-158, :118), zero on the first call
+    auto ulin = [&](int i, real* u) {
+      const int src = (i + 1 < Nst) ? i + 1 : Nst - 1;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) u[a] = started ? uPrev[(size_t)src * NU + a] : 0.0;
+    };
+    if (BMPC_LANE_ID == 0) {
+      real x[NXP], b[9], bn[9], u[NU], xn[NXP];
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) x[i] = x0[i];
+      // the rollout reads the belief column-major (np.reshape(b0, -1, 1) with the legacy integer order, :121)
+      for (int i = 0; i < PP.hmm_M; ++i)
+        for (int j = 0; j < PP.zm; ++j) b[j * PP.hmm_M + i] = b0[i * PP.zm + j];
+      for (int k = 0; k <= Nst; ++k) {
+        real* o = belX(k);
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) o[i] = x[i];
+        for (int q = 0; q < nb; ++q) o[4 + q] = b[q];
+        if (k == Nst) break;
+        ulin(k, u);
+        BeliefModel::transition(PP, x, xbk, PP.xb_cols, k, b, bn, nullptr, nullptr);
+        M::step(PP, x, u, xn);
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) x[i] = xn[i];
+        for (int q = 0; q < nb; ++q) b[q] = bn[q];
+      }
+    }
+    team_sync();
+    const real* xref = PP.xref + (size_t)prob * NXP;
+#pragma unroll 1
+    for (int k = BMPC_LANE_ID; k <= Nst; k += BMPC_LANES) {
+      const int kp = kp_chain(k);
+      const int kl = (k < Nst) ? k + 1 : Nst;               // stage k is linearised about xLin[k+1]
+      real xb[NXP], ub[NU], xn[NXP], lin[M::NLIN], cc[M::NCC];
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) xb[i] = belX(kl)[i];
+      ulin(kl, ub);
+      M::linearize(PP, xb, ub, lin, cc, xn);
+#pragma unroll
+      for (int i = 0; i < M::NLIN; ++i) F(F_LIN + i, kp) = lin[i];
+#pragma unroll
+      for (int i = 0; i < M::NCC; ++i) F(F_CC + i, kp) = cc[i];
+      const real* Ql = (k == Nst) ? PP.Qf : PP.Q;           // buildCost :271-280: q = -2 xRef' blockdiag(Q.., Qf)
+#pragma unroll
+      for (int jj = 0; jj < NXP; ++jj) {
+        real a = 0.0;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) a += xref[i] * Ql[i * NXP + jj];
+        F(F_Q + jj, kp) = -2.0 * a;
+      }
+      // gated rows of node k (1 <= k <= N-1): belief of xLin[k] in the row-major view, h0 / Jh of linearisation k
+      // (about xLin[k+1], backup states of step k)
+      int slot = 0;
+      const real* xk = belX(k);        // ADMM start: rows evaluated at the node's own linearisation state
+      if (k >= 1 && k <= Nst - 1) {
+        for (int j = 0; j < PP.hmm_M; ++j)
+          for (int q = 0; q < PP.zm; ++q) {
+            if (belX(k)[4 + j * PP.zm + q] > PP.hmm_thres && slot < NC) {
+              real gx, gy;
+              const real h = BeliefModel::safety(PP, xb, xbk + (size_t)(PP.zm * j + q) * PP.xb_cols + 4 * k, gx, gy);
+              const real hi0 = h - (gx * xb[0] + gy * xb[1]);
+              F(F_FC + 2 * slot, kp) = -gx;
+              F(F_FC + 2 * slot + 1, kp) = -gy;
+              F(F_HC + slot, kp) = hi0;
+              F(F_S + slot, kp) = fmin(-gx * xk[0] - gy * xk[1], hi0);
+              ++slot;
+            }
+          }
+      }
+      for (; slot < NC; ++slot) {
+        F(F_FC + 2 * slot, kp) = 0.0;       // empty slot: a zero row gets rho = 0 and is ignored
+        F(F_FC + 2 * slot + 1, kp) = 0.0;
+        F(F_HC + slot, kp) = 1.0e30;
+        F(F_S + slot, kp) = 0.0;
+      }
+#pragma unroll
+      for (int j = NC; j < NR; ++j) {
+        real v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) v += PP.rf[j - NC][i] * xk[i];
+        F(F_S + j, kp) = bmpc_clamp(v, PP.rlo[j - NC], PP.rhi[j - NC]);
+      }
+      real uk[NU];
+      ulin(k, uk);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) F(F_SU + a, kp) = bmpc_clamp(uk[a], PP.ulo[a], PP.uhi[a]);
+      if (use_codes) stp()[kp] = codes[(k + 1 < Nst) ? k + 1 : k];
+    }
+    if (BMPC_LANE_ID == 0) {
+      Wbp()[0] = 1.0;     // slack weights are not weighted (:287-289)
+      Wbp()[1] = 1.0;
+    }
+    rlin = 0.0;
+    team_sync();
+    prof_end(2, prof_t0);
+  }
+
+  // belief part of xPred: b_0 = b0 in the row-major flattening the equality rows use (:147), then
+  // b_(i+1) = C_b + (d b+/d(x,y)) x_i + H' b_i with the Jacobians of linearisation i (about xLin[i+1], backup states of step i)
+  BMPC_DN void belief_outputs() {
+    if (!PP.out.bPred) return;
+    if (BMPC_LANE_ID == 0) {
+      const int Nst = PP.totalu - 1, nb = PP.hmm_M * PP.zm, Mh = PP.hmm_M, m = PP.zm;
+      const real* b0 = PP.b0 + (size_t)prob * nb;
+      const real* xbk = PP.xbackup + (size_t)prob * nb * PP.xb_cols;
+      real* out = PP.out.bPred + (size_t)prob * PP.pub_totalx * nb;
+      auto kp_chain = [&](int k) { return k == 0 ? kp_of(0, 0) : kp_of(1, k - 1); };
+      real b[9], bn[9], bl[9], dbx[18], Hm[36];
+      for (int q = 0; q < nb; ++q) { b[q] = b0[q]; out[q] = b[q]; }
+      for (int i = 0; i < Nst; ++i) {
+        const real* xl = belX(i + 1);
+        BeliefModel::transition(PP, xl, xbk, PP.xb_cols, i, xl + 4, bl, dbx, Hm);
+        const real x0s = F(F_XQ, kp_chain(i)), x1s = F(F_XQ + 1, kp_chain(i));
+        for (int q = 0; q < nb; ++q) {
+          const int ag = q % Mh, k = q / Mh;               // column-major position -> (agent, policy)
+          real v = bl[q] + dbx[2 * q] * (x0s - xl[0]) + dbx[2 * q + 1] * (x1s - xl[1]);
+          for (int r = 0; r < m; ++r) v += Hm[(ag * m + r) * m + k] * (b[r * Mh + ag] - xl[4 + r * Mh + ag]);
+          bn[q] = v;
+        }
+        for (int q = 0; q < nb; ++q) { b[q] = bn[q]; out[(size_t)(i + 1) * nb + q] = bn[q]; }
+      }
+    }
+    team_sync();
+  }
+
   // ========================================================================================
   // Riccati factorisation over the tree
   // ========================================================================================
@@ -966,7 +1114,7 @@ struct Solver {
           for (int i = 0; i < NX; ++i)
 #pragma unroll
             for (int j = 0; j < NX; ++j)
-              Pn[i * NX + j] = (i < NXP && j < NXP && PP.ctrl != BMPC_CTRL_ROBUST && PP.ctrl != BMPC_CTRL_CVAR)
+              Pn[i * NX + j] = (i < NXP && j < NXP && !bmpc_is_chain(PP.ctrl) && PP.ctrl != BMPC_CTRL_CVAR)
                                    ? w * (PP.Qf[i * NXP + j] + PP.Qf[j * NXP + i]) : 0.0;   // no terminal cost in robustMPC / BranchMPC_CVaR
         } else {
           sum_children(b, d, Pn);
@@ -974,7 +1122,7 @@ struct Solver {
 #pragma unroll 1
         for (int t = nt - 1; t >= 0; --t)
           node_factor(kp_of(b, t), w, Pn, mode, (d == 0) ? 0.0 : w, (d == PP.NB && t == nt - 1) ? 0.0 : 1.0, d == 0,
-                      PP.ctrl == BMPC_CTRL_ROBUST && d == PP.NB && t == nt - 1);
+                      bmpc_is_chain(PP.ctrl) && d == PP.NB && t == nt - 1);
         pack_sym(Pn, EXp() + NS * b);
       }
       bsync();
@@ -1019,6 +1167,7 @@ struct Solver {
         F(F_RHO + j, kp) = r0;
         F(F_S + j, kp) *= r0;
       }
+      const bool no_state_rows = PP.ctrl == BMPC_CTRL_BELIEF && kp == kp_of(1, PP.N - 1);   // last state: unconstrained (:199)
 #pragma unroll
       for (int j = NC; j < NR; ++j) {
         real q = 0.0;
@@ -1026,7 +1175,7 @@ struct Solver {
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
           for (int i2 = 0; i2 < NXP; ++i2) q += PP.rf[j - NC][i] * PP.rf[j - NC][i2] * Sg[i * NX + i2];
-        const real rj = (q > 1e-12) ? fmin(PP.theta / q, rho_max) : 0.0;
+        const real rj = (q > 1e-12 && !no_state_rows) ? fmin(PP.theta / q, rho_max) : 0.0;
         F(F_RHO + j, kp) = rj;
         F(F_S + j, kp) *= rj;
       }
@@ -1778,7 +1927,7 @@ struct Solver {
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
             real v = 0.0;
-            if (i < NXP && PP.ctrl != BMPC_CTRL_ROBUST && PP.ctrl != BMPC_CTRL_CVAR) {
+            if (i < NXP && !bmpc_is_chain(PP.ctrl) && PP.ctrl != BMPC_CTRL_CVAR) {
 #pragma unroll
               for (int j = 0; j < NXP; ++j) {
                 v += w * (PP.Qf[(i < NXP ? i : 0) * NXP + j] + PP.Qf[j * NXP + (i < NXP ? i : 0)]) * xT[j];
@@ -2300,7 +2449,8 @@ struct Solver {
     real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
     real* xP = PP.out.xPred ? PP.out.xPred + (size_t)prob * PP.pub_totalx * NXP : nullptr;
     real* xprev = PP.xprev ? PP.xprev + (size_t)prob * PP.pub_totalx * NXP : nullptr;   // robustMPC's LTV shift source
-    const bool robust = PP.ctrl == BMPC_CTRL_ROBUST;
+    const bool robust = bmpc_is_chain(PP.ctrl);
+    const bool belief = PP.ctrl == BMPC_CTRL_BELIEF;
 #pragma unroll 1
     BMPC_FOR_NODES(k) {
       int b, t;
@@ -2345,7 +2495,7 @@ struct Solver {
         for (int b2 = 0; b2 < NU; ++b2) v += PP.R[a * NU + b2] * u[b2];
         J += w * u[a] * v + ((k == 0) ? rlin * u[a] : 0.0);
       }
-      const real lam = PP.lam_lin * w;
+      const real lam = (belief && leaf_last) ? 0.0 : PP.lam_lin * w;   // the belief chain's last state carries no rows (:199)
 #pragma unroll 1
       for (int j = 0; j < NR; ++j) {
         real lo, hi;
@@ -2388,7 +2538,7 @@ struct Solver {
     const long long prof_t0 = prof_begin(9);
     real J = 0.0;
     real* xP = PP.out.xPred ? PP.out.xPred + (size_t)prob * PP.pub_totalx * NXP : nullptr;
-    const bool robust = PP.ctrl == BMPC_CTRL_ROBUST;
+    const bool robust = bmpc_is_chain(PP.ctrl);
     if (team_leader()) {
 #pragma unroll 1
     for (int d = 0; d <= PP.NB; ++d) {
@@ -2435,6 +2585,7 @@ struct Solver {
     }
     team_sync();
     J += emit_nodes();
+    if (PP.ctrl == BMPC_CTRL_BELIEF) belief_outputs();
     { const auto prof_rv = lanes_sum(J); prof_end(9, prof_t0); return prof_rv; }
   }
 
@@ -2879,6 +3030,7 @@ struct Solver {
     use_codes = warm && PP.warm_polish && cstate[1] == 1 && (reuse_rho || cvar);
     t_phase = 0;
     if (PP.ctrl == BMPC_CTRL_ROBUST) expand_chain();
+    else if (PP.ctrl == BMPC_CTRL_BELIEF) expand_belief();
     else expand_tree();
     nsolve = 0;
     ipm_iters = 0;

@@ -63,6 +63,28 @@ class Quad_constants:
 
 
 @dataclass
+class HMM_constants:
+    """Constants of the belief-state model.  The reference's HMM_backup_dyn.py imports this name from utils (:5) but its
+    utils.py does not define it (the module does not import as shipped); the fields are the ones the module reads."""
+    s1: float = _f()
+    s2: float = _f()
+    c2: float = _f()
+    tran_diag: float = _f()
+    alpha: float = _f()
+    R: float = _f()
+    am: float = _f()
+    rm: float = _f()
+    J_c: float = _f()
+    s_c: float = _f()
+    ylb: float = _f()
+    yub: float = _f()
+    W: float = _f()
+    L: float = _f()
+    col_alpha: float = _f()
+    Kpsi: float = _f()
+
+
+@dataclass
 class MPCParams(PythonMsg):
     """Belief-state MPC parameters (utils.py:61-90)."""
     n: int = _f()

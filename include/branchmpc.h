@@ -42,6 +42,9 @@ extern "C" {
 #define BMPC_CTRL_BRANCH 0 /* MPC_branch.BranchMPC (effective, second definition, :881) */
 #define BMPC_CTRL_PROX 1   /* MPC_branch.BranchMPCProx (:82)                             */
 #define BMPC_CTRL_ROBUST 2 /* MPC_branch.robustMPC (:1275): total_u = N*NB+1, total_x = N*NB+2; xLin/zPred outputs unused */
+#define BMPC_CTRL_BELIEF 4 /* PredictiveControllers.MPC (:56-340) on HMM_backup_dyn.PredictiveModel (:177-276): one ego chain of N
+                              stages whose state is augmented with the beliefs over the other agents' policies; solved through
+                              bmpc_solve_belief (x0, b0, xbackup, xRef); highway model, m * hmm_M <= 9 */
 #define BMPC_CTRL_CVAR 3   /* MPC_branch.BranchMPC_CVaR (:1598): nested-CVaR objective (the controller main_branch.py:48 builds);
                               highway model; solved as a cutting-plane loop over the risk multipliers of the cones whose
                               inner problems are branch-weighted tree QPs */
@@ -124,6 +127,10 @@ typedef struct bmpc_config {
   double polish_big;       /* lower bound of the stiff penalty, times branch weight (1e4)        */
   double polish_mult;      /* stiff penalty = polish_mult x curvature-matched stiffness (1e5)    */
   double cvar_alpha;       /* BMPC_CTRL_CVAR: the `ralpha` of BranchMPC_CVaR (MPC_branch.py:1601, :1798); in (0, 1]        */
+  /* BMPC_CTRL_BELIEF: constants of the belief-state model (HMM_backup_dyn.py:238-267; lane_lo / lane_hi hold ylb / yub, s1 the
+     sharpness of softsat) and the belief threshold above which a policy's row is imposed (PredictiveControllers.py:76, :213) */
+  int32_t hmm_M;           /* number of uncontrolled agents                                       */
+  double hmm_col_alpha, hmm_tran_diag, hmm_thres;
 
   int32_t slab_mode;      /* BMPC_SLAB_*: where a problem's working set lives (0 = library picks) */
   int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */
@@ -152,6 +159,7 @@ typedef struct bmpc_outputs {
   int32_t* nfact;    /* [count]               Riccati factorisations used                    */
   int32_t* nsolve;   /* [count]               KKT solves (backward+forward sweeps): ADMM + polish */
   int64_t* cycles;   /* [count]               SM clock cycles the owning warp spent on the problem */
+  double* bPred;     /* [count][totalx][m*hmm_M]  BMPC_CTRL_BELIEF: belief part of the predicted augmented state (xPred[:, 4:]) */
 } bmpc_outputs;
 
 typedef struct bmpc_handle bmpc_handle;
@@ -190,6 +198,22 @@ int bmpc_ulin_rows(const bmpc_handle* h);
  * concurrently with other solves on the same device.  bmpc_last_kernel_ms() does not see replayed launches. */
 int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                const double* policy_params, int64_t count, const bmpc_outputs* out, void* stream);
+
+/* One step of the belief-state MPC (BMPC_CTRL_BELIEF) for episodes 0..count-1: PredictiveControllers.MPC.solve(x0, b0, xbackup,
+ * xRef) (:130-160).  Device pointers, float64:
+ *   x0 [count][4], b0 [count][hmm_M][m] (the array the reference caller passes), xref [count][4],
+ *   xbackup [count][hmm_M*m][xbackup_cols]: row m*i+j = agent i under policy j, time-major, column block 4k..4k+3 = backup state
+ *   at step k (Highway_env.py:135-142 hands over N+1 states; at least N are read).
+ * Outputs: u0, uPred [count][N][2], xPred [count][N+1][4] (physical part), bPred [count][N+1][hmm_M*m], objective, status ... */
+int bmpc_solve_belief(bmpc_handle* h, const double* x0, const double* b0, const double* xbackup, int32_t xbackup_cols,
+                      const double* xref, int64_t count, const bmpc_outputs* out, void* stream);
+
+/* Point-wise belief-state model (HMM_backup_dyn.PredictiveModel.regressionAndLinearization, :216-229) on a BMPC_CTRL_BELIEF
+ * handle, device pointers: xb [count][4+nb] augmented states (belief column-major, nb = hmm_M*m), xbackup [count][nb][4] the
+ * backup state of every (agent, policy) row, u [count][2] -> A [count][n][n], B [count][n][2], C [count][n], next state xbp
+ * [count][n], and per row the safety value's linearisation: h0 [count][nb] (h - Jh x) and Jh [count][nb][2] (d h / d(x, y)). */
+int bmpc_eval_belief(bmpc_handle* h, const double* xb, const double* xbackup, const double* u, int64_t count, double* A,
+                     double* B, double* C, double* h0, double* Jh, double* xbp, void* stream);
 
 /* Same step on HOST buffers: copies inputs to the device, solves, copies every non-NULL output
  * back and synchronises.  `out` holds HOST pointers here.  Inputs and outputs each travel in ONE transfer through

@@ -328,8 +328,106 @@ def hmm_vectors():
                         b_next_env=np.array(bnext_env).reshape(K, M, m), t_index=np.array(3))
 
 
+def _hmm_module():
+    """The belief-state model module of the reference.  It imports a name its `utils.py` does not define (`HMM_constants`,
+    HMM_backup_dyn.py:5); a dataclass with the fields the module reads is injected before the import - nothing else."""
+    import dataclasses
+
+    @dataclasses.dataclass
+    class HMM_constants:
+        s1: float = None; s2: float = None; c2: float = None; tran_diag: float = None; alpha: float = None
+        R: float = None; am: float = None; rm: float = None; J_c: float = None; s_c: float = None
+        ylb: float = None; yub: float = None; W: float = None; L: float = None; col_alpha: float = None
+        Kpsi: float = None
+
+    with refenv.reference_imports():
+        rutils.HMM_constants = HMM_constants
+        import HMM_backup_dyn as hmm
+        import PredictiveControllers as pc
+    cons = HMM_constants(s1=2, s2=3, c2=0.5, tran_diag=0.3, alpha=1, R=1.2, am=6.0, rm=0.3, J_c=20, s_c=1, ylb=0., yub=7.2,
+                         L=4, W=2.5, col_alpha=5, Kpsi=0.1)
+    return hmm, pc, cons
+
+
+class _legacy_numpy_reshape:
+    """`np.reshape(b0, -1, 1)` (PredictiveControllers.py:121) passes the integer 1 as `order`: the numpy of the reference's
+    era converted it through NPY_ORDER (0 = C, 1 = Fortran), numpy 2 raises.  The old conversion is restored for the
+    duration of the reference call; nothing in the reference is touched."""
+
+    def __enter__(self):
+        self._orig = np.reshape
+
+        def reshape(a, *args, **kw):
+            if len(args) == 2 and isinstance(args[1], (int, np.integer)):
+                return self._orig(a, args[0], order={0: "C", 1: "F"}[int(args[1])])
+            return self._orig(a, *args, **kw)
+
+        np.reshape = reshape
+        return self
+
+    def __exit__(self, *exc):
+        np.reshape = self._orig
+
+
+def run_belief_mpc(name, x0, others, b0, ydes, vdes, steps, N=10, M=2):
+    """Belief-state MPC: the UNMODIFIED `PredictiveControllers.MPC` (:56-340) on the UNMODIFIED
+    `HMM_backup_dyn.PredictiveModel` (:177-276) with `Init_MPC.initMPCParams` (:7-34), closed loop: the ego applies uPred[0],
+    the other agents keep 'maintain', the belief follows the model's own transition.  Recorded per step: inputs, xbackup, the
+    assembled QP (through the osqp stand-in), its optimum, xLin/uLin, and the model's linearisation at every stage."""
+    print("belief-state MPC fixture", name)
+    hmm, pc, cons = _hmm_module()
+    m, dt = 2, 0.1
+    backupcons = [lambda s: hmm.backup_maintain(s, cons), lambda s: hmm.backup_brake(s, cons)]
+    model = hmm.PredictiveModel(4, 2, M, backupcons, dt, cons)
+    par = Init_MPC.initMPCParams(4, 2, N, M, m, ydes, vdes, 6.0, 0.3, 2, cons.W)
+    mpc = pc.MPC(par, model)
+    store = {"meta_N": np.array(N), "meta_M": np.array(M), "meta_m": np.array(m), "meta_steps": np.array(steps),
+             "meta_ydes": np.array(ydes), "meta_vdes": np.array(vdes), "meta_dt": np.array(dt)}
+    x = np.array(x0, dtype=float)
+    Z = np.array(others, dtype=float)
+    b = np.array(b0, dtype=float)
+    xref = np.array([0, ydes, vdes, 0.])
+    f0 = np.array([20., 0, 0, 0])
+    for k in range(steps):
+        # xbackup exactly as the reference's own caller builds it (Highway_env.py:135-142): per other agent and policy the
+        # module-level rollout from the CURRENT state, first N+1 states, flattened time-major
+        xbackup = np.empty([0, (N + 1) * 4])
+        for zz in Z:
+            for j in range(m):
+                tt, xx, uu, QQ, Qt = hmm.generate_backup_traj(zz, backupcons[j], lambda s, t: t > dt * N + 2, f0, dt, True)
+                xbackup = np.vstack((xbackup, np.reshape(np.array(xx[0:N + 1]), [1, -1])))
+        ulin_before = None if mpc.uLin is None else np.array(mpc.uLin)
+        with _legacy_numpy_reshape():
+            mpc.solve(x, b, xbackup, xref)
+        lp = osqp.last_problem
+        assert lp["ok"], "oracle QP solve did not certify"
+        pre = "s%d_" % k
+        store[pre + "x0"], store[pre + "b0"], store[pre + "xbackup"], store[pre + "xref"] = x.copy(), b.copy(), xbackup, xref
+        for nm, mat in (("P", sp.triu(lp["P"])), ("A", lp["A"])):
+            r, c, v, shp = coo(mat)
+            store[pre + nm + "_r"], store[pre + nm + "_c"], store[pre + nm + "_v"], store[pre + nm + "_shape"] = r, c, v, shp
+        store[pre + "q"], store[pre + "l"], store[pre + "u"] = lp["q"], lp["l"], lp["u"]
+        store[pre + "sol"] = lp["x"]
+        store[pre + "objective"] = np.array(lp["cert"]["objective"])
+        store[pre + "xPred"], store[pre + "uPred"] = np.array(mpc.xPred), np.array(mpc.uPred)
+        store[pre + "A"], store[pre + "B"], store[pre + "C"] = np.array(mpc.A), np.array(mpc.B), np.array(mpc.C)
+        store[pre + "h0"] = np.array([[np.ravel(hh) for hh in h0i] for h0i in mpc.h0])          # (N, M, m)
+        store[pre + "Jh"] = np.array([[np.array(jj) for jj in jhi] for jhi in mpc.Jh])           # (N, M, m, n)
+        if ulin_before is not None:
+            store[pre + "uLin_before"] = ulin_before
+        print("   step %d: obj %.6f  u0 %s  rows %d  kkt %.1e/%.1e" % (k, lp["cert"]["objective"],
+              np.array2string(mpc.uPred[0], precision=6), lp["A"].shape[0], lp["cert"]["primal"], lp["cert"]["dual"]))
+        # plants: ego under its first input, the others under 'maintain'; belief through the model's own transition
+        xb = np.append(x, np.reshape(b, [-1, 1]))
+        xbp = np.array(model.xbpsym(xb, mpc.uPred[0], xbackup[:, 0:4])).ravel()
+        x = xbp[:4]
+        b = np.reshape(xbp[4:], b.shape)
+        Z = np.array([zz + dt * np.array([zz[2] * np.cos(zz[3]), zz[2] * np.sin(zz[3]), 0., -cons.Kpsi * zz[3]]) for zz in Z])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "cvar", "quad", "hmm"]
+    which = sys.argv[1:] or ["models", "hw_default", "hw_close", "hw_sweep", "robust", "cvar", "belief", "quad", "hmm"]
     if "models" in which:
         model_function_vectors()
     if "hw_default" in which:
@@ -358,6 +456,11 @@ if __name__ == "__main__":
                          [0, 5.4, 20, 0], steps=3, ralpha=0.1)
         run_highway_cvar("highway_cvar_m2_nb1", ["maintain", "brake"], 1, [0, 1.8, 20, 0], [8, 1.9, 16, 0],
                          [0, 1.8, 24, 0], steps=3, ralpha=0.1)
+    if "belief" in which:
+        run_belief_mpc("belief_mpc_default", [0, 1.8, 20, 0], [[12, 1.8, 16, 0], [-8, 5.4, 22, 0]], [[0.5, 0.5], [0.5, 0.5]],
+                       1.8, 22.0, steps=3)
+        run_belief_mpc("belief_mpc_close", [0, 1.9, 21, 0.01], [[9, 1.8, 14, 0], [6, 5.2, 20, -0.02]], [[0.7, 0.3], [0.2, 0.8]],
+                       1.8, 24.0, steps=3)
     if "quad" in which:
         run_quadruped("quadruped_prox_default", [0, 0, 0], [2, 0.3, np.pi], [5., 5., 0.], steps=3)
     if "hmm" in which:

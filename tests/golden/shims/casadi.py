@@ -339,10 +339,22 @@ def norm_1(x):
 
 
 def reshape(x, *shape):
-    """casadi.reshape is column-major (numeric inputs only here; used by HMM_backup_dyn.py:213)."""
+    """casadi.reshape is column-major (numeric: HMM_backup_dyn.py:213; symbolic: :244, :258 of the belief-state model)."""
     if len(shape) == 1:
         shape = tuple(shape[0])
+    if isinstance(x, SX):
+        return SX._wrap(x._e.reshape(-1, order="F").reshape(shape, order="F").copy())
     return _np.reshape(_np.asarray(x, dtype=float), shape, order="F")
+
+
+def sumsqr(x):
+    e = _lift(x)._e.reshape(-1)
+    acc = _bin("mul", e[0], e[0])
+    for nd in e[1:]:
+        acc = _bin("add", acc, _bin("mul", nd, nd))
+    out = _np.empty((1, 1), dtype=object)
+    out[0, 0] = acc
+    return SX._wrap(out)
 
 
 def kron(a, b):

@@ -193,3 +193,28 @@ def check_cvar_fixture(solve, set_state, g):
         assert np.abs(r["u0"][0] - u0).max() < TOL_U0, (k, r["u0"][0], u0)
         obj = float(g[pre + "objective"])
         assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj), (k, r["objective"][0], obj)
+
+
+# ---- belief-state MPC (PredictiveControllers.MPC) ---------------------------------------------------------------------
+BELIEF_FIXTURES = ["belief_mpc_default", "belief_mpc_close"]
+
+
+def belief_fixture_config(g, **kw):
+    return scenarios.belief_config(N=int(g["meta_N"]), M=int(g["meta_M"]), m=int(g["meta_m"]), **kw)
+
+
+def check_belief_fixture(solve_belief, g, tol=1e-6):
+    """Closed loop recorded from the UNMODIFIED PredictiveControllers.MPC + HMM_backup_dyn.PredictiveModel + initMPCParams:
+    `solve_belief(x0, b0 (1,M,m), xbackup (1,M*m,cols), xref)` must reproduce every step's plan - inputs, physical states and
+    predicted beliefs - and the QP objective; the controller carries its own warm start from step to step."""
+    for k in range(int(g["meta_steps"])):
+        pre = "s%d_" % k
+        r = solve_belief(g[pre + "x0"], g[pre + "b0"][None], g[pre + "xbackup"][None], g[pre + "xref"][:4])
+        assert r["status"][0] in (0, 1), (k, r["status"][0])
+        xP = g[pre + "xPred"]
+        np.testing.assert_allclose(r["uPred"][0], g[pre + "uPred"], atol=tol)
+        np.testing.assert_allclose(r["xPred"][0], xP[:, :4], atol=tol)
+        np.testing.assert_allclose(r["bPred"][0], xP[:, 4:], atol=tol)
+        assert np.abs(r["u0"][0] - g[pre + "uPred"][0]).max() < TOL_U0
+        obj = float(g[pre + "objective"])
+        assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj)

@@ -36,7 +36,7 @@ class HostBackend:
             self._hs.started[e] = 0
             self._hs.cache_state[e] = -1
 
-    def solve_host(self, x0, z0, xref, policy_params=None, outputs=tuple(abi.OUTPUT_NAMES)):
+    def solve_host(self, x0, z0, xref, policy_params=None, outputs=tuple(k for k in abi.OUTPUT_NAMES if k != "bPred")):
         r = self._hs.solve(x0, z0, xref, policy_params)
         return {k: r[k] for k in outputs}
 

@@ -58,7 +58,7 @@ class HostSim:
             raise RuntimeError("hostsim_sizes: %d %s" % (rc, lib().hostsim_last_error().decode()))
         self.nbranch, self.totalx, self.totalu = nb.value, tx.value, tu.value
         self.cap = capacity
-        internal_u = self.totalu + (1 if cfg.controller == abi.CTRL_ROBUST else 0)   # robust chains carry a dummy stage
+        internal_u = self.totalu + (1 if cfg.controller in (abi.CTRL_ROBUST, abi.CTRL_BELIEF) else 0)   # robust chains carry a dummy stage
         self.uLin = np.zeros((capacity, internal_u + 1, cfg.d))
         self.xprev = np.zeros((capacity, self.totalx, cfg.n))
         self.pbest = np.zeros((capacity, self.nbranch), dtype=np.int32)
@@ -76,7 +76,17 @@ class HostSim:
         self.started[0] = 1
         self.cache_state[0] = -1
 
-    def solve(self, x0, z0, xref, policy_params=None):
+    def solve_belief(self, x0, b0, xbackup, xref):
+        """PredictiveControllers.MPC.solve(x0, b0, xbackup, xRef) for a batch (bmpc_solve_belief on the device)."""
+        b0 = np.ascontiguousarray(b0, dtype=float)
+        xbackup = np.ascontiguousarray(xbackup, dtype=float)
+        lib().hostsim_set_belief(_ptr(b0), _ptr(xbackup), C.c_int32(xbackup.shape[-1]))
+        try:
+            return self.solve(x0, np.atleast_2d(x0), xref, belief=True)
+        finally:
+            lib().hostsim_set_belief(None, None, C.c_int32(0))
+
+    def solve(self, x0, z0, xref, policy_params=None, belief=False):
         cfg = self.cfg
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=float)
         z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=float)
@@ -92,6 +102,8 @@ class HostSim:
             "status": np.full(B, -1, dtype=np.int32), "iters": np.zeros(B, dtype=np.int32),
             "nfact": np.zeros(B, dtype=np.int32), "nsolve": np.zeros(B, dtype=np.int32), "cycles": np.zeros(B, dtype=np.int64),
         }
+        if belief:
+            res["bPred"] = np.zeros((B, self.totalx, cfg.hmm_M * cfg.m))
         out = abi.Outputs(**{k: _ptr(v) for k, v in res.items()})
         rc = lib().hostsim_solve(C.byref(cfg), _ptr(x0), _ptr(z0), _ptr(xref), _ptr(pp), C.c_int64(B), _ptr(self.uLin),
                                  _ptr(self.pbest), _ptr(self.oldin), _ptr(self.started), _ptr(self.rho_cache),

@@ -25,6 +25,10 @@ void run(KParams& P) {
   if (g_split) run_layout<M, NR, BMPC_SLAB_SPLIT>(P); else run_layout<M, NR, BMPC_SLAB_SHARED>(P);
 }
 std::string g_err;
+// belief-state MPC inputs of the next hostsim_solve call (hostsim_set_belief)
+const double* g_b0 = nullptr;
+const double* g_xbackup = nullptr;
+int g_xb_cols = 0;
 }  // namespace
 
 extern "C" {
@@ -72,8 +76,13 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   std::vector<real> cv(P.cv_reals + 4, 0.0), nu((size_t)count * P.nbranch + 1, 0.0);
   P.cv = cv.data();
   P.nu_cache = nu.data();
+  std::vector<real> bel(P.bel_reals + 4, 0.0);
+  P.bel = bel.data();
+  P.b0 = g_b0;
+  P.xbackup = g_xbackup;
+  P.xb_cols = g_xb_cols;
   const bool prox = cfg->controller == BMPC_CTRL_PROX;
-  if (cfg->controller == BMPC_CTRL_ROBUST) {
+  if (bmpc_is_chain(cfg->controller)) {
     if (g_split) run_layout<HighwayModel, 11, BMPC_SLAB_SPLIT, 9>(P); else run_layout<HighwayModel, 11, BMPC_SLAB_SHARED, 9>(P);
     return BMPC_OK;
   }
@@ -86,6 +95,13 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   } else {
     prox ? run<RateAug<QuadrupedModel>, 1>(P) : run<QuadrupedModel, 1>(P);
   }
+  return BMPC_OK;
+}
+
+int hostsim_set_belief(const double* b0, const double* xbackup, int32_t cols) {
+  g_b0 = b0;
+  g_xbackup = xbackup;
+  g_xb_cols = cols;
   return BMPC_OK;
 }
 

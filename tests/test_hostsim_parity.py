@@ -7,7 +7,7 @@ on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.
 import numpy as np
 import pytest
 
-from tests.helpers import (CVAR_FIXTURES, cvar_fixture_config, check_cvar_fixture, check_quadruped_hard_cases, check_forced_interior_point, force_interior_point, SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+from tests.helpers import (BELIEF_FIXTURES, belief_fixture_config, check_belief_fixture, CVAR_FIXTURES, cvar_fixture_config, check_cvar_fixture, check_quadruped_hard_cases, check_forced_interior_point, force_interior_point, SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
                      oracle_episode)
 from _bmpc import scenarios
 from tests.hostsim.driver import HostSim
@@ -26,6 +26,15 @@ def test_cvar_fixture_closed_loop(name):
     g = load_fixture(name)
     hs = HostSim(cvar_fixture_config(g), 1)
     check_cvar_fixture(lambda x, z, r: hs.solve(x, z, r), hs.set_state, g)
+
+
+@pytest.mark.parametrize("name", BELIEF_FIXTURES)
+def test_belief_mpc_fixture_closed_loop(name):
+    """Belief-state MPC (PredictiveControllers.MPC on HMM_backup_dyn.PredictiveModel): chain instance of the solver."""
+    g = load_fixture(name)
+    hs = HostSim(belief_fixture_config(g), 1)
+    assert (hs.totalx, hs.totalu) == (int(g["meta_N"]) + 1, int(g["meta_N"]))
+    check_belief_fixture(hs.solve_belief, g)
 
 
 def test_quadruped_prox_fixture_closed_loop():
