@@ -172,20 +172,38 @@ __global__ void bmpc_belief_eval_kernel(const __grid_constant__ KParams P, const
   const real* xb = a.xb + (size_t)e * n;
   const real* xbk = a.xbackup + (size_t)e * nb * 4;
   const real* u = a.u + (size_t)e * 2;
-  real lin[HighwayModel::NLIN], cc[HighwayModel::NCC], xn[4], bp[9], dbx[18], Hm[36];
+  real lin[HighwayModel::NLIN], cc[HighwayModel::NCC], xn[4], bp[9];
   HighwayModel::linearize(P, xb, u, lin, cc, xn);
-  BeliefModel::transition(P, xb, xbk, 4, 0, xb + 4, bp, dbx, Hm);
   real* A = a.A + (size_t)e * n * n;
   for (int q = 0; q < n * n; ++q) A[q] = 0.0;
   real A4[16];
   HighwayModel::denseA(P, lin, A4);
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) A[i * n + j] = A4[i * 4 + j];
-  for (int q = 0; q < nb; ++q) {
-    const int ag = q % M, k = q / M;
-    A[(4 + q) * n] = dbx[2 * q];
-    A[(4 + q) * n + 1] = dbx[2 * q + 1];
-    for (int r = 0; r < m; ++r) A[(4 + q) * n + 4 + r * M + ag] = Hm[(ag * m + r) * m + k];
+  // belief rows, agent by agent (same formulas as BeliefModel::transition, written straight into the dense matrix)
+  const real tau = P.hmm_tran_diag;
+  for (int i = 0; i < M; ++i) {
+    real mh[BMPC_MAX_POLICIES], gx[BMPC_MAX_POLICIES], gy[BMPC_MAX_POLICIES], msum = 0.0, bsum = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const real hv = BeliefModel::safety(P, xb, xbk + (size_t)(m * i + j) * 4, gx[j], gy[j]);
+      mh[j] = 1.0 / (1.0 + exp(-P.s1 * hv));
+      msum += mh[j];
+      bsum += xb[4 + j * M + i];
+    }
+    for (int k = 0; k < m; ++k) {
+      const int q = k * M + i;
+      const real pik = mh[k] / msum;
+      bp[q] = (1.0 - tau) * bsum * pik + tau * xb[4 + q];
+      for (int r = 0; r < m; ++r) A[(4 + q) * n + 4 + r * M + i] = (1.0 - tau) * pik + (r == k ? tau : 0.0);
+      real ax = 0.0, ay = 0.0;
+      for (int l = 0; l < m; ++l) {
+        const real c = (1.0 - tau) * bsum * ((((l == k) ? 1.0 : 0.0) - pik) / msum) * P.s1 * mh[l] * (1.0 - mh[l]);
+        ax += c * gx[l];
+        ay += c * gy[l];
+      }
+      A[(4 + q) * n] = ax;
+      A[(4 + q) * n + 1] = ay;
+    }
   }
   real* B = a.B + (size_t)e * n * 2;
   for (int q = 0; q < n * 2; ++q) B[q] = 0.0;
