@@ -112,6 +112,9 @@ class _BatchedController:
                                  batch_capacity=capacity, **self._knobs)
         self._kinds = [dd.kind for dd in model.descriptors]
         solver = batch.BatchedBranchMPC(cfg)
+        table = getattr(model, "lookup_table", None)
+        if table is not None:
+            solver.set_lookup_table(table.xs, table.ys)
         self.totalx, self.totalu = solver.totalx, solver.totalu
         topo = solver.topology()
         self.ndx = {int(r[0]): int(r[2]) for r in topo}
@@ -248,23 +251,50 @@ class BranchMPC_CVaR(_BatchedController):
     scenario tree (the reference hands a second-order-cone program to ECOS).  Same constructor and `solve` signature as the
     reference (`ralpha` :1601, `solve(x, z, xRef, S, Fx, bx)` :2043); on the device the cone program is solved as a
     cutting-plane loop over the risk multipliers whose inner problems are branch-weighted tree QPs (csrc/bmpc_solver.h).
-    The state transformation `S` / time-varying `Fx, bx` of the merge scene (:2057-2063) are not built."""
+    The state transformation `S` and the per-call bounds `bx` of the merge scene (:2054-2059) need a model built as
+    `PredictiveModel_merge` (BMPC_MODEL_MERGE on the device); a different `Fx` per call is not built."""
     controller_kind = abi.CTRL_CVAR
 
     def __init__(self, mpcParameters, predictiveModel, ralpha=0.1, S=None, **solver_knobs):
-        if S is not None:
-            raise NotImplementedError("BranchMPC_CVaR with a state transformation S (merge scenario) is not built")
         super().__init__(mpcParameters, predictiveModel, cvar_alpha=float(ralpha), **solver_knobs)
         self.ralpha = ralpha
-        self.S = None
+        self.S = S
         self.param = mpcParameters
         self.psimax = np.squeeze(np.asarray(mpcParameters.bx, dtype=float)).reshape(-1)[2]     # bx[0][2][0], :1622
 
+    def _transformed(self):
+        return self.predictiveModel.spec().kind == abi.MODEL_MERGE
+
     def solve(self, x, z, xRef=None, S=None, Fx=None, bx=None):
-        if S is not None:
-            raise NotImplementedError("BranchMPC_CVaR.solve with a state transformation S (merge scenario) is not built")
-        for given, own in ((Fx, self.Fx), (bx, self.bx)):
-            if given is not None and not np.array_equal(np.squeeze(np.asarray(given, dtype=float)),
-                                                        np.squeeze(np.asarray(own, dtype=float))):
-                raise NotImplementedError("time-varying state constraints (merge scenario) are not built")
-        return super().solve(x, z, xRef)
+        """solve(x, z, xRef, S, Fx, bx) (:2043-2059).  Batched: x, z (B, n); S (n, n) or (B, n, n); bx (4,) or (B, 4)."""
+        if Fx is not None and not np.array_equal(np.squeeze(np.asarray(Fx, dtype=float)),
+                                                 np.squeeze(np.asarray(self.Fx, dtype=float))):
+            raise NotImplementedError("a different Fx per call is not built (the reference's callers pass Fx=None)")
+        if not self._transformed():
+            if S is not None:
+                raise NotImplementedError("a state transformation S needs a model built as PredictiveModel_merge")
+            if bx is not None and not np.array_equal(np.squeeze(np.asarray(bx, dtype=float)),
+                                                     np.squeeze(np.asarray(self.bx, dtype=float))):
+                raise NotImplementedError("per-call state bounds need a model built as PredictiveModel_merge")
+            return super().solve(x, z, xRef)
+        if xRef is not None:
+            self.xRef = xRef
+        self.S = S                                    # :2054 (None = no transform, also for the collision-gradient rule)
+        if bx is not None:
+            self.bx = bx
+        x = np.asarray(x, dtype=float)
+        single = x.ndim == 1
+        X = np.atleast_2d(x)
+        Z = np.atleast_2d(np.asarray(z, dtype=float))
+        B = X.shape[0]
+        R = np.broadcast_to(np.atleast_2d(np.asarray(self.xRef, dtype=float)), (B, self.n))
+        Sb = None if S is None else np.broadcast_to(np.asarray(S, dtype=float).reshape(-1, self.n, self.n), (B, self.n, self.n))
+        bxb = np.broadcast_to(np.asarray(self.bx, dtype=float).reshape(-1, 4), (B, 4))
+        bounds = np.stack([np.stack([-bxb[:, 1], bxb[:, 0]], axis=1), np.stack([-bxb[:, 3], bxb[:, 2]], axis=1)], axis=1)
+        model = self.predictiveModel
+        solver = self._ensure_solver(B)
+        pp = np.broadcast_to(model.policy_params(), (B, self.m, 4))
+        t0 = datetime.datetime.now()
+        r = solver.solve_transformed_host_views(X, Z, R, Sb, bounds, pp)
+        self.solverTime = datetime.datetime.now() - t0
+        return self._absorb(r, single)

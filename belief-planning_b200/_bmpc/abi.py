@@ -7,9 +7,9 @@ import os
 
 MAX_N, MAX_D, MAX_POLICIES, MAX_ROWS, MAX_NB = 4, 3, 4, 4, 3
 
-MODEL_HIGHWAY, MODEL_QUADRUPED = 0, 1
+MODEL_HIGHWAY, MODEL_QUADRUPED, MODEL_MERGE = 0, 1, 2
 CTRL_BRANCH, CTRL_PROX, CTRL_ROBUST, CTRL_CVAR, CTRL_BELIEF = 0, 1, 2, 3, 4
-POLICY_MAINTAIN, POLICY_BRAKE, POLICY_LC, POLICY_TRACKV, POLICY_FORWARD, POLICY_STOP = range(6)
+POLICY_MAINTAIN, POLICY_BRAKE, POLICY_LC, POLICY_TRACKV, POLICY_FORWARD, POLICY_STOP, POLICY_TRACKV_REF, POLICY_BRAKE_REF = range(8)
 STATUS_POLISHED, STATUS_CONVERGED, STATUS_MAXITER, STATUS_NUMERIC = range(4)
 SLAB_AUTO, SLAB_SHARED, SLAB_SPLIT, SLAB_GLOBAL = range(4)
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
@@ -83,6 +83,10 @@ SYMBOLS = [
     ("bmpc_ulin_rows", C.c_int, [C.c_void_p]),
     ("bmpc_solve", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                              C.POINTER(Outputs), C.c_void_p]),
+    ("bmpc_set_lookup_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("bmpc_solve_transformed", C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int64, C.POINTER(Outputs), C.c_void_p]),
+    ("bmpc_solve_transformed_host_views", C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int64, C.POINTER(Outputs),
+                                                                                      C.POINTER(Outputs)]),
     ("bmpc_solve_belief", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                     C.POINTER(Outputs), C.c_void_p]),
     ("bmpc_eval_belief", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_void_p]),

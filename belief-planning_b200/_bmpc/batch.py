@@ -167,6 +167,46 @@ class BatchedBranchMPC:
             res[k] = np.frombuffer(buf, dtype=dt).reshape(shape)
         return res
 
+    # -- merge scenario: BranchMPC_CVaR.solve(x, z, xRef, S, Fx=None, bx) -----------------------------------------
+    def set_lookup_table(self, xs, ys):
+        """psiref(x) of the ramp policies (casadi interpolant 'linear'): grid xs (strictly increasing) and values ys."""
+        xs = np.ascontiguousarray(xs, np.float64).reshape(-1)
+        ys = np.ascontiguousarray(ys, np.float64).reshape(-1)
+        if xs.shape != ys.shape:
+            raise ValueError("lookup grid and values disagree")
+        self._check(self.lib.bmpc_set_lookup_table(self.h, xs.ctypes.data, ys.ctypes.data, len(xs)), "bmpc_set_lookup_table")
+
+    def solve_transformed_host_views(self, x0, z0, xref, S=None, state_bounds=None, policy_params=None, outputs=ALL_OUTPUTS):
+        """As solve_host_views for a BMPC_MODEL_MERGE handle, with the call's state transform S (count, n, n) and the (lo, hi)
+        bounds of the state rows (count, n_rows, 2); either may be None."""
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=np.float64)
+        xref = np.ascontiguousarray(np.atleast_2d(xref), dtype=np.float64)
+        count, n = x0.shape[0], self.cfg.n
+        if x0.shape != (count, n) or z0.shape != x0.shape or xref.shape != x0.shape:
+            raise ValueError("x0, z0, xref must have shape (count, n)")
+        pp = None
+        if policy_params is not None:
+            pp = np.ascontiguousarray(policy_params, dtype=np.float64).reshape(count, self.cfg.m, 4)
+        if S is not None:
+            S = np.ascontiguousarray(S, dtype=np.float64).reshape(count, n, n)
+        if state_bounds is not None:
+            state_bounds = np.ascontiguousarray(state_bounds, dtype=np.float64).reshape(count, self.cfg.n_rows, 2)
+        want = abi.Outputs(**{k: 1 for k in outputs})
+        views = abi.Outputs()
+        self._check(self.lib.bmpc_solve_transformed_host_views(
+            self.h, x0.ctypes.data, z0.ctypes.data, xref.ctypes.data, None if pp is None else pp.ctypes.data,
+            None if S is None else S.ctypes.data, None if state_bounds is None else state_bounds.ctypes.data, count,
+            C.byref(want), C.byref(views)), "bmpc_solve_transformed_host_views")
+        res = {}
+        for k in outputs:
+            dt = np.int64 if k == "cycles" else (np.int32 if k in _INT_OUTPUTS else np.float64)
+            shape = (count,) + _OUT_SHAPES[k](self)
+            nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+            buf = (C.c_char * nbytes).from_address(getattr(views, k))
+            res[k] = np.frombuffer(buf, dtype=dt).reshape(shape)
+        return res
+
     # -- belief-state MPC -----------------------------------------------------------------------------------------
     def solve_belief_host(self, x0, b0, xbackup, xref, outputs=("u0", "uPred", "xPred", "bPred", "objective", "status", "iters")):
         """PredictiveControllers.MPC.solve(x0, b0, xbackup, xRef) for a batch: x0 (B,4), b0 (B,M,m), xbackup (B, M*m, cols),

@@ -109,5 +109,10 @@ def highway_spec(N, dt, policies, L, W, Kpsi, s1, N_lane_model=3):
                      lane_lo=W / 2.0, lane_hi=N_lane_model * 3.6 - W / 2.0)
 
 
+def merge_spec(N, dt, policies, L, W, Kpsi, s1):
+    """highway_branch_dyn.PredictiveModel_merge constants (:400-456): no lane-boundary term in the branching probability."""
+    return ModelSpec(abi.MODEL_MERGE, 4, 2, N, dt, policies, veh_L=L, veh_W=W, Kpsi=Kpsi, s1=s1)
+
+
 def quadruped_spec(N, dt, policies, L1, L2, col_tol, s1):
     return ModelSpec(abi.MODEL_QUADRUPED, 3, 3, N, dt, policies, s1=s1, quad_margin=(L1 + L2) / 2.0 + col_tol)

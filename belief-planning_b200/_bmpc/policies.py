@@ -19,10 +19,11 @@ class PolicyProbe:
 
 
 class PolicyDescriptor:
-    def __init__(self, kind, params=(), consts=None):
+    def __init__(self, kind, params=(), consts=None, table=None):
         self.kind = int(kind)
         self.params = [float(v) for v in params] + [0.0] * (4 - len(params))
         self.consts = dict(consts or {})
+        self.table = table        # lookup table psiref(x) of the merge scenario's ramp policies, or None
 
     def entry(self):
         return self.kind, self.params

@@ -30,7 +30,8 @@ def highway_batch(count, seed=1237, n_lanes=4):
 
 def highway_policies(names=("maintain", "brake", "lc"), lc_target=(0.5, 1.8, 15.0, 0.0), v0=20.0):
     table = {"maintain": (abi.POLICY_MAINTAIN, [0, 0, 0, 0]), "brake": (abi.POLICY_BRAKE, [0, 0, 0, 0]),
-             "lc": (abi.POLICY_LC, list(lc_target)), "trackv": (abi.POLICY_TRACKV, [v0, 0, 0, 0])}
+             "lc": (abi.POLICY_LC, list(lc_target)), "trackv": (abi.POLICY_TRACKV, [v0, 0, 0, 0]),
+             "trackv_ref": (abi.POLICY_TRACKV_REF, [v0, 0, 0, 0]), "brake_ref": (abi.POLICY_BRAKE_REF, [0, 0, 0, 0])}
     return [table[n] for n in names]
 
 
@@ -44,6 +45,26 @@ def highway_config(policies=("maintain", "brake", "lc"), NB=2, N=8, lc_target=(0
     bu = np.array([am, am, rm, rm])
     return config.make_config(spec, 4, 2, N, NB, np.diag([0., 3., 3., 10.]), np.diag([1., 100.]), Fx, bx, Fu, bu,
                               np.array([0., 300.]), batch_capacity=batch_capacity, device=device, **knobs)
+
+
+def merge_config(policies=("trackv", "brake"), NB=1, N=40, v0=20.0, am=7.0, rm=0.3, N_lane=2, W=2.5, L=4.0, ralpha=0.1,
+                 batch_capacity=1, device=0, **knobs):
+    """sim_merge of main_branch.py (:53-88): PredictiveModel_merge without lookup-table policies (`backupcons_normal`),
+    initBranchMPC and BranchMPC_CVaR(ralpha=0.1) as a bmpc_config."""
+    spec = config.merge_spec(N, 0.1, highway_policies(policies, v0=v0), L, W, 0.1, 2.0)
+    Fx = np.array([[0., 1., 0., 0.], [0., -1., 0., 0.], [0., 0., 0., 1.], [0., 0., 0., -1.]])
+    bx = np.array([N_lane * LANE_W - W / 2, -W / 2, 0.25, 0.25])
+    Fu = np.kron(np.eye(2), np.array([1., -1.])).T
+    bu = np.array([am, am, rm, rm])
+    return config.make_config(spec, 4, 2, N, NB, np.diag([0., 3., 3., 10.]), np.diag([1., 100.]), Fx, bx, Fu, bu,
+                              np.array([0., 300.]), controller=abi.CTRL_CVAR, cvar_alpha=ralpha,
+                              batch_capacity=batch_capacity, device=device, **knobs)
+
+
+def bounds_from_bx(bx):
+    """The reference's bx of the four one-sided rows [y <= b0, -y <= b1, psi <= b2, -psi <= b3] as (lo, hi) pairs."""
+    bx = np.asarray(bx, dtype=float).reshape(-1, 4)
+    return np.stack([np.stack([-bx[:, 1], bx[:, 0]], axis=1), np.stack([-bx[:, 3], bx[:, 2]], axis=1)], axis=1)
 
 
 def euler_highway(x, u, dt=0.1):

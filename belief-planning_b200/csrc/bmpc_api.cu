@@ -295,6 +295,7 @@ struct bmpc_handle {
   real* ipm_ws = nullptr;   // per-warp scratch of the interior-point fallback
   real* nu_cache = nullptr; // BranchMPC_CVaR: risk multipliers of each episode's last step
   real* cv_ws = nullptr;    // BranchMPC_CVaR: per-team scratch of the master problem
+  real* lut = nullptr;      // lookup table of the *_REF policies: grid then values
   real* bel_ws = nullptr;   // belief-state MPC: per-team linearisation trajectory of the augmented state
   KParams* captured = nullptr;            // pinned parameter blocks for launches recorded into CUDA graphs (BMPC_MAX_CAPTURED,
   int captured_used = 0;                  // allocated at create: nothing may be allocated while a stream is capturing)
@@ -414,6 +415,7 @@ static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStrea
 // robustMPC: highway model, 2 state rows + up to 9 obstacle nodes per time slot
 #define BMPC_DISPATCH(h, fn, ...)                                                                       \
   (bmpc_is_chain((h)->cfg.controller) ? fn<HighwayModel, 11, 9>(__VA_ARGS__) :                     \
+   (h)->cfg.model == BMPC_MODEL_MERGE ? fn<MergeModel, 3>(__VA_ARGS__) :                                \
    (h)->cfg.controller == BMPC_CTRL_PROX                                                                \
        ? BMPC_DISPATCH_M(h, fn, RateAug<HighwayModel>, RateAug<QuadrupedModel>, __VA_ARGS__)            \
        : BMPC_DISPATCH_M(h, fn, HighwayModel, QuadrupedModel, __VA_ARGS__))
@@ -436,6 +438,7 @@ static void free_handle(bmpc_handle* h) {
   cudaFree(h->ipm_ws);
   cudaFree(h->nu_cache);
   cudaFree(h->cv_ws);
+  cudaFree(h->lut);
   cudaFree(h->bel_ws);
   if (h->pstage) cudaFreeHost(h->pstage);
   if (h->captured) cudaFreeHost(h->captured);
@@ -579,8 +582,9 @@ int bmpc_get_topology(const bmpc_handle* h, int32_t* ndx, int32_t* ndu, int32_t*
 }
 
 struct BeliefArgs { const double* b0; const double* xbackup; int cols; };
+struct XformArgs { const double* S; const double* bounds; };
 static int solve_impl(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
-                      int64_t count, const bmpc_outputs* out, void* stream, const BeliefArgs* bel);
+                      int64_t count, const bmpc_outputs* out, void* stream, const BeliefArgs* bel, const XformArgs* xf = nullptr);
 
 int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
                int64_t count, const bmpc_outputs* out, void* stream) {
@@ -599,11 +603,47 @@ int bmpc_solve_belief(bmpc_handle* h, const double* x0, const double* b0, const 
   return solve_impl(h, x0, x0, xref, nullptr, count, out, stream, &bel);
 }
 
+int bmpc_set_lookup_table(bmpc_handle* h, const double* xs, const double* ys, int32_t n) {
+  if (!h) return BMPC_E_INVALID;
+  if (!xs || !ys || n < 2 || n > 4096) { h->err = "lookup table needs 2..4096 points"; return BMPC_E_INVALID; }
+  for (int i = 1; i < n; ++i)
+    if (!(xs[i] > xs[i - 1])) { h->err = "lookup grid must be strictly increasing"; return BMPC_E_INVALID; }
+  BMPC_CK(h, cudaSetDevice(h->device));
+  BMPC_CK(h, cudaStreamSynchronize(h->last_stream));   // a solve in flight may still read the old table
+  real* t = nullptr;
+  BMPC_CK(h, cudaMalloc(&t, (size_t)2 * n * sizeof(real)));
+  cudaError_t e = cudaMemcpy(t, xs, (size_t)n * sizeof(real), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t + n, ys, (size_t)n * sizeof(real), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(t); h->err = cudaGetErrorString(e); return BMPC_E_CUDA; }
+  cudaFree(h->lut);
+  h->lut = t;
+  h->P.lut_x = t;
+  h->P.lut_y = t + n;
+  h->P.lut_n = n;
+  return BMPC_OK;
+}
+
+static bool needs_lookup(const bmpc_handle* h) {
+  for (int i = 0; i < h->cfg.m; ++i)
+    if (h->cfg.policy_kind[i] == BMPC_POLICY_TRACKV_REF || h->cfg.policy_kind[i] == BMPC_POLICY_BRAKE_REF) return h->P.lut_n < 2;
+  return false;
+}
+
+int bmpc_solve_transformed(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
+                           const double* S, const double* state_bounds, int64_t count, const bmpc_outputs* out, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (h->cfg.model != BMPC_MODEL_MERGE) { h->err = "state transforms are built for BMPC_MODEL_MERGE handles"; return BMPC_E_INVALID; }
+  if (!z0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  const XformArgs xf{S, state_bounds};
+  return solve_impl(h, x0, z0, xref, policy_params, count, out, stream, nullptr, &xf);
+}
+
 static int solve_impl(bmpc_handle* h, const double* x0, const double* z0, const double* xref, const double* policy_params,
-                      int64_t count, const bmpc_outputs* out, void* stream, const BeliefArgs* bel) {
+                      int64_t count, const bmpc_outputs* out, void* stream, const BeliefArgs* bel, const XformArgs* xf) {
   if (!h) return BMPC_E_INVALID;
   if (!x0 || !z0 || !xref || !out || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
   if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
+  if (needs_lookup(h)) { h->err = "the policy table uses a lookup-table policy: call bmpc_set_lookup_table first"; return BMPC_E_INVALID; }
   if (count == 0) return BMPC_OK;
   BMPC_CK(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -613,6 +653,8 @@ static int solve_impl(bmpc_handle* h, const double* x0, const double* z0, const 
   P.z0 = z0;
   P.xref = xref;
   P.polpar = policy_params;
+  P.xform = xf ? xf->S : nullptr;
+  P.xbounds = xf ? xf->bounds : nullptr;
   P.uLin = h->uLin;
   P.pbest = h->pbest;
   P.oldin = h->oldin;
@@ -705,7 +747,8 @@ static void** out_slots(bmpc_outputs* o, void*** slots) {
 
 // want: which outputs to produce (non-NULL members); views: receives host pointers into the pinned mirror
 static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
-                           const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views) {
+                           const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views,
+                           const XformArgs* xf = nullptr) {
   if (!h) return BMPC_E_INVALID;
   if (!x0 || !z0 || !xref || !want || !views || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
   if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
@@ -721,7 +764,8 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
   size_t sz[kNumOut], per = 0;
   out_sizes(h, sz);
   for (int i = 0; i < kNumOut; ++i) per += sz[i];
-  const size_t in_reals = cap * (3 * n + 4 * m);
+  const size_t nrw = (size_t)h->cfg.n_rows;
+  const size_t in_reals = cap * (3 * n + 4 * m + n * n + 2 * nrw);
   if (!h->stage_in) {
     BMPC_CK(h, cudaMalloc(&h->stage_in, in_reals * sizeof(real)));
     BMPC_CK(h, cudaMallocHost(&h->stage_in_host, in_reals * sizeof(real)));
@@ -747,6 +791,19 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
     memcpy(hin + in_used, policy_params, rows * m * 4 * 8);
     in_used += rows * m * 4;
   }
+  // merge scenario: state transform and state bounds of the call, each optional
+  real* dS = nullptr;
+  real* dbd = nullptr;
+  if (xf && xf->S) {
+    memcpy(hin + in_used, xf->S, rows * n * n * 8);
+    dS = h->stage_in + in_used;
+    in_used += rows * n * n;
+  }
+  if (xf && xf->bounds) {
+    memcpy(hin + in_used, xf->bounds, rows * nrw * 2 * 8);
+    dbd = h->stage_in + in_used;
+    in_used += rows * nrw * 2;
+  }
   BMPC_CK(h, cudaMemcpyAsync(h->stage_in, hin, in_used * sizeof(real), cudaMemcpyHostToDevice, s));
   real* dx0 = h->stage_in;
   real* dz0 = dx0 + rows * n;
@@ -770,7 +827,8 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
         *dslot[i] = nullptr;
       }
     }
-  const int rc = bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
+  const int rc = xf ? bmpc_solve_transformed(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, dS, dbd, count, &dout, s)
+                    : bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
   if (rc != BMPC_OK) return rc;
   BMPC_CK(h, cudaMemcpyAsync(host_out, h->stage_out, off, cudaMemcpyDeviceToHost, s));
   BMPC_CK(h, cudaStreamSynchronize(s));
@@ -782,6 +840,15 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
 int bmpc_solve_host_views(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                           const double* policy_params, int64_t count, const bmpc_outputs* want, bmpc_outputs* views) {
   return solve_host_impl(h, x0, z0, xref, policy_params, count, want, views);
+}
+
+int bmpc_solve_transformed_host_views(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                                      const double* policy_params, const double* S, const double* state_bounds, int64_t count,
+                                      const bmpc_outputs* want, bmpc_outputs* views) {
+  if (!h) return BMPC_E_INVALID;
+  if (h->cfg.model != BMPC_MODEL_MERGE) { h->err = "state transforms are built for BMPC_MODEL_MERGE handles"; return BMPC_E_INVALID; }
+  const XformArgs xf{S, state_bounds};
+  return solve_host_impl(h, x0, z0, xref, policy_params, count, want, views, &xf);
 }
 
 int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
@@ -849,12 +916,14 @@ int bmpc_eval_model(bmpc_handle* h, const double* x, const double* z, const doub
                     double* dh, void* stream) {
   if (!h) return BMPC_E_INVALID;
   if (!x || count < 0) { h->err = "null argument"; return BMPC_E_INVALID; }
+  if (needs_lookup(h)) { h->err = "the policy table uses a lookup-table policy: call bmpc_set_lookup_table first"; return BMPC_E_INVALID; }
   if (count == 0) return BMPC_OK;
   BMPC_CK(h, cudaSetDevice(h->device));
   EvalArgs a{x, z, u, policy_params, A, B, C, xp, zpred, p, hlin, dh, (int)count};
   const int threads = 128, blocks = (int)((count + threads - 1) / threads);
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.model == BMPC_MODEL_HIGHWAY) bmpc_eval_kernel<HighwayModel><<<blocks, threads, 0, s>>>(h->P, a);
+  else if (h->cfg.model == BMPC_MODEL_MERGE) bmpc_eval_kernel<MergeModel><<<blocks, threads, 0, s>>>(h->P, a);
   else bmpc_eval_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, a);
   BMPC_CK(h, cudaGetLastError());
   h->launches += 1;
@@ -883,7 +952,7 @@ int bmpc_plant_step(bmpc_handle* h, double* x, const double* u, double* z, int32
   BMPC_CK(h, cudaSetDevice(h->device));
   const int threads = 128, blocks = (int)((count + threads - 1) / threads);
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->cfg.model == BMPC_MODEL_HIGHWAY)
+  if (h->cfg.model == BMPC_MODEL_HIGHWAY || h->cfg.model == BMPC_MODEL_MERGE)
     bmpc_plant_kernel<HighwayModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
   else
     bmpc_plant_kernel<QuadrupedModel><<<blocks, threads, 0, s>>>(h->P, x, u, z, obstacle_policy, policy_params, (int)count);
@@ -900,6 +969,7 @@ int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int3
     h->err = "bmpc_env_step needs x, z, obs_policy, collided, xref, u_obs and out->u0";
     return BMPC_E_INVALID;
   }
+  if (h->cfg.model == BMPC_MODEL_MERGE) { h->err = "the merge environment (Highway_env_merge) is stepped by the host caller"; return BMPC_E_UNSUPPORTED; }
   const bool highway = h->cfg.model == BMPC_MODEL_HIGHWAY;
   if (highway && (!env->lane || !env->policy_params || n_lane < 1)) {
     h->err = "highway environment needs lane, policy_params and n_lane";

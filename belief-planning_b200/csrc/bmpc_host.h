@@ -13,7 +13,7 @@
 namespace bmpc {
 
 inline int model_dims(int model, int* n, int* d) {
-  if (model == BMPC_MODEL_HIGHWAY) { *n = 4; *d = 2; return 0; }
+  if (model == BMPC_MODEL_HIGHWAY || model == BMPC_MODEL_MERGE) { *n = 4; *d = 2; return 0; }
   if (model == BMPC_MODEL_QUADRUPED) { *n = 3; *d = 3; return 0; }
   return -1;
 }
@@ -37,10 +37,14 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
     return BMPC_E_INVALID;
   }
   if (c.controller == BMPC_CTRL_CVAR) {
-    if (c.model != BMPC_MODEL_HIGHWAY) { *err = "BranchMPC_CVaR is built for the highway model"; return BMPC_E_UNSUPPORTED; }
+    if (c.model != BMPC_MODEL_HIGHWAY && c.model != BMPC_MODEL_MERGE) { *err = "BranchMPC_CVaR is built for the highway models"; return BMPC_E_UNSUPPORTED; }
     if (!(c.cvar_alpha > 0.0 && c.cvar_alpha <= 1.0)) { *err = "cvar_alpha (ralpha) must be in (0, 1]"; return BMPC_E_INVALID; }
     for (int a = 0; a < d; ++a)
       if (c.dR[a] != 0.0) { *err = "BranchMPC_CVaR ignores input-rate costs; dR must be 0"; return BMPC_E_UNSUPPORTED; }
+  }
+  if (c.model == BMPC_MODEL_MERGE && (c.controller != BMPC_CTRL_CVAR || c.n_rows != 2)) {
+    *err = "the merge model is built for BranchMPC_CVaR with the reference's two state rows (main_branch.py:87)";
+    return BMPC_E_UNSUPPORTED;
   }
   const bool belief = c.controller == BMPC_CTRL_BELIEF;
   if (belief) {
@@ -60,9 +64,10 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   if (!(c.Qslack[1] > 0.0)) { *err = "linear slack weight Qslack[1] must be positive"; return BMPC_E_INVALID; }
   for (int i = 0; i < c.m; ++i) {
     const int k = c.policy_kind[i];
-    const bool hw = (k == BMPC_POLICY_MAINTAIN || k == BMPC_POLICY_BRAKE || k == BMPC_POLICY_LC || k == BMPC_POLICY_TRACKV);
+    const bool hw = (k == BMPC_POLICY_MAINTAIN || k == BMPC_POLICY_BRAKE || k == BMPC_POLICY_LC || k == BMPC_POLICY_TRACKV ||
+                     k == BMPC_POLICY_TRACKV_REF || k == BMPC_POLICY_BRAKE_REF);
     const bool qd = (k == BMPC_POLICY_FORWARD || k == BMPC_POLICY_STOP);
-    if ((c.model == BMPC_MODEL_HIGHWAY && !hw) || (c.model == BMPC_MODEL_QUADRUPED && !qd)) {
+    if ((c.model != BMPC_MODEL_QUADRUPED && !hw) || (c.model == BMPC_MODEL_QUADRUPED && !qd)) {
       *err = "policy kind does not belong to the model";
       return BMPC_E_INVALID;
     }
@@ -203,6 +208,7 @@ inline bool supported_instance(int model, int n_rows, int controller = BMPC_CTRL
     return model == BMPC_MODEL_HIGHWAY && n_rows == 2 && obstacle_leaves <= 9;
   if (model == BMPC_MODEL_HIGHWAY) return n_rows >= 0 && n_rows <= 2;
   if (model == BMPC_MODEL_QUADRUPED) return n_rows == 0;
+  if (model == BMPC_MODEL_MERGE) return controller == BMPC_CTRL_CVAR && n_rows == 2;
   return false;
 }
 

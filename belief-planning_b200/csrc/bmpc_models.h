@@ -39,6 +39,19 @@ BMPC_D void soft_box(real dx, real dy, real& h, real& gx, real& gy) {
 
 BMPC_D real sgn(real v) { return (v > 0) - (v < 0); }
 
+// piecewise-linear lookup table of the handle (casadi interpolant 'linear', main_branch.py:78-79): segment by bisection, the
+// end segments continue outside the grid
+BMPC_D real bmpc_lookup(const KParams& P, real x) {
+  if (P.lut_n < 2) return 0.0;
+  int lo = 0, hi = P.lut_n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (P.lut_x[mid] <= x) lo = mid; else hi = mid;
+  }
+  const real x0 = P.lut_x[lo], y0 = P.lut_y[lo];
+  return y0 + bmpc_div(P.lut_y[lo + 1] - y0, P.lut_x[lo + 1] - x0) * (x - x0);
+}
+
 // ------------------------------------------------------------------------------------------
 // Highway: x = (x, y, v, psi), u = (a, r).   highway_branch_dyn.py
 // ------------------------------------------------------------------------------------------
@@ -49,6 +62,7 @@ struct HighwayModel {
   static constexpr int NU = 2;
   static constexpr int NLIN = 4;  // dt*cos, -dt*v*sin, dt*sin, dt*v*cos  (the four non-trivial entries of A)
   static constexpr int NCC = 2;   // C has two non-zero entries
+  static constexpr bool kStateTransform = false;   // per-episode state transform S and bounds bx (merge scenario only)
 
   // one Euler step of dubin (:17-34, :369)
   BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) {
@@ -84,6 +98,18 @@ struct HighwayModel {
         u[0] = 0.5 * (par[0] - x[2]);
         u[1] = -P.Kpsi * x[3];
         break;
+      case BMPC_POLICY_TRACKV_REF:   // ramp policies of the merge scenario (:89-96, :122-131)
+        u[0] = 0.5 * (par[0] - x[2]);
+        u[1] = bmpc_lookup(P, x[0]) - P.Kpsi * x[3];
+        break;
+      case BMPC_POLICY_BRAKE_REF: {
+        const real a = -5.0, b = -x[2];
+        const real e = bmpc_exp(-3.0 * fabs(a - b));
+        const real ea = (a >= b) ? 1.0 : e, eb = (a >= b) ? e : 1.0;
+        u[0] = bmpc_div(ea * a + eb * b, ea + eb);
+        u[1] = bmpc_lookup(P, x[0]) - P.Kpsi * x[3];
+        break;
+      }
       default:
         u[0] = 0.0;
         u[1] = 0.0;
@@ -213,12 +239,51 @@ struct HighwayModel {
 };
 
 // ------------------------------------------------------------------------------------------
+// Merge scenario: PredictiveModel_merge (highway_branch_dyn.py:400-502).  Vehicle, policies, linearisation and collision
+// row are the highway model's; the safety value of a policy measures the vehicle distance only, with size [L+1, W+0.2]
+// (BF_traj :452-456, no lane-boundary term), and the controller is called with a state transform S and its own state
+// bounds per solve (Highway_env_branch.py:352-366), which the solver keeps per episode (kStateTransform).
+// ------------------------------------------------------------------------------------------
+struct MergeModel : HighwayModel {
+  static constexpr bool kStateTransform = true;
+  static constexpr int NSAFE = 1;
+  BMPC_D static void safety_terms(const KParams& P, const real* z, real xe0, real xe1, real* v) {
+    real gx, gy;
+    soft_box(fabs(z[0] - xe0) - (P.veh_L + 1.0), fabs(z[1] - xe1) - (P.veh_W + 0.2), v[0], gx, gy);
+  }
+  template <class Emit>
+  BMPC_D static real policy_safety(const KParams& P, int kind, const real* par, int kind0, const real* par0,
+                                   const real* xe0, const real* z0, real* zlast, int nsteps, Emit emit) {
+    real xe[4] = {xe0[0], xe0[1], xe0[2], xe0[3]};
+    real z[4] = {z0[0], z0[1], z0[2], z0[3]};
+    SoftMinAcc acc(5.0);
+#pragma unroll 1
+    for (int t = 0; t < nsteps; ++t) {
+      real u[2], xn[4];
+      policy(P, kind0, par0, xe, u);
+      step(P, xe, u, xn);
+      for (int i = 0; i < 4; ++i) xe[i] = xn[i];
+      policy(P, kind, par, z, u);
+      step(P, z, u, xn);
+      for (int i = 0; i < 4; ++i) z[i] = xn[i];
+      emit(t, z);
+      real v;
+      safety_terms(P, z, xe[0], xe[1], &v);
+      acc.add(v);
+    }
+    for (int i = 0; i < 4; ++i) zlast[i] = z[i];
+    return acc.value();
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // Quadruped: x = (x, y, theta), u = (vx, vy, r).   quadruped_branch_dyn.py
 // ------------------------------------------------------------------------------------------
 struct QuadrupedModel {
   static constexpr int NX = 3;
   static constexpr int NXP = 3;
   static constexpr bool RATE = false;
+  static constexpr bool kStateTransform = false;
   static constexpr int NU = 3;
   static constexpr int NLIN = 4;  // dt*cos, dt*sin, A[0][2], A[1][2]
   static constexpr int NCC = 2;
@@ -409,6 +474,7 @@ struct RateAug {
   static constexpr int NLIN = M::NLIN;
   static constexpr int NCC = M::NCC;
   static constexpr bool RATE = true;
+  static constexpr bool kStateTransform = false;
 
   BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) { M::step(P, x, u, xn); }
   BMPC_D static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) { M::policy(P, kind, par, x, u); }

@@ -21,6 +21,9 @@ struct KParams {
   real dt, veh_L, veh_W, Kpsi, s1, lane_lo, lane_hi, quad_margin;
   int pol_kind[BMPC_MAX_POLICIES];
   real pol_par[BMPC_MAX_POLICIES][4];
+  const real* lut_x;            // lookup table psiref(x) of the *_REF policies: grid (strictly increasing) and values, or null
+  const real* lut_y;
+  int lut_n;
   // ---- cost / constraints ----
   int ctrl;
   real Q[BMPC_MAX_N * BMPC_MAX_N], Qf[BMPC_MAX_N * BMPC_MAX_N], R[BMPC_MAX_D * BMPC_MAX_D], dR[BMPC_MAX_D];
@@ -60,6 +63,8 @@ struct KParams {
   const real* z0;
   const real* xref;
   const real* polpar;           // [count][m][4] or null
+  const real* xform;            // [count][n][n] state transform S of this call, or null (merge scenario, MPC_branch.py:2043)
+  const real* xbounds;          // [count][nrows][2] (lo, hi) of the state rows of this call, or null
   real* uLin;                   // persistent [cap][totalu+1][d]
   int* pbest;                   // persistent [cap][nbranch]
   real* oldin;                  // persistent [cap][d]

@@ -82,8 +82,11 @@ struct Solver {
   static constexpr int NFW = SPLIT ? NF - NFA : NF;   // fields kept in the slab
   static constexpr int NFWP = NFW | 1;                // slab record stride, odd (bank-conflict-free)
 
+  // merge scenario: the episode's transformed stage Hessian S'QS, state rows Fx S and their bounds (kStateTransform)
+  static constexpr bool XF = M::kStateTransform;
+  static constexpr int XFR = XF ? NXP * NXP + (NR - NC) * (NXP + 2) : 0;
   BMPC_HD static size_t slab_reals(int nup, int nbranch) {   // nbranch = KParams::nbx
-    return (size_t)NFWP * nup + (size_t)nup + (size_t)BR * nbranch;
+    return (size_t)NFWP * nup + (size_t)nup + (size_t)BR * nbranch + XFR;
   }
   BMPC_HD static size_t factor_reals(int nup) { return SPLIT ? (size_t)NFAP * nup : 0; }
   // interior-point fallback: per-node scratch in this warp's global region (rare path, see ipm_solve)
@@ -115,6 +118,7 @@ struct Solver {
   BMPC_D int oEXL() const { return oEX() + NS * PP.nbx; }
   BMPC_D int oEXZ() const { return oEXL() + NX * PP.nbx; }
   BMPC_D int oEXX() const { return oEXZ() + NX * PP.nbx; }
+  BMPC_D int oXF() const { return oEXX() + NX * PP.nbx; }
 #if defined(__CUDA_ARCH__)
 #define BMPC_LANE_ID ((int)threadIdx.x)
 #else
@@ -179,6 +183,13 @@ struct Solver {
   BMPC_D real* EXLp() { return slab() + oEXL(); }
   BMPC_D real* EXZp() { return slab() + oEXZ(); }
   BMPC_D real* EXXp() { return slab() + oEXX(); }
+  // stage Hessian (NXP x NXP), state rows and their bounds of this problem: the handle's, or the episode's transformed ones
+  BMPC_D real* XFp() { return slab() + oXF(); }
+  BMPC_D const real* QH() { if constexpr (XF) return XFp(); else return PP.Q; }
+  BMPC_D real RF(int r, int i) { if constexpr (XF) return XFp()[NXP * NXP + r * NXP + i]; else return PP.rf[r][i]; }
+  BMPC_D real RLO(int r) { if constexpr (XF) return XFp()[NXP * NXP + (NR - NC) * NXP + r]; else return PP.rlo[r]; }
+  BMPC_D real RHI(int r) { if constexpr (XF) return XFp()[NXP * NXP + (NR - NC) * (NXP + 1) + r]; else return PP.rhi[r]; }
+  BMPC_D int RF_ONE(int r) { if constexpr (XF) return -1; else return PP.rf_one[r]; }
   // active-set code of a node: 3 bits per soft row, then 2 bits per input
   BMPC_D static int row_of(code_t c, int j) { return (int)((c >> (3 * j)) & 7); }
   BMPC_D static int in_of(code_t c, int a) { return (int)((c >> (3 * NR + 2 * a)) & 3); }
@@ -212,8 +223,13 @@ struct Solver {
         real zxy[2] = {F(F_FC + 2 * j, kp), F(F_FC + 2 * j + 1, kp)};
         real h, dhx, dhy;
         M::collision(PP, xbar, zxy, h, dhx, dhy);
-        const real fx = -dhx, fy = -dhy;
         const real hi0 = h - (dhx * xbar[0] + dhy * xbar[1]);
+        if constexpr (XF) {
+          // updateIneqConstr with a state transform (MPC_branch.py:2027-2031): on every solve after the first the x-component
+          // of the collision gradient is pushed away from zero AFTER col_eval formed the row's offset with the true one
+          if (PP.xform && PP.started[prob]) dhx = sgn(dhx) * fmax(0.1, fabs(dhx));
+        }
+        const real fx = -dhx, fy = -dhy;
         F(F_FC + 2 * j, kp) = fx;
         F(F_FC + 2 * j + 1, kp) = fy;
         F(F_HC + j, kp) = hi0;
@@ -229,8 +245,8 @@ struct Solver {
     for (int j = NC; j < NR; ++j) {
       real v = 0.0;
 #pragma unroll
-      for (int i = 0; i < NXP; ++i) v += PP.rf[j - NC][i] * xbar[i];
-      F(F_S + j, kp) = bmpc_clamp(v, PP.rlo[j - NC], PP.rhi[j - NC]);
+      for (int i = 0; i < NXP; ++i) v += RF(j - NC, i) * xbar[i];
+      F(F_S + j, kp) = bmpc_clamp(v, RLO(j - NC), RHI(j - NC));
     }
   }
 
@@ -399,6 +415,34 @@ struct Solver {
     int* pbest = PP.pbest + (size_t)prob * PP.nbranch;
     const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
     const int m = PP.m;
+    if constexpr (XF) {
+      // solve(x, z, xRef, S, Fx, bx) (MPC_branch.py:2043-2059): stage Hessian S'QS (:1938), state rows Fx S (:1899) and the
+      // bounds of this call; identity / the handle's bounds where the caller passes none
+      const real* Sx = PP.xform ? PP.xform + (size_t)prob * NXP * NXP : nullptr;
+      const real* bd = PP.xbounds ? PP.xbounds + (size_t)prob * (NR - NC) * 2 : nullptr;
+      real* xf = XFp();
+      for (int e = BMPC_LANE_ID; e < XFR; e += BMPC_LANES) {
+        real v = 0.0;
+        if (e < NXP * NXP) {
+          const int i = e / NXP, j = e - i * NXP;
+          for (int a2 = 0; a2 < NXP; ++a2)
+            for (int b2 = 0; b2 < NXP; ++b2) {
+              const real sa = Sx ? Sx[a2 * NXP + i] : (a2 == i ? 1.0 : 0.0), sb = Sx ? Sx[b2 * NXP + j] : (b2 == j ? 1.0 : 0.0);
+              v += sa * PP.Q[a2 * NXP + b2] * sb;
+            }
+        } else if (e < NXP * NXP + (NR - NC) * NXP) {
+          const int r = (e - NXP * NXP) / NXP, i = (e - NXP * NXP) - r * NXP;
+          for (int a2 = 0; a2 < NXP; ++a2) v += PP.rf[r][a2] * (Sx ? Sx[a2 * NXP + i] : (a2 == i ? 1.0 : 0.0));
+        } else if (e < NXP * NXP + (NR - NC) * (NXP + 1)) {
+          const int r = e - NXP * NXP - (NR - NC) * NXP;
+          v = bd ? bd[2 * r] : PP.rlo[r];
+        } else {
+          const int r = e - NXP * NXP - (NR - NC) * (NXP + 1);
+          v = bd ? bd[2 * r + 1] : PP.rhi[r];
+        }
+        xf[e] = v;
+      }
+    }
 #pragma unroll 1
     BMPC_FOR_NODES(k) {
       int b, t;
@@ -739,8 +783,8 @@ struct Solver {
       for (int j = NC; j < NR; ++j) {
         real v = 0.0;
 #pragma unroll
-        for (int i = 0; i < NXP; ++i) v += PP.rf[j - NC][i] * xk[i];
-        F(F_S + j, kp) = bmpc_clamp(v, PP.rlo[j - NC], PP.rhi[j - NC]);
+        for (int i = 0; i < NXP; ++i) v += RF(j - NC, i) * xk[i];
+        F(F_S + j, kp) = bmpc_clamp(v, RLO(j - NC), RHI(j - NC));
       }
       real uk[NU];
       ulin(k, uk);
@@ -882,7 +926,7 @@ struct Solver {
   // rate = weight of the input-rate pair (previous input, this input), sig = 0 where the reference drops the pair's
   // own-input term (leaf last node, MPC_branch.py:303), root = the root-input quirks apply (:311-312)
   BMPC_D void node_factor(int kp, real w, real* Pn, int mode, real rate, real sig, bool root, bool use_qf = false) {
-    const real* Qs = use_qf ? PP.Qf : PP.Q;   // robustMPC: the dummy stage carries the terminal cost Qf
+    const real* Qs = use_qf ? PP.Qf : QH();   // robustMPC: the dummy stage carries the terminal cost Qf
     real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
     for (int i = 0; i < M::NLIN; ++i) lin[i] = F(F_LIN + i, kp);
@@ -1020,16 +1064,16 @@ struct Solver {
         }
   #pragma unroll
         for (int j = NC; j < NR; ++j) {
-          const int one = PP.rf_one[j - NC];
+          const int one = RF_ONE(j - NC);
           if (one >= 0) {
   #pragma unroll
             for (int i = 0; i < NXP; ++i)
-              if (i == one) Pnew[i * NX + i] += pr[j] * PP.rf[j - NC][i] * PP.rf[j - NC][i];
+              if (i == one) Pnew[i * NX + i] += pr[j] * RF(j - NC, i) * RF(j - NC, i);
           } else {
   #pragma unroll
             for (int i = 0; i < NXP; ++i)
   #pragma unroll
-              for (int i2 = i; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * PP.rf[j - NC][i] * PP.rf[j - NC][i2];
+              for (int i2 = i; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * RF(j - NC, i) * RF(j - NC, i2);
           }
         }
       }
@@ -1077,7 +1121,7 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * PP.rf[j - NC][i] * PP.rf[j - NC][i2];
+          for (int i2 = 0; i2 < NXP; ++i2) Pnew[i * NX + i2] += pr[j] * RF(j - NC, i) * RF(j - NC, i2);
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i)
@@ -1174,7 +1218,7 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NXP; ++i)
 #pragma unroll
-          for (int i2 = 0; i2 < NXP; ++i2) q += PP.rf[j - NC][i] * PP.rf[j - NC][i2] * Sg[i * NX + i2];
+          for (int i2 = 0; i2 < NXP; ++i2) q += RF(j - NC, i) * RF(j - NC, i2) * Sg[i * NX + i2];
         const real rj = (q > 1e-12 && !no_state_rows) ? fmin(PP.theta / q, rho_max) : 0.0;
         F(F_RHO + j, kp) = rj;
         F(F_S + j, kp) *= rj;
@@ -1431,11 +1475,11 @@ struct Solver {
     if (j < NC) return F(F_FC + 2 * j, kp) * x[0] + F(F_FC + 2 * j + 1, kp) * x[1];
     real v = 0.0;
 #pragma unroll
-    for (int i = 0; i < NXP; ++i) v += PP.rf[j - NC][i] * x[i];
+    for (int i = 0; i < NXP; ++i) v += RF(j - NC, i) * x[i];
     return v;
   }
   BMPC_D void row_bounds(int kp, int j, real& lo, real& hi) {
-    if (j < NC) { lo = BMPC_NOLO; hi = F(F_HC + j, kp); } else { lo = PP.rlo[j - NC]; hi = PP.rhi[j - NC]; }
+    if (j < NC) { lo = BMPC_NOLO; hi = F(F_HC + j, kp); } else { lo = RLO(j - NC); hi = RHI(j - NC); }
   }
   BMPC_D void add_row_grad(int kp, int j, real gcoef, real* qx) {
     if (j < NC) {
@@ -1443,7 +1487,7 @@ struct Solver {
       qx[1] += F(F_FC + 2 * j + 1, kp) * gcoef;
     } else {
 #pragma unroll
-      for (int i = 0; i < NXP; ++i) qx[i] += PP.rf[j - NC][i] * gcoef;
+      for (int i = 0; i < NXP; ++i) qx[i] += RF(j - NC, i) * gcoef;
     }
   }
 
@@ -1867,7 +1911,7 @@ struct Solver {
         if (i < NXP) {
           v = F(F_Q + (i < NXP ? i : 0), kp);
 #pragma unroll
-          for (int j = 0; j < NXP; ++j) v += qs * (PP.Q[(i < NXP ? i : 0) * NXP + j] + PP.Q[j * NXP + (i < NXP ? i : 0)]) * x[j];
+          for (int j = 0; j < NXP; ++j) v += qs * (QH()[(i < NXP ? i : 0) * NXP + j] + QH()[j * NXP + (i < NXP ? i : 0)]) * x[j];
         } else if (RATE) {
           v = 2.0 * rate * PP.dR[i - NXP] * (x[i] - u[i - NXP]);
         }
@@ -2460,7 +2504,7 @@ struct Solver {
       const bool leaf_last = (b >= PP.off[PP.NB] && t == PP.N - 1);
       const real rate = (k == 0) ? 0.0 : w;
       const real sig = leaf_last ? 0.0 : 1.0;
-      const real* Qs = (robust && leaf_last) ? PP.Qf : PP.Q;   // robustMPC: the dummy stage carries the terminal cost Qf
+      const real* Qs = (robust && leaf_last) ? PP.Qf : QH();   // robustMPC: the dummy stage carries the terminal cost Qf
       real x[NX], u[NU];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = F(F_XQ + i, kp);
@@ -2695,9 +2739,20 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NXP; ++i) {
           real a = 0.0;
+          if constexpr (XF) {
+            // (S x)' Q (S x) - 2 xRef' Q x + xRef' Q xRef: the reference transforms the quadratic term only (:1938, :1962)
+            real g = 0.0;
 #pragma unroll
-          for (int j = 0; j < NXP; ++j) a += PP.Q[i * NXP + j] * (x[j] - xref[j]);
-          c += (x[i] - xref[i]) * a;
+            for (int j = 0; j < NXP; ++j) {
+              a += QH()[i * NXP + j] * x[j];
+              g += PP.Q[i * NXP + j] * xref[j];
+            }
+            c += x[i] * a + g * (xref[i] - 2.0 * x[i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NXP; ++j) a += PP.Q[i * NXP + j] * (x[j] - xref[j]);
+            c += (x[i] - xref[i]) * a;
+          }
         }
       }
 #pragma unroll

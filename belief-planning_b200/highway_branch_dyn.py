@@ -6,7 +6,8 @@ policy TABLE (kind + parameters) instead of closures.  The numeric branches of t
 simulation environments call with numpy arrays) are plain numpy.
 
 Reference: highway_branch_dyn.py:17-34 dubin, :38 softsat, :54-148 policies, :151-162 softmin/softmax, :174-187
-propagate_backup, :195-206 lane_bdry_h, :223-254 veh_col, :262-398 PredictiveModel.
+propagate_backup, :195-206 lane_bdry_h, :223-254 veh_col, :262-398 PredictiveModel, :400-502 PredictiveModel_merge.
+`interpolant` is the one CasADi name the reference's scripts reach through this module's star import (main_branch.py:78).
 """
 import numpy as np
 
@@ -14,7 +15,28 @@ from _bmpc import abi, batch, config, policies
 from _bmpc.policies import PolicyProbe, PolicyDescriptor
 
 __all__ = ["dubin", "softsat", "backup_maintain", "backup_maintain_trackV", "backup_brake", "backup_lc", "softmin",
-           "softmax", "propagate_backup", "lane_bdry_h", "veh_col", "PredictiveModel"]
+           "softmax", "propagate_backup", "lane_bdry_h", "veh_col", "PredictiveModel", "PredictiveModel_merge", "interpolant"]
+
+
+class interpolant:
+    """casadi.interpolant(name, 'linear', [grid], values) for one dimension, the form main_branch.py:78-79 and
+    Highway_env_branch.py:310-311 build (refY, refpsi): piecewise linear, end segments continued outside the grid.  Called
+    with a number it returns a float; handed to a ramp policy it becomes the lookup table of the device model."""
+
+    def __init__(self, name, kind, grid, values, *args, **kwargs):
+        if kind != "linear" or len(grid) != 1:
+            raise NotImplementedError("only one-dimensional linear lookup tables are built")
+        self.name = name
+        self.xs = np.ascontiguousarray(grid[0], dtype=float).reshape(-1)
+        self.ys = np.ascontiguousarray(values, dtype=float).reshape(-1)
+        if self.xs.shape != self.ys.shape or self.xs.size < 2 or np.any(np.diff(self.xs) <= 0):
+            raise ValueError("a lookup table needs a strictly increasing grid and one value per grid point")
+
+    def __call__(self, x):
+        x = float(np.asarray(x, dtype=float).reshape(-1)[0])
+        k = min(max(int(np.searchsorted(self.xs, x, side="right")) - 1, 0), self.xs.size - 2)
+        slope = (self.ys[k + 1] - self.ys[k]) / (self.xs[k + 1] - self.xs[k])
+        return float(self.ys[k] + slope * (x - self.xs[k]))
 
 
 def dubin(x, u):
@@ -38,7 +60,13 @@ def softmax(x, gamma=1):
 
 def _no_psiref(psiref):
     if psiref is not None:
-        raise NotImplementedError("psiref (merge scenario, PredictiveModel_merge) is not built yet")
+        raise NotImplementedError("backup_maintain with a heading table is not built (no reference script uses it)")
+
+
+def _table(psiref):
+    if not isinstance(psiref, interpolant):
+        raise TypeError("psiref must be this module's `interpolant` (a one-dimensional linear lookup table)")
+    return psiref
 
 
 def backup_maintain(x, cons, psiref=None):
@@ -50,20 +78,23 @@ def backup_maintain(x, cons, psiref=None):
 
 
 def backup_maintain_trackV(x, cons, v0, psiref=None):
-    """Track speed v0 (reference :80-96)."""
-    _no_psiref(psiref)
+    """Track speed v0 (reference :80-96); with `psiref` the steering follows the ramp's heading table (:89-96)."""
     if isinstance(x, PolicyProbe):
+        if psiref is not None:
+            return PolicyDescriptor(abi.POLICY_TRACKV_REF, [v0], consts={"Kpsi": cons.Kpsi}, table=_table(psiref))
         return PolicyDescriptor(abi.POLICY_TRACKV, [v0], consts={"Kpsi": cons.Kpsi})
-    return np.array([0.5 * (v0 - x[2]), -cons.Kpsi * x[3]])
+    return np.array([0.5 * (v0 - x[2]), (psiref(x[0]) if psiref is not None else 0.0) - cons.Kpsi * x[3]])
 
 
 def backup_brake(x, cons, psiref=None):
     """Brake (reference :108-121).  The model uses the symbolic branch softmax([-7, -v], 5) (in the kernels); the
-    numeric branch, which only the environment calls, is softmax([-5, -v], 3) (:121)."""
-    _no_psiref(psiref)
+    numeric branch, which only the environment calls, is softmax([-5, -v], 3) (:121).  With `psiref` both branches are
+    softmax([-5, -v], 3) and the steering follows the ramp's heading table (:122-131)."""
     if isinstance(x, PolicyProbe):
+        if psiref is not None:
+            return PolicyDescriptor(abi.POLICY_BRAKE_REF, consts={"Kpsi": cons.Kpsi}, table=_table(psiref))
         return PolicyDescriptor(abi.POLICY_BRAKE, consts={"Kpsi": cons.Kpsi})
-    return np.array([softmax(np.array([-5., -x[2]]), 3), -cons.Kpsi * x[3]])
+    return np.array([softmax(np.array([-5., -x[2]]), 3), (psiref(x[0]) if psiref is not None else 0.0) - cons.Kpsi * x[3]])
 
 
 def backup_lc(x, x0):
@@ -175,3 +206,46 @@ class PredictiveModel:
     def col_eval(self, x, z):
         r = self._eval_points(x, z=z)
         return r["hlin"][0], r["dh"][0]
+
+
+class PredictiveModel_merge(PredictiveModel):
+    """highway_branch_dyn.PredictiveModel_merge(n, d, N, backupcons, dt, cons, merge_ref, laneID, N_lane1, N_lane2) (reference
+    :400-502): the highway vehicle with the merge scenario's branching probability (vehicle distance only, size [L+1, W+0.2],
+    :452-456) and, for the ramp lane, policies that steer along a heading lookup table.  On the device this is
+    BMPC_MODEL_MERGE; a controller built on it takes the state transform `S` and the bounds `bx` of every solve."""
+
+    def __init__(self, n, d, N, backupcons, dt, cons, merge_ref, laneID=0, N_lane1=3, N_lane2=2):
+        self.refY, self.refpsi = merge_ref
+        self.laneID, self.N_lane2 = laneID, N_lane2
+        self.LB1 = [cons.W / 2, N_lane1 * 3.6 - cons.W / 2]
+        super().__init__(n, d, N, backupcons, dt, cons, N_lane=N_lane1)
+
+    def update_backup(self, backupcons):
+        super().update_backup(backupcons)
+        tables = [dd.table for dd in self.descriptors if dd.table is not None]
+        if any(t is not tables[0] for t in tables):
+            raise NotImplementedError("the policies of one model share one heading table")
+        self.lookup_table = tables[0] if tables else None
+        if self._eval is not None and self.lookup_table is not None:
+            self._eval.set_lookup_table(self.lookup_table.xs, self.lookup_table.ys)
+
+    def spec(self):
+        return config.merge_spec(self.N, self.dt, policies.table(self.descriptors), self.cons.L, self.cons.W, self.cons.Kpsi,
+                                 self.cons.s1)
+
+    def _handle(self):
+        if self._eval is None:
+            Fx = np.array([[0., 1., 0., 0.], [0., -1., 0., 0.], [0., 0., 0., 1.], [0., 0., 0., -1.]])
+            cfg = config.make_config(self.spec(), 4, 2, self.N, 1, np.eye(4), np.eye(2), Fx, np.ones(4),
+                                     np.kron(np.eye(2), np.array([1., -1.])).T, np.ones(4), np.array([0., 1.]),
+                                     controller=abi.CTRL_CVAR, cvar_alpha=0.5)
+            self._eval = batch.BatchedBranchMPC(cfg)
+            self._eval_kinds = [dd.kind for dd in self.descriptors]
+            if self.lookup_table is not None:
+                self._eval.set_lookup_table(self.lookup_table.xs, self.lookup_table.ys)
+        return self._eval
+
+    def xpred_eval(self, x):
+        """(ego rollout under the first policy, that policy's input at x) (reference :498-499)."""
+        x = np.asarray(x, dtype=float).reshape(-1)
+        return self._eval_points(x, z=x)["zpred"][0][:, :4], self.backupcons[0](x)

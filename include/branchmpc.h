@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BMPC_VERSION 200
+#define BMPC_VERSION 201
 
 #define BMPC_MAX_N 4          /* state dimension supported by this build            */
 #define BMPC_MAX_D 3          /* input dimension                                    */
@@ -37,6 +37,10 @@ extern "C" {
 /* model kinds: which closed-form predictive model the kernels evaluate */
 #define BMPC_MODEL_HIGHWAY 0   /* highway_branch_dyn.PredictiveModel   (n=4, d=2) */
 #define BMPC_MODEL_QUADRUPED 1 /* quadruped_branch_dyn.PredictiveModel (n=3, d=3) */
+#define BMPC_MODEL_MERGE 2     /* highway_branch_dyn.PredictiveModel_merge (:400-502; n=4, d=2): the highway vehicle with the
+                                  merge scenario's safety value (vehicle distance only, size [L+1, W+0.2], :452-456); handles of
+                                  this model take a per-episode state transform and state bounds (bmpc_solve_transformed);
+                                  BMPC_CTRL_CVAR with n_rows = 2 (what main_branch.py:87 builds) */
 
 /* controller kinds */
 #define BMPC_CTRL_BRANCH 0 /* MPC_branch.BranchMPC (effective, second definition, :881) */
@@ -56,6 +60,9 @@ extern "C" {
 #define BMPC_POLICY_TRACKV 3   /* highway_branch_dyn.backup_maintain_trackV :80,  param[0] = v0 */
 #define BMPC_POLICY_FORWARD 4  /* quadruped_branch_dyn.backup_forward       :34,  param[0] = v0 */
 #define BMPC_POLICY_STOP 5     /* quadruped_branch_dyn.backup_stop          :46  */
+#define BMPC_POLICY_TRACKV_REF 6 /* backup_maintain_trackV(x, cons, v0, psiref) :89-96: steering psiref(x) - Kpsi psi with the
+                                    handle's lookup table (bmpc_set_lookup_table), param[0] = v0 */
+#define BMPC_POLICY_BRAKE_REF 7  /* backup_brake(x, cons, psiref) :122-131: softmax([-5, -v], 3), steering as above */
 
 /* working-set placement (bmpc_config.slab_mode) */
 #define BMPC_SLAB_AUTO 0
@@ -198,6 +205,27 @@ int bmpc_ulin_rows(const bmpc_handle* h);
  * concurrently with other solves on the same device.  bmpc_last_kernel_ms() does not see replayed launches. */
 int bmpc_solve(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                const double* policy_params, int64_t count, const bmpc_outputs* out, void* stream);
+
+/* BranchMPC_CVaR.solve(x, z, xRef, S, Fx=None, bx) (MPC_branch.py:2043-2059) - the call Highway_env_merge.step makes
+ * (Highway_env_branch.py:364) - for episodes 0..count-1 of a BMPC_MODEL_MERGE handle.  As bmpc_solve, plus per episode
+ *   S            : [count][n][n] device float64, row-major state transform: stage cost (S x)' Q (S x) - 2 xRef' Q x (:1938,
+ *                  :1962 - the reference transforms the quadratic term only) and state rows  lo <= Fx S x <= hi  (:1899)
+ *   state_bounds : [count][n_rows][2] device float64, (lo, hi) of the handle's state rows for this call (the reference's bx
+ *                  holds them as [hi_0, -lo_0, hi_1, -lo_1])
+ * Either may be NULL: identity / the bounds of the configuration. */
+int bmpc_solve_transformed(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                           const double* policy_params, const double* S, const double* state_bounds, int64_t count,
+                           const bmpc_outputs* out, void* stream);
+/* The same call on HOST buffers with zero-copy result views (see bmpc_solve_host_views). */
+int bmpc_solve_transformed_host_views(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
+                                      const double* policy_params, const double* S, const double* state_bounds,
+                                      int64_t count, const bmpc_outputs* want, bmpc_outputs* views);
+
+/* 1-D piecewise-linear lookup table psiref(x) of the merge scenario's ramp policies (casadi `interpolant('refpsi', 'linear',
+ * [X], psi)`, main_branch.py:79; the end segments continue outside the grid).  HOST pointers, xs strictly increasing,
+ * 2 <= n <= 4096; copied to the device, replaces the handle's previous table.  Required before the first solve / model
+ * evaluation of a handle whose policy table holds a *_REF kind. */
+int bmpc_set_lookup_table(bmpc_handle* h, const double* xs, const double* ys, int32_t n);
 
 /* One step of the belief-state MPC (BMPC_CTRL_BELIEF) for episodes 0..count-1: PredictiveControllers.MPC.solve(x0, b0, xbackup,
  * xRef) (:130-160).  Device pointers, float64:

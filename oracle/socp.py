@@ -256,7 +256,13 @@ def solve_qcqp(c, Gl, hl, quads, A, b, tol=1e-9, max_iter=300, verbose=False, pr
         aa = min(max_step(s, dsa), max_step(lam, dla))
         mu_aff = float((s + aa * dsa) @ (lam + aa * dla)) / m
         sigma = (mu_aff / mu) ** 3
-        dx, dy, ds, dl = newton(sigma * mu - s * lam - dsa * dla)
+        # the barrier parameter is not driven below what the gap test asks for: past that point the steps only remove the
+        # residuals (a long horizon's KKT matrix loses the late iterations to conditioning otherwise)
+        mu_floor = 0.1 * tol * (1.0 + abs(pcost)) / m
+        if sigma * mu < mu_floor:
+            dx, dy, ds, dl = newton(max(mu_floor, 0.0) - s * lam)
+        else:
+            dx, dy, ds, dl = newton(sigma * mu - s * lam - dsa * dla)
         a_p = min(1.0, 0.995 * max_step(s, ds) if (ds < 0).any() else 1.0)
         a_d = min(1.0, 0.995 * max_step(lam, dl) if (dl < 0).any() else 1.0)
         a = min(a_p, a_d)

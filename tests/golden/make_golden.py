@@ -520,6 +520,132 @@ def run_highway_env(name, steps, x_ego=None, x_obs=None, N_lane=4):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
 
 
+def run_highway_merge(name="highway_merge_default", T=6.0):
+    """`sim_merge()` of the UNMODIFIED main_branch.py (:53-88): N = 40, NB = 1, two `PredictiveModel_merge` (lookup-table
+    policies for the ramp), `BranchMPC_CVaR(ralpha=0.1)` called as `solve(x, z, xRef, S, Fx=None, bx=bx)` by
+    `Highway_env_merge.step` (Highway_env_branch.py:324-380) inside `Highway_sim` - all of it the reference's own code; only
+    the plotting call is replaced by a no-op and the duration can be shortened.  Every MPC call is recorded (inputs, state
+    transform, bounds, warm start the step linearised about, plan, objective, tree) together with the closed-loop records
+    `Highway_sim` returns."""
+    print("highway merge fixture", name)
+    with refenv.reference_imports():
+        import Highway_env_branch as henv
+        import main_branch
+    calls = []
+    orig_solve = MPC_branch.BranchMPC_CVaR.solve
+
+    def spy(self, x, z, xRef=None, S=None, Fx=None, bx=None):
+        before = None if self.uLin is None or self.BT is None else np.array(self.uLin)
+        pbest = None if self.BT is None else np.array([int(np.argmax(b.p)) if b.p is not None else 0 for b in self.ndx])
+        assert Fx is None
+        out = orig_solve(self, x, z, xRef, S, Fx, bx)
+        lp = ecos.last_problem
+        assert self.feasible and lp["info"]["exitFlag"] == 0, "oracle cone solve did not converge"
+        tab, w, p, xbar, zbar, ubar = tree_tables(self)
+        calls.append(dict(x0=np.array(x, dtype=float), z0=np.array(z, dtype=float), xref=np.array(xRef, dtype=float),
+                          S=np.array(S, dtype=float), bx=np.asarray(bx, dtype=float).reshape(-1), uLin_before=before,
+                          pbest_before=pbest, xPred=np.array(self.xPred), uPred=np.array(self.uPred),
+                          objective=np.array(lp["info"]["pcost"]),
+                          cert=np.array([lp["info"]["gap"], lp["info"]["pres"], lp["info"]["dres"]]),
+                          w=w, p=p, xbar=xbar, zbar=zbar, ubar=ubar, tree=tab, mpc=self))
+        print("   step %d: J %.8f  u0 %s  gap %.1e pres %.1e dres %.1e (%d it)" % (
+            len(calls) - 1, lp["info"]["pcost"], np.array2string(self.uPred[0], precision=6), lp["info"]["gap"],
+            lp["info"]["pres"], lp["info"]["dres"], lp["info"]["iter"]))
+        return out
+
+    sim_out = {}
+    orig_sim = henv.Highway_sim
+
+    def sim(env, T_):
+        sim_out["env"] = env
+        sim_out["x_init"] = np.array([v.state for v in env.veh_set])
+        sim_out["rec"] = orig_sim(env, T)
+        return sim_out["rec"]
+
+    MPC_branch.BranchMPC_CVaR.solve = spy
+    henv.Highway_sim = sim
+    animate = henv.animate_scenario
+    henv.animate_scenario = lambda *a, **k: None
+    try:
+        main_branch.sim_merge()
+    finally:
+        MPC_branch.BranchMPC_CVaR.solve = orig_solve
+        henv.Highway_sim = orig_sim
+        henv.animate_scenario = animate
+    env = sim_out["env"]
+    mpc = calls[0]["mpc"]
+    state_rec, input_rec, backup_rec, backup_choice_rec, xPred_rec, zPred_rec, branch_w_rec, collision = sim_out["rec"]
+    store = {"meta_ctrl": np.array("BranchMPC_CVaR"), "meta_NB": np.array(mpc.NB), "meta_N": np.array(mpc.N),
+             "meta_steps": np.array(len(calls)), "meta_ralpha": np.array(mpc.ralpha), "meta_dt": np.array(env.dt),
+             "meta_v0": np.array(henv.v0), "meta_N_lane": np.array(env.N_lane), "meta_merge_lane": np.array(env.merge_lane),
+             "meta_merge_s": np.array(env.merge_s), "meta_merge_R": np.array(env.merge_R),
+             "meta_merge_side": np.array(env.merge_side), "meta_am": np.array(env.cons.am), "meta_rm": np.array(env.cons.rm),
+             "meta_bx": np.asarray(mpc.param.bx, dtype=float).reshape(-1), "meta_Q": np.array(mpc.Q), "meta_R": np.array(mpc.R),
+             "meta_dR": np.array(mpc.dR), "meta_Qslack": np.array(mpc.Qslack),
+             "table_X": np.array(env.merge_lane_ref_X), "table_Y": np.array(env.merge_lane_ref_Y),
+             "table_psi": np.array(env.merge_lane_ref_psi), "x_init": sim_out["x_init"],
+             "state_rec": np.array(state_rec), "input_rec": np.array(input_rec), "collision": np.array(bool(collision)),
+             "backup_choice_rec": np.array(backup_choice_rec, dtype=np.int64),
+             "backup_rec_ego": np.array([np.array(b) for b in backup_rec[0]]),
+             "backup_rec_obs": np.array([np.array(b) for b in backup_rec[1]])}
+    for k, c in enumerate(calls):
+        pre = "s%d_" % k
+        for key, val in c.items():
+            if key != "mpc" and val is not None:
+                store[pre + key] = val
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+
+
+def merge_model_vectors():
+    """Point-wise values of the reference's PredictiveModel_merge (highway_branch_dyn.py:400-502) at seeded random inputs, for
+    both models sim_merge builds (main_branch.py:82-85): plain policies, and the ramp policies that steer along the heading
+    lookup table."""
+    print("merge model-function fixture")
+    with refenv.reference_imports():
+        import Highway_env_branch as henv
+        from casadi import interpolant
+    rng = np.random.default_rng(20241019)
+    cons = rutils.Branch_constants(s1=2, s2=3, c2=0.5, tran_diag=0.3, alpha=1, R=1.2, am=7.0, rm=0.3, J_c=20, s_c=1, ylb=0.,
+                                   yub=7.2, L=4, W=2.5, col_alpha=5, Kpsi=0.1)
+    X1, X2, Y1, Y2, P1, P2 = henv.merge_geometry(2, 1, 50, 300, 0)
+    gx, gy, gpsi = np.append(X1, X2), np.append(Y1, Y2), np.append(P1, P2)
+    refY = interpolant('refY', 'linear', [gx], gy)
+    refpsi = interpolant('refpsi', 'linear', [gx], gpsi)
+    v0, N = float(henv.v0), 40
+    normal = [lambda x: hw.backup_maintain_trackV(x, cons, v0), lambda x: hw.backup_brake(x, cons)]
+    ramp = [lambda x: hw.backup_maintain_trackV(x, cons, v0, refpsi), lambda x: hw.backup_brake(x, cons, refpsi)]
+    models = [hw.PredictiveModel_merge(4, 2, N, normal, 0.1, cons, (refY, refpsi), laneID=0, N_lane1=2, N_lane2=1),
+              hw.PredictiveModel_merge(4, 2, N, ramp, 0.1, cons, (refY, refpsi), laneID=1, N_lane1=2, N_lane2=1)]
+    K = 10
+    X = np.column_stack([rng.uniform(5, 80, K), rng.uniform(1, 14, K), rng.uniform(8, 25, K), rng.normal(-0.1, 0.1, K)])
+    Z = np.column_stack([X[:, 0] + rng.uniform(-12, 12, K), rng.uniform(1, 14, K), rng.uniform(8, 25, K), rng.normal(-0.05, 0.1, K)])
+    U = np.column_stack([rng.uniform(-7, 7, K), rng.uniform(-0.3, 0.3, K)])
+    out = {"X": X, "Z": Z, "U": U, "table_X": gx, "table_Y": gy, "table_psi": gpsi, "v0": np.array(v0), "N": np.array(N)}
+    for mi, model in enumerate(models):
+        A, B, C, XP, ZP, P, H, DH, X1P, U0 = [], [], [], [], [], [], [], [], [], []
+        for k in range(K):
+            a, b, c, xp = model.dyn_linearization(X[k], U[k])
+            A.append(a); B.append(b); C.append(c); XP.append(xp)
+            ZP.append(model.zpred_eval(Z[k]))
+            p, _ = model.branch_eval(X[k], Z[k])
+            P.append(p)
+            h, dh = model.col_eval(X[k], Z[k])
+            H.append(h); DH.append(dh)
+            x1, u0 = model.xpred_eval(X[k])
+            X1P.append(np.array(x1)); U0.append(np.array(u0).reshape(-1))
+        pre = "m%d_" % mi
+        out.update({pre + "A": np.array(A), pre + "B": np.array(B), pre + "C": np.array(C), pre + "xp": np.array(XP),
+                    pre + "zpred": np.array(ZP), pre + "p": np.array(P), pre + "hlin": np.array(H), pre + "dh": np.array(DH),
+                    pre + "xpred": np.array(X1P), pre + "u0": np.array(U0)})
+    np.savez_compressed(os.path.join(HERE, "merge_model_functions.npz"), **out)
+
+
+if __name__ == "__main__" and "merge_models" in sys.argv[1:]:
+    merge_model_vectors()
+
+if __name__ == "__main__" and "merge" in sys.argv[1:]:
+    run_highway_merge()
+
 if __name__ == "__main__" and ("env" in sys.argv[1:] or len(sys.argv) == 1):
     run_highway_env("highway_env_default", steps=30)
     run_highway_env("highway_env_overtake", steps=24, x_ego=[2.0, 5.5, 24.0, 0.0], x_obs=[14.0, 5.4, 17.0, 0.0])

@@ -25,7 +25,7 @@ casadi = _sys.modules[__name__]
 # ----------------------------------------------------------------------------
 # scalar expression nodes
 # ----------------------------------------------------------------------------
-_OPS = ("const", "sym", "add", "sub", "mul", "div", "neg", "cos", "sin", "exp", "fabs")
+_OPS = ("const", "sym", "add", "sub", "mul", "div", "neg", "cos", "sin", "exp", "fabs", "lut")
 
 
 class _Node:
@@ -369,8 +369,37 @@ def kron(a, b):
     return SX._wrap(out)
 
 
-def interpolant(*args, **kwargs):
-    raise NotImplementedError("interpolant (merge scenario) is outside the golden-fixture scope")
+class interpolant:
+    """1-D piecewise-linear lookup table `interpolant(name, 'linear', [grid], values)` (main_branch.py:78-79): callable on
+    numbers (returns a DM) and on symbolic scalars (a graph node whose derivative is the slope of the active segment).
+    Outside the grid the end segments are continued, as CasADi's 'linear' plugin does."""
+
+    def __init__(self, name, kind, grid, values, *args, **kwargs):
+        if kind != "linear" or len(grid) != 1:
+            raise NotImplementedError("only 1-D linear lookup tables")
+        self.name = name
+        self.xs = _np.asarray(grid[0], dtype=float).reshape(-1)
+        self.ys = _np.asarray(values, dtype=float).reshape(-1)
+        if self.xs.size != self.ys.size or self.xs.size < 2 or _np.any(_np.diff(self.xs) <= 0):
+            raise ValueError("lookup table needs a strictly increasing grid")
+
+    def segment(self, x):
+        k = int(_np.searchsorted(self.xs, x, side="right")) - 1
+        k = min(max(k, 0), self.xs.size - 2)
+        slope = (self.ys[k + 1] - self.ys[k]) / (self.xs[k + 1] - self.xs[k])
+        return self.ys[k] + slope * (x - self.xs[k]), slope
+
+    def __call__(self, x):
+        if isinstance(x, SX):
+            nd = _n(x)
+            if nd.op == "const":
+                nd = _Node("const", val=self.segment(nd.val)[0])
+            else:
+                nd = _Node("lut", nd, val=self)
+            e = _np.empty((1, 1), dtype=object)
+            e[0, 0] = nd
+            return SX._wrap(e)
+        return _LookupValue(_np.array([[self.segment(float(_np.asarray(x).reshape(-1)[0]))[0]]]))
 
 
 # ----------------------------------------------------------------------------
@@ -416,19 +445,27 @@ class DM:
             o = o.reshape(-1, 1)
         return o
 
-    def __matmul__(self, o): return DM(self._a @ self._col(o))
-    def __rmatmul__(self, o): return DM(self._col(o) @ self._a)
-    def __add__(self, o): return DM(self._a + self._col(o))
-    def __radd__(self, o): return DM(self._col(o) + self._a)
-    def __sub__(self, o): return DM(self._a - self._col(o))
-    def __rsub__(self, o): return DM(self._col(o) - self._a)
-    def __mul__(self, o): return DM(self._a * self._col(o))
-    def __rmul__(self, o): return DM(self._col(o) * self._a)
-    def __neg__(self): return DM(-self._a)
+    def __matmul__(self, o): return type(self)(self._a @ self._col(o))
+    def __rmatmul__(self, o): return type(self)(self._col(o) @ self._a)
+    def __add__(self, o): return type(self)(self._a + self._col(o))
+    def __radd__(self, o): return type(self)(self._col(o) + self._a)
+    def __sub__(self, o): return type(self)(self._a - self._col(o))
+    def __rsub__(self, o): return type(self)(self._col(o) - self._a)
+    def __mul__(self, o): return type(self)(self._a * self._col(o))
+    def __rmul__(self, o): return type(self)(self._col(o) * self._a)
+    def __neg__(self): return type(self)(-self._a)
     def __float__(self): return float(self._a.reshape(-1)[0])
 
     def full(self):
         return self._a.copy()
+
+
+class _LookupValue(DM):
+    """Value of a lookup table at a number: a 1x1 DM that numpy sees as a scalar, so that the reference's
+    `np.array([a, psiref(x[0]) - K * x[3]])` (highway_branch_dyn.py:96) builds a length-2 vector."""
+
+    def __array__(self, dtype=None, copy=None):
+        return _np.asarray(self._a.reshape(-1)[0], dtype=dtype or float)
 
 
 class Function:
@@ -517,6 +554,9 @@ class Function:
                 elif op == "exp":
                     v = _math.exp(va)
                     g = v * ga if grad is not None else None
+                elif op == "lut":
+                    v, slope = nd.val.segment(va)
+                    g = slope * ga if grad is not None else None
                 elif op == "fabs":
                     v = abs(va)
                     sgn = 1.0 if va > 0 else (-1.0 if va < 0 else 0.0)

@@ -195,6 +195,62 @@ def check_cvar_fixture(solve, set_state, g):
         assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj), (k, r["objective"][0], obj)
 
 
+# ---- merge scenario (sim_merge) ---------------------------------------------------------------------------------------
+def merge_fixture_config(g, **kw):
+    return scenarios.merge_config(N=int(g["meta_N"]), NB=int(g["meta_NB"]), v0=float(g["meta_v0"]), am=float(g["meta_am"]),
+                                  rm=float(g["meta_rm"]), N_lane=int(g["meta_N_lane"]), ralpha=float(g["meta_ralpha"]), **kw)
+
+
+def check_merge_fixture(solve_transformed, set_state, g, steps=None):
+    """Replay of the UNMODIFIED `sim_merge()` (tests/golden/make_golden.py run_highway_merge): every
+    `mpc.solve(x, z, xRef, S, Fx=None, bx=bx)` the reference's `Highway_env_merge.step` made in 6 s of closed loop, with the
+    warm start that step linearised about restored first (see check_cvar_fixture).  `solve_transformed(x, z, xref, S (1,4,4),
+    bounds (1,2,2))`."""
+    steps = range(int(g["meta_steps"])) if steps is None else steps
+    assert int(g["meta_NB"]) == 1
+    Q = g["meta_Q"]
+
+    def jc(v):
+        return float(v @ Q @ v)
+
+    for k in steps:
+        pre = "s%d_" % k
+        if k > 0:
+            set_state(g[pre + "uLin_before"], g[pre + "pbest_before"], g["s%d_uPred" % (k - 1)][0])
+        r = solve_transformed(g[pre + "x0"], g[pre + "z0"], g[pre + "xref"], g[pre + "S"][None],
+                              scenarios.bounds_from_bx(g[pre + "bx"]))
+        assert r["status"][0] in (0, 1), "step %d status %d" % (k, r["status"][0])
+        np.testing.assert_allclose(r["branch_w"][0], g[pre + "w"], atol=1e-6)
+        np.testing.assert_allclose(r["xLin"][0], g[pre + "xbar"], atol=1e-6)
+        np.testing.assert_allclose(r["zPred"][0], g[pre + "zbar"], atol=1e-9)
+        u0 = g[pre + "uPred"][0]
+        assert np.abs(r["u0"][0] - u0).max() < TOL_U0, (k, r["u0"][0], u0)
+        # the reference's cones keep the constant xRef' Q xRef of its FIRST solve (updateIneqConstr computes Jcons and never
+        # writes it into b, MPC_branch.py:1999): N stale constants per child cone, the same for every branch, so the optimiser
+        # does not see them; the library reports the objective with the constants of the current xRef
+        obj = float(g[pre + "objective"]) - int(g["meta_N"]) * (jc(g["s0_xref"]) - jc(g[pre + "xref"]))
+        assert abs(r["objective"][0] - obj) <= TOL_OBJ * abs(obj), (k, r["objective"][0], obj)
+
+
+def check_merge_model_functions(make_backend):
+    """PredictiveModel_merge point functions (dyn_linearization, zpred_eval, branch_eval, col_eval, xpred_eval) of both models
+    sim_merge builds against the reference's CasADi MX graphs (tests/golden/merge_model_functions.npz); `make_backend(cfg)`
+    returns an object with eval_model / set_lookup_table."""
+    g = load_fixture("merge_model_functions")
+    for mi, pols in enumerate((("trackv", "brake"), ("trackv_ref", "brake_ref"))):
+        be = make_backend(scenarios.merge_config(policies=pols, N=int(g["N"]), v0=float(g["v0"])))
+        if mi == 1:
+            be.set_lookup_table(g["table_X"], g["table_psi"])
+        r = be.eval_model(g["X"], g["Z"], g["U"])
+        pre = "m%d_" % mi
+        for k in ("A", "B", "C", "xp", "zpred", "p", "dh"):
+            np.testing.assert_allclose(r[k], g[pre + k], atol=1e-10, err_msg="%s model %d" % (k, mi))
+        np.testing.assert_allclose(r["hlin"], g[pre + "hlin"], atol=1e-10)
+        # xpred_eval: the ego rollout under policy 0 = the first policy block of zpred evaluated at x
+        rx = be.eval_model(g["X"], g["X"], g["U"])
+        np.testing.assert_allclose(rx["zpred"][:, :, :4], g[pre + "xpred"], atol=1e-10)
+
+
 # ---- belief-state MPC (PredictiveControllers.MPC) ---------------------------------------------------------------------
 BELIEF_FIXTURES = ["belief_mpc_default", "belief_mpc_close"]
 

@@ -42,6 +42,16 @@ class HostBackend:
 
     solve_host_views = solve_host
 
+    def set_lookup_table(self, xs, ys):
+        xs = np.ascontiguousarray(xs, np.float64).reshape(-1)
+        ys = np.ascontiguousarray(ys, np.float64).reshape(-1)
+        assert lib().hostsim_set_lookup(_ptr(xs), _ptr(ys), C.c_int32(len(xs))) == 0
+
+    def solve_transformed_host_views(self, x0, z0, xref, S=None, state_bounds=None, policy_params=None,
+                                     outputs=tuple(k for k in abi.OUTPUT_NAMES if k != "bPred")):
+        r = self._hs.solve_transformed(x0, z0, xref, S, state_bounds, policy_params)
+        return {k: r[k] for k in outputs}
+
     def eval_model(self, x, z, u, policy_params=None):
         n, d, m, N = self.cfg.n, self.cfg.d, self.cfg.m, self.cfg.N
         x = np.ascontiguousarray(x, np.float64)

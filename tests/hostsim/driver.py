@@ -86,6 +86,16 @@ class HostSim:
         finally:
             lib().hostsim_set_belief(None, None, C.c_int32(0))
 
+    def solve_transformed(self, x0, z0, xref, S=None, state_bounds=None, policy_params=None):
+        """BranchMPC_CVaR.solve(x, z, xRef, S, Fx=None, bx) for a batch (bmpc_solve_transformed on the device)."""
+        S = None if S is None else np.ascontiguousarray(S, dtype=float)
+        bd = None if state_bounds is None else np.ascontiguousarray(state_bounds, dtype=float)
+        lib().hostsim_set_transform(_ptr(S), _ptr(bd))
+        try:
+            return self.solve(x0, z0, xref, policy_params)
+        finally:
+            lib().hostsim_set_transform(None, None)
+
     def solve(self, x0, z0, xref, policy_params=None, belief=False):
         cfg = self.cfg
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=float)

@@ -29,6 +29,16 @@ std::string g_err;
 const double* g_b0 = nullptr;
 const double* g_xbackup = nullptr;
 int g_xb_cols = 0;
+// merge scenario inputs of the next hostsim_solve call (hostsim_set_transform)
+const double* g_xform = nullptr;
+const double* g_xbounds = nullptr;
+// lookup table of the *_REF policies (hostsim_set_lookup): stays until replaced
+std::vector<double> g_lut_x, g_lut_y;
+void apply_lookup(KParams& P) {
+  P.lut_x = g_lut_x.empty() ? nullptr : g_lut_x.data();
+  P.lut_y = g_lut_y.empty() ? nullptr : g_lut_y.data();
+  P.lut_n = (int)g_lut_x.size();
+}
 }  // namespace
 
 extern "C" {
@@ -63,6 +73,9 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
   P.z0 = z0;
   P.xref = xref;
   P.polpar = policy_params;
+  P.xform = g_xform;
+  P.xbounds = g_xbounds;
+  apply_lookup(P);
   P.uLin = uLin;
   P.pbest = pbest;
   P.oldin = oldin;
@@ -86,6 +99,10 @@ int hostsim_solve(const bmpc_config* cfg, const double* x0, const double* z0, co
     if (g_split) run_layout<HighwayModel, 11, BMPC_SLAB_SPLIT, 9>(P); else run_layout<HighwayModel, 11, BMPC_SLAB_SHARED, 9>(P);
     return BMPC_OK;
   }
+  if (cfg->model == BMPC_MODEL_MERGE) {
+    run<MergeModel, 3>(P);
+    return BMPC_OK;
+  }
   if (cfg->model == BMPC_MODEL_HIGHWAY) {
     switch (cfg->n_rows) {
       case 0: prox ? run<RateAug<HighwayModel>, 1>(P) : run<HighwayModel, 1>(P); break;
@@ -102,6 +119,18 @@ int hostsim_set_belief(const double* b0, const double* xbackup, int32_t cols) {
   g_b0 = b0;
   g_xbackup = xbackup;
   g_xb_cols = cols;
+  return BMPC_OK;
+}
+
+int hostsim_set_lookup(const double* xs, const double* ys, int32_t n) {
+  g_lut_x.assign(xs, xs + (n > 0 ? n : 0));
+  g_lut_y.assign(ys, ys + (n > 0 ? n : 0));
+  return BMPC_OK;
+}
+
+int hostsim_set_transform(const double* S, const double* state_bounds) {
+  g_xform = S;
+  g_xbounds = state_bounds;
   return BMPC_OK;
 }
 
@@ -168,7 +197,9 @@ int hostsim_eval_model(const bmpc_config* cfg, const double* x, const double* z,
   KParams P;
   const int rc = bmpc::make_params(*cfg, &P, &g_err);
   if (rc != BMPC_OK) return rc;
+  apply_lookup(P);
   if (cfg->model == BMPC_MODEL_HIGHWAY) eval_points<HighwayModel>(P, x, z, u, polpar, count, A, B, C, xp, zpred, p, hlin, dh);
+  else if (cfg->model == BMPC_MODEL_MERGE) eval_points<MergeModel>(P, x, z, u, polpar, count, A, B, C, xp, zpred, p, hlin, dh);
   else eval_points<QuadrupedModel>(P, x, z, u, polpar, count, A, B, C, xp, zpred, p, hlin, dh);
   return BMPC_OK;
 }

@@ -23,7 +23,7 @@ def test_library_is_built_and_loads():
     import __graft_entry__ as entry
     entry.build()
     lib = abi.load_library()
-    assert lib.bmpc_version() == 200
+    assert lib.bmpc_version() == 201
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -7,7 +7,7 @@ on a CPU-only box; the -m gpu tests repeat the same checks through libbranchmpc.
 import numpy as np
 import pytest
 
-from tests.helpers import (BELIEF_FIXTURES, belief_fixture_config, check_belief_fixture, CVAR_FIXTURES, cvar_fixture_config, check_cvar_fixture, check_quadruped_hard_cases, check_forced_interior_point, force_interior_point, SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
+from tests.helpers import (BELIEF_FIXTURES, belief_fixture_config, check_belief_fixture, CVAR_FIXTURES, cvar_fixture_config, check_cvar_fixture, merge_fixture_config, check_merge_fixture, check_merge_model_functions, check_quadruped_hard_cases, check_forced_interior_point, force_interior_point, SWEEP, check_sweep_case, check_robust_fixture, robust_fixture_config, quadruped_fixture_config, HIGHWAY_FIXTURES, TOL_OBJ, TOL_U0, check_fixture_closed_loop, fixture_config, load_fixture,
                      oracle_episode)
 from _bmpc import scenarios
 from tests.hostsim.driver import HostSim
@@ -18,6 +18,23 @@ def test_fixture_closed_loop(name):
     g = load_fixture(name)
     hs = HostSim(fixture_config(g), 1)
     check_fixture_closed_loop(lambda x, z, r: hs.solve(x, z, r), g)
+
+
+def test_merge_model_functions_match_reference():
+    from tests.hostsim.backend import HostBackend
+    check_merge_model_functions(HostBackend)
+
+
+def test_merge_fixture_replay():
+    """sim_merge of the unmodified main_branch.py, all 60 controller calls: PredictiveModel_merge, N = 40, NB = 1, ralpha = 0.1,
+    state transform S and bounds bx per call (Highway_env_branch.py:352-366)."""
+    g = load_fixture("highway_merge_default")
+    hs = HostSim(merge_fixture_config(g), 1)
+
+    def set_state(uLin, pbest, old):
+        hs.set_state(uLin, pbest, old)
+
+    check_merge_fixture(lambda x, z, r, S, bd: hs.solve_transformed(x, z, r, S, bd), set_state, g)
 
 
 @pytest.mark.parametrize("name", CVAR_FIXTURES)

@@ -112,3 +112,68 @@ def test_main_quadruped_runs_as_the_reference_does(reference_world):
     assert mpc.uPred.shape == (151, 3) and mpc.xPred.shape == (155, 3)
     assert len(mpc.BT2array()) == 4
     assert "reference" in os.path.realpath(qenv.__file__)
+
+
+def _run_sim_merge(tmp_path, henv):
+    """`sim_merge()` of the unmodified main_branch.py (:53-88; the script's __main__ block has the call commented out) with
+    the animation replaced by a no-op; returns (Highway_sim records, the controller)."""
+    os.symlink(os.path.join(REFERENCE, "main_branch.py"), tmp_path / "main_branch.py")
+    sys.modules.pop("main_branch", None)
+    import main_branch
+    import MPC_branch
+    got = {}
+    sim = henv.Highway_sim
+
+    def spy(env, T):
+        got["rec"] = sim(env, T)
+        got["env"] = env
+        return got["rec"]
+
+    henv.Highway_sim = spy
+    if hasattr(henv, "animate_scenario"):
+        henv.animate_scenario = lambda *a, **k: None
+    try:
+        main_branch.sim_merge()
+    finally:
+        henv.Highway_sim = sim
+        sys.modules.pop("main_branch", None)
+    mpc = got["env"].mpc
+    assert os.path.realpath(MPC_branch.__file__).startswith(os.path.realpath(PKG))
+    assert type(mpc) is MPC_branch.BranchMPC_CVaR and mpc.ralpha == 0.1 and mpc.N == 40 and mpc.NB == 1
+    assert type(mpc.predictiveModel).__name__ == "PredictiveModel_merge"
+    return got["rec"], mpc, got["env"]
+
+
+def _check_merge_run(rec, mpc, env):
+    state, inputs, collision = np.array(rec[0]), np.array(rec[1]), rec[-1]
+    assert state.shape == (2, 60, 4) and np.isfinite(state).all() and inputs.shape == (2, 60, 2)
+    assert mpc.timeStep == 60 and mpc.feasible == 1
+    assert mpc.uPred.shape == (81, 2) and mpc.xPred.shape == (83, 4)
+    assert (np.abs(inputs[0, :, 0]) <= 7.0 + 1e-9).all() and (np.abs(inputs[0, :, 1]) <= 0.3 + 1e-9).all()
+    assert not np.any(collision)
+    assert env.laneID == [0, 0], "the ego has left the ramp"
+    # the ego came down from the ramp (y = 13) into the highway's lanes and drives along them
+    assert 1.25 - 0.5 < state[0, -1, 1] < 7.2 and abs(state[0, -1, 3]) < 0.3
+    # the first controller call has no warm start, so it is the reference's call exactly: the recorded first input
+    g = np.load(os.path.join(ROOT, "tests", "golden", "highway_merge_default.npz"))
+    np.testing.assert_allclose(inputs[0, 0], g["input_rec"][0, 0], atol=1e-3)
+    np.testing.assert_allclose(state[:, 0], g["state_rec"][:, 0], atol=1e-4)
+
+
+def test_sim_merge_runs_unmodified_on_the_reference_environment(reference_world, tmp_path):
+    """main_branch.sim_merge -> PredictiveModel_merge x 2 (one with lookup-table policies), BranchMPC_CVaR(ralpha=0.1),
+    the reference's own Highway_env_merge.step calling mpc.solve(x, z, xRef, S, Fx=None, bx=bx) for 60 steps."""
+    import Highway_env_branch as henv
+    assert "reference" in os.path.realpath(henv.__file__)
+    rec, mpc, env = _run_sim_merge(tmp_path, henv)
+    _check_merge_run(rec, mpc, env)
+
+
+def test_sim_merge_runs_unmodified_on_the_dropin_environment(reference_world, tmp_path):
+    """The same script with this package's Highway_env_branch (merge_geometry, Highway_env_merge, sim_merge) on the path."""
+    os.remove(tmp_path / "Highway_env_branch.py")
+    sys.modules.pop("Highway_env_branch", None)
+    import Highway_env_branch as henv
+    assert os.path.realpath(henv.__file__).startswith(os.path.realpath(PKG))
+    rec, mpc, env = _run_sim_merge(tmp_path, henv)
+    _check_merge_run(rec, mpc, env)
