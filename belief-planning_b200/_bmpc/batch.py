@@ -176,6 +176,27 @@ class BatchedBranchMPC:
             raise ValueError("lookup grid and values disagree")
         self._check(self.lib.bmpc_set_lookup_table(self.h, xs.ctypes.data, ys.ctypes.data, len(xs)), "bmpc_set_lookup_table")
 
+    def solve_transformed(self, x0, z0, xref, S=None, state_bounds=None, policy_params=None, outputs=LIGHT_OUTPUTS, stream=None):
+        """bmpc_solve_transformed on CUDA float64 tensors: S (count, n, n), state_bounds (count, n_rows, 2), either None."""
+        import torch
+        count = x0.shape[0]
+        for t in (x0, z0, xref):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.shape == (count, self.cfg.n)):
+                raise ValueError("inputs must be contiguous CUDA float64 tensors of shape (count, n)")
+        for t, numel in ((S, count * self.cfg.n ** 2), (state_bounds, count * self.cfg.n_rows * 2),
+                         (policy_params, count * self.cfg.m * 4)):
+            if t is not None and not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == numel):
+                raise ValueError("S, state_bounds, policy_params must be contiguous CUDA float64 tensors of their documented shapes")
+        bufs = self.device_outputs(count, outputs)
+        out = abi.Outputs(**{k: bufs[k].data_ptr() for k in bufs})
+        if stream is None:
+            stream = torch.cuda.current_stream(x0.device).cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self._check(self.lib.bmpc_solve_transformed(self.h, x0.data_ptr(), z0.data_ptr(), xref.data_ptr(), ptr(policy_params),
+                                                    ptr(S), ptr(state_bounds), count, C.byref(out), C.c_void_p(stream)),
+                    "bmpc_solve_transformed")
+        return bufs
+
     def solve_transformed_host_views(self, x0, z0, xref, S=None, state_bounds=None, policy_params=None, outputs=ALL_OUTPUTS):
         """As solve_host_views for a BMPC_MODEL_MERGE handle, with the call's state transform S (count, n, n) and the (lo, hi)
         bounds of the state rows (count, n_rows, 2); either may be None."""

@@ -61,6 +61,28 @@ def merge_config(policies=("trackv", "brake"), NB=1, N=40, v0=20.0, am=7.0, rm=0
                               batch_capacity=batch_capacity, device=device, **knobs)
 
 
+def merge_batch(count, seed=1242, N_lane=2, merge_lane=1, merge_s=50.0, merge_R=300.0, v0=20.0, W=2.5, psimax=0.25):
+    """Synthetic ramp scenes of the merge scenario: the ego somewhere along the ramp's centre line (offset 1.8 m as the
+    reference's initial state, Highway_env_branch.py:315), an obstacle in the highway lane next to it, and the reference,
+    state transform and bounds Highway_env_merge.step builds from the ramp tables at the ego's x (:357-363).
+    Returns x0, z0, xref (count, 4), S (count, 4, 4), state bounds (count, 2, 2)."""
+    from Highway_env_branch import merge_geometry
+    rng = np.random.default_rng(seed)
+    X1, X2, Y1, Y2, P1, P2 = merge_geometry(N_lane, merge_lane, merge_s, merge_R, 0)
+    gx, gy, gpsi = np.append(X1, X2), np.append(Y1, Y2), np.append(P1, P2)
+    xe = rng.uniform(15.0, merge_s, count)
+    y0, psi0 = np.interp(xe, gx, gy), np.interp(xe, gx, gpsi)
+    x0 = np.column_stack([xe, y0 + 1.8 + rng.normal(0, 0.15, count), rng.uniform(14.0, 22.0, count), psi0 + rng.normal(0, 0.02, count)])
+    z0 = np.column_stack([xe + rng.uniform(-15.0, 12.0, count), np.full(count, 5.4) + rng.normal(0, 0.1, count),
+                          rng.uniform(16.0, 22.0, count), np.zeros(count)])
+    t = np.tan(psi0)
+    S = np.tile(np.eye(4), (count, 1, 1))
+    S[:, 1, 0] = -t
+    xref = np.column_stack([np.zeros(count), -t * xe + y0 + 1.8, np.full(count, v0), psi0])
+    bx = np.column_stack([-t * xe + y0 + 3.6 * merge_lane - W / 2, t * xe - y0 - W / 2, psi0 + psimax, -psi0 + psimax])
+    return x0, z0, xref, S, bounds_from_bx(bx)
+
+
 def bounds_from_bx(bx):
     """The reference's bx of the four one-sided rows [y <= b0, -y <= b1, psi <= b2, -psi <= b3] as (lo, hi) pairs."""
     bx = np.asarray(bx, dtype=float).reshape(-1, 4)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Branch-MPC throughput benchmark (BASELINE.json metric: highway Branch-MPC solves/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--config {2,3,4,5,cvar}] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--config {2,3,4,5,cvar,merge}] [--impl reference]
 
 Workload (N=1): BASELINE.json configs[2] - highway Branch MPC (m=3 policies, NB=2, N=8; 13 branches, 106 state nodes,
 97 input nodes), 16384 independent episodes per GPU in closed loop: a *step* is one MPC solve of every episode
@@ -217,8 +217,10 @@ CONFIG_NAMES = {
     "4": "quadruped BranchMPCProx (BASELINE configs[3]): m=2, NB=2, N=25 -> 7 branches / 155 state nodes / 151 input nodes; %d episodes per GPU",
     "5": "highway tree sweep (BASELINE configs[4]): m in {2,3,4} x NB in {1,2,3}, N=8; %d episodes in total, sharded over the ranks",
     "cvar": "highway BranchMPC_CVaR (what main_branch.py:48 builds, ralpha=0.9): m=3, NB=2, N=8; %d episodes per GPU",
+    "merge": "merge scenario (main_branch.sim_merge): PredictiveModel_merge, BranchMPC_CVaR ralpha=0.1, m=2, NB=1, N=40 -> 81 input "
+             "nodes, per-episode state transform S and bounds; %d episodes per GPU",
 }
-DEFAULT_BATCH = {"2": 4096, "3": 16384, "4": 8192, "5": 65536, "cvar": 16384}
+DEFAULT_BATCH = {"2": 4096, "3": 16384, "4": 8192, "5": 65536, "cvar": 16384, "merge": 4096}
 
 
 def make_workload(which, B, rank, world, local):
@@ -232,6 +234,8 @@ def make_workload(which, B, rank, world, local):
         mpc = batch.BatchedBranchMPC(cfg)
         t = [None if a is None else torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in arrays]
         parts.append({"mpc": mpc, "x": t[0], "z": t[1], "r": t[2], "p": t[3], "B": arrays[0].shape[0], "sizes": sizes, "c": rows})
+        if len(t) > 4:
+            parts[-1]["S"], parts[-1]["bd"] = t[4], t[5]
 
     if which in ("3", "cvar", "2"):
         x0, z0, xref, pp = scenarios.highway_batch(B, seed={"3": 1237, "cvar": 1241, "2": 1236}[which] + 1000 * rank)
@@ -245,6 +249,9 @@ def make_workload(which, B, rank, world, local):
     elif which == "4":
         x0, z0, xref = scenarios.quadruped_batch(B, seed=1238 + 1000 * rank)
         part(scenarios.quadruped_config(batch_capacity=B, device=local), (x0, z0, xref, None), tree_sizes(2, 2, 25, 3, 3), 1)
+    elif which == "merge":
+        x0, z0, xref, S, bd = scenarios.merge_batch(B, seed=1242 + 1000 * rank)
+        part(scenarios.merge_config(batch_capacity=B, device=local), (x0, z0, xref, None, S, bd), tree_sizes(2, 1, 40), 3)
     elif which == "5":
         per_shape = B // len(SWEEP)
         for m, NB in SWEEP:
@@ -275,7 +282,10 @@ def timed_steps(parts, K, W, flush, barrier, outputs=("u0", "status", "iters", "
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for i, pt in enumerate(parts):
-            out = pt["mpc"].solve(pt["x"], pt["z"], pt["r"], pt["p"], outputs=outputs)
+            if "S" in pt:
+                out = pt["mpc"].solve_transformed(pt["x"], pt["z"], pt["r"], pt["S"], pt["bd"], pt["p"], outputs=outputs)
+            else:
+                out = pt["mpc"].solve(pt["x"], pt["z"], pt["r"], pt["p"], outputs=outputs)
             pt["mpc"].plant_step(pt["x"], out["u0"], pt["z"], 0, pt["p"])
             keep = {k: out[k].clone() for k in stats[i]}     # warm-up steps do exactly what timed steps do
             if timed:
@@ -491,7 +501,7 @@ def run_gpu(args):
     others = None
     if which == "3" and not args.no_others:
         others = {}
-        for oc in ("2", "4", "5", "cvar"):
+        for oc in ("2", "4", "5", "cvar", "merge"):
             ob = DEFAULT_BATCH[oc] if oc != "cvar" else 4096
             op = make_workload(oc, ob, rank, world, local)
             ms, st, _, _ = timed_steps(op, 3, 3, flush, barrier)
@@ -568,7 +578,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (config 5: in total); 0 = the config's BASELINE size")
-    ap.add_argument("--config", default="3", choices=["2", "3", "4", "5", "cvar"], help="BASELINE.json config to run")
+    ap.add_argument("--config", default="3", choices=["2", "3", "4", "5", "cvar", "merge"], help="BASELINE.json config to run")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other configs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
