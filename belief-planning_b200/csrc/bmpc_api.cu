@@ -420,6 +420,12 @@ static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStrea
        ? BMPC_DISPATCH_M(h, fn, RateAug<HighwayModel>, RateAug<QuadrupedModel>, __VA_ARGS__)            \
        : BMPC_DISPATCH_M(h, fn, HighwayModel, QuadrupedModel, __VA_ARGS__))
 
+#ifdef BMPC_DEV_HIGHWAY_ONLY
+// development builds (tools/build_variant.sh ... -DBMPC_DEV_HIGHWAY_ONLY): only the default highway instance, seconds to compile
+#undef BMPC_DISPATCH
+#define BMPC_DISPATCH(h, fn, ...) fn<HighwayModel, 3>(__VA_ARGS__)
+#endif
+
 static void free_handle(bmpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);

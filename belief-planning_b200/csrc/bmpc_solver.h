@@ -61,26 +61,39 @@ struct Solver {
   static constexpr int NS = NX * (NX + 1) / 2;
   static constexpr int NSU = NU * (NU + 1) / 2;
   // field offsets (each field is one real per padded node)
+  // Multi-real fields start on even offsets of a record with even stride: records are 16-byte aligned, so the compiler
+  // fetches neighbouring reals with one LDS.128 (a backward-sweep step: 14 shared loads instead of 27).  The order keeps the
+  // padding small (highway, 3 rows: 49 reals in a record of 50).
+#if defined(BMPC_ODD_FIELDS)
+  static constexpr int ev(int v) { return v; }
+#else
+  static constexpr int ev(int v) { return (v + 1) & ~1; }
+#endif
   static constexpr int F_LIN = 0;
-  static constexpr int F_CC = F_LIN + M::NLIN;
-  static constexpr int F_Q = F_CC + M::NCC;
-  static constexpr int F_FC = F_Q + NXP;     // collision row f (x,y components); holds the obstacle (x,y) before setup
-  static constexpr int F_HC = F_FC + 2 * NC; // collision row upper bounds
-  static constexpr int F_RHO = F_HC + NC;    // rho of the NR soft rows then of the NU inputs
-  static constexpr int F_K = F_RHO + NR + NU;
-  static constexpr int F_SI = F_K + NU * NX; // S^-1, packed upper triangle
-  static constexpr int F_H0 = F_SI + NSU;    // P+ C
-  static constexpr int F_S = F_H0 + NX;      // ADMM state: scaled Moreau variable per soft row
-  static constexpr int F_SU = F_S + NR;      // same for the inputs
-  static constexpr int F_XQ = F_SU + NU;     // x after a forward sweep / q~x before a backward sweep
-  static constexpr int F_UQ = F_XQ + NX;     // u (kff between the sweeps) / q~u before a backward sweep
-  static constexpr int F_Y = F_UQ + NU;      // polish multipliers (rows then inputs)
+  static constexpr int F_CC = ev(F_LIN + M::NLIN);
+  static constexpr int F_Q = ev(F_CC + M::NCC);
+  static constexpr int F_FC = ev(F_Q + NXP);       // collision row f (x,y components); holds the obstacle (x,y) before setup
+  static constexpr int F_K = ev(F_FC + 2 * NC);    // feedback gain
+  static constexpr int F_H0 = ev(F_K + NU * NX);   // P+ C
+  static constexpr int F_SI = ev(F_H0 + NX);       // S^-1, packed upper triangle
+  static constexpr int F_HC = F_SI + NSU;          // collision row upper bounds
+  static constexpr int F_RHO = F_HC + NC;          // rho of the NR soft rows then of the NU inputs
+  // ---- iterate fields (kept in the slab in every placement) ----
+  static constexpr int F_XQ = ev(F_RHO + NR + NU); // x after a forward sweep / q~x before a backward sweep
+  static constexpr int F_UQ = ev(F_XQ + NX);       // u (kff between the sweeps) / q~u before a backward sweep
+  static constexpr int F_SU = ev(F_UQ + NU);       // ADMM state of the inputs: scaled Moreau variable
+  static constexpr int F_S = ev(F_SU + NU);        // same per soft row
+  static constexpr int F_Y = F_S + NR;             // polish multipliers (rows then inputs)
   static constexpr int NF = F_Y + NR + NU;
   static constexpr int BR = 1 + NS + 3 * NX; // per-branch reals: w, exchange(NS), x last, z last, x after last
-  static constexpr int NFA = F_S;                 // factor fields per node
+  static constexpr int NFA = F_XQ;                // factor fields per node
   static constexpr int NFAP = (NFA + 1) & ~1;     // ... padded to an even count (16-byte aligned records in global)
   static constexpr int NFW = SPLIT ? NF - NFA : NF;   // fields kept in the slab
-  static constexpr int NFWP = NFW | 1;                // slab record stride, odd (bank-conflict-free)
+#if defined(BMPC_ODD_FIELDS)
+  static constexpr int NFWP = NFW | 1;                // round-1 layout: odd stride (conflict-free for 64-bit accesses)
+#else
+  static constexpr int NFWP = (NFW + 1) & ~1;         // even stride (see ev above); 128-bit accesses of 8 lanes cover the 32 banks
+#endif
 
   // merge scenario: the episode's transformed stage Hessian S'QS, state rows Fx S and their bounds (kStateTransform)
   static constexpr bool XF = M::kStateTransform;
