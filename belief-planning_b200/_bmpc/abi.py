@@ -108,6 +108,7 @@ SYMBOLS = [
                                   C.c_void_p]),
     ("bmpc_env_step", C.c_int, [C.c_void_p, C.POINTER(EnvState), C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.POINTER(Outputs), C.c_void_p]),
+    ("bmpc_staging_enabled", C.c_int, [C.c_void_p]),
     ("bmpc_get_launch_info", C.c_int, [C.c_void_p, _pi, _pi, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("bmpc_launch_count", C.c_int64, [C.c_void_p]),
     ("bmpc_measure_fp64_peak", C.c_double, [C.c_int, C.c_int]),

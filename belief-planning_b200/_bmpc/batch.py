@@ -323,6 +323,10 @@ class BatchedBranchMPC:
         torch.cuda.synchronize(dev)
         return {k: v.cpu().numpy() for k, v in t.items()}
 
+    def staging_enabled(self):
+        """True if the kernel prefetches the next episode's state into shared memory with bulk copies (TMA)."""
+        return bool(self.lib.bmpc_staging_enabled(self.h))
+
     def launch_info(self):
         mode, warps, smem, gl = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
         self._check(self.lib.bmpc_get_launch_info(self.h, C.byref(mode), C.byref(warps), C.byref(smem), C.byref(gl)),

@@ -38,19 +38,29 @@ __global__ void __launch_bounds__(BMPC_LANES, 4) bmpc_solve_kernel() {
     if (SPLIT) factor = P.gws + (size_t)blockIdx.x * P.factor_reals;
   }
   Solver<M, NR, MODE, NC> S(P, slab, factor, P.ipm + (size_t)blockIdx.x * P.ipm_reals, lane);
-  for (;;) {
-    int idx = 0;
-    if (lane == 0) idx = atomicAdd(P.counter, 1);
-#if BMPC_TEAM_WARPS > 1
-    __shared__ int next_problem;
-    if (lane == 0) next_problem = idx;
-    __syncthreads();
-    idx = next_problem;   // rewritten only after the barriers inside solve()
-#else
-    idx = __shfl_sync(BMPC_FULL_MASK, idx, 0);
-#endif
-    if (idx >= P.count) break;
-    S.solve(P.order ? P.order[idx] : idx);
+  __shared__ int next_problem[4];                       // [0] next work index, [1] its state is being staged, [2] wait verdict
+  __shared__ __align__(8) unsigned long long stage_bar; // completion barrier of the staging copies
+  const bool staging = (MODE == BMPC_SLAB_SHARED) && P.stage_on;
+  if (staging) {
+    if (lane == 0) bmpc_mbar_init(&stage_bar, 1);
+    S.stage_bar = &stage_bar;
+    S.stage_slot = next_problem;
+  }
+  if (lane == 0) next_problem[0] = atomicAdd(P.counter, 1);
+  __syncthreads();
+  int idx = next_problem[0];
+  while (idx < P.count) {
+    S.solve(P.order ? P.order[idx] : idx);   // ends with a team barrier
+    if (staging && !S.stage_broken && next_problem[0] >= 0) {
+      // the solve claimed the next work item itself and started the copies of its episode's state (Solver::stage_next)
+      idx = next_problem[0];
+      S.stage_have = next_problem[1] != 0;
+    } else {
+      __syncthreads();
+      if (lane == 0) next_problem[0] = atomicAdd(P.counter, 1);
+      __syncthreads();
+      idx = next_problem[0];
+    }
   }
 }
 
@@ -385,6 +395,32 @@ static int configure_instance(bmpc_handle* h) {
   }
   h->slab_bytes = (h->mode == BMPC_SLAB_GLOBAL) ? 0 : h->P.slab_reals * sizeof(real);
   h->P.ipm_reals = Solver<M, NR, BMPC_SLAB_SHARED, NC>::ipm_reals(h->P.nup);
+  // Staging of the next episode's state (uLin | codes | rho cache) behind the slab by bulk copies (cp.async.bulk + mbarrier):
+  // shared placement, tree controllers.  Opt-in (reserved[6] bit 1): measured, it does not pay - the data it prefetches is
+  // 8 KB per episode out of L2, read once by 96 lanes, while the hand-over (claim, fences, three copies, one more team
+  // barrier per solve) costs 2-10 % on small trees, and on the default highway tree the 6 KB of extra shared memory moves the
+  // SM to the next carve-out step, which alone costs 3 % in L1 capacity (profiles/r02_staging_ab.md).
+  h->P.stage_on = 0;
+  {
+    using S = Solver<M, NR, BMPC_SLAB_SHARED, NC>;
+    if (h->mode == BMPC_SLAB_SHARED && !bmpc_is_chain(h->cfg.controller) && S::stage_possible(h->P.totalu) &&
+        (h->cfg.reserved[6] & 2) != 0) {
+      const size_t with_stage = (S::stage_offset(h->P.nup, h->P.nbx) + S::stage_reals(h->P.totalu)) * sizeof(real);
+      int fit = 0;
+      if (with_stage <= (size_t)max_optin) {
+        BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_stage));
+        BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, BMPC_LANES, with_stage));
+      }
+      const int resident = h->grid / h->num_sms;
+      if (fit >= resident) {
+        h->P.stage_on = 1;
+        h->slab_bytes = with_stage;
+      }
+    }
+  }
+#ifdef BMPC_DEV_EXTRA_SMEM
+  if (!h->P.stage_on && h->mode == BMPC_SLAB_SHARED) h->slab_bytes += BMPC_DEV_EXTRA_SMEM;   // experiment: shared-memory carve-out vs L1
+#endif
   return BMPC_OK;
 }
 
@@ -482,7 +518,7 @@ static int create_impl(const bmpc_config* cfg, bmpc_handle* h) {
   BMPC_CK(h, cudaMalloc(&h->started, cap * sizeof(int)));
   if (cfg->controller == BMPC_CTRL_ROBUST) BMPC_CK(h, cudaMalloc(&h->xprev, cap * P.pub_totalx * cfg->n * sizeof(real)));
   BMPC_CK(h, cudaMalloc(&h->rho_cache, cap * P.totalu * 16 * sizeof(real))  /* up to 11 rows + 3 inputs per node */);
-  BMPC_CK(h, cudaMalloc(&h->code_cache, cap * P.totalu * sizeof(long long)));
+  BMPC_CK(h, cudaMalloc(&h->code_cache, cap * (P.totalu + 1) * sizeof(long long)));   // per-episode stride padded to 16 bytes
   BMPC_CK(h, cudaMalloc(&h->cache_state, cap * 2 * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->cost, cap * sizeof(int)));
   BMPC_CK(h, cudaMalloc(&h->order, cap * sizeof(int)));
@@ -671,7 +707,7 @@ static int solve_impl(bmpc_handle* h, const double* x0, const double* z0, const 
   P.cache_state = h->cache_state;
   P.cost = h->cost;
   P.order = nullptr;
-  if (count > h->grid && h->cfg.reserved[6] == 0) {
+  if (count > h->grid && (h->cfg.reserved[6] & 1) == 0) {
     bmpc_order_kernel<<<1, 1024, 0, s>>>(h->cost, (int)count, h->order);
     BMPC_CK(h, cudaGetLastError());
     P.order = h->order;
@@ -1004,6 +1040,8 @@ int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int3
   h->launches += 1;
   return BMPC_OK;
 }
+
+int bmpc_staging_enabled(const bmpc_handle* h) { return h ? h->P.stage_on : BMPC_E_INVALID; }
 
 int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warps, int64_t* smem_bytes,
                          int64_t* global_bytes_per_warp) {

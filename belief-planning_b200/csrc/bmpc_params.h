@@ -76,6 +76,8 @@ struct KParams {
   bmpc_outputs out;
   int* cost;                    // solver cache [cap]: cycles >> 10 of the previous solve (scheduling hint), may be null
   const int* order;             // work order of this launch (longest expected first), or null = natural order
+  int stage_on;                 // 1: the next episode's uLin / active-set codes / rho cache are staged into shared memory by bulk
+                                //    copies while the current episode is being solved (shared slab placement, tree controllers)
   int* counter;                 // work queue head
   real* gws;                    // global workspace (only when the per-problem slab does not fit shared memory)
   size_t slab_reals;            // reals per problem slab

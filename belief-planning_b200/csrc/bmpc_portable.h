@@ -52,6 +52,35 @@ BMPC_D void bsync() {
   __syncwarp();
 #endif
 }
+// ---- asynchronous staging of the next episode's state: 1-D bulk copies (TMA, cp.async.bulk) completing on an mbarrier ----
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned bmpc_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bmpc_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bmpc_smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
+__device__ __forceinline__ void bmpc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bmpc_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bmpc_smem_addr(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bmpc_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bmpc_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(bmpc_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool bmpc_mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bmpc_smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#endif
+
 BMPC_D bool team_leader() {
 #if defined(__CUDA_ARCH__)
   return threadIdx.x < 32;

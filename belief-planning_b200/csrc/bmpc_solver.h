@@ -102,6 +102,14 @@ struct Solver {
     return (size_t)NFWP * nup + (size_t)nup + (size_t)BR * nbranch + XFR;
   }
   BMPC_HD static size_t factor_reals(int nup) { return SPLIT ? (size_t)NFAP * nup : 0; }
+  // per-episode strides of the solver caches in global memory, padded to 16 bytes so that one episode's block can travel
+  // as one bulk copy; the stage behind the slab holds the NEXT episode's uLin | active-set codes | rho cache
+  BMPC_HD static size_t code_stride(int totalu) { return ((size_t)totalu + 1) & ~(size_t)1; }
+  BMPC_HD static size_t rho_stride(int totalu) { return ((size_t)totalu * (NR + NU) + 1) & ~(size_t)1; }
+  BMPC_HD static size_t ulin_reals(int totalu) { return (size_t)(totalu + 1) * NU; }
+  BMPC_HD static bool stage_possible(int totalu) { return (ulin_reals(totalu) & 1) == 0; }
+  BMPC_HD static size_t stage_offset(int nup, int nbranch) { return (slab_reals(nup, nbranch) + 1) & ~(size_t)1; }
+  BMPC_HD static size_t stage_reals(int totalu) { return ulin_reals(totalu) + code_stride(totalu) + rho_stride(totalu); }
   // interior-point fallback: per-node scratch in this warp's global region (rare path, see ipm_solve)
   static constexpr int IP_X = 0;                    // current iterate x, u
   static constexpr int IP_U = IP_X + NX;
@@ -139,6 +147,16 @@ struct Solver {
 #define BMPC_LANE_ID lane_host
 #endif
   int prob;
+#if defined(__CUDA_ARCH__)
+  // staging of the next episode (P.stage_on): mbarrier + hand-over slots in static shared memory of the team's block
+  unsigned long long* stage_bar;
+  int* stage_slot;        // [0] work index claimed for the next solve, [1] 1 if bulk copies for it are in flight, [2] wait verdict
+  unsigned stage_parity;  // phase of the mbarrier the next wait looks for
+  bool stage_have;        // copies for THIS episode were issued during the previous solve
+  bool stage_broken;      // a wait timed out: staging stays off for the rest of the launch (this team)
+  bool stage_pending;     // the hand-over (claim + copies for the next episode) has not run yet in this solve
+  bool staged;            // this episode's uLin / codes / rho are read from the stage
+#endif
   bool use_codes;   // this solve starts its polish from the cached active set of the previous step
   real gap_r, stp_r, gap_u, stp_u;   // last residual check: max primal gap |f'x - v| and max step |v+ - v| (rows / inputs)
   int set_changes;                   // last residual check: nodes whose implied active set differs from the previous check
@@ -155,6 +173,12 @@ struct Solver {
   BMPC_D Solver(const KParams& P_, real* slab, real* factor, real* ipm, int lane_) : P_host(P_), ws(slab), fa(factor), ip(ipm), lane_host(lane_) {
 #endif
     prob = 0;
+#if defined(__CUDA_ARCH__)
+    stage_bar = nullptr;
+    stage_slot = nullptr;
+    stage_parity = 0;
+    stage_have = stage_broken = stage_pending = staged = false;
+#endif
     use_codes = false;
     nsolve = 0;
     rlin = 0.0;
@@ -221,6 +245,71 @@ struct Solver {
     if (k == 0) { b = 0; t = 0; } else { const int q = bmpc_idiv(k - 1, PP.inv_N); b = 1 + q; t = (k - 1) - q * PP.N; }
   }
   BMPC_D const real* pol_par(int i) const { return polpar ? polpar + 4 * i : PP.pol_par[i]; }
+  // persistent per-episode blocks: from the stage when this episode was prefetched, else from global memory
+  BMPC_D real* stage_base() { return slab() + stage_offset(PP.nup, PP.nbx); }
+  BMPC_D const real* ep_uLin() {
+#if defined(__CUDA_ARCH__)
+    if (staged) return stage_base();
+#endif
+    return PP.uLin + (size_t)prob * ulin_reals(PP.totalu);
+  }
+  BMPC_D const code_t* ep_codes() {
+#if defined(__CUDA_ARCH__)
+    if (staged) return reinterpret_cast<const code_t*>(stage_base() + ulin_reals(PP.totalu));
+#endif
+    return PP.code_cache + (size_t)prob * code_stride(PP.totalu);
+  }
+  BMPC_D const real* ep_rho() {
+#if defined(__CUDA_ARCH__)
+    if (staged) return stage_base() + ulin_reals(PP.totalu) + code_stride(PP.totalu);
+#endif
+    return PP.rho_cache + (size_t)prob * rho_stride(PP.totalu);
+  }
+#if defined(__CUDA_ARCH__)
+  // Start of a solve: wait (bounded) for the bulk copies issued for this episode during the previous solve.
+  BMPC_DN void stage_acquire() {
+    staged = false;
+    if (stage_have) {
+      stage_have = false;
+      if (BMPC_LANE_ID == 0) {
+        bool ok = false;
+        const long long t0 = clock64();
+        while (!(ok = bmpc_mbar_try_wait(stage_bar, stage_parity)) && clock64() - t0 < (4ll << 20)) {}
+        stage_slot[2] = ok ? 1 : 0;
+      }
+      team_sync();
+      stage_parity ^= 1u;
+      staged = stage_slot[2] == 1;
+      if (!staged) stage_broken = true;   // never observed; the episode is then read from global memory as without staging
+    }
+    stage_pending = PP.stage_on && !stage_broken;
+  }
+  // Hand-over, once per solve behind the team barrier that follows the last read of the stage: claim the next work item
+  // and start the three bulk copies (TMA, 1-D) of its episode's uLin | codes | rho; they land while this episode is solved.
+  BMPC_DN void stage_next() {
+    stage_pending = false;
+    if (BMPC_LANE_ID == 0) {
+      // claiming ahead fixes a team's next item one solve early; near the end of the queue that would cost the balance of
+      // the tail (measured: -3 %), so the last gridDim.x items are claimed when their team is actually free
+      int nxt = -1, issued = 0;
+      if (*(volatile int*)PP.counter + (int)gridDim.x < PP.count) nxt = atomicAdd(PP.counter, 1);
+      if (nxt >= 0 && nxt < PP.count) {
+        const size_t e = (size_t)(PP.order ? PP.order[nxt] : nxt);
+        const unsigned b0 = (unsigned)(ulin_reals(PP.totalu) * sizeof(real)), b1 = (unsigned)(code_stride(PP.totalu) * sizeof(code_t)),
+                       b2 = (unsigned)(rho_stride(PP.totalu) * sizeof(real));
+        real* st = stage_base();
+        bmpc_fence_proxy_async();
+        bmpc_mbar_expect_tx(stage_bar, b0 + b1 + b2);
+        bmpc_bulk_g2s(st, PP.uLin + e * ulin_reals(PP.totalu), b0, stage_bar);
+        bmpc_bulk_g2s(st + ulin_reals(PP.totalu), PP.code_cache + e * code_stride(PP.totalu), b1, stage_bar);
+        bmpc_bulk_g2s(st + ulin_reals(PP.totalu) + code_stride(PP.totalu), PP.rho_cache + e * rho_stride(PP.totalu), b2, stage_bar);
+        issued = 1;
+      }
+      stage_slot[0] = nxt;
+      stage_slot[1] = issued;
+    }
+  }
+#endif
 
   // ========================================================================================
   // Tree expansion: obstacle rollouts, branch probabilities/weights, ego linearisation rollouts,
@@ -424,9 +513,9 @@ struct Solver {
   BMPC_DN void expand_tree() {
     const long long prof_t0 = prof_begin(2);
     const int started = PP.started[prob];
-    const real* uLin = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
+    const real* uLin = ep_uLin();
     int* pbest = PP.pbest + (size_t)prob * PP.nbranch;
-    const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    const code_t* codes = ep_codes();
     const int m = PP.m;
     if constexpr (XF) {
       // solve(x, z, xRef, S, Fx, bx) (MPC_branch.py:2043-2059): stage Hessian S'QS (:1938), state rows Fx S (:1899) and the
@@ -592,7 +681,7 @@ struct Solver {
     const int Nx = PP.totalu, Nu = PP.totalu - 1;   // states incl. the terminal one / real inputs
     const real* uPrev = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
     const real* xPrev = PP.xprev + (size_t)prob * PP.pub_totalx * NXP;
-    const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    const code_t* codes = PP.code_cache + (size_t)prob * code_stride(PP.totalu);
     const real* x0 = PP.x0 + (size_t)prob * NXP;
     const real* z0 = PP.z0 + (size_t)prob * NXP;
     auto kp_chain = [&](int k) { return k == 0 ? kp_of(0, 0) : kp_of(1, k - 1); };
@@ -712,7 +801,7 @@ struct Solver {
     const int Nst = PP.totalu - 1;                          // stages N; chain states 0..N
     const int nb = PP.hmm_M * PP.zm;
     const real* uPrev = PP.uLin + (size_t)prob * (PP.totalu + 1) * NU;
-    const code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    const code_t* codes = PP.code_cache + (size_t)prob * code_stride(PP.totalu);
     const real* x0 = PP.x0 + (size_t)prob * NXP;
     const real* b0 = PP.b0 + (size_t)prob * nb;
     const real* xbk = PP.xbackup + (size_t)prob * nb * PP.xb_cols;
@@ -1606,7 +1695,7 @@ struct Solver {
   // values of the previous step (refreshed every P.rho_refresh solves) and skip the free factorisation + covariance sweep.
   BMPC_DN void store_rho() {
     const long long prof_t0 = prof_begin(3);
-    real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
+    real* cache = PP.rho_cache + (size_t)prob * rho_stride(PP.totalu);
 #pragma unroll 1
     BMPC_FOR_NODES(k) {
       int b, t;
@@ -1620,7 +1709,7 @@ struct Solver {
   }
   BMPC_DN void load_rho() {
     const long long prof_t0 = prof_begin(3);
-    const real* cache = PP.rho_cache + (size_t)prob * PP.totalu * (NR + NU);
+    const real* cache = ep_rho();
 #pragma unroll 1
     BMPC_FOR_NODES(k) {
       int b, t;
@@ -1673,7 +1762,7 @@ struct Solver {
   }
   BMPC_DN void store_codes() {
     const long long prof_t0 = prof_begin(9);
-    code_t* codes = PP.code_cache + (size_t)prob * PP.totalu;
+    code_t* codes = PP.code_cache + (size_t)prob * code_stride(PP.totalu);
 #pragma unroll 1
     BMPC_FOR_NODES(k) {
       int b, t;
@@ -3006,6 +3095,9 @@ struct Solver {
       if (keep_rho) store_rho();
       ++nfact;
     }
+#if defined(__CUDA_ARCH__)
+    if (stage_pending) stage_next();   // every read of the stage (expansion, load_rho) lies behind a team barrier by now
+#endif
     if (use_codes) {
       // warm solve: the previous optimum's active set, shifted in time, is usually one or two changes away
       guess_from_codes();
@@ -3097,6 +3189,9 @@ struct Solver {
     const bool reuse_rho = !cvar && warm && PP.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < PP.rho_refresh;
     use_codes = warm && PP.warm_polish && cstate[1] == 1 && (reuse_rho || cvar);
     t_phase = 0;
+#if defined(__CUDA_ARCH__)
+    stage_acquire();
+#endif
     if (PP.ctrl == BMPC_CTRL_ROBUST) expand_chain();
     else if (PP.ctrl == BMPC_CTRL_BELIEF) expand_belief();
     else expand_tree();

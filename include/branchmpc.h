@@ -146,7 +146,7 @@ typedef struct bmpc_config {
                              warps per SM; [2] polish when at most this many nodes changed their implied set between
                              checks; [3] polish at the latest every this many ADMM iterations (80; quadruped 20); [4] interior-point
                              fallback after this many failed polish attempts (3; quadruped 1; <0 = never; 100 = always, without a polish attempt first); [5] its iteration cap (40);
-                             [6] 1 = natural work order instead of longest-first; [7] k > 0 = the cycles output counts phase k only
+                             [6] bit 0 = natural work order instead of longest-first, bit 1 = stage the next episode's state into shared memory by bulk copies while the current one is solved (off by default: measured slower); [7] k > 0 = the cycles output counts phase k only
                              (1 interior point, 2 expansion, 3 rho, 4 factorisations, 5 sweeps, 6 polish passes,
                              7 adjoint, 8 ADMM rows, 9 final pass) */
 } bmpc_config;
@@ -333,6 +333,12 @@ typedef struct bmpc_env_state {
  * for the quadruped (Quad_constants), NULL on the highway. */
 int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int32_t t, int32_t n_lane,
                   const double* quad_sizes, const bmpc_outputs* out, void* stream);
+
+/* 1 if the solve kernel of this handle stages the NEXT episode's persistent state (uLin, active-set codes, rho cache) into
+ * shared memory with bulk copies (cp.async.bulk + mbarrier) while it solves the current one; 0 if it reads them from global
+ * memory at the start of each solve (the default; staging is requested with reserved[6] bit 1 and applies to the tree
+ * controllers in the shared slab placement). */
+int bmpc_staging_enabled(const bmpc_handle* h);
 
 /* How the solve kernel is launched for this handle: resolved BMPC_SLAB_* placement, number of persistent warps
  * (= thread blocks of 32), dynamic shared memory per warp, bytes of the per-warp global region. */

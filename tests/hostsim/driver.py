@@ -65,7 +65,7 @@ class HostSim:
         self.oldin = np.zeros((capacity, cfg.d))
         self.started = np.zeros(capacity, dtype=np.int32)
         self.rho_cache = np.zeros(capacity * internal_u * 16)          # flat: the kernel strides by its own row width
-        self.code_cache = np.zeros(capacity * internal_u, dtype=np.int64)
+        self.code_cache = np.zeros(capacity * (internal_u + 2), dtype=np.int64)   # per-episode stride padded to 16 bytes
         self.cache_state = np.full((capacity, 2), -1, dtype=np.int32)
 
     def set_state(self, uLin, pbest, old_input):

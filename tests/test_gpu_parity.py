@@ -412,3 +412,38 @@ def test_handles_with_different_trees_share_a_kernel_instance(bmpc):
         assert (r["status"] <= abi.STATUS_CONVERGED).all()
     for h in (small, large, tiny):
         h.close()
+
+
+def test_staged_episode_state_gives_identical_results(bmpc):
+    """The next episode's uLin / active-set codes / rho cache staged into shared memory by bulk copies (cp.async.bulk +
+    mbarrier) while the current episode is solved: same arithmetic, so three closed-loop steps of 4096 episodes must agree
+    bit for bit with the handle that reads the same data from global memory.  Staging is opt-in (reserved[6] bit 1): it
+    measured slower than the plain loads (profiles/r02_staging_ab.md)."""
+    import torch
+    B = 4096
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=99)
+    runs = []
+    for flag in (2, 0):
+        cfg = scenarios.highway_config(batch_capacity=B)
+        cfg.reserved[6] = flag
+        mpc = bmpc.BatchedBranchMPC(cfg)
+        assert mpc.staging_enabled() == (flag == 2)
+        t = [torch.as_tensor(a.copy(), device="cuda") for a in (x0, z0, xref, pp)]
+        outs = []
+        for _ in range(3):
+            r = mpc.solve(t[0], t[1], t[2], t[3], outputs=("u0", "objective", "status", "iters", "nfact", "nsolve"))
+            outs.append({k: v.clone() for k, v in r.items()})
+            mpc.plant_step(t[0], r["u0"], t[1], 0, t[3])
+        torch.cuda.synchronize()
+        runs.append(outs)
+        mpc.close()
+    for a, b in zip(*runs):
+        assert int((a["status"] <= 1).sum()) == B
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    chain = scenarios.highway_config(batch_capacity=8)
+    chain.controller = abi.CTRL_ROBUST
+    chain.reserved[6] = 2
+    ch = bmpc.BatchedBranchMPC(chain)
+    assert not ch.staging_enabled()              # chain controllers read their state from global memory
+    ch.close()
