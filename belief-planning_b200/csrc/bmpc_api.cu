@@ -23,7 +23,9 @@
 // MODE = BMPC_SLAB_SHARED (whole slab in shared memory), BMPC_SLAB_SPLIT (iterate fields in shared memory, factor fields
 // in this warp's global region, which stays L2-resident), BMPC_SLAB_GLOBAL (everything in the global region).
 template <class M, int NR, int MODE, int NC = 1>
-__global__ void __launch_bounds__(BMPC_LANES, 4) bmpc_solve_kernel() {
+// Launch bounds 384 x 1 = at most 168 registers per thread: four teams of 96 lanes, two of 192 or one of 256 fit an SM; the
+// block size is the team size the host picked for the tree (configure_instance).
+__global__ void __launch_bounds__(384, 1) bmpc_solve_kernel() {
   const KParams& P = bmpc_cP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
@@ -306,6 +308,7 @@ struct bmpc_handle {
   real* nu_cache = nullptr; // BranchMPC_CVaR: risk multipliers of each episode's last step
   real* cv_ws = nullptr;    // BranchMPC_CVaR: per-team scratch of the master problem
   real* lut = nullptr;      // lookup table of the *_REF policies: grid then values
+  int team_lanes = 96;      // threads per block = lanes of one team
   real* bel_ws = nullptr;   // belief-state MPC: per-team linearisation trajectory of the augmented state
   KParams* captured = nullptr;            // pinned parameter blocks for launches recorded into CUDA graphs (BMPC_MAX_CAPTURED,
   int captured_used = 0;                  // allocated at create: nothing may be allocated while a stream is capturing)
@@ -351,7 +354,7 @@ static int try_mode(bmpc_handle* h, int max_optin, int* per_sm) {
   if (smem > (size_t)max_optin) return BMPC_OK;   // does not fit: caller falls through to the next mode
   if (smem > 0)
     BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, MODE, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE, NC>, BMPC_LANES, smem));
+  BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, bmpc_solve_kernel<M, NR, MODE, NC>, 96, smem));
   return BMPC_OK;
 }
 
@@ -382,6 +385,27 @@ static int configure_instance(bmpc_handle* h) {
   if (per_sm < 1 || h->mode == 0) { h->err = "kernel does not fit on an SM"; return BMPC_E_CUDA; }
   if (h->cfg.reserved[1] > 0 && per_sm > h->cfg.reserved[1]) per_sm = h->cfg.reserved[1];   // occupancy cap (experiments)
   h->grid = per_sm * h->num_sms;
+  // Team size: three warps when four teams share an SM (the default highway tree); trees that leave the SM emptier get more
+  // lanes for their node-parallel passes, as far as nodes, registers (168 per thread) and the placement's occupancy allow.
+  h->team_lanes = 96;
+  {
+    int want_lanes = per_sm >= 3 ? 96 : (per_sm == 2 ? 192 : 256);   // measured (profiles/r02_staging_ab.md)
+    if (const char* e = getenv("BMPC_TEAM_LANES")) want_lanes = atoi(e);   // experiments
+    const int node_lanes = ((h->P.totalu + 31) / 32) * 32;
+    if (want_lanes > node_lanes) want_lanes = node_lanes < 96 ? 96 : node_lanes;
+    if (want_lanes < 32 || want_lanes > 32 * BMPC_MAX_TEAM_WARPS || (want_lanes & 31)) want_lanes = 96;
+    if (want_lanes != 96) {
+      int fit = 0;
+      const size_t smem_now = (h->mode == BMPC_SLAB_GLOBAL) ? 0 : (h->mode == BMPC_SLAB_SPLIT
+          ? Solver<M, NR, BMPC_SLAB_SPLIT, NC>::slab_reals(h->P.nup, h->P.nbx) : Solver<M, NR, BMPC_SLAB_SHARED, NC>::slab_reals(h->P.nup, h->P.nbx)) * sizeof(real);
+      cudaError_t e2 = h->mode == BMPC_SLAB_SHARED
+          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, want_lanes, smem_now)
+          : h->mode == BMPC_SLAB_SPLIT
+              ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC>, want_lanes, smem_now)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC>, want_lanes, smem_now);
+      if (e2 == cudaSuccess && fit >= per_sm) h->team_lanes = want_lanes;
+    }
+  }
   if (h->mode == BMPC_SLAB_SPLIT) {
     using S = Solver<M, NR, BMPC_SLAB_SPLIT, NC>;
     h->P.slab_reals = S::slab_reals(h->P.nup, h->P.nbx);
@@ -409,7 +433,7 @@ static int configure_instance(bmpc_handle* h) {
       int fit = 0;
       if (with_stage <= (size_t)max_optin) {
         BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_stage));
-        BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, BMPC_LANES, with_stage));
+        BMPC_CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, h->team_lanes, with_stage));
       }
       const int resident = h->grid / h->num_sms;
       if (fit >= resident) {
@@ -430,12 +454,12 @@ static int launch_instance(bmpc_handle* h, const KParams& P, int grid, cudaStrea
   // instance with a smaller tree may have lowered it since this one was created
   if (h->mode == BMPC_SLAB_SHARED) {
     BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->slab_bytes));
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, BMPC_LANES, h->slab_bytes, s>>>();
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SHARED, NC><<<grid, h->team_lanes, h->slab_bytes, s>>>();
   } else if (h->mode == BMPC_SLAB_SPLIT) {
     BMPC_CK(h, cudaFuncSetAttribute(bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->slab_bytes));
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, BMPC_LANES, h->slab_bytes, s>>>();
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_SPLIT, NC><<<grid, h->team_lanes, h->slab_bytes, s>>>();
   } else {
-    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, BMPC_LANES, 0, s>>>();
+    bmpc_solve_kernel<M, NR, BMPC_SLAB_GLOBAL, NC><<<grid, h->team_lanes, 0, s>>>();
   }
   BMPC_CK(h, cudaGetLastError());
   return BMPC_OK;

@@ -1,6 +1,7 @@
 // Portability layer of libbranchmpc: the solver text in bmpc_models.h / bmpc_solver.h is written once
-// against these few primitives.  nvcc builds it as the sm_100a kernel: one TEAM of BMPC_TEAM_WARPS warps (one thread
-// block) owns one problem, BMPC_LANES = 32 * BMPC_TEAM_WARPS lanes; the node-parallel passes spread the tree's nodes
+// against these few primitives.  nvcc builds it as the sm_100a kernel: one TEAM of warps (one thread block: three warps
+// for the default trees, up to eight for trees that leave the SM emptier) owns one problem, BMPC_LANES = blockDim.x lanes;
+// the node-parallel passes spread the tree's nodes
 // over all lanes of the team (97 highway nodes = one round of 96 lanes + the root), the tree sweeps use one lane per
 // branch of a level.  tests/hostsim builds the SAME text with g++ as a single-lane program
 // (BMPC_LANES = 1, barriers and reductions degenerate) so that the algorithm can be checked against
@@ -19,7 +20,10 @@
 #ifndef BMPC_TEAM_WARPS
 #define BMPC_TEAM_WARPS 3
 #endif
-#define BMPC_LANES (32 * BMPC_TEAM_WARPS)
+#define BMPC_MAX_TEAM_WARPS 8
+// lanes of a team = threads of its block: 96 by default, more for trees that leave room on the SM (chosen per handle by the
+// host, bmpc_api.cu configure_instance); device code only
+#define BMPC_LANES ((int)blockDim.x)
 #define BMPC_BLANES 32
 #else
 #define BMPC_HD
@@ -93,12 +97,14 @@ BMPC_D bool team_leader() {
 #if defined(__CUDA_ARCH__) && BMPC_TEAM_WARPS > 1
 #define BMPC_TEAM_COMBINE(T, v, OP)                                  \
   {                                                                  \
-    __shared__ T red_[BMPC_TEAM_WARPS];                              \
+    __shared__ T red_[BMPC_MAX_TEAM_WARPS];                          \
     __syncthreads();                                                 \
     if ((threadIdx.x & 31) == 0) red_[threadIdx.x >> 5] = v;         \
     __syncthreads();                                                 \
     v = red_[0];                                                     \
-    _Pragma("unroll") for (int w_ = 1; w_ < BMPC_TEAM_WARPS; ++w_) { \
+    /* unrolled with an early exit: a loop with a runtime trip count here cost 6 % of the whole kernel (measured) */ \
+    _Pragma("unroll") for (int w_ = 1; w_ < BMPC_MAX_TEAM_WARPS; ++w_) { \
+      if (w_ >= (BMPC_LANES >> 5)) break;                            \
       const T o_ = red_[w_];                                         \
       v = OP;                                                        \
     }                                                                \
