@@ -273,7 +273,13 @@ def timed_steps(parts, K, W, flush, barrier, outputs=("u0", "status", "iters", "
     """W untimed + K timed closed-loop steps; one step = solve + plant step of every part.  Returns per-step event times (ms),
     per-part stats of the timed steps and the kernel launches counted by the library."""
     import torch
-    stats = [{k: [] for k in ("iters", "nfact", "nsolve", "status")} for _ in parts]
+    names = ("iters", "nfact", "nsolve", "status")
+    stats = [{k: [] for k in names} for _ in parts]
+    # per-step statistics are copied into rows of buffers allocated BEFORE the timed region (row K = scratch of the untimed
+    # steps): a tensor allocated inside it can make the caching allocator call cudaMalloc, which drains the queue and shows
+    # up as a 20-30 ms step (seen once in ~20 steps before this)
+    bufs = [None] * len(parts)
+    timed_count = [0]
 
     def one_step(timed):
         if flush is not None:
@@ -287,12 +293,15 @@ def timed_steps(parts, K, W, flush, barrier, outputs=("u0", "status", "iters", "
             else:
                 out = pt["mpc"].solve(pt["x"], pt["z"], pt["r"], pt["p"], outputs=outputs)
             pt["mpc"].plant_step(pt["x"], out["u0"], pt["z"], 0, pt["p"])
-            keep = {k: out[k].clone() for k in stats[i]}     # warm-up steps do exactly what timed steps do
-            if timed:
-                for k in stats[i]:
-                    stats[i][k].append(keep[k])
+            if bufs[i] is None:
+                bufs[i] = {k: torch.empty((K + 1,) + tuple(out[k].shape), dtype=out[k].dtype, device=out[k].device) for k in names}
+            row = timed_count[0] if timed else K
+            for k in names:                                   # warm-up steps do exactly what timed steps do
+                bufs[i][k][row].copy_(out[k])
             pt["last"] = out
         e1.record()
+        if timed:
+            timed_count[0] += 1
         return e0, e1
 
     for _ in range(W):
@@ -316,6 +325,9 @@ def timed_steps(parts, K, W, flush, barrier, outputs=("u0", "status", "iters", "
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = sum(pt["mpc"].launch_count() for pt in parts) - l0
+    for i in range(len(parts)):
+        for k in names:
+            stats[i][k] = [bufs[i][k][s] for s in range(K)]
     return [e0.elapsed_time(e1) for e0, e1 in events], stats, launches, t_wall
 
 
