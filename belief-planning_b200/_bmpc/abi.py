@@ -70,6 +70,13 @@ class EnvState(C.Structure):
                 ("u_obs", C.c_void_p)]
 
 
+class MergeEnvState(C.Structure):
+    """bmpc_merge_env_state (include/branchmpc.h)."""
+    _fields_ = [("x", C.c_void_p), ("z", C.c_void_p), ("lane_id", C.c_void_p), ("collided", C.c_void_p), ("xref", C.c_void_p),
+                ("S", C.c_void_p), ("state_bounds", C.c_void_p), ("u_obs", C.c_void_p), ("table_x", C.c_void_p),
+                ("table_y", C.c_void_p), ("table_psi", C.c_void_p), ("table_n", _i32)]
+
+
 # every symbol include/branchmpc.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("bmpc_version", C.c_int, []),
@@ -109,6 +116,8 @@ SYMBOLS = [
     ("bmpc_env_step", C.c_int, [C.c_void_p, C.POINTER(EnvState), C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.POINTER(Outputs), C.c_void_p]),
     ("bmpc_staging_enabled", C.c_int, [C.c_void_p]),
+    ("bmpc_env_step_merge", C.c_int, [C.c_void_p, C.POINTER(MergeEnvState), C.c_int64, C.c_int32, C.c_int32, _dbl, _dbl,
+                                      C.POINTER(Outputs), C.c_void_p]),
     ("bmpc_get_launch_info", C.c_int, [C.c_void_p, _pi, _pi, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("bmpc_launch_count", C.c_int64, [C.c_void_p]),
     ("bmpc_measure_fp64_peak", C.c_double, [C.c_int, C.c_int]),

@@ -112,3 +112,58 @@ class BatchedQuadEnv(_BatchedEnv):
 
     def _extra(self):
         return 0, C.cast(self._sizes, C.c_void_p)
+
+
+class BatchedMergeEnv:
+    """Highway_env_branch.Highway_env_merge (:271-380) for a batch of episodes, stepped on the device by
+    `bmpc_env_step_merge`: x0, z0 (count, 4); the ramp tables are the arrays `merge_geometry` returns."""
+    _fields = ("x", "z", "lane_id", "collided", "xref", "S", "state_bounds", "u_obs")
+
+    def __init__(self, mpc, x0, z0, table_x, table_y, table_psi, N_lane=2, merge_lane=1, merge_s=50.0, v0=20.0, lane_id=1):
+        import torch
+        if not isinstance(mpc, batch.BatchedBranchMPC) or mpc.cfg.model != abi.MODEL_MERGE:
+            raise TypeError("mpc must be a BatchedBranchMPC of the merge model")
+        self.mpc = mpc
+        self.dev = torch.device("cuda", mpc.cfg.device)
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        z0 = np.ascontiguousarray(np.atleast_2d(z0), dtype=np.float64)
+        B = self.count = x0.shape[0]
+        if x0.shape != (B, 4) or z0.shape != (B, 4) or B > mpc.capacity:
+            raise ValueError("x0, z0 must be (count, 4) with count <= batch_capacity")
+        t64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.dev)
+        self.x, self.z = t64(x0), t64(z0)
+        self.lane_id = torch.full((B,), int(lane_id), dtype=torch.int32, device=self.dev)
+        self.collided = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.xref = torch.zeros((B, 4), dtype=torch.float64, device=self.dev)
+        self.S = torch.zeros((B, 4, 4), dtype=torch.float64, device=self.dev)
+        self.state_bounds = torch.zeros((B, 2, 2), dtype=torch.float64, device=self.dev)
+        self.u_obs = torch.zeros((B, 2), dtype=torch.float64, device=self.dev)
+        self.tab = [t64(np.asarray(a).reshape(-1)) for a in (table_x, table_y, table_psi)]
+        if not (len(self.tab[0]) == len(self.tab[1]) == len(self.tab[2]) >= 2):
+            raise ValueError("the three ramp tables must have the same length")
+        self.N_lane, self.merge_lane, self.merge_s, self.v0 = int(N_lane), int(merge_lane), float(merge_s), float(v0)
+        self.t = 0
+        self.last = None
+
+    def step(self, outputs=batch.LIGHT_OUTPUTS, stream=None):
+        import torch
+        mpc = self.mpc
+        if "u0" not in outputs:
+            outputs = ("u0",) + tuple(outputs)
+        bufs = mpc.device_outputs(self.count, outputs)
+        out = abi.Outputs(**{k: bufs[k].data_ptr() for k in bufs})
+        if stream is None:
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+        st = abi.MergeEnvState(x=self.x.data_ptr(), z=self.z.data_ptr(), lane_id=self.lane_id.data_ptr(),
+                               collided=self.collided.data_ptr(), xref=self.xref.data_ptr(), S=self.S.data_ptr(),
+                               state_bounds=self.state_bounds.data_ptr(), u_obs=self.u_obs.data_ptr(),
+                               table_x=self.tab[0].data_ptr(), table_y=self.tab[1].data_ptr(), table_psi=self.tab[2].data_ptr(),
+                               table_n=len(self.tab[0]))
+        mpc._check(mpc.lib.bmpc_env_step_merge(mpc.h, C.byref(st), self.count, self.N_lane, self.merge_lane, self.merge_s,
+                                               self.v0, C.byref(out), C.c_void_p(stream)), "bmpc_env_step_merge")
+        self.t += 1
+        self.last = bufs
+        return bufs
+
+    def host(self):
+        return {k: getattr(self, k).cpu().numpy() for k in self._fields}

@@ -1065,6 +1065,37 @@ int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int3
   return BMPC_OK;
 }
 
+int bmpc_env_step_merge(bmpc_handle* h, const bmpc_merge_env_state* env, int64_t count, int32_t n_lane, int32_t merge_lane,
+                        double merge_s, double v0, const bmpc_outputs* out, void* stream) {
+  if (!h) return BMPC_E_INVALID;
+  if (h->cfg.model != BMPC_MODEL_MERGE) { h->err = "bmpc_env_step_merge drives BMPC_MODEL_MERGE handles"; return BMPC_E_INVALID; }
+  if (!env || !out || count < 0 || n_lane < 1 || merge_lane < 1) { h->err = "bad argument"; return BMPC_E_INVALID; }
+  if (!env->x || !env->z || !env->lane_id || !env->collided || !env->xref || !env->S || !env->state_bounds || !env->u_obs ||
+      !env->table_x || !env->table_y || !env->table_psi || env->table_n < 2 || !out->u0) {
+    h->err = "bmpc_env_step_merge needs every state array, the three tables and out->u0";
+    return BMPC_E_INVALID;
+  }
+  if (count == 0) return BMPC_OK;
+  if (count > h->cfg.batch_capacity) { h->err = "count exceeds batch_capacity"; return BMPC_E_CAPACITY; }
+  BMPC_CK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  MergeEnvArgs a;
+  a.x = env->x; a.z = env->z; a.lane_id = env->lane_id; a.collided = env->collided; a.xref = env->xref; a.S = env->S;
+  a.bounds = env->state_bounds; a.u_obs = env->u_obs; a.tab_x = env->table_x; a.tab_y = env->table_y; a.tab_psi = env->table_psi;
+  a.tab_n = env->table_n; a.count = (int)count; a.n_lane = n_lane; a.merge_lane = merge_lane; a.merge_s = merge_s; a.v0 = v0;
+  a.psimax = h->P.rhi[1];   // mpc.psimax = bx[0][2][0] (MPC_branch.py:1621): the upper bound of the heading row
+  const int threads = 128, blocks = (int)((count + threads - 1) / threads);
+  bmpc_env_pre_merge<<<blocks, threads, 0, s>>>(h->P, a);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  const int rc = bmpc_solve_transformed(h, env->x, env->z, env->xref, nullptr, env->S, env->state_bounds, count, out, stream);
+  if (rc != BMPC_OK) return rc;
+  bmpc_env_post<HighwayModel><<<blocks, threads, 0, s>>>(h->P, env->x, env->z, out->u0, env->u_obs, (int)count);
+  BMPC_CK(h, cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
 int bmpc_staging_enabled(const bmpc_handle* h) { return h ? h->P.stage_on : BMPC_E_INVALID; }
 
 int bmpc_get_launch_info(const bmpc_handle* h, int32_t* slab_mode, int32_t* warps, int64_t* smem_bytes,

@@ -2,6 +2,8 @@
 // controller calls, one thread per episode, so that consecutive MPC steps never leave the GPU.
 //   highway  : Highway_env_branch.py:83-184 (Highway_env.step) + the collision flag of Highway_sim (:421-429)
 //   quadruped: quadruped_env.py:67-130 (Quad_env.step)
+//   merge    : Highway_env_branch.py:324-380 (Highway_env_merge.step): lane id of the ego, ramp coordinates (state transform S,
+//              reference and bounds from the ramp's lookup tables at the ego's x), the obstacle follows its first policy
 // `pre` runs before the solve (obstacle arg-max policy, lane bookkeeping, lane-change target, xRef rule); `post` applies
 // both Euler plants.  The reference's quirks are kept (see oracle/env.py for the list and the pinning fixtures):
 // rollouts use the symbolic policy branches and the lane-change target from BEFORE this step's update; the collision
@@ -184,4 +186,65 @@ __global__ void bmpc_env_post(const __grid_constant__ KParams P, real* x, real* 
   for (int q = 0; q < NU; ++q) u[q] = u_obs[(size_t)i * NU + q];
   M::step(P, s, u, sn);
   for (int q = 0; q < NX; ++q) z[(size_t)i * NX + q] = sn[q];
+}
+
+// ---- merge scenario ------------------------------------------------------------------------------------------------
+struct MergeEnvArgs {
+  real* x;            // [count][4] ego (in/out over pre+post)
+  real* z;            // [count][4] obstacle
+  int* lane_id;       // [count] ego: 1 = on the ramp, 0 = on the highway (sticky once x > merge_s + 8, :329-330)
+  int* collided;      // [count] in/out, sticky (Highway_sim :421-429)
+  real* xref;         // [count][4] out
+  real* S;            // [count][4][4] out
+  real* bounds;       // [count][2][2] out: (lo, hi) of the y row and of the psi row
+  real* u_obs;        // [count][2] out
+  const real* tab_x;  // ramp centre line: grid, y and heading (merge_geometry :227-262), n points
+  const real* tab_y;
+  const real* tab_psi;
+  int tab_n;
+  int count, n_lane, merge_lane;
+  real merge_s, v0, psimax;
+};
+
+BMPC_D real env_table(const real* gx, const real* gv, int n, real x) {
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (gx[mid] <= x) lo = mid; else hi = mid;
+  }
+  return gv[lo] + (gv[lo + 1] - gv[lo]) / (gx[lo + 1] - gx[lo]) * (x - gx[lo]);
+}
+
+__global__ void bmpc_env_pre_merge(const __grid_constant__ KParams P, const MergeEnvArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count) return;
+  real x[4], z[4];
+  for (int q = 0; q < 4; ++q) { x[q] = a.x[(size_t)i * 4 + q]; z[q] = a.z[(size_t)i * 4 + q]; }
+  const real dis = fmax(fabs(x[0] - z[0]) - 4.0, fabs(x[1] - z[1]) - 2.4);
+  if (dis < 0.0) a.collided[i] = 1;
+  int lane = a.lane_id[i];
+  if (x[0] > a.merge_s + 8.0) lane = 0;
+  a.lane_id[i] = lane;
+  real* S = a.S + (size_t)i * 16;
+  real* r = a.xref + (size_t)i * 4;
+  real* bd = a.bounds + (size_t)i * 4;
+  for (int q = 0; q < 16; ++q) S[q] = (q % 5 == 0) ? 1.0 : 0.0;
+  if (lane == 0) {
+    r[0] = 0.0; r[1] = (a.n_lane - 0.5) * 3.6; r[2] = a.v0; r[3] = 0.0;          // :351-353
+    bd[0] = P.rlo[0]; bd[1] = P.rhi[0]; bd[2] = P.rlo[1]; bd[3] = P.rhi[1];        // mpc.param.bx
+  } else {
+    const real y0 = env_table(a.tab_x, a.tab_y, a.tab_n, x[0]), psi0 = env_table(a.tab_x, a.tab_psi, a.tab_n, x[0]);
+    const real t = tan(psi0);
+    S[4] = -t;                                                                     // :357
+    r[0] = 0.0; r[1] = -t * x[0] + y0 + 1.8; r[2] = a.v0; r[3] = psi0;             // :358
+    bd[0] = -(t * x[0] - y0 - P.veh_W / 2.0);                                      // -bx[1]
+    bd[1] = -t * x[0] + y0 + 3.6 * a.merge_lane - P.veh_W / 2.0;                   //  bx[0]
+    bd[2] = -(-psi0 + a.psimax);                                                   // -bx[3]
+    bd[3] = psi0 + a.psimax;                                                       //  bx[2]
+  }
+  // every vehicle but the ego follows its first policy (:347-348); the obstacle drives on the highway (numeric branch)
+  real uo[2];
+  env_highway_policy_numeric(P, P.pol_kind[0], P.pol_par[0], z, uo);
+  a.u_obs[(size_t)i * 2] = uo[0];
+  a.u_obs[(size_t)i * 2 + 1] = uo[1];
 }

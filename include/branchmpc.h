@@ -334,6 +334,29 @@ typedef struct bmpc_env_state {
 int bmpc_env_step(bmpc_handle* h, const bmpc_env_state* env, int64_t count, int32_t t, int32_t n_lane,
                   const double* quad_sizes, const bmpc_outputs* out, void* stream);
 
+/* Merge scenario, one control period of Highway_env_merge.step (Highway_env_branch.py:324-380) for every episode, on the
+ * device: collision flag, the ego's lane id (1 = ramp, 0 = highway, sticky once x > merge_s + 8), the reference / state
+ * transform / state bounds of the call (ramp coordinates from the lookup tables refY, refpsi at the ego's x while on the ramp),
+ * the controller solve (as bmpc_solve_transformed), and both plants (the obstacle follows the handle's first policy).
+ * BMPC_MODEL_MERGE handles.  All pointers of the state are DEVICE pointers; the tables are device arrays of table_n points
+ * (grid strictly increasing). */
+typedef struct bmpc_merge_env_state {
+  double* x;            /* [count][4] ego state, in/out */
+  double* z;            /* [count][4] obstacle state, in/out */
+  int32_t* lane_id;     /* [count] in/out */
+  int32_t* collided;    /* [count] in/out, sticky */
+  double* xref;         /* [count][4] out */
+  double* S;            /* [count][4][4] out */
+  double* state_bounds; /* [count][2][2] out */
+  double* u_obs;        /* [count][2] out */
+  const double* table_x;   /* ramp centre line (merge_geometry :227-262): grid */
+  const double* table_y;   /*   y of the centre line   (refY)   */
+  const double* table_psi; /*   heading                (refpsi) */
+  int32_t table_n;
+} bmpc_merge_env_state;
+int bmpc_env_step_merge(bmpc_handle* h, const bmpc_merge_env_state* env, int64_t count, int32_t n_lane, int32_t merge_lane,
+                        double merge_s, double v0, const bmpc_outputs* out, void* stream);
+
 /* 1 if the solve kernel of this handle stages the NEXT episode's persistent state (uLin, active-set codes, rho cache) into
  * shared memory with bulk copies (cp.async.bulk + mbarrier) while it solves the current one; 0 if it reads them from global
  * memory at the start of each solve (the default; staging is requested with reserved[6] bit 1 and applies to the tree
