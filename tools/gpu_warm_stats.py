@@ -26,6 +26,11 @@ for s in range(int(os.environ.get("STEPS", "8"))):
     torch.cuda.synchronize()
     ms = mpc.last_kernel_ms()
     it, nf, ns, cy = (out[k].cpu().numpy() for k in ("iters", "nfact", "nsolve", "cycles"))
+    st = np.bincount(out["status"].cpu().numpy(), minlength=4).tolist()
+    if os.environ.get("BRIEF"):
+        print("step %d  %.2f ms  status %s  ADMM path %.1f %%  iters %.1f nfact %.2f" % (s, ms, st, 100 * (it > 0).mean(), it.mean(), nf.mean()), flush=True)
+        mpc.plant_step(t[0], out["u0"], t[1], 0, t[3])
+        continue
     warm = it == 0
     print("step %d  %.2f ms | warm-polish only %.1f %% (nfact %.2f nsolve %.1f, %.0f kcycles) | ADMM path %.1f %% (iters %.1f nfact %.2f nsolve %.1f, %.0f kcycles) | share of time on the ADMM path %.1f %%"
           % (s, ms, 100 * warm.mean(), nf[warm].mean() if warm.any() else 0, ns[warm].mean() if warm.any() else 0,
