@@ -169,7 +169,7 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.polish_careful = c.polish_careful > 0 ? c.polish_careful : 0;   // off: the interior-point fallback handles cycling sets
   P.warm_polish = c.warm_polish >= 0 ? 1 : 0;
   P.warm_passes = c.warm_polish > 0 ? c.warm_polish : (c.model == BMPC_MODEL_QUADRUPED ? 6 : 3);   // measured (profiles/r01_knob_matrix.md)
-  P.rho_refresh = c.rho_refresh > 0 ? c.rho_refresh : (c.rho_refresh < 0 ? 0 : 8);
+  P.rho_refresh = c.rho_refresh > 0 ? c.rho_refresh : (c.rho_refresh < 0 ? 0 : 16);   // 8 / 16 / 32: 5.06 / 5.01 / 4.97 ms per highway step (profiles/r02_staging_ab.md)
   P.alpha = c.alpha > 0.0 ? c.alpha : 1.6;
   P.theta = c.theta > 0.0 ? c.theta : 1.0;
   P.theta_u = c.theta_u > 0.0 ? c.theta_u : 1.0;
@@ -196,7 +196,13 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.ipm_y0 = 0.5;
   P.ipm = nullptr;
   P.ipm_reals = 0;
-  P.rebalance = c.reserved[0] == 1 ? 0 : 1;   // experimental switch
+  P.rebalance = (c.reserved[0] & 1) ? 0 : 1;   // experimental switches
+  P.warm_on_refresh = (c.reserved[0] & 2) ? 0 : 1;
+  P.warm_backoff = (c.reserved[0] & 4) ? 0 : 1;
+  {
+    const int ws = (c.reserved[0] >> 4) & 15;    // 0 = default, 15 = never skip
+    P.warm_skip = ws == 0 ? 3 : (ws == 15 ? 0 : ws);
+  }
   *out = P;
   return BMPC_OK;
 }

@@ -65,9 +65,14 @@ struct HighwayModel {
   static constexpr bool kStateTransform = false;   // per-episode state transform S and bounds bx (merge scenario only)
 
   // one Euler step of dubin (:17-34, :369)
+  static constexpr int HEADING = 3;   // index of the heading angle: the only argument of a transcendental in step / linearize
   BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) {
     real s, c;
     bmpc_sincos(x[3], &s, &c);
+    step_sc(P, x, u, s, c, xn);
+  }
+  // ... with sine and cosine of the heading supplied by the caller (Solver::rollouts evaluates three headings side by side)
+  BMPC_D static void step_sc(const KParams& P, const real* x, const real* u, real s, real c, real* xn) {
     xn[0] = x[0] + P.dt * (x[2] * c);
     xn[1] = x[1] + P.dt * (x[2] * s);
     xn[2] = x[2] + P.dt * u[0];
@@ -116,10 +121,24 @@ struct HighwayModel {
     }
   }
 
+  // the same, with the commonest policy answered in line: the out-of-line switch above is an indirect branch plus arguments
+  // through local memory, and the ego rollout under policy 0 (maintain in every reference scenario) pays it at every step
+  BMPC_D static void policy_fast(const KParams& P, int kind, const real* par, const real* x, real* u) {
+    if (kind == BMPC_POLICY_MAINTAIN) {
+      u[0] = 0.0;
+      u[1] = -P.Kpsi * x[3];
+    } else {
+      policy(P, kind, par, x, u);
+    }
+  }
+
   // dyn_linearization (:284-291): compressed A, C and the successor state
   BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
     real s, c;
     bmpc_sincos(x[3], &s, &c);
+    linearize_sc(P, x, u, s, c, lin, cc, xn);
+  }
+  BMPC_D static void linearize_sc(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc, real* xn) {
     const real dt = P.dt, v = x[2];
     lin[0] = dt * c;
     lin[1] = -dt * v * s;
@@ -288,9 +307,13 @@ struct QuadrupedModel {
   static constexpr int NLIN = 4;  // dt*cos, dt*sin, A[0][2], A[1][2]
   static constexpr int NCC = 2;
 
+  static constexpr int HEADING = 2;
   BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) {
     real s, c;
     bmpc_sincos(x[2], &s, &c);
+    step_sc(P, x, u, s, c, xn);
+  }
+  BMPC_D static void step_sc(const KParams& P, const real* x, const real* u, real s, real c, real* xn) {
     xn[0] = x[0] + P.dt * (u[0] * c - u[1] * s);
     xn[1] = x[1] + P.dt * (u[0] * s + u[1] * c);
     xn[2] = x[2] + P.dt * u[2];
@@ -300,9 +323,13 @@ struct QuadrupedModel {
     u[1] = 0.0;
     u[2] = 0.0;
   }
+  BMPC_D static void policy_fast(const KParams& P, int kind, const real* par, const real* x, real* u) { policy(P, kind, par, x, u); }
   BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
     real s, c;
     bmpc_sincos(x[2], &s, &c);
+    linearize_sc(P, x, u, s, c, lin, cc, xn);
+  }
+  BMPC_D static void linearize_sc(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc, real* xn) {
     const real dt = P.dt;
     lin[0] = dt * c;
     lin[1] = dt * s;
@@ -476,8 +503,14 @@ struct RateAug {
   static constexpr bool RATE = true;
   static constexpr bool kStateTransform = false;
 
+  static constexpr int HEADING = M::HEADING;
   BMPC_D static void step(const KParams& P, const real* x, const real* u, real* xn) { M::step(P, x, u, xn); }
+  BMPC_D static void step_sc(const KParams& P, const real* x, const real* u, real s, real c, real* xn) { M::step_sc(P, x, u, s, c, xn); }
+  BMPC_D static void linearize_sc(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc, real* xn) {
+    M::linearize_sc(P, x, u, s, c, lin, cc, xn);
+  }
   BMPC_D static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) { M::policy(P, kind, par, x, u); }
+  BMPC_D static void policy_fast(const KParams& P, int kind, const real* par, const real* x, real* u) { M::policy_fast(P, kind, par, x, u); }
   BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {
     M::linearize(P, x, u, lin, cc, xn);
   }

@@ -34,6 +34,9 @@ struct KParams {
   int rf_one[BMPC_MAX_ROWS];    // index of the row's only non-zero entry, or -1 for a general row
   real ulo[BMPC_MAX_D], uhi[BMPC_MAX_D];
   // ---- solver ----
+  int warm_on_refresh;          // 1: the warm polish is also tried on the solves that refresh rho
+  int warm_backoff;             // 1: that skip doubles with every further failed attempt in a row (at most 24 solves)
+  int warm_skip;                // solves without a warm-polish attempt after one that ended on the ADMM path
   int max_iter, polish_first, polish_every, polish_passes, polish_al_iters, polish_careful, warm_polish, rebalance, rho_refresh, warm_passes, check_every, polish_stable, polish_force;
   real alpha, theta, theta_u, eps_abs, polish_big, polish_mult, rho_u_feedback;
   float inv_N, inv_m;           // reciprocals, rounded up, for exact small-integer division (bmpc_idiv)

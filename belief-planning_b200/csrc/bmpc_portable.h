@@ -184,3 +184,48 @@ BMPC_DN void bmpc_sincos(real a, real* s, real* c) {
 #endif
 }
 BMPC_DN real bmpc_exp(real a) { return exp(a); }
+// sin and cos of one angle as straight-line code (device): three-term Cody-Waite reduction by pi/2 with fused multiply-adds and
+// the degree-13 / degree-14 minimax kernels of fdlibm (k_sin.c, k_cos.c), within 1 ulp for |a| < 1e5.  No branch and no call, so
+// several of them written one after the other are scheduled into each other - the three rollouts of a tree level (bmpc_sincos3)
+// pay one latency instead of three out-of-line calls.  Larger or non-finite arguments take the library routine.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void bmpc_sincos_core(real a, real& s, real& c) {
+  const real magic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer and leaves it in the low word
+  const real t = fma(a, 0.6366197723675814, magic);
+  const int q = __double2loint(t);
+  const real j = t - magic;
+  real r = fma(-j, 1.5707963267948966, a);
+  r = fma(-j, 6.123233995736766e-17, r);
+  r = fma(-j, -1.4973849048591698e-33, r);
+  const real z = r * r;
+  real ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  real pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const real sr = fma(ps * z, r, r);
+  const real cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const real s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+  s = (q & 2) ? -s0 : s0;
+  c = ((q + 1) & 2) ? -c0 : c0;
+}
+#endif
+// sc = {sin a0, cos a0, sin a1, cos a1, sin a2, cos a2}
+BMPC_D void bmpc_sincos3(real a0, real a1, real a2, real* sc) {
+#if defined(__CUDA_ARCH__)
+  if (fmax(fabs(a0), fmax(fabs(a1), fabs(a2))) < 1.0e5) {
+    bmpc_sincos_core(a0, sc[0], sc[1]);
+    bmpc_sincos_core(a1, sc[2], sc[3]);
+    bmpc_sincos_core(a2, sc[4], sc[5]);
+    return;
+  }
+#endif
+  bmpc_sincos(a0, &sc[0], &sc[1]);
+  bmpc_sincos(a1, &sc[2], &sc[3]);
+  bmpc_sincos(a2, &sc[4], &sc[5]);
+}

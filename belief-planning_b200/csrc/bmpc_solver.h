@@ -466,13 +466,15 @@ struct Solver {
 #pragma unroll 1
         for (int t = 0; t < PP.N; ++t) {
           const int kp = kpc + t;
-          real u[NU], xn[NXP];
-          M::policy(PP, kind0, par0, xe, u);
-          M::step(PP, xe, u, xn);
+          real u[NU], xn[NXP], sc[6];
+          // the three headings are known at the top of the step: their sines and cosines are computed side by side
+          bmpc_sincos3(xe[M::HEADING], z[M::HEADING], xb[M::HEADING], sc);
+          M::policy_fast(PP, kind0, par0, xe, u);
+          M::step_sc(PP, xe, u, sc[0], sc[1], xn);
 #pragma unroll
           for (int q = 0; q < NXP; ++q) xe[q] = xn[q];
           M::policy(PP, kind, par, z, u);
-          M::step(PP, z, u, xn);
+          M::step_sc(PP, z, u, sc[2], sc[3], xn);
 #pragma unroll
           for (int q = 0; q < NXP; ++q) {
             z[q] = xn[q];
@@ -486,7 +488,7 @@ struct Solver {
           real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
           for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
-          M::linearize(PP, xb, u, lin, cc, xn);
+          M::linearize_sc(PP, xb, u, sc[4], sc[5], lin, cc, xn);
 #pragma unroll
           for (int q = 0; q < M::NLIN; ++q) F(F_LIN + q, kp) = lin[q];
 #pragma unroll
@@ -511,7 +513,8 @@ struct Solver {
   }
 
   BMPC_DN void expand_tree() {
-    const long long prof_t0 = prof_begin(2);
+    const long long prof_t0 = prof_begin(2) + prof_begin(11);   // (11: staging of the shifted inputs, 10: rollouts, 13: safety values
+                                                                // and probabilities, 12: node set-up - parts of phase 2)
     const int started = PP.started[prob];
     const real* uLin = ep_uLin();
     int* pbest = PP.pbest + (size_t)prob * PP.nbranch;
@@ -566,8 +569,12 @@ struct Solver {
       if (use_codes) stp()[kp] = codes[ksrc];   // the active set shifts in time like the inputs
     }
     team_sync();
+    prof_end(11, prof_t0);
+    const long long prof_t1 = prof_begin(10);
     if (team_leader()) rollouts();
     team_sync();
+    prof_end(10, prof_t1);
+    const long long prof_t2 = prof_begin(13);
     // safety value of every child branch: soft-min (gamma = 5) over the safety terms of its N steps
 #pragma unroll 1
     BMPC_FOR_NODES(k) {
@@ -638,12 +645,17 @@ struct Solver {
         for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
         real sum = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < m; ++j) sum += M::branch_weight(PP, EXp()[NS * (fc + j)], himax);
+        for (int j = 0; j < m; ++j) {
+          const real wj = M::branch_weight(PP, EXp()[NS * (fc + j)], himax);
+          EXp()[NS * (fc + j) + 1] = wj;   // kept for the normalisation below (two exponentials per child)
+          sum += wj;
+        }
         int best = 0;
         real pb = -1.0;
+        const real rsum = bmpc_div(1.0, sum);
 #pragma unroll 1
         for (int j = 0; j < m; ++j) {
-          const real p = bmpc_div(M::branch_weight(PP, EXp()[NS * (fc + j)], himax), sum);
+          const real p = EXp()[NS * (fc + j) + 1] * rsum;
           Wbp()[fc + j] = Wbp()[b] * p;
           if (PP.out.branch_p) PP.out.branch_p[((size_t)prob * PP.nbranch + b) * m + j] = p;
           if (PP.ctrl == BMPC_CTRL_CVAR) cvP()[b * m + j] = p;
@@ -659,7 +671,10 @@ struct Solver {
       for (int b = BMPC_LANE_ID; b < PP.nbranch; b += BMPC_LANES) PP.out.branch_w[(size_t)prob * PP.nbranch + b] = Wbp()[b];
     }
     if (PP.ctrl == BMPC_CTRL_CVAR) cvar_first_weights();
+    prof_end(13, prof_t2);
+    const long long prof_t3 = prof_begin(12);
     node_setup_all();
+    prof_end(12, prof_t3);
     rlin = 0.0;
     if (PP.ctrl != BMPC_CTRL_CVAR) {
 #pragma unroll
@@ -3187,7 +3202,15 @@ struct Solver {
     int* cstate = PP.cache_state + (size_t)prob * 2;   // [0] age of the cached rho (-1: none), [1] cached codes valid
     // the risk multipliers move the branch weights, and with them the curvature rho is matched to: no rho cache for CVaR
     const bool reuse_rho = !cvar && warm && PP.rho_refresh > 0 && cstate[0] >= 0 && cstate[0] < PP.rho_refresh;
-    use_codes = warm && PP.warm_polish && cstate[1] == 1 && (reuse_rho || cvar);
+    // cstate[1]: 0 = no valid codes; 1 = valid, start with the warm polish; k > 1 = valid, but the episode's last warm attempt
+    // ended on the ADMM path - and then the next one does too, 19 times out of 20 (measured: its active set is in flux for
+    // many steps in a row) - so the attempt is skipped for k - 1 more solves
+    // (low byte: that countdown; above it: how many attempts in a row have failed - the skip doubles with each, PP.warm_backoff)
+    const int code_state = cstate[1];
+    const int cs_count = code_state > 0 ? (code_state & 0xff) : 0, cs_level = code_state > 0 ? (code_state >> 8) : 0;
+    const bool skip_warm = !cvar && cs_count > 1;
+    use_codes = warm && PP.warm_polish && cs_count >= 1 && !skip_warm && (reuse_rho || cvar || PP.warm_on_refresh);
+    const bool tried_warm = use_codes;
     t_phase = 0;
 #if defined(__CUDA_ARCH__)
     stage_acquire();
@@ -3224,7 +3247,15 @@ struct Solver {
         if (PP.out.objective) PP.out.objective[prob] = J;
         PP.started[prob] = 1;
         cstate[0] = reuse_rho ? cstate[0] + 1 : 0;
-        cstate[1] = (status == BMPC_STATUS_POLISHED) ? 1 : 0;
+        if (status != BMPC_STATUS_POLISHED) cstate[1] = 0;
+        else if (skip_warm) cstate[1] = code_state - 1;
+        else if (cvar || !tried_warm) cstate[1] = (cs_level << 8) | 1;
+        else if (iters == 0) cstate[1] = 1;
+        else {
+          const int lvl = !PP.warm_backoff ? 1 : (cs_level < 3 ? cs_level + 1 : 4);
+          const int skip = PP.warm_skip << (lvl - 1);
+          cstate[1] = (lvl << 8) | (1 + (skip < 24 ? skip : 24));
+        }
       }
     } else {
       keep_plan();

@@ -127,7 +127,7 @@ typedef struct bmpc_config {
   int32_t polish_careful;  /* extra one-change-at-a-time passes when the set iteration cycles (0 = off, the default) */
   int32_t warm_polish;     /* warm solves first try a polish from the previous optimum's shifted active set:
                               number of active-set passes for that attempt (3; quadruped 6; <0 = off)        */
-  int32_t rho_refresh;     /* warm solves reuse the cached rho for this many steps (8; <0 = recompute every solve)   */
+  int32_t rho_refresh;     /* warm solves reuse the cached rho for this many steps (16; <0 = recompute every solve)  */
   double alpha;            /* over-relaxation (1.6)                                              */
   double theta, theta_u;   /* curvature-matched rho scale for state rows / inputs (1)            */
   double eps_abs;          /* ADMM residual tolerance for STATUS_CONVERGED (1e-6)                */
@@ -142,7 +142,10 @@ typedef struct bmpc_config {
   int32_t slab_mode;      /* BMPC_SLAB_*: where a problem's working set lives (0 = library picks) */
   int32_t batch_capacity; /* maximum number of episodes (persistent state slots)      */
   int32_t device;         /* CUDA device ordinal                                      */
-  int32_t reserved[8];    /* experiment switches, 0 = default: [0] 1 = no residual balancing of rho; [1] cap of resident
+  int32_t reserved[8];    /* experiment switches, 0 = default: [0] bit 0 = no residual balancing of rho, bit 1 = no warm-polish attempt on
+                             the solves that refresh rho, bit 2 = no doubling of the skip below, bits 4..7 = k: an episode whose warm-polish attempt
+                             ended on the ADMM path skips the attempt on its next k solves (0 = the default 3, 15 = never skip; with
+                             bit 2 clear k doubles with every further failed attempt in a row, up to 24); [1] cap of resident
                              warps per SM; [2] polish when at most this many nodes changed their implied set between
                              checks; [3] polish at the latest every this many ADMM iterations (80; quadruped 20); [4] interior-point
                              fallback after this many failed polish attempts (3; quadruped 1; <0 = never; 100 = always, without a polish attempt first); [5] its iteration cap (40);

@@ -447,3 +447,37 @@ def test_staged_episode_state_gives_identical_results(bmpc):
     ch = bmpc.BatchedBranchMPC(chain)
     assert not ch.staging_enabled()              # chain controllers read their state from global memory
     ch.close()
+
+
+def test_warm_polish_skip_does_not_change_the_plans(bmpc):
+    """An episode whose warm-polish attempt ended on the ADMM path skips the attempt on its next solves (reserved[0] bits 4..7,
+    doubling with bit 2 clear) and the attempt is also made on rho-refresh solves (bit 1 clear).  Either way the solve ends on
+    the certified optimum of the same QP: 14 closed-loop steps of 2048 episodes with the default schedule against the handle
+    that tries the warm polish on every solve (0xF0 | 2 | 4), every step from the same states."""
+    import torch
+    B = 2048
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=123)
+    handles = []
+    for flags in (0, 0xF0 | 2 | 4):
+        cfg = scenarios.highway_config(batch_capacity=B)
+        cfg.reserved[0] = flags
+        handles.append(bmpc.BatchedBranchMPC(cfg))
+    t = [torch.as_tensor(a.copy(), device="cuda") for a in (x0, z0, xref, pp)]
+    skipped_some = False
+    for step in range(14):
+        res = [h.solve(t[0], t[1], t[2], t[3], outputs=("u0", "objective", "status", "iters", "nfact")) for h in handles]
+        res = [{k: v.clone() for k, v in r.items()} for r in res]
+        a, b = res
+        assert int((a["status"] <= 1).sum()) == B and int((b["status"] <= 1).sum()) == B
+        du = (a["u0"] - b["u0"]).abs().amax(dim=1)
+        dj = (a["objective"] - b["objective"]).abs() / b["objective"].abs().clamp_min(1.0)
+        assert du.max().item() < TOL_U0 and dj.max().item() < TOL_OBJ, (step, du.max().item(), dj.max().item())
+        both = (a["status"] == 0) & (b["status"] == 0)      # certified by the polish on both sides: the same vertex
+        # (the polish certifies stationarity to 1e-7: flat directions of the cost leave the inputs free to ~1e-5)
+        assert du[both].max().item() < 1e-4 and dj[both].max().item() < 1e-6, (step, du[both].max().item(), dj[both].max().item())
+        if step > 2:
+            skipped_some |= bool((a["nfact"] < b["nfact"]).any().item())
+        handles[0].plant_step(t[0], b["u0"], t[1], 0, t[3])      # both handles continue from the same plant state
+    assert skipped_some      # the default schedule did save factorisations somewhere
+    for h in handles:
+        h.close()

@@ -12,13 +12,15 @@ from _bmpc import batch, scenarios  # noqa: E402
 
 NAMES = {0: "whole solve", 1: "interior point", 2: "tree expansion", 3: "rho selection / cache", 4: "factorisations",
          5: "backward + forward sweeps", 6: "node-parallel polish passes", 7: "adjoint sweep", 8: "ADMM row phase",
-         9: "final pass + caches"}
+         9: "final pass + caches", 10: "  expansion: rollouts", 11: "  expansion: input staging", 12: "  expansion: node set-up",
+         13: "  expansion: safety values, probabilities"}
+KS = [int(v) for v in os.environ["PHASES"].split(",")] if os.environ.get("PHASES") else list(range(10))
 kind = sys.argv[1] if len(sys.argv) > 1 else "hw"
 B = int(os.environ.get("B", "16384" if kind == "hw" else "8192"))
 steps = int(os.environ.get("STEPS", "5"))
 dev = torch.device("cuda", 0)
 rows = {}
-for k in range(10):
+for k in KS:
     if kind == "hw":
         cfg = scenarios.highway_config(batch_capacity=B)
         x0, z0, xref, pp = scenarios.highway_batch(B)
@@ -43,8 +45,8 @@ for s in (0, steps - 1):
     tot = rows[0][s][0]
     print("step %d (%s): kernel %.2f ms, mean problem time %.3f ms" % (s, "cold" if s == 0 else "warm", rows[0][s][1], tot))
     acc = 0.0
-    for k in range(1, 10):
+    for k in KS[1:]:
         v = rows[k][s][0]
-        acc += v
+        acc += v if k < 10 else 0.0
         print("   %-30s %.4f ms  %5.1f %%" % (NAMES[k], v, 100 * v / tot))
     print("   %-30s %.4f ms  %5.1f %%" % ("(unaccounted)", tot - acc, 100 * (tot - acc) / tot))

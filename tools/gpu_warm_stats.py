@@ -21,12 +21,18 @@ mpc = batch.BatchedBranchMPC(cfg)
 x0, z0, xref, pp = scenarios.highway_batch(B)
 t = [torch.as_tensor(a, device="cuda") for a in (x0, z0, xref, pp)]
 outs = ("u0", "status", "iters", "nfact", "nsolve", "cycles")
+prev_admm = None
 for s in range(int(os.environ.get("STEPS", "8"))):
     out = mpc.solve(*t, outputs=outs)
     torch.cuda.synchronize()
     ms = mpc.last_kernel_ms()
     it, nf, ns, cy = (out[k].cpu().numpy() for k in ("iters", "nfact", "nsolve", "cycles"))
     st = np.bincount(out["status"].cpu().numpy(), minlength=4).tolist()
+    admm = it > 0
+    if prev_admm is not None and os.environ.get("CORR"):
+        print("   P(ADMM path | ADMM path last step) = %.2f, P(ADMM path | warm-only last step) = %.2f; warm passes wasted by the first group: nfact of its warm successes %.2f"
+              % (admm[prev_admm].mean(), admm[~prev_admm].mean(), nf[prev_admm & ~admm].mean()))
+    prev_admm = admm
     if os.environ.get("BRIEF"):
         print("step %d  %.2f ms  status %s  ADMM path %.1f %%  iters %.1f nfact %.2f" % (s, ms, st, 100 * (it > 0).mean(), it.mean(), nf.mean()), flush=True)
         mpc.plant_step(t[0], out["u0"], t[1], 0, t[3])
