@@ -121,14 +121,36 @@ struct HighwayModel {
     }
   }
 
-  // the same, with the commonest policy answered in line: the out-of-line switch above is an indirect branch plus arguments
-  // through local memory, and the ego rollout under policy 0 (maintain in every reference scenario) pays it at every step
+  // The same for the rollouts of the tree expansion, in line and on values: the out-of-line switch above is an indirect
+  // branch with its arguments in local memory, paid at every step of a rollout.  `par` is the caller's register copy of the
+  // policy's parameters; only the lookup-table policies of the merge scenario go through a call.
+  struct Input2 { real a, r; };
+  BMPC_DN static Input2 policy_ref(const KParams& P, int kind, real par0, real x0, real v, real psi) {
+    const real xs[4] = {x0, 0.0, v, psi}, ps[4] = {par0, 0.0, 0.0, 0.0};
+    real u[2];
+    policy(P, kind, ps, xs, u);
+    return Input2{u[0], u[1]};
+  }
   BMPC_D static void policy_fast(const KParams& P, int kind, const real* par, const real* x, real* u) {
     if (kind == BMPC_POLICY_MAINTAIN) {
       u[0] = 0.0;
       u[1] = -P.Kpsi * x[3];
+    } else if (kind == BMPC_POLICY_BRAKE) {
+      const real a = -7.0, b = -x[2];
+      const real e = bmpc_exp(-5.0 * fabs(a - b));
+      const real ea = (a >= b) ? 1.0 : e, eb = (a >= b) ? e : 1.0;
+      u[0] = bmpc_div(ea * a + eb * b, ea + eb);
+      u[1] = -P.Kpsi * x[3];
+    } else if (kind == BMPC_POLICY_LC) {
+      u[0] = -0.8558 * (x[2] - par[2]);
+      u[1] = -0.3162 * (x[1] - par[1]) - 3.9889 * (x[3] - par[3]);
+    } else if (kind == BMPC_POLICY_TRACKV) {
+      u[0] = 0.5 * (par[0] - x[2]);
+      u[1] = -P.Kpsi * x[3];
     } else {
-      policy(P, kind, par, x, u);
+      const Input2 r = policy_ref(P, kind, par[0], x[0], x[2], x[3]);
+      u[0] = r.a;
+      u[1] = r.r;
     }
   }
 
@@ -139,15 +161,16 @@ struct HighwayModel {
     linearize_sc(P, x, u, s, c, lin, cc, xn);
   }
   BMPC_D static void linearize_sc(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc, real* xn) {
+    lin_only(P, x, u, s, c, lin, cc);
+    step_sc(P, x, u, s, c, xn);
+  }
+  // compressed A and C alone (the successor state is step_sc's)
+  BMPC_D static void lin_only(const KParams& P, const real* x, const real*, real s, real c, real* lin, real* cc) {
     const real dt = P.dt, v = x[2];
     lin[0] = dt * c;
     lin[1] = -dt * v * s;
     lin[2] = dt * s;
     lin[3] = dt * v * c;
-    xn[0] = x[0] + dt * (v * c);
-    xn[1] = x[1] + dt * (v * s);
-    xn[2] = x[2] + dt * u[0];
-    xn[3] = x[3] + dt * u[1];
     // C = xp - A x - B u; rows 2,3 vanish identically
     cc[0] = dt * v * x[3] * s;
     cc[1] = -dt * v * x[3] * c;
@@ -330,14 +353,15 @@ struct QuadrupedModel {
     linearize_sc(P, x, u, s, c, lin, cc, xn);
   }
   BMPC_D static void linearize_sc(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc, real* xn) {
+    lin_only(P, x, u, s, c, lin, cc);
+    step_sc(P, x, u, s, c, xn);
+  }
+  BMPC_D static void lin_only(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc) {
     const real dt = P.dt;
     lin[0] = dt * c;
     lin[1] = dt * s;
     lin[2] = dt * (-u[0] * s - u[1] * c);
     lin[3] = dt * (u[0] * c - u[1] * s);
-    xn[0] = x[0] + dt * (u[0] * c - u[1] * s);
-    xn[1] = x[1] + dt * (u[0] * s + u[1] * c);
-    xn[2] = x[2] + dt * u[2];
     // C = xp - A x - B u = -A[:,2]*theta in rows 0,1
     cc[0] = -lin[2] * x[2];
     cc[1] = -lin[3] * x[2];
@@ -509,6 +533,7 @@ struct RateAug {
   BMPC_D static void linearize_sc(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc, real* xn) {
     M::linearize_sc(P, x, u, s, c, lin, cc, xn);
   }
+  BMPC_D static void lin_only(const KParams& P, const real* x, const real* u, real s, real c, real* lin, real* cc) { M::lin_only(P, x, u, s, c, lin, cc); }
   BMPC_D static void policy(const KParams& P, int kind, const real* par, const real* x, real* u) { M::policy(P, kind, par, x, u); }
   BMPC_D static void policy_fast(const KParams& P, int kind, const real* par, const real* x, real* u) { M::policy_fast(P, kind, par, x, u); }
   BMPC_D static void linearize(const KParams& P, const real* x, const real* u, real* lin, real* cc, real* xn) {

@@ -215,6 +215,15 @@ __device__ __forceinline__ void bmpc_sincos_core(real a, real& s, real& c) {
   c = ((q + 1) & 2) ? -c0 : c0;
 }
 #endif
+BMPC_D void bmpc_sincos_inline(real a, real& s, real& c) {
+#if defined(__CUDA_ARCH__)
+  if (fabs(a) < 1.0e5) {
+    bmpc_sincos_core(a, s, c);
+    return;
+  }
+#endif
+  bmpc_sincos(a, &s, &c);
+}
 // sc = {sin a0, cos a0, sin a1, cos a1, sin a2, cos a2}
 BMPC_D void bmpc_sincos3(real a0, real a1, real a2, real* sc) {
 #if defined(__CUDA_ARCH__)

@@ -399,15 +399,14 @@ struct Solver {
 
   // Order of the expansion (everything that is not a recursion in time runs node-parallel over the whole team):
   //   1. node-parallel: time-shifted previous inputs and active-set codes of every node (updatetree :1025-1033)
-  //   2. per tree level, lanes = child branches: the three rollouts of a branch in one loop - obstacle under its policy
+  //   2. per tree level, lanes = (chain, child branch): the three rollouts of a branch - obstacle under its policy
   //      (zpred_eval), ego under policy 0 (BF_traj) and the ego linearisation trajectory with its per-node A, B, C
-  //      (:1048-1059); they do not depend on the branch probabilities
+  //      (:1048-1059) - are stepped by one instruction stream; they do not depend on the branch probabilities
   //   3. node-parallel: safety terms of every (branch, step); soft-min per branch in two passes (minimum, then the
   //      shifted exponentials - identical to the reference's unshifted form, highway_branch_dyn.py:151-162)
   //   4. lanes = parents: probabilities, weights, arg-max children (branch_eval)
   //   5. node-parallel: cost vectors, collision rows (col_eval), ADMM start
-  // lanes = child branches of a tree level (first warp of the team only): obstacle rollout under the child's policy,
-  // ego rollout under policy 0, ego linearisation rollout with its per-node A, B, C
+  // first warp of the team only; the root by lane 0, then level by level (see the level loop)
   BMPC_DN void rollouts() {
     const real* x0 = PP.x0 + (size_t)prob * NXP;
     const real* z0 = PP.z0 + (size_t)prob * NXP;
@@ -443,69 +442,73 @@ struct Solver {
     bsync();
 #pragma unroll 1
     for (int d = 0; d < PP.NB; ++d) {
+      // lanes = (chain, child branch): chain 0 the ego under policy 0 (BF_traj), chain 1 the obstacle under the child's policy
+      // (zpred_eval), chain 2 the ego linearisation trajectory under the shifted previous inputs (:1048-1059).  The three
+      // chains of a branch are the same recursion x+ = f(x, u(x)) with different inputs, so one instruction stream steps all
+      // of them: the leader warp's time follows its instruction count (profiles/r02_staging_ab.md), and a lane that walked the
+      // three chains one after the other issued the step three times.
       const int cnt = PP.pw[d] * m;
 #pragma unroll 1
-      for (int idx = BMPC_LANE_ID; idx < cnt; idx += BMPC_BLANES) {
-        const int bq = bmpc_idiv(idx, PP.inv_m);
+      for (int idx = BMPC_LANE_ID; idx < 3 * cnt; idx += BMPC_BLANES) {
+        const int ch = (idx >= 2 * cnt) ? 2 : (idx >= cnt ? 1 : 0);
+        const int ci = idx - ch * cnt;
+        const int bq = bmpc_idiv(ci, PP.inv_m);
         const int b = PP.off[d] + bq;
-        const int i = idx - bq * m;
+        const int i = ci - bq * m;
         const int c = bmpc_first_child(PP, b, d) + i;
         const int kc = bmpc_ndu(PP, c);
         const int kpc = kp_of(c, 0);
-        const real* par = pol_par(i);
-        const real* par0 = pol_par(0);
-        const int kind = PP.pol_kind[i], kind0 = PP.pol_kind[0];
-        real* zout = PP.out.zPred ? PP.out.zPred + ((size_t)prob * PP.totalu + kc) * NXP : nullptr;
-        real z[NXP], xe[NXP], xb[NXP];
+        const real* parg = pol_par(ch == 0 ? 0 : i);
+        const real par[4] = {parg[0], parg[1], parg[2], parg[3]};   // in registers for the whole rollout
+        const int kind = PP.pol_kind[ch == 0 ? 0 : i];
+        real* zout = (ch == 1 && PP.out.zPred) ? PP.out.zPred + ((size_t)prob * PP.totalu + kc) * NXP : nullptr;
+        const real* start = (ch == 0 ? EXLp() : (ch == 1 ? EXZp() : EXXp())) + NX * b;
+        real x[NXP];
 #pragma unroll
-        for (int q = 0; q < NXP; ++q) {
-          z[q] = EXZp()[NX * b + q];
-          xe[q] = EXLp()[NX * b + q];
-          xb[q] = EXXp()[NX * b + q];
-        }
+        for (int q = 0; q < NXP; ++q) x[q] = start[q];
 #pragma unroll 1
         for (int t = 0; t < PP.N; ++t) {
           const int kp = kpc + t;
-          real u[NU], xn[NXP], sc[6];
-          // the three headings are known at the top of the step: their sines and cosines are computed side by side
-          bmpc_sincos3(xe[M::HEADING], z[M::HEADING], xb[M::HEADING], sc);
-          M::policy_fast(PP, kind0, par0, xe, u);
-          M::step_sc(PP, xe, u, sc[0], sc[1], xn);
+          real u[NU], xn[NXP], sn, cs;
+          bmpc_sincos_inline(x[M::HEADING], sn, cs);
+          if (ch == 2) {
+            real lin[M::NLIN], cc[M::NCC];
 #pragma unroll
-          for (int q = 0; q < NXP; ++q) xe[q] = xn[q];
-          M::policy(PP, kind, par, z, u);
-          M::step_sc(PP, z, u, sc[2], sc[3], xn);
+            for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
+            M::lin_only(PP, x, u, sn, cs, lin, cc);
 #pragma unroll
-          for (int q = 0; q < NXP; ++q) {
-            z[q] = xn[q];
-            F(F_ZS + q, kp) = xn[q];
-            if (zout) zout[t * NXP + q] = xn[q];
+            for (int q = 0; q < M::NLIN; ++q) F(F_LIN + q, kp) = lin[q];
+#pragma unroll
+            for (int q = 0; q < M::NCC; ++q) F(F_CC + q, kp) = cc[q];
+#pragma unroll
+            for (int q = 0; q < NXP; ++q) F(F_XQ + q, kp) = x[q];
+            if (t == PP.N - 1) {
+#pragma unroll
+              for (int q = 0; q < NXP; ++q) EXLp()[NX * c + q] = x[q];
+            }
+          } else {
+            M::policy_fast(PP, kind, par, x, u);
           }
-          F(F_FC, kp) = z[0];
-          F(F_FC + 1, kp) = z[1];
-          F(F_ZE, kp) = xe[0];
-          F(F_ZE + 1, kp) = xe[1];
-          real lin[M::NLIN], cc[M::NCC];
+          M::step_sc(PP, x, u, sn, cs, xn);
 #pragma unroll
-          for (int a = 0; a < NU; ++a) u[a] = F(F_UQ + a, kp);
-          M::linearize_sc(PP, xb, u, sc[4], sc[5], lin, cc, xn);
+          for (int q = 0; q < NXP; ++q) x[q] = xn[q];
+          if (ch == 0) {
+            F(F_ZE, kp) = x[0];
+            F(F_ZE + 1, kp) = x[1];
+          } else if (ch == 1) {
 #pragma unroll
-          for (int q = 0; q < M::NLIN; ++q) F(F_LIN + q, kp) = lin[q];
-#pragma unroll
-          for (int q = 0; q < M::NCC; ++q) F(F_CC + q, kp) = cc[q];
-#pragma unroll
-          for (int q = 0; q < NXP; ++q) F(F_XQ + q, kp) = xb[q];
-          if (t == PP.N - 1) {
-#pragma unroll
-            for (int q = 0; q < NXP; ++q) EXLp()[NX * c + q] = xb[q];
+            for (int q = 0; q < NXP; ++q) {
+              F(F_ZS + q, kp) = x[q];
+              if (zout) zout[t * NXP + q] = x[q];
+            }
+            F(F_FC, kp) = x[0];
+            F(F_FC + 1, kp) = x[1];
           }
-#pragma unroll
-          for (int q = 0; q < NXP; ++q) xb[q] = xn[q];
         }
+        if (ch != 0) {
+          real* end = (ch == 1 ? EXZp() : EXXp()) + NX * c;
 #pragma unroll
-        for (int q = 0; q < NXP; ++q) {
-          EXXp()[NX * c + q] = xb[q];
-          EXZp()[NX * c + q] = z[q];
+          for (int q = 0; q < NXP; ++q) end[q] = x[q];
         }
       }
       bsync();

@@ -578,9 +578,9 @@ def run_gpu(args):
 WORKLOAD = ("highway Branch MPC (BASELINE configs[2]): m=3 policies [maintain, brake, lane-change], NB=2, N=8 -> 13 branches / "
             "106 state nodes / 97 input nodes; closed-loop warm solves (updatetree path), 16384 episodes per GPU")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of bmpc_solve_kernel<HighwayModel,3,...>, keyed by (config, episodes)
-NCU_DRAM_BYTES_PER_LAUNCH = {("3", 16384): 105988608 + 22319360}
-NCU_SOURCE = ("profiles/r02_solve_kernel_v20_ncu_raw.csv: ncu --set full of one warm launch over 16384 episodes (tools/gpu_ncu.sh), "
-              "dram__bytes_read.sum 106.0 MB + dram__bytes_write.sum 22.3 MB; the launch's dirty lines are still in the 126 MB L2 "
+NCU_DRAM_BYTES_PER_LAUNCH = {("3", 16384): 105128704 + 20563456}
+NCU_SOURCE = ("profiles/r02_solve_kernel_v22_ncu_raw.csv: ncu --set full of one warm launch over 16384 episodes (tools/gpu_ncu.sh), "
+              "dram__bytes_read.sum 105.1 MB + dram__bytes_write.sum 20.6 MB; the launch's dirty lines are still in the 126 MB L2 "
               "when it ends, so the written share is below the algorithmic figure")
 
 
