@@ -846,31 +846,32 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
   cudaStream_t s = h->last_stream;
   BMPC_CK(h, cudaStreamSynchronize(s));
   char* host_out = (char*)h->stage_out_host[h->stage_out_turn++ & 1];   // the views handed out two calls ago die here
-  // inputs: x0 | z0 | xref | polpar, [count] rows each, contiguous
+  // inputs: x0 | z0 | xref | polpar, [count] rows each, contiguous on the device.  Arrays the caller keeps in page-locked
+  // memory travel straight from there (one DMA each); pageable ones are gathered into the pinned block first and travel in one
+  // DMA.  Either way the stream is drained before this call returns, so the caller's arrays are free again.
   real* hin = h->stage_in_host;
   const size_t rows = (size_t)count;
-  memcpy(hin, x0, rows * n * 8);
-  memcpy(hin + rows * n, z0, rows * n * 8);
-  memcpy(hin + 2 * rows * n, xref, rows * n * 8);
-  size_t in_used = 3 * rows * n;
-  if (policy_params) {
-    memcpy(hin + in_used, policy_params, rows * m * 4 * 8);
-    in_used += rows * m * 4;
+  const void* src[6] = {x0, z0, xref, policy_params, xf ? xf->S : nullptr, xf ? xf->bounds : nullptr};
+  const size_t len[6] = {rows * n, rows * n, rows * n, rows * m * 4, rows * n * n, rows * nrw * 2};
+  bool direct = rows * n * 8 >= 4096;   // small batches: one gathered copy is cheaper than several DMAs
+  for (int i = 0; i < 6 && direct; ++i) {
+    if (!src[i]) continue;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src[i]) != cudaSuccess) { cudaGetLastError(); direct = false; }
+    else if (attr.type != cudaMemoryTypeHost) direct = false;
   }
-  // merge scenario: state transform and state bounds of the call, each optional
+  size_t in_used = 0;
   real* dS = nullptr;
   real* dbd = nullptr;
-  if (xf && xf->S) {
-    memcpy(hin + in_used, xf->S, rows * n * n * 8);
-    dS = h->stage_in + in_used;
-    in_used += rows * n * n;
+  for (int i = 0; i < 6; ++i) {
+    if (!src[i]) continue;
+    if (direct) BMPC_CK(h, cudaMemcpyAsync(h->stage_in + in_used, src[i], len[i] * sizeof(real), cudaMemcpyHostToDevice, s));
+    else memcpy(hin + in_used, src[i], len[i] * sizeof(real));
+    if (i == 4) dS = h->stage_in + in_used;     // merge scenario: state transform and state bounds of the call, each optional
+    if (i == 5) dbd = h->stage_in + in_used;
+    in_used += len[i];
   }
-  if (xf && xf->bounds) {
-    memcpy(hin + in_used, xf->bounds, rows * nrw * 2 * 8);
-    dbd = h->stage_in + in_used;
-    in_used += rows * nrw * 2;
-  }
-  BMPC_CK(h, cudaMemcpyAsync(h->stage_in, hin, in_used * sizeof(real), cudaMemcpyHostToDevice, s));
+  if (!direct) BMPC_CK(h, cudaMemcpyAsync(h->stage_in, hin, in_used * sizeof(real), cudaMemcpyHostToDevice, s));
   real* dx0 = h->stage_in;
   real* dz0 = dx0 + rows * n;
   real* dxr = dz0 + rows * n;

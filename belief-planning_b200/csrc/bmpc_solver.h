@@ -637,22 +637,30 @@ struct Solver {
       EXp()[NS * c] = bmpc_div(num, den);   // exchange slot: safety value of child c
     }
     bsync();
+    // un-normalised weight of every child branch (two exponentials), lanes = children of all levels at once: a parent lane
+    // that walked its children paid them one after the other, on every level
+#pragma unroll 1
+    for (int c = 1 + BMPC_LANE_ID; c < PP.nbranch; c += BMPC_BLANES) {
+      real himax = 0.0;
+      if (M::kWeightNeedsMax) {
+        const int dc = bmpc_depth(PP, c);
+        const int fc = bmpc_first_child(PP, bmpc_parent(PP, c, dc), dc - 1);
+        himax = -1e300;
+#pragma unroll 1
+        for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
+      }
+      EXp()[NS * c + 1] = M::branch_weight(PP, EXp()[NS * c], himax);
+    }
+    bsync();
 #pragma unroll 1
     for (int d = 0; d < PP.NB; ++d) {
       // probabilities p = softmax over the siblings, weights w = w_parent p, arg-max child (lanes = parents)
 #pragma unroll 1
       for (int b = PP.off[d] + BMPC_LANE_ID; b < PP.off[d + 1]; b += BMPC_BLANES) {
         const int fc = bmpc_first_child(PP, b, d);
-        real himax = -1e300;
-#pragma unroll 1
-        for (int j = 0; j < m; ++j) himax = fmax(himax, EXp()[NS * (fc + j)]);
         real sum = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < m; ++j) {
-          const real wj = M::branch_weight(PP, EXp()[NS * (fc + j)], himax);
-          EXp()[NS * (fc + j) + 1] = wj;   // kept for the normalisation below (two exponentials per child)
-          sum += wj;
-        }
+        for (int j = 0; j < m; ++j) sum += EXp()[NS * (fc + j) + 1];
         int best = 0;
         real pb = -1.0;
         const real rsum = bmpc_div(1.0, sum);

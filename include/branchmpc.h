@@ -248,7 +248,8 @@ int bmpc_eval_belief(bmpc_handle* h, const double* xb, const double* xbackup, co
 
 /* Same step on HOST buffers: copies inputs to the device, solves, copies every non-NULL output
  * back and synchronises.  `out` holds HOST pointers here.  Inputs and outputs each travel in ONE transfer through
- * pinned staging owned by the handle (runs on the stream of the handle's last solve). */
+ * pinned staging owned by the handle (runs on the stream of the handle's last solve); input arrays that already lie in
+ * page-locked memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) are sent from where they lie instead. */
 int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                     const double* policy_params, int64_t count, const bmpc_outputs* out);
 /* Zero-copy variant (the call the drop-in BranchMPC.solve makes): `want` marks the requested outputs with non-NULL

@@ -481,3 +481,26 @@ def test_warm_polish_skip_does_not_change_the_plans(bmpc):
     assert skipped_some      # the default schedule did save factorisations somewhere
     for h in handles:
         h.close()
+
+
+def test_host_solve_from_pinned_and_pageable_arrays_agree(bmpc):
+    """bmpc_solve_host sends page-locked caller arrays straight to the device (one DMA each) and gathers pageable ones into
+    its pinned block first: same inputs, same results, bit for bit, over three closed-loop steps."""
+    import torch
+    B = 1024
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=321)
+    runs = []
+    for pinned in (True, False):
+        arrs = [torch.as_tensor(a.copy()).pin_memory().numpy() if pinned else a.copy() for a in (x0, z0, xref, pp)]
+        mpc = bmpc.BatchedBranchMPC(scenarios.highway_config(batch_capacity=B))
+        outs = []
+        for _ in range(3):
+            r = mpc.solve_host(*arrs, outputs=("u0", "uPred", "xPred", "objective", "status"))
+            outs.append({k: v.copy() for k, v in r.items()})
+            arrs[0][:] = scenarios.euler_highway(arrs[0], r["u0"])
+        runs.append(outs)
+        mpc.close()
+    for a, b in zip(*runs):
+        assert (a["status"] <= 1).all()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
