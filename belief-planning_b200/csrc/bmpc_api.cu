@@ -842,6 +842,8 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
     BMPC_CK(h, cudaMemset(h->stage_out, 0, h->stage_out_bytes));
     BMPC_CK(h, cudaMallocHost(&h->stage_out_host[0], h->stage_out_bytes));
     BMPC_CK(h, cudaMallocHost(&h->stage_out_host[1], h->stage_out_bytes));
+    memset(h->stage_out_host[0], 0, h->stage_out_bytes);
+    memset(h->stage_out_host[1], 0, h->stage_out_bytes);
   }
   cudaStream_t s = h->last_stream;
   BMPC_CK(h, cudaStreamSynchronize(s));
@@ -876,7 +878,12 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
   real* dz0 = dx0 + rows * n;
   real* dxr = dz0 + rows * n;
   real* dpp = dxr + rows * n;
-  // outputs: only the requested ones, packed; 8-byte outputs first keeps every block aligned
+  // outputs: only the requested ones, packed; 8-byte outputs first keeps every block aligned.  The kernel writes them straight
+  // into the pinned host block (page-locked memory is device-addressable under unified addressing): every team's rows cross the
+  // bus while the other teams are still solving, so the 190 MB of a full-interface step of 16 384 episodes cost no transfer time
+  // after the launch.  reserved[6] bit 2: through the device block and one DMA instead (the former path; tests compare the two).
+  static const bool via_device_env = getenv("BMPC_HOST_VIA_DEVICE") != nullptr;   // experiments (A/B of the two paths)
+  const bool direct_out = (h->cfg.reserved[6] & 4) == 0 && !via_device_env;
   bmpc_outputs dout;
   void** dslot[kNumOut];
   out_slots(&dout, dslot);
@@ -887,7 +894,7 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
       const bool wide = (sz[i] % 8) == 0;
       if (wide != (pass == 0)) continue;
       if (*wslot[i]) {
-        *dslot[i] = (char*)h->stage_out + off;
+        *dslot[i] = (direct_out ? host_out : (char*)h->stage_out) + off;
         offs[i] = off;
         off += rows * sz[i];
       } else {
@@ -897,7 +904,7 @@ static int solve_host_impl(bmpc_handle* h, const double* x0, const double* z0, c
   const int rc = xf ? bmpc_solve_transformed(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, dS, dbd, count, &dout, s)
                     : bmpc_solve(h, dx0, dz0, dxr, policy_params ? dpp : nullptr, count, &dout, s);
   if (rc != BMPC_OK) return rc;
-  BMPC_CK(h, cudaMemcpyAsync(host_out, h->stage_out, off, cudaMemcpyDeviceToHost, s));
+  if (!direct_out) BMPC_CK(h, cudaMemcpyAsync(host_out, h->stage_out, off, cudaMemcpyDeviceToHost, s));
   BMPC_CK(h, cudaStreamSynchronize(s));
   for (int i = 0; i < kNumOut; ++i)
     if (*wslot[i]) *vslot[i] = host_out + offs[i];

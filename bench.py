@@ -454,7 +454,8 @@ def run_gpu(args):
         e2e_max = shard.reduce_stats({"max_e2e_s": e2e_t}, device=dev)["max_e2e_s"]
         e2e = {"value": world * B * K / e2e_max, "unit": UNIT,
                "h2d_bytes_per_step": int(B * (3 * 4 + 3 * 4) * 8), "d2h_bytes_per_step": int(B * (2 * 8 + 8 + 4)),
-               "what": "bmpc_solve_host: host arrays in, first input + objective + status out, copies inside the timed region"}
+               "what": "bmpc_solve_host: pinned host arrays in (one DMA each), first input + objective + status out (written by the "
+                       "kernel into pinned host memory, then copied into the caller's arrays); all of it inside the timed region"}
         # ---- the same through the reference-facing drop-in class with EVERY result array of the reference interface ----
         import Init_MPC
         import MPC_branch
@@ -487,8 +488,8 @@ def run_gpu(args):
         e2e_full = {"value": world * B * Kf / full_max, "unit": UNIT, "steps": Kf,
                     "h2d_bytes_per_step": int(B * (3 * 4 + 3 * 4) * 8), "d2h_bytes_per_step": int(B * per_solve_bytes),
                     "what": "drop-in MPC_branch.BranchMPC.solve(x (B,4), z (B,4), xRef (B,4)) -> uPred, xPred, xLin, zPred, branch "
-                            "weights/probabilities, objective, status on the host (one DMA each way through pinned staging, then "
-                            "the copies into the controller's result arrays)"}
+                            "weights/probabilities, objective, status on the host (inputs in one DMA through pinned staging, results "
+                            "written by the kernel into the library's pinned host block, which the controller's arrays view)"}
         ctl._solver.close()
     if rank == 0 and which == "3":
         # p50 latency of a single warm solve through the host API (batch of one)

@@ -149,7 +149,7 @@ typedef struct bmpc_config {
                              warps per SM; [2] polish when at most this many nodes changed their implied set between
                              checks; [3] polish at the latest every this many ADMM iterations (80; quadruped 20); [4] interior-point
                              fallback after this many failed polish attempts (3; quadruped 1; <0 = never; 100 = always, without a polish attempt first); [5] its iteration cap (40);
-                             [6] bit 0 = natural work order instead of longest-first, bit 1 = stage the next episode's state into shared memory by bulk copies while the current one is solved (off by default: measured slower); [7] k > 0 = the cycles output counts phase k only
+                             [6] bit 0 = natural work order instead of longest-first, bit 1 = stage the next episode's state into shared memory by bulk copies while the current one is solved (off by default: measured slower), bit 2 = bmpc_solve_host* packs the results into a device block and copies it back in one DMA instead of letting the kernel write them into the pinned host block; [7] k > 0 = the cycles output counts phase k only
                              (1 interior point, 2 expansion, 3 rho, 4 factorisations, 5 sweeps, 6 polish passes,
                              7 adjoint, 8 ADMM rows, 9 final pass) */
 } bmpc_config;
@@ -247,9 +247,11 @@ int bmpc_eval_belief(bmpc_handle* h, const double* xb, const double* xbackup, co
                      double* B, double* C, double* h0, double* Jh, double* xbp, void* stream);
 
 /* Same step on HOST buffers: copies inputs to the device, solves, copies every non-NULL output
- * back and synchronises.  `out` holds HOST pointers here.  Inputs and outputs each travel in ONE transfer through
- * pinned staging owned by the handle (runs on the stream of the handle's last solve); input arrays that already lie in
- * page-locked memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) are sent from where they lie instead. */
+ * back and synchronises.  `out` holds HOST pointers here.  Inputs travel in ONE transfer through pinned staging owned by
+ * the handle (runs on the stream of the handle's last solve); input arrays that already lie in page-locked memory
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory) are sent from where they lie instead.  The kernel writes the requested
+ * results straight into a pinned host block of the handle (no transfer after the launch), from which they are copied into
+ * the caller's arrays. */
 int bmpc_solve_host(bmpc_handle* h, const double* x0, const double* z0, const double* xref,
                     const double* policy_params, int64_t count, const bmpc_outputs* out);
 /* Zero-copy variant (the call the drop-in BranchMPC.solve makes): `want` marks the requested outputs with non-NULL

@@ -504,3 +504,28 @@ def test_host_solve_from_pinned_and_pageable_arrays_agree(bmpc):
         assert (a["status"] <= 1).all()
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_host_results_written_in_place_match_the_copied_ones(bmpc):
+    """bmpc_solve_host lets the kernel write the requested results straight into the pinned host block (default) or packs
+    them into a device block that comes back in one DMA (reserved[6] bit 2): every output of three closed-loop steps must
+    agree bit for bit."""
+    B = 1500
+    x0, z0, xref, pp = scenarios.highway_batch(B, seed=78)
+    runs = []
+    for flag in (0, 4):
+        cfg = scenarios.highway_config(batch_capacity=B)
+        cfg.reserved[6] = flag
+        mpc = bmpc.BatchedBranchMPC(cfg)
+        x = x0.copy()
+        outs = []
+        for _ in range(3):
+            r = mpc.solve_host(x, z0, xref, pp)
+            outs.append({k: v.copy() for k, v in r.items() if k != "cycles"})
+            x = scenarios.euler_highway(x, r["u0"])
+        runs.append(outs)
+        mpc.close()
+    for a, b in zip(*runs):
+        assert (a["status"] <= 1).all()
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
