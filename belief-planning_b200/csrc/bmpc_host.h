@@ -201,7 +201,9 @@ inline int make_params(const bmpc_config& c, KParams* out, std::string* err) {
   P.warm_backoff = (c.reserved[0] & 4) ? 0 : 1;
   {
     const int ws = (c.reserved[0] >> 4) & 15;    // 0 = default, 15 = never skip
-    P.warm_skip = ws == 0 ? 3 : (ws == 15 ? 0 : ws);
+    // quadruped: a failed attempt does not predict the next one (its hard episodes are the interior-point ones): skipping
+    // costs 4 % in the first steps of a closed loop and gains nothing later (profiles/r02_staging_ab.md)
+    P.warm_skip = ws == 0 ? (quad ? 0 : 3) : (ws == 15 ? 0 : ws);
   }
   *out = P;
   return BMPC_OK;

@@ -144,7 +144,7 @@ typedef struct bmpc_config {
   int32_t device;         /* CUDA device ordinal                                      */
   int32_t reserved[8];    /* experiment switches, 0 = default: [0] bit 0 = no residual balancing of rho, bit 1 = no warm-polish attempt on
                              the solves that refresh rho, bit 2 = no doubling of the skip below, bits 4..7 = k: an episode whose warm-polish attempt
-                             ended on the ADMM path skips the attempt on its next k solves (0 = the default 3, 15 = never skip; with
+                             ended on the ADMM path skips the attempt on its next k solves (0 = the default: 3, the quadruped model never skips; 15 = never skip; with
                              bit 2 clear k doubles with every further failed attempt in a row, up to 24); [1] cap of resident
                              warps per SM; [2] polish when at most this many nodes changed their implied set between
                              checks; [3] polish at the latest every this many ADMM iterations (80; quadruped 20); [4] interior-point
